@@ -1,0 +1,160 @@
+/* nmb200.h -- C ABI of libnmb200.so: the B200 (sm_100a) implementation of py_neuromodulation's
+ * per-window feature-extraction hot path.
+ *
+ * The reference (py_neuromodulation v0.1.4) is pure Python and has NO foreign-function
+ * interface; this ABI is new.  Each entry point cites the reference interface whose work it
+ * takes over (paths relative to the reference's py_neuromodulation/ directory).  A reference
+ * maintainer binds it with ctypes -- see INTEGRATION.md for the stub.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and -1 on
+ * failure, in which case nm_last_error() describes the problem (thread local).  The caller
+ * owns all host memory; device memory is owned by the opaque pipeline handle.
+ * All feature values are float64, laid out row-major as (n_windows, n_features); the column
+ * of every value is chosen by the caller through the `colmap` arrays (-1 = do not emit), so
+ * the host side keeps the reference's dict-insertion column order without a permutation pass.
+ *
+ * A pipeline is built for ONE window length W (samples) and one channel set:
+ *   create -> set_* (preprocessing) -> add_* (feature families) -> finalize
+ *   -> upload -> run_windows (offline batch, stream/stream.py:280-330)
+ *   or process_window (one window at a time, stream/data_processor.py:238-311).
+ */
+#ifndef NMB200_H
+#define NMB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMB200_ABI_VERSION 1
+
+typedef struct nm_pipeline nm_pipeline;
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* nm_last_error(void);
+int nm_abi_version(void);
+int nm_device_count(int* count);
+/* pinned host memory for recordings / result matrices (host<->device copies at full PCIe rate) */
+int nm_host_alloc(void** ptr, long long bytes);
+int nm_host_free(void* ptr);
+
+/* ---- pipeline life cycle ------------------------------------------------------------------ */
+/* n_raw_rows: rows of the array handed to Stream.run / DataProcessor.process (all channels);
+ * n_ch: rows used for features (stream/data_processor.py:141-160 `feature_idx`);
+ * window_samples: W; n_features: F, number of output columns. */
+int nm_pipeline_create(int device, int n_raw_rows, int n_ch, int window_samples, int n_features, nm_pipeline** out);
+void nm_pipeline_destroy(nm_pipeline* p);
+int nm_finalize(nm_pipeline* p);
+/* forget cross-window state (burst history, normaliser history): what constructing a new
+ * DataProcessor does in stream/stream.py:233-242 */
+int nm_reset_state(nm_pipeline* p);
+
+/* ---- preprocessing (stream/data_processor.py:253-257, processing/data_preprocessor.py:74-84) */
+/* pick[n_ch]: raw row of each feature channel (np.nan_to_num(data)[feature_idx, :]) */
+int nm_set_pick(nm_pipeline* p, const int* pick);
+/* ReReferencer.process == ref_matrix @ data (processing/rereference.py:88-102), handed over
+ * factored: y_i = sum_g gcoef[i,g] * S_g + sum_k sp_val[k] * x[sp_col[k]],  S_g = sum of the
+ * channels with group_of[j] == g.  n_groups <= 8. */
+int nm_set_reref(nm_pipeline* p, int n_groups, const int* group_of, const double* gcoef,
+                 const int* sp_ptr, const int* sp_col, const double* sp_val);
+/* NotchFilter.process: zero-phase FIR with reflect-limited padding (filter/notch_filter.py:78-93) */
+int nm_set_notch(nm_pipeline* p, const double* taps, int n_taps);
+/* NaN re-insertion (stream/data_processor.py:297-306): columns [col_ptr[r], col_ptr[r+1]) of `cols`
+ * become NaN in every window where raw row r contains a NaN */
+int nm_set_nan_columns(nm_pipeline* p, const int* col_ptr, const int* cols);
+
+/* ---- feature families ---------------------------------------------------------------------- */
+/* Hjorth / Raw / LineLength (features/hjorth_raw.py:24-57, features/linelength.py:11-21);
+ * colmap[n_ch*5]: activity, mobility, complexity, raw, linelength */
+int nm_add_scan(nm_pipeline* p, int hjorth, int raw, int linelength, const int* colmap);
+
+/* FFT / Welch / STFT band features (features/oscillatory.py:90-119,150-182,215-250) described as
+ * nseg segment DFTs of nper samples; see csrc/nm_spec.cuh for the three parameterisations. */
+typedef struct {
+    int nper, nseg, hop, start;
+    int ext_even, ext_len;
+    int detrend;
+    int power;          /* 0: |Z|*scale   1: |Z|^2*scale, interior bins doubled */
+    double scale;
+    int log;
+    int keep_segments;  /* 1: estimators over the (bin, segment) matrix (STFT) */
+    int n_bands;
+    int est_mask;       /* bit0 mean, bit1 median, bit2 std, bit3 max */
+    int want_spectrum;
+    const double* win;  /* [nper] or NULL */
+    const int* band_lo; /* [n_bands] first bin  */
+    const int* band_hi; /* [n_bands] one past the last bin */
+    const int* colmap;  /* [n_ch * (n_bands*4 + nper/2+1)]: band b estimator e at b*4+e, then spectrum bins */
+} nm_spectral_cfg;
+int nm_add_spectral(nm_pipeline* p, const nm_spectral_cfg* cfg);
+
+/* BandPower: MNEFilter.filter_data + tail variance features (filter/mne_filter.py:82-128,
+ * features/bandpower.py:165-207); taps[n_bands*n_taps] symmetric; colmap[n_ch*n_bands*3] */
+int nm_add_bandpower(nm_pipeline* p, int n_bands, const double* taps, int n_taps, const int* seglen,
+                     int activity, int mobility, int complexity, int log_transform, const int* colmap);
+
+/* Bursts (features/bursts.py:149-298): band-pass bank -> analytic-signal envelope -> quantile of the
+ * last ring_samples envelope samples -> run-length features.
+ * colmap[n_ch*n_bands*6]: duration_mean, duration_max, amplitude_mean, amplitude_max, burst_rate_per_s, in_burst.
+ * qlo/qgamma give numpy's 'linear' quantile position for every possible history length:
+ * the host passes a callback-free closed form: quantile q in [0,1]; the library evaluates
+ * numpy's virtual index n*q + (1 - q) - 1 in float64 exactly as numpy does. */
+int nm_add_bursts(nm_pipeline* p, int n_bands, const double* taps, int n_taps, int samples_overlap,
+                  int ring_samples, double quantile, double sfreq, double segment_length_s, const int* colmap);
+
+/* SharpwaveAnalyzer (features/sharpwaves.py:225-465).  feat_ids/est_ids[n_combo] list the
+ * (feature, estimator) pairs in output order; colmap[n_ch*n_filters*(n_combo+1)*2]: slot (f*(n_combo+1)+k)*2+pol,
+ * k == n_combo being num_peaks; pol 0 holds the joined value when pair_estimator is set, else pol 0/1 = Peak/Trough pass.  Feature ids: 0 peak_left 1 peak_right 2 num_peaks 3 trough 4 width 5 prominence
+ * 6 interval 7 decay_time 8 rise_time 9 sharpness 10 rise_steepness 11 decay_steepness 12 slope_ratio.
+ * Estimator ids: 0 mean 1 median 2 max 3 min 4 var. */
+int nm_add_sharpwave(nm_pipeline* p, int n_filters, const double* taps, int n_taps, int dist_peaks, int dist_troughs,
+                     int sharp_offset, double ms_per_sample, int n_combo, const int* feat_ids, const int* est_ids,
+                     int pair_estimator, int want_num_peaks, const int* colmap);
+
+/* FeatureNormalizer (processing/normalization.py:81-111): rolling normalisation of the columns listed in
+ * `cols` over the previous n_keep windows (current included); method 0 mean, 1 median, 2 zscore,
+ * 3 zscore-median; clip <= 0 disables clipping. */
+int nm_add_feature_normalizer(nm_pipeline* p, int method, double clip, int n_keep, int n_cols, const int* cols);
+
+/* ---- data path ------------------------------------------------------------------------------ */
+/* Recording (n_raw_rows, n_samples), row pitch in elements; copies host -> device and runs the
+ * window-independent preprocessing (nan_to_num, pick, re-reference). */
+int nm_upload_f32(nm_pipeline* p, const float* data, long long n_samples, long long pitch);
+int nm_upload_f64(nm_pipeline* p, const double* data, long long n_samples, long long pitch);
+/* RawDataGenerator windows (stream/generator.py:41-53): window k = samples [starts[k], starts[k]+W).
+ * out_host may be NULL (results stay on the device; use nm_download). */
+int nm_run_windows(nm_pipeline* p, const long long* starts, int n_windows, double* out_host);
+int nm_download(nm_pipeline* p, double* out_host, int n_windows);
+/* DataProcessor.process for one (n_raw_rows, W) float64 window; keeps cross-window state. */
+int nm_process_window(nm_pipeline* p, const double* window, double* out_features);
+
+/* DataPreprocessor.process_data for one window (processing/data_preprocessor.py:74-84): nan_to_num -> pick ->
+ * re-reference -> notch; out_rows (n_ch, W) float64.  Feeds user-defined Python features that run next to the
+ * GPU families (features/feature_processor.py:52-53) and the stand-alone ReReferencer class. */
+int nm_preprocess_window(nm_pipeline* p, const double* window, double* out_rows);
+
+/* ---- stand-alone FIR application -------------------------------------------------------------- */
+/* MNEFilter.filter_data (mode 0: scipy fftconvolve 'same', filter/mne_filter.py:82-128) and NotchFilter.process
+ * (mode 1: reflect-limited zero-phase overlap-add, filter/notch_filter.py:78-93) for callers that use those
+ * classes outside a pipeline.  data (n_ch, n_samples) -> out (n_ch, n_filters, n_samples), float64. */
+int nm_fir_apply(int device, const double* taps, int n_filters, int n_taps, int mode, const double* data, int n_ch,
+                 int n_samples, double* out);
+
+/* ---- measurement ---------------------------------------------------------------------------- */
+/* CUDA events on the pipeline's stream */
+int nm_timer_start(nm_pipeline* p);
+int nm_timer_stop(nm_pipeline* p, double* elapsed_ms);
+/* number of kernels this library launched since the pipeline was created */
+long long nm_kernel_launches(nm_pipeline* p);
+/* device pointer / geometry of the last result matrix (for NCCL gathers by the host side) */
+int nm_result_device_ptr(nm_pipeline* p, void** ptr, long long* n_rows, int* n_cols);
+int nm_stream_handle(nm_pipeline* p, void** cuda_stream);
+/* channel-sharded multi-GPU runs: per-sample group sums of the local shard are exposed so that the
+ * host can all-reduce them across ranks before the re-reference is applied */
+int nm_upload_begin_f32(nm_pipeline* p, const float* data, long long n_samples, long long pitch);
+int nm_group_sums_device_ptr(nm_pipeline* p, void** ptr, long long* n_values);
+int nm_upload_finish(nm_pipeline* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMB200_H */

@@ -1,0 +1,849 @@
+// nm_pipeline.cu -- the C ABI (include/nmb200.h): pipeline object, plan construction, launches.
+//
+// Data flow of one offline run (Stream.run fast path):
+//
+//   host recording (C_all x T, f32/f64) --H2D--> raw
+//   raw --nm_prep_kernel--> xr (C x T, f64): nan_to_num, pick, re-reference       [once]
+//   for each chunk of windows (sized so that the notched chunk stays L2-resident):
+//       xr windows --nm_fir_kernel<store>--> Y chunk (notch, reflect-limited)       [if notch]
+//       Y / xr rows --scan / spectral / band-power / bursts / sharp-wave kernels--> out columns
+//   out --normaliser--> out, NaN re-insertion                                      [whole run]
+//   out (n_windows x F, f64) --D2H--> host
+#include <cstdarg>
+#include <memory>
+#include <vector>
+
+#include "../../include/nmb200.h"
+#include "nm_host.h"
+#include "nm_prep.cuh"
+#include "nm_firbank.h"
+#include "nm_scan.cuh"
+#include "nm_spec.cuh"
+#include "nm_bursts.cuh"
+#include "nm_sharpwave.cuh"
+#include "nm_norm.cuh"
+
+// ------------------------------------------------------------------------------- errors
+static thread_local char g_err[1024] = "";
+void nm_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* nm_last_error(void) { return g_err; }
+extern "C" int nm_abi_version(void) { return NMB200_ABI_VERSION; }
+extern "C" int nm_device_count(int* count) {
+    NM_CHECK(count, "count is NULL");
+    NM_CUDA_CHECK(cudaGetDeviceCount(count));
+    return 0;
+}
+extern "C" int nm_host_alloc(void** ptr, long long bytes) {
+    NM_CHECK(ptr && bytes >= 0, "bad arguments");
+    NM_CUDA_CHECK(cudaMallocHost(ptr, (size_t)(bytes ? bytes : 16)));
+    return 0;
+}
+extern "C" int nm_host_free(void* ptr) {
+    NM_CUDA_CHECK(cudaFreeHost(ptr));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- families
+struct SpectralFam {
+    nm_spectral_cfg cfg;
+    FftPlanHost fft;
+    DevBuf d_win, d_lo, d_hi, d_colmap;
+    int k0 = 0, nk = 0, per_ch = 0;
+};
+
+struct BandpowerFam {
+    FirBank bank;
+    DevBuf d_seglen, d_colmap;
+    int act = 0, mob = 0, comp = 0, logt = 0;
+};
+
+struct nm_pipeline {
+    int device = 0, C_all = 0, C = 0, W = 0, F = 0;
+    bool finalized = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int n_sm = 1, smem_max = 48 * 1024;
+    long long launches = 0;
+
+    // preprocessing
+    std::vector<int> pick;
+    DevBuf d_pick, d_group_of, d_gcoef, d_sp_ptr, d_sp_col, d_sp_val;
+    int G = 0;
+    bool has_reref = false;
+    std::unique_ptr<FirBank> notch;
+    std::vector<double> notch_taps;
+    DevBuf d_nan_ptr, d_nan_cols;
+    bool has_nan_cols = false;
+
+    // families
+    bool has_scan = false;
+    int scan_h = 0, scan_r = 0, scan_l = 0;
+    DevBuf d_scan_colmap;
+    std::vector<std::unique_ptr<SpectralFam>> spectral;
+    std::unique_ptr<BandpowerFam> bandpower;
+    std::unique_ptr<BurstsFam> bursts;
+    std::unique_ptr<SharpwaveFam> sharpwave;
+    std::unique_ptr<NormFam> norm;
+
+    // data
+    DevBuf d_raw, d_xr, d_nanblk, d_gsum;
+    bool raw_f64 = false;
+    long long T = 0, raw_pitch = 0, xr_pitch = 0, nanblk_pitch = 0, gsum_pitch = 0;
+    bool have_data = false, upload_pending = false;
+    DevBuf d_starts, d_yoff, d_y, d_out, d_nanflags;
+    long long out_rows = 0;
+    int chunk = 1, Wp = 0;
+    std::vector<long long> h_starts_one;
+    DevBuf d_win_in;  // staging of a single streamed window
+
+    int grid_for(size_t smem, int n_items, int threads) const {
+        int occ = (int)std::max<size_t>(1, std::min<size_t>(2048 / threads, (size_t)(smem_max + 1024) / (smem + 1024)));
+        long long g = (long long)n_sm * occ;
+        return (int)std::max<long long>(1, std::min<long long>(g, n_items));
+    }
+};
+
+#define NM_P_CHECK(p) NM_CHECK((p) != nullptr, "pipeline is NULL")
+
+template <class K>
+static int nm_allow_smem(K kernel, size_t bytes, const nm_pipeline* p) {
+    NM_CHECK((long long)bytes <= (long long)p->smem_max, "kernel needs %zu bytes of shared memory (> %d available per CTA)", bytes,
+             p->smem_max);
+    if (bytes > 48 * 1024) NM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- family launches
+static NmOut nm_out_for(nm_pipeline* p, const DevBuf& colmap, int per_ch, int w0) {
+    NmOut o;
+    o.out = p->d_out.as<double>();
+    o.row0 = w0;
+    o.F = p->F;
+    o.colmap = colmap.as<int>();
+    o.per_ch = per_ch;
+    return o;
+}
+
+int BurstsFam::allow_smem(const nm_pipeline* p) {
+    if (nm_allow_smem(nm_fir_kernel<NmEpiBursts>, fir_smem(), p)) return -1;
+    return nm_allow_smem(nm_burst_thr_kernel, thr_smem(), p);
+}
+
+int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
+    const int n = rows.n_windows;
+    // numpy 'linear' quantile bookkeeping per window (numpy/lib/_function_base_impl.py _quantile, alpha = beta = 1)
+    std::vector<long long> e_end(n);
+    std::vector<int> nh(n), klo(n), khi(n);
+    std::vector<double> gam(n);
+    for (int k = 0; k < n; ++k) {
+        const long long gw = batch + k;
+        const long long e = (long long)W + gw * S;
+        const int cnt = (int)std::min<long long>(ring_n, e);
+        e_end[k] = e;
+        nh[k] = cnt;
+        const double virt = (double)cnt * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0;
+        long long lo = (long long)std::floor(virt), hi = lo + 1;
+        double g = virt - (double)lo;
+        if (virt >= (double)(cnt - 1)) { lo = hi = cnt - 1; }
+        if (virt < 0) { lo = hi = 0; }
+        klo[k] = (int)lo; khi[k] = (int)hi; gam[k] = g;
+    }
+    if (d_e_end.upload(e_end, p->stream) || d_n.upload(nh, p->stream) || d_lo.upload(klo, p->stream) || d_hi.upload(khi, p->stream) ||
+        d_gamma.upload(gam, p->stream))
+        return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));  // the staging vectors above are temporaries
+
+    NmFirArgs fa = bank.args(rows);
+    NmEpiBursts epi;
+    epi.hfft = hfft.dev();
+    epi.need_scratch = hfft.generic ? 1 : 0;
+    epi.env = d_env.as<double>();
+    epi.Wp = Wp;
+    epi.nB = nB;
+    epi.ring = d_ring.as<double>();
+    epi.cap = cap;
+    epi.win0 = batch;
+    epi.S = S;
+    const size_t sm = fir_smem();
+    NM_LAUNCH(nm_fir_kernel<NmEpiBursts>, dim3(p->grid_for(sm, fa.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, fa, epi);
+
+    NmBurstThrArgs ta;
+    ta.ring = d_ring.as<double>();
+    ta.cap = cap;
+    ta.n_ch = C; ta.nB = nB; ta.n_windows = n;
+    ta.e_end = d_e_end.as<long long>();
+    ta.n_hist = d_n.as<int>();
+    ta.k_lo = d_lo.as<int>(); ta.k_hi = d_hi.as<int>();
+    ta.gamma = d_gamma.as<double>();
+    ta.thr = d_thr.as<double>();
+    const int n_thr = n * C * nB;
+    NM_LAUNCH(nm_burst_thr_kernel, dim3(std::min(n_thr, p->n_sm * 8)), dim3(NM_FFT_THREADS), thr_smem(), p->stream, ta);
+
+    NmBurstFeatArgs ba;
+    ba.env = d_env.as<double>();
+    ba.Wp = Wp;
+    ba.thr = d_thr.as<double>();
+    ba.n_windows = n; ba.n_ch = C; ba.nB = nB; ba.W = W;
+    ba.sfreq = sfreq; ba.seg_s = seg_s;
+    ba.out = nm_out_for(p, d_colmap, nB * 6, w0);
+    const int wpc = NM_ROW_THREADS / 32;
+    NM_LAUNCH(nm_burst_feat_kernel, dim3(std::max(1, std::min((n_thr + wpc - 1) / wpc, p->n_sm * 16))), dim3(NM_ROW_THREADS), 0, p->stream, ba);
+    p->launches += 3;
+    batch += n;
+    return 0;
+}
+
+int SharpwaveFam::allow_smem(const nm_pipeline* p) { return nm_allow_smem(nm_fir_kernel<NmEpiSharpwave>, smem(), p); }
+
+int SharpwaveFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
+    NmFirArgs fa = bank.args(rows);
+    NmEpiSharpwave epi;
+    epi.cfg = cfg;
+    epi.out = nm_out_for(p, d_colmap, per_ch, w0);
+    const size_t sm = smem();
+    NM_LAUNCH(nm_fir_kernel<NmEpiSharpwave>, dim3(p->grid_for(sm, fa.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, fa, epi);
+    p->launches++;
+    return 0;
+}
+
+int NormFam::run(nm_pipeline* p, int n_windows) {
+    if (n_cols == 0) return 0;
+    const size_t rows = (size_t)n_prev + n_windows;
+    if (d_ext.ensure(rows * n_cols * sizeof(double))) return -1;
+    double* ext = d_ext.as<double>();
+    if (n_prev)
+        NM_CUDA_CHECK(cudaMemcpyAsync(ext, d_hist.p, (size_t)n_prev * n_cols * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    const long long tot = (long long)n_windows * n_cols;
+    const unsigned grid = (unsigned)((tot + NM_ROW_THREADS - 1) / NM_ROW_THREADS);
+    NM_LAUNCH(nm_norm_gather_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, (const double*)p->d_out.as<double>(), p->F,
+              (const int*)d_cols.as<int>(), n_cols, n_windows, ext + (size_t)n_prev * n_cols);
+    NmNormArgs a;
+    a.ext = ext;
+    a.n_prev = n_prev;
+    a.n_windows = n_windows;
+    a.n_cols = n_cols;
+    a.cols = d_cols.as<int>();
+    a.g0 = batch;
+    a.n_keep = n_keep;
+    a.method = method;
+    a.clip = clip;
+    a.out = p->d_out.as<double>();
+    a.F = p->F;
+    NM_LAUNCH(nm_norm_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
+    p->launches += 2;
+    // keep the last (n_keep - 1) raw rows for the next call
+    const int keep = (int)std::min<size_t>(rows, (size_t)std::max(0, n_keep - 1));
+    if (keep)
+        NM_CUDA_CHECK(cudaMemcpyAsync(d_hist.p, ext + (rows - keep) * n_cols, (size_t)keep * n_cols * sizeof(double),
+                                      cudaMemcpyDeviceToDevice, p->stream));
+    n_prev = keep;
+    batch += n_windows;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- life cycle
+extern "C" int nm_pipeline_create(int device, int n_raw_rows, int n_ch, int window_samples, int n_features, nm_pipeline** out) {
+    NM_CHECK(out, "out is NULL");
+    NM_CHECK(n_raw_rows > 0 && n_ch > 0 && n_ch <= n_raw_rows, "bad channel counts (%d raw rows, %d feature channels)", n_raw_rows, n_ch);
+    NM_CHECK(window_samples >= 3, "window must have at least 3 samples, got %d", window_samples);
+    NM_CHECK(n_features > 0, "n_features must be positive");
+    int n_dev = 0;
+    NM_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
+    NM_CHECK(n_dev > 0, "no CUDA device visible: libnmb200 has no CPU path");
+    NM_CHECK(device >= 0 && device < n_dev, "device %d out of range (%d visible)", device, n_dev);
+    NM_CUDA_CHECK(cudaSetDevice(device));
+    auto p = std::make_unique<nm_pipeline>();
+    p->device = device;
+    p->C_all = n_raw_rows;
+    p->C = n_ch;
+    p->W = window_samples;
+    p->F = n_features;
+    NM_CUDA_CHECK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    NM_CUDA_CHECK(cudaEventCreate(&p->ev0));
+    NM_CUDA_CHECK(cudaEventCreate(&p->ev1));
+    NM_CUDA_CHECK(cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, device));
+    NM_CUDA_CHECK(cudaDeviceGetAttribute(&p->smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    p->pick.resize(n_ch);
+    for (int i = 0; i < n_ch; ++i) p->pick[i] = i;
+    *out = p.release();
+    return 0;
+}
+
+extern "C" void nm_pipeline_destroy(nm_pipeline* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    cudaStream_t s = p->stream;
+    delete p;
+    if (s) cudaStreamDestroy(s);
+}
+
+extern "C" int nm_set_pick(nm_pipeline* p, const int* pick) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    for (int i = 0; i < p->C; ++i) {
+        NM_CHECK(pick[i] >= 0 && pick[i] < p->C_all, "pick[%d] = %d out of range", i, pick[i]);
+        p->pick[i] = pick[i];
+    }
+    return 0;
+}
+
+extern "C" int nm_set_reref(nm_pipeline* p, int n_groups, const int* group_of, const double* gcoef, const int* sp_ptr,
+                            const int* sp_col, const double* sp_val) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    NM_CHECK(n_groups >= 0 && n_groups <= NM_MAX_GROUPS, "n_groups must be in [0, %d]", NM_MAX_GROUPS);
+    NM_CHECK(sp_ptr && sp_ptr[0] == 0, "sp_ptr must start at 0");
+    cudaSetDevice(p->device);
+    const int nnz = sp_ptr[p->C];
+    for (int k = 0; k < nnz; ++k) NM_CHECK(sp_col[k] >= 0 && sp_col[k] < p->C, "sp_col out of range");
+    p->G = n_groups;
+    std::vector<int> go(p->C, -1);
+    if (n_groups > 0) {
+        NM_CHECK(group_of && gcoef, "group arrays missing");
+        for (int i = 0; i < p->C; ++i) {
+            NM_CHECK(group_of[i] >= -1 && group_of[i] < n_groups, "group_of out of range");
+            go[i] = group_of[i];
+        }
+    }
+    if (p->d_group_of.upload(go, p->stream)) return -1;
+    if (p->d_gcoef.upload(gcoef, (size_t)p->C * n_groups, p->stream)) return -1;
+    if (p->d_sp_ptr.upload(sp_ptr, (size_t)p->C + 1, p->stream)) return -1;
+    if (p->d_sp_col.upload(sp_col, (size_t)nnz, p->stream)) return -1;
+    if (p->d_sp_val.upload(sp_val, (size_t)nnz, p->stream)) return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    p->has_reref = true;
+    return 0;
+}
+
+extern "C" int nm_set_notch(nm_pipeline* p, const double* taps, int n_taps) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    if (n_taps <= 0) {
+        p->notch.reset();
+        return 0;
+    }
+    NM_CHECK(taps, "taps is NULL");
+    cudaSetDevice(p->device);
+    p->notch = std::make_unique<FirBank>();
+    if (p->notch->build(taps, 1, n_taps, p->W, NM_FIR_REFLECT, p->stream)) return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int nm_set_nan_columns(nm_pipeline* p, const int* col_ptr, const int* cols) {
+    NM_P_CHECK(p);
+    NM_CHECK(col_ptr && col_ptr[0] == 0, "col_ptr must start at 0");
+    cudaSetDevice(p->device);
+    const int n = col_ptr[p->C_all];
+    for (int k = 0; k < n; ++k) NM_CHECK(cols[k] >= 0 && cols[k] < p->F, "NaN column out of range");
+    if (p->d_nan_ptr.upload(col_ptr, (size_t)p->C_all + 1, p->stream)) return -1;
+    if (p->d_nan_cols.upload(cols, (size_t)n, p->stream)) return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    p->has_nan_cols = true;
+    return 0;
+}
+
+static int nm_check_colmap(const nm_pipeline* p, const int* colmap, size_t n) {
+    NM_CHECK(colmap, "colmap is NULL");
+    for (size_t i = 0; i < n; ++i) NM_CHECK(colmap[i] >= -1 && colmap[i] < p->F, "colmap[%zu] = %d out of range (F = %d)", i, colmap[i], p->F);
+    return 0;
+}
+
+extern "C" int nm_add_scan(nm_pipeline* p, int hjorth, int raw, int linelength, const int* colmap) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    if (nm_check_colmap(p, colmap, (size_t)p->C * 5)) return -1;
+    cudaSetDevice(p->device);
+    p->has_scan = true;
+    p->scan_h = hjorth; p->scan_r = raw; p->scan_l = linelength;
+    if (p->d_scan_colmap.upload(colmap, (size_t)p->C * 5, p->stream)) return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int nm_add_spectral(nm_pipeline* p, const nm_spectral_cfg* cfg) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    NM_CHECK(cfg && cfg->nper >= 2 && cfg->nseg >= 1 && cfg->n_bands >= 0, "bad spectral configuration");
+    cudaSetDevice(p->device);
+    auto f = std::make_unique<SpectralFam>();
+    f->cfg = *cfg;
+    const int nbins = cfg->nper / 2 + 1;
+    f->per_ch = cfg->n_bands * 4 + nbins;
+    if (nm_check_colmap(p, cfg->colmap, (size_t)p->C * f->per_ch)) return -1;
+    int kmin = nbins, kmax = 0;
+    for (int b = 0; b < cfg->n_bands; ++b) {
+        NM_CHECK(cfg->band_lo[b] >= 0 && cfg->band_hi[b] <= nbins && cfg->band_lo[b] <= cfg->band_hi[b],
+                 "band %d bin range [%d, %d) outside the %d-bin spectrum", b, cfg->band_lo[b], cfg->band_hi[b], nbins);
+        if (cfg->band_hi[b] > cfg->band_lo[b]) {
+            kmin = std::min(kmin, cfg->band_lo[b]);
+            kmax = std::max(kmax, cfg->band_hi[b]);
+        }
+    }
+    if (cfg->want_spectrum) { kmin = 0; kmax = nbins; }
+    if (kmax <= kmin) { kmin = 0; kmax = 1; }
+    f->k0 = kmin;
+    f->nk = kmax - kmin;
+    if (f->fft.build(cfg->nper, p->stream)) return -1;
+    if (cfg->win && f->d_win.upload(cfg->win, (size_t)cfg->nper, p->stream)) return -1;
+    if (f->d_lo.upload(cfg->band_lo, (size_t)cfg->n_bands, p->stream)) return -1;
+    if (f->d_hi.upload(cfg->band_hi, (size_t)cfg->n_bands, p->stream)) return -1;
+    if (f->d_colmap.upload(cfg->colmap, (size_t)p->C * f->per_ch, p->stream)) return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    f->cfg.win = cfg->win ? f->d_win.as<double>() : nullptr;
+    p->spectral.push_back(std::move(f));
+    return 0;
+}
+
+extern "C" int nm_add_bandpower(nm_pipeline* p, int n_bands, const double* taps, int n_taps, const int* seglen, int activity,
+                                int mobility, int complexity, int log_transform, const int* colmap) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    NM_CHECK(n_bands > 0 && taps && n_taps > 0 && seglen, "bad band-power configuration");
+    if (nm_check_colmap(p, colmap, (size_t)p->C * n_bands * 3)) return -1;
+    cudaSetDevice(p->device);
+    auto f = std::make_unique<BandpowerFam>();
+    if (f->bank.build(taps, n_bands, n_taps, p->W, NM_FIR_SAME, p->stream)) return -1;
+    for (int b = 0; b < n_bands; ++b) NM_CHECK(seglen[b] >= 1, "segment length must be >= 1 sample");
+    if (f->d_seglen.upload(seglen, (size_t)n_bands, p->stream)) return -1;
+    if (f->d_colmap.upload(colmap, (size_t)p->C * n_bands * 3, p->stream)) return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    f->act = activity; f->mob = mobility; f->comp = complexity; f->logt = log_transform;
+    p->bandpower = std::move(f);
+    return 0;
+}
+
+extern "C" int nm_add_bursts(nm_pipeline* p, int n_bands, const double* taps, int n_taps, int samples_overlap, int ring_samples,
+                             double quantile, double sfreq, double segment_length_s, const int* colmap) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    NM_CHECK(n_bands > 0 && taps && n_taps > 0, "bad bursts configuration");
+    NM_CHECK(samples_overlap >= 0 && samples_overlap <= p->W, "samples_overlap must be in [0, W]");
+    NM_CHECK(ring_samples >= 1, "ring_samples must be >= 1");
+    NM_CHECK(quantile >= 0.0 && quantile <= 1.0, "quantile must be in [0, 1]");
+    if (nm_check_colmap(p, colmap, (size_t)p->C * n_bands * 6)) return -1;
+    cudaSetDevice(p->device);
+    auto f = std::make_unique<BurstsFam>();
+    if (f->build(taps, n_bands, n_taps, p->C, p->W, samples_overlap, ring_samples, quantile, sfreq, segment_length_s, colmap, p->stream))
+        return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    p->bursts = std::move(f);
+    return 0;
+}
+
+extern "C" int nm_add_sharpwave(nm_pipeline* p, int n_filters, const double* taps, int n_taps, int dist_peaks, int dist_troughs,
+                                int sharp_offset, double ms_per_sample, int n_combo, const int* feat_ids, const int* est_ids,
+                                int pair_estimator, int want_num_peaks, const int* colmap) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    NM_CHECK(n_filters > 0 && taps && n_taps > 0 && n_combo >= 0, "bad sharp-wave configuration");
+    if (nm_check_colmap(p, colmap, (size_t)p->C * n_filters * (n_combo + 1))) return -1;
+    cudaSetDevice(p->device);
+    auto f = std::make_unique<SharpwaveFam>();
+    if (f->build(taps, n_filters, n_taps, p->C, p->W, dist_peaks, dist_troughs, sharp_offset, ms_per_sample, n_combo, feat_ids, est_ids,
+                 pair_estimator, want_num_peaks, colmap, p->stream))
+        return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    p->sharpwave = std::move(f);
+    return 0;
+}
+
+extern "C" int nm_add_feature_normalizer(nm_pipeline* p, int method, double clip, int n_keep, int n_cols, const int* cols) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    NM_CHECK(method >= 0 && method <= 3, "normalisation method must be 0..3 (mean, median, zscore, zscore-median)");
+    NM_CHECK(n_keep >= 1 && n_cols >= 0, "bad normaliser configuration");
+    for (int i = 0; i < n_cols; ++i) NM_CHECK(cols[i] >= 0 && cols[i] < p->F, "normaliser column out of range");
+    cudaSetDevice(p->device);
+    auto f = std::make_unique<NormFam>();
+    if (f->build(method, clip, n_keep, n_cols, cols, p->stream)) return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    p->norm = std::move(f);
+    return 0;
+}
+
+extern "C" int nm_finalize(nm_pipeline* p) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    cudaSetDevice(p->device);
+    if (p->d_pick.upload(p->pick, p->stream)) return -1;
+    if (!p->has_reref) {  // identity
+        std::vector<int> go(p->C, -1), ptr(p->C + 1), col(p->C);
+        std::vector<double> val(p->C, 1.0);
+        for (int i = 0; i <= p->C; ++i) ptr[i] = i;
+        for (int i = 0; i < p->C; ++i) col[i] = i;
+        p->G = 0;
+        if (p->d_group_of.upload(go, p->stream) || p->d_gcoef.ensure(16) || p->d_sp_ptr.upload(ptr, p->stream) ||
+            p->d_sp_col.upload(col, p->stream) || p->d_sp_val.upload(val, p->stream))
+            return -1;
+    }
+    p->Wp = (p->W + 1) & ~1;
+    // chunk of windows whose notched copy (and burst envelopes) stays comfortably inside the 126 MB L2
+    const size_t per_window = (size_t)p->C * p->Wp * sizeof(double) * (1 + (p->bursts ? p->bursts->nB : 0));
+    p->chunk = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)48 << 20) / per_window));
+    std::vector<long long> yoff(p->chunk);
+    for (int k = 0; k < p->chunk; ++k) yoff[k] = (long long)k * p->C * p->Wp;
+    if (p->d_yoff.upload(yoff, p->stream)) return -1;
+    if (p->notch && p->d_y.ensure((size_t)p->chunk * p->C * p->Wp * sizeof(double))) return -1;
+    if (p->bursts && p->bursts->alloc_chunk(p->chunk, p->Wp)) return -1;
+
+    // opt in to large dynamic shared memory once
+    if (p->notch && nm_allow_smem(nm_fir_kernel<NmEpiStore>, p->notch->smem(NmEpiStore::smem_bytes(NM_FFT_THREADS)), p)) return -1;
+    if (p->bandpower && nm_allow_smem(nm_fir_kernel<NmEpiBandpower>, p->bandpower->bank.smem(NmEpiBandpower::smem_bytes(NM_FFT_THREADS)), p)) return -1;
+    size_t spec_max = 0;
+    for (auto& f : p->spectral)
+        spec_max = std::max(spec_max, nm_spec_smem_bytes(f->cfg.nper, f->fft.generic, f->nk, f->cfg.keep_segments ? f->cfg.nseg : 1));
+    if (!p->spectral.empty() && nm_allow_smem(nm_spec_kernel, spec_max, p)) return -1;
+    if (p->bursts && p->bursts->allow_smem(p)) return -1;
+    if (p->sharpwave && p->sharpwave->allow_smem(p)) return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    p->finalized = true;
+    return 0;
+}
+
+extern "C" int nm_reset_state(nm_pipeline* p) {
+    NM_P_CHECK(p);
+    if (p->bursts) p->bursts->reset();
+    if (p->norm) p->norm->reset();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- data path
+static NmPrepArgs nm_prep_args(nm_pipeline* p) {
+    NmPrepArgs a;
+    a.raw = p->d_raw.p;
+    a.raw_is_f64 = p->raw_f64 ? 1 : 0;
+    a.raw_pitch = p->raw_pitch;
+    a.C_all = p->C_all;
+    a.T = p->T;
+    a.C = p->C;
+    a.pick = p->d_pick.as<int>();
+    a.G = p->G;
+    a.group_of = p->d_group_of.as<int>();
+    a.gcoef = p->d_gcoef.as<double>();
+    a.sp_ptr = p->d_sp_ptr.as<int>();
+    a.sp_col = p->d_sp_col.as<int>();
+    a.sp_val = p->d_sp_val.as<double>();
+    a.xr = p->d_xr.as<double>();
+    a.xr_pitch = p->xr_pitch;
+    a.nanblk = p->d_nanblk.as<unsigned char>();
+    a.nanblk_pitch = p->nanblk_pitch;
+    a.gsum_ext = nullptr;
+    a.gsum_pitch = 0;
+    return a;
+}
+
+static int nm_stage_raw(nm_pipeline* p, const void* data, bool f64, long long n_samples, long long pitch) {
+    const size_t esz = f64 ? 8 : 4;
+    p->raw_f64 = f64;
+    p->T = n_samples;
+    p->raw_pitch = (n_samples + 3) & ~3LL;
+    p->xr_pitch = (n_samples + 1) & ~1LL;
+    p->nanblk_pitch = (n_samples + 31) / 32;
+    if (p->d_raw.ensure((size_t)p->C_all * p->raw_pitch * esz)) return -1;
+    if (p->d_xr.ensure((size_t)p->C * p->xr_pitch * sizeof(double))) return -1;
+    if (p->d_nanblk.ensure((size_t)p->C_all * p->nanblk_pitch)) return -1;
+    if (pitch == p->raw_pitch) {
+        NM_CUDA_CHECK(cudaMemcpyAsync(p->d_raw.p, data, (size_t)p->C_all * pitch * esz, cudaMemcpyHostToDevice, p->stream));
+    } else {
+        for (int r = 0; r < p->C_all; ++r)
+            NM_CUDA_CHECK(cudaMemcpyAsync((char*)p->d_raw.p + (size_t)r * p->raw_pitch * esz, (const char*)data + (size_t)r * pitch * esz,
+                                          (size_t)n_samples * esz, cudaMemcpyHostToDevice, p->stream));
+    }
+    return 0;
+}
+
+static int nm_upload_impl(nm_pipeline* p, const void* data, bool f64, long long n_samples, long long pitch) {
+    NM_P_CHECK(p);
+    NM_CHECK(p->finalized, "call nm_finalize first");
+    NM_CHECK(data && n_samples >= p->W && pitch >= n_samples, "bad recording geometry (n_samples %lld, pitch %lld, W %d)", n_samples,
+             pitch, p->W);
+    cudaSetDevice(p->device);
+    if (nm_stage_raw(p, data, f64, n_samples, pitch)) return -1;
+    const int threads = NM_ROW_THREADS;
+    const unsigned grid = (unsigned)((n_samples + threads - 1) / threads);
+    NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(threads), 0, p->stream, nm_prep_args(p));
+    p->launches++;
+    NM_CUDA_CHECK(cudaGetLastError());
+    p->have_data = true;
+    p->upload_pending = false;
+    return 0;
+}
+
+extern "C" int nm_upload_f32(nm_pipeline* p, const float* data, long long n_samples, long long pitch) {
+    return nm_upload_impl(p, data, false, n_samples, pitch);
+}
+extern "C" int nm_upload_f64(nm_pipeline* p, const double* data, long long n_samples, long long pitch) {
+    return nm_upload_impl(p, data, true, n_samples, pitch);
+}
+
+static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
+    NmRows rows;
+    rows.base = p->d_xr.as<double>();
+    rows.ch_stride = p->xr_pitch;
+    rows.off = p->d_starts.as<long long>() + w0;
+    rows.n_windows = n;
+    rows.n_ch = p->C;
+    rows.W = p->W;
+
+    if (p->notch) {
+        NmFirArgs a = p->notch->args(rows);
+        NmEpiStore epi{p->d_y.as<double>(), (long long)p->Wp, 1};
+        const size_t sm = p->notch->smem(NmEpiStore::smem_bytes(NM_FFT_THREADS));
+        NM_LAUNCH(nm_fir_kernel<NmEpiStore>, dim3(p->grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, a, epi);
+        p->launches++;
+        rows.base = p->d_y.as<double>();
+        rows.ch_stride = p->Wp;
+        rows.off = p->d_yoff.as<long long>();
+    }
+    auto out_for = [&](const DevBuf& colmap, int per_ch) {
+        NmOut o;
+        o.out = p->d_out.as<double>();
+        o.row0 = w0;
+        o.F = p->F;
+        o.colmap = colmap.as<int>();
+        o.per_ch = per_ch;
+        return o;
+    };
+    if (p->has_scan) {
+        NmScanArgs a;
+        a.in = rows;
+        a.want_hjorth = p->scan_h; a.want_raw = p->scan_r; a.want_ll = p->scan_l;
+        a.out = out_for(p->d_scan_colmap, 5);
+        const int wpc = NM_ROW_THREADS / 32;
+        const long long n_rows = (long long)n * p->C;
+        const int grid = (int)std::max<long long>(1, std::min<long long>((n_rows + wpc - 1) / wpc, (long long)p->n_sm * 16));
+        NM_LAUNCH(nm_scan_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
+        p->launches++;
+    }
+    for (auto& f : p->spectral) {
+        NmSpecArgs a;
+        const nm_spectral_cfg& c = f->cfg;
+        a.in = rows;
+        a.fft = f->fft.dev();
+        a.need_scratch = f->fft.generic ? 1 : 0;
+        a.nseg = c.nseg; a.hop = c.hop; a.start = c.start;
+        a.ext_even = c.ext_even; a.ext_len = c.ext_len;
+        a.detrend = c.detrend;
+        a.win = c.win;
+        a.power = c.power; a.scale = c.scale; a.log = c.log;
+        a.keep_segments = c.keep_segments;
+        a.k0 = f->k0; a.nk = f->nk;
+        a.n_bands = c.n_bands;
+        a.band_lo = f->d_lo.as<int>(); a.band_hi = f->d_hi.as<int>();
+        a.est_mask = c.est_mask;
+        a.want_spectrum = c.want_spectrum;
+        a.out = out_for(f->d_colmap, f->per_ch);
+        a.n_items = n * ((p->C + 1) / 2);
+        const size_t sm = nm_spec_smem_bytes(c.nper, f->fft.generic, f->nk, c.keep_segments ? c.nseg : 1);
+        NM_LAUNCH(nm_spec_kernel, dim3(p->grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, a);
+        p->launches++;
+    }
+    if (p->bandpower) {
+        BandpowerFam& f = *p->bandpower;
+        NmFirArgs a = f.bank.args(rows);
+        NmEpiBandpower epi;
+        epi.seglen = f.d_seglen.as<int>();
+        epi.want_act = f.act; epi.want_mob = f.mob; epi.want_comp = f.comp; epi.log_act = f.logt;
+        epi.out = out_for(f.d_colmap, f.bank.nF * 3);
+        const size_t sm = f.bank.smem(NmEpiBandpower::smem_bytes(NM_FFT_THREADS));
+        NM_LAUNCH(nm_fir_kernel<NmEpiBandpower>, dim3(p->grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, a, epi);
+        p->launches++;
+    }
+    if (p->sharpwave && p->sharpwave->run(p, rows, w0)) return -1;
+    if (p->bursts && p->bursts->run(p, rows, w0)) return -1;
+    NM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_windows, double* out_host) {
+    NM_P_CHECK(p);
+    NM_CHECK(p->finalized && p->have_data, "finalize the pipeline and upload a recording first");
+    NM_CHECK(starts && n_windows > 0, "no windows given");
+    for (int k = 0; k < n_windows; ++k)
+        NM_CHECK(starts[k] >= 0 && starts[k] + p->W <= p->T, "window %d [%lld, %lld) outside the recording (%lld samples)", k, starts[k],
+                 starts[k] + p->W, p->T);
+    cudaSetDevice(p->device);
+    if (p->d_starts.upload(starts, (size_t)n_windows, p->stream)) return -1;
+    if (p->d_out.ensure((size_t)n_windows * p->F * sizeof(double))) return -1;
+    p->out_rows = n_windows;
+    NM_CUDA_CHECK(cudaMemsetAsync(p->d_out.p, 0, (size_t)n_windows * p->F * sizeof(double), p->stream));
+    for (int w0 = 0; w0 < n_windows; w0 += p->chunk)
+        if (nm_run_chunk(p, w0, std::min(p->chunk, n_windows - w0))) return -1;
+    if (p->norm && p->norm->run(p, n_windows)) return -1;
+    if (p->has_nan_cols) {
+        if (p->d_nanflags.ensure((size_t)n_windows * p->C_all)) return -1;
+        NmNanArgs na;
+        na.p = nm_prep_args(p);
+        na.start = p->d_starts.as<long long>();
+        na.n_windows = n_windows;
+        na.W = p->W;
+        na.flags = p->d_nanflags.as<unsigned char>();
+        const long long tot = (long long)n_windows * p->C_all;
+        const unsigned grid = (unsigned)((tot + NM_ROW_THREADS - 1) / NM_ROW_THREADS);
+        NM_LAUNCH(nm_nanflag_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, na);
+        NmNanFillArgs nf;
+        nf.flags = na.flags;
+        nf.n_windows = n_windows;
+        nf.C_all = p->C_all;
+        nf.col_ptr = p->d_nan_ptr.as<int>();
+        nf.cols = p->d_nan_cols.as<int>();
+        nf.out = p->d_out.as<double>();
+        nf.row0 = 0;
+        nf.F = p->F;
+        NM_LAUNCH(nm_nanfill_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, nf);
+        p->launches += 2;
+    }
+    NM_CUDA_CHECK(cudaGetLastError());
+    if (out_host) return nm_download(p, out_host, n_windows);
+    return 0;
+}
+
+extern "C" int nm_download(nm_pipeline* p, double* out_host, int n_windows) {
+    NM_P_CHECK(p);
+    NM_CHECK(out_host && n_windows > 0 && n_windows <= p->out_rows, "nothing to download");
+    cudaSetDevice(p->device);
+    NM_CUDA_CHECK(cudaMemcpyAsync(out_host, p->d_out.p, (size_t)n_windows * p->F * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int nm_process_window(nm_pipeline* p, const double* window, double* out_features) {
+    NM_P_CHECK(p);
+    NM_CHECK(window && out_features, "NULL argument");
+    if (nm_upload_impl(p, window, true, p->W, p->W)) return -1;
+    const long long zero = 0;
+    return nm_run_windows(p, &zero, 1, out_features);
+}
+
+// Preprocessed rows of one window (nan_to_num -> pick -> re-reference -> notch), float64 (n_ch, W).
+// Needed by user-defined (Python) features that run next to the GPU families, and by the stand-alone
+// ReReferencer / DataPreprocessor classes.
+extern "C" int nm_preprocess_window(nm_pipeline* p, const double* window, double* out_rows) {
+    NM_P_CHECK(p);
+    NM_CHECK(window && out_rows, "NULL argument");
+    if (nm_upload_impl(p, window, true, p->W, p->W)) return -1;
+    const long long zero = 0;
+    if (p->d_starts.upload(&zero, 1, p->stream)) return -1;
+    const double* src = p->d_xr.as<double>();
+    long long pitch = p->xr_pitch;
+    if (p->notch) {
+        NmRows rows;
+        rows.base = p->d_xr.as<double>();
+        rows.ch_stride = p->xr_pitch;
+        rows.off = p->d_starts.as<long long>();
+        rows.n_windows = 1;
+        rows.n_ch = p->C;
+        rows.W = p->W;
+        NmFirArgs a = p->notch->args(rows);
+        NmEpiStore epi{p->d_y.as<double>(), (long long)p->Wp, 1};
+        const size_t sm = p->notch->smem(NmEpiStore::smem_bytes(NM_FFT_THREADS));
+        NM_LAUNCH(nm_fir_kernel<NmEpiStore>, dim3(p->grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, a, epi);
+        p->launches++;
+        NM_CUDA_CHECK(cudaGetLastError());
+        src = p->d_y.as<double>();
+        pitch = p->Wp;
+    }
+    for (int c = 0; c < p->C; ++c)
+        NM_CUDA_CHECK(cudaMemcpyAsync(out_rows + (size_t)c * p->W, src + (size_t)c * pitch, (size_t)p->W * sizeof(double),
+                                      cudaMemcpyDeviceToHost, p->stream));
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- measurement
+extern "C" int nm_timer_start(nm_pipeline* p) {
+    NM_P_CHECK(p);
+    cudaSetDevice(p->device);
+    NM_CUDA_CHECK(cudaEventRecord(p->ev0, p->stream));
+    return 0;
+}
+extern "C" int nm_timer_stop(nm_pipeline* p, double* elapsed_ms) {
+    NM_P_CHECK(p);
+    cudaSetDevice(p->device);
+    NM_CUDA_CHECK(cudaEventRecord(p->ev1, p->stream));
+    NM_CUDA_CHECK(cudaEventSynchronize(p->ev1));
+    float ms = 0;
+    NM_CUDA_CHECK(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    if (elapsed_ms) *elapsed_ms = ms;
+    return 0;
+}
+extern "C" long long nm_kernel_launches(nm_pipeline* p) { return p ? p->launches : 0; }
+extern "C" int nm_result_device_ptr(nm_pipeline* p, void** ptr, long long* n_rows, int* n_cols) {
+    NM_P_CHECK(p);
+    if (ptr) *ptr = p->d_out.p;
+    if (n_rows) *n_rows = p->out_rows;
+    if (n_cols) *n_cols = p->F;
+    return 0;
+}
+extern "C" int nm_stream_handle(nm_pipeline* p, void** cuda_stream) {
+    NM_P_CHECK(p);
+    if (cuda_stream) *cuda_stream = (void*)p->stream;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- stand-alone FIR
+// MNEFilter.filter_data (mode 0, filter/mne_filter.py:82-128) and NotchFilter.process (mode 1,
+// filter/notch_filter.py:78-93) as one-shot calls for users of those classes outside a pipeline.
+extern "C" int nm_fir_apply(int device, const double* taps, int n_filters, int n_taps, int mode, const double* data, int n_ch,
+                            int n_samples, double* out) {
+    NM_CHECK(taps && data && out && n_filters > 0 && n_taps > 0 && n_ch > 0 && n_samples >= 2, "bad arguments");
+    NM_CHECK(mode == NM_FIR_SAME || mode == NM_FIR_REFLECT, "mode must be 0 (same) or 1 (reflect-limited)");
+    int n_dev = 0;
+    NM_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
+    NM_CHECK(n_dev > 0, "no CUDA device visible: libnmb200 has no CPU path");
+    NM_CHECK(device >= 0 && device < n_dev, "device %d out of range", device);
+    NM_CUDA_CHECK(cudaSetDevice(device));
+    cudaStream_t s = nullptr;
+    NM_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int rc = -1;
+    {
+        FirBank bank;
+        DevBuf d_in, d_out, d_off;
+        nm_pipeline probe;  // only for the launch-geometry helpers
+        cudaDeviceGetAttribute(&probe.n_sm, cudaDevAttrMultiProcessorCount, device);
+        cudaDeviceGetAttribute(&probe.smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        const long long zero = 0;
+        const size_t sm_need = 0;
+        (void)sm_need;
+        do {
+            if (bank.build(taps, n_filters, n_taps, n_samples, mode, s)) break;
+            if (d_in.upload(data, (size_t)n_ch * n_samples, s)) break;
+            if (d_off.upload(&zero, 1, s)) break;
+            if (d_out.ensure((size_t)n_ch * n_filters * n_samples * sizeof(double))) break;
+            NmRows rows;
+            rows.base = d_in.as<double>();
+            rows.ch_stride = n_samples;
+            rows.off = d_off.as<long long>();
+            rows.n_windows = 1;
+            rows.n_ch = n_ch;
+            rows.W = n_samples;
+            NmFirArgs a = bank.args(rows);
+            NmEpiStore epi{d_out.as<double>(), (long long)n_samples, n_filters};
+            const size_t sm = bank.smem(0);
+            if (nm_allow_smem(nm_fir_kernel<NmEpiStore>, sm, &probe)) break;
+            NM_LAUNCH(nm_fir_kernel<NmEpiStore>, dim3(probe.grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, s, a, epi);
+            if (cudaGetLastError() != cudaSuccess) { nm_set_error("FIR kernel launch failed"); break; }
+            if (cudaMemcpyAsync(out, d_out.p, (size_t)n_ch * n_filters * n_samples * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaStreamSynchronize(s) != cudaSuccess) {
+                nm_set_error("FIR result copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+            rc = 0;
+        } while (false);
+    }
+    cudaStreamDestroy(s);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------- sharded upload
+// (implemented with the multi-GPU path; see nm_multi.cuh)
+#include "nm_multi.cuh"

@@ -1,0 +1,162 @@
+// nm_prep.cuh -- once-per-recording preprocessing that is independent of the window grid:
+//   nan_to_num -> channel pick -> re-reference            (stream/data_processor.py:255,
+//                                                           processing/rereference.py:99-100)
+// plus the per-32-sample NaN block map that makes the per-window NaN-channel mask
+// (stream/data_processor.py:253) cheap.
+//
+// Re-referencing is linear and acts across channels, the notch FIR is linear and acts along
+// time, so they commute: the reference applies notch then re-reference per window; here the
+// re-reference is applied ONCE to the whole recording and the (window-boundary dependent)
+// notch afterwards -- identical up to float64 rounding, and 10x less work at 90 % overlap.
+//
+// The (C x C) reference matrix is handed over factored as  group-sum coefficients + a sparse
+// remainder (common-average rows collapse to one coefficient on the per-sample group sum).
+#pragma once
+
+#include "nm_common.cuh"
+
+#define NM_MAX_GROUPS 8
+
+struct NmPrepArgs {
+    const void* raw;       // (C_all, T) float32 or float64, row pitch raw_pitch elements
+    int raw_is_f64;
+    long long raw_pitch;
+    int C_all;
+    long long T;
+    int C;                 // feature channels
+    const int* pick;       // [C] raw row of feature channel j
+    int G;                 // number of group sums (<= NM_MAX_GROUPS)
+    const int* group_of;   // [C] group id or -1
+    const double* gcoef;   // [C * G]
+    const int* sp_ptr;     // [C + 1]
+    const int* sp_col;     // feature-channel index
+    const double* sp_val;
+    double* xr;            // (C, xr_pitch) output
+    long long xr_pitch;
+    unsigned char* nanblk; // (C_all, nanblk_pitch): 1 if any NaN in the 32-sample block
+    long long nanblk_pitch;
+    // channel-sharded multi-GPU runs: group sums over ALL ranks' channels, (G, gsum_pitch), all-reduced by
+    // the host between nm_gsum_kernel and nm_prep_kernel; nullptr = sum the local channels in-kernel
+    const double* gsum_ext;
+    long long gsum_pitch;
+};
+
+NM_DEV double nm_raw_at(const NmPrepArgs& a, int row, long long t) {
+    return a.raw_is_f64 ? nm_ldg(reinterpret_cast<const double*>(a.raw) + (size_t)row * a.raw_pitch + t)
+                        : (double)nm_ldg(reinterpret_cast<const float*>(a.raw) + (size_t)row * a.raw_pitch + t);
+}
+
+NM_GLOBAL void nm_prep_kernel(NmPrepArgs a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = t < a.T;
+    const int lane = threadIdx.x & 31;
+
+    for (int r = 0; r < a.C_all; ++r) {
+        double v = active ? nm_raw_at(a, r, t) : 0.0;
+        unsigned bits = __ballot_sync(0xffffffffu, v != v);
+        if (lane == 0 && active) a.nanblk[(size_t)r * a.nanblk_pitch + (t >> 5)] = bits ? 1 : 0;
+    }
+    if (!active) return;
+
+    double S[NM_MAX_GROUPS];
+#pragma unroll
+    for (int g = 0; g < NM_MAX_GROUPS; ++g) S[g] = 0.0;
+    if (a.G > 0 && a.gsum_ext) {
+#pragma unroll
+        for (int g = 0; g < NM_MAX_GROUPS; ++g)
+            if (g < a.G) S[g] = a.gsum_ext[(size_t)g * a.gsum_pitch + t];
+    } else if (a.G > 0) {
+        for (int j = 0; j < a.C; ++j) {
+            const int g = nm_ldg(a.group_of + j);
+            if (g >= 0) {
+                const double v = nm_nan_to_num(nm_raw_at(a, nm_ldg(a.pick + j), t));
+#pragma unroll
+                for (int gg = 0; gg < NM_MAX_GROUPS; ++gg)
+                    if (gg == g) S[gg] += v;
+            }
+        }
+    }
+    for (int i = 0; i < a.C; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int g = 0; g < NM_MAX_GROUPS; ++g)
+            if (g < a.G) acc += nm_ldg(a.gcoef + (size_t)i * a.G + g) * S[g];
+        const int k1 = nm_ldg(a.sp_ptr + i + 1);
+        for (int k = nm_ldg(a.sp_ptr + i); k < k1; ++k)
+            acc += nm_ldg(a.sp_val + k) * nm_nan_to_num(nm_raw_at(a, nm_ldg(a.pick + nm_ldg(a.sp_col + k)), t));
+        a.xr[(size_t)i * a.xr_pitch + t] = acc;
+    }
+}
+
+// local per-sample group sums of this rank's shard -> gsum (G, gsum_pitch)
+NM_GLOBAL void nm_gsum_kernel(NmPrepArgs a, double* gsum) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.T) return;
+    double S[NM_MAX_GROUPS];
+#pragma unroll
+    for (int g = 0; g < NM_MAX_GROUPS; ++g) S[g] = 0.0;
+    for (int j = 0; j < a.C; ++j) {
+        const int g = nm_ldg(a.group_of + j);
+        if (g >= 0) {
+            const double v = nm_nan_to_num(nm_raw_at(a, nm_ldg(a.pick + j), t));
+#pragma unroll
+            for (int gg = 0; gg < NM_MAX_GROUPS; ++gg)
+                if (gg == g) S[gg] += v;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < NM_MAX_GROUPS; ++g)
+        if (g < a.G) gsum[(size_t)g * a.gsum_pitch + t] = S[g];
+}
+
+// flags[w * C_all + r] = 1 iff raw row r has a NaN inside window [start[w], start[w] + W)
+struct NmNanArgs {
+    NmPrepArgs p;
+    const long long* start;
+    int n_windows;
+    int W;
+    unsigned char* flags;
+};
+
+NM_GLOBAL void nm_nanflag_kernel(NmNanArgs a) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)a.n_windows * a.p.C_all) return;
+    const int w = (int)(idx / a.p.C_all), r = (int)(idx - (long long)w * a.p.C_all);
+    const long long i0 = a.start[w], i1 = i0 + a.W;
+    int flag = 0;
+    for (long long b = i0 >> 5; b <= ((i1 - 1) >> 5) && !flag; ++b) {
+        if (!a.p.nanblk[(size_t)r * a.p.nanblk_pitch + b]) continue;
+        const long long lo = b << 5, hi = lo + 32;
+        if (lo >= i0 && hi <= i1) {
+            flag = 1;
+        } else {
+            const long long s0 = lo > i0 ? lo : i0, s1 = (hi < i1 ? hi : i1) < a.p.T ? (hi < i1 ? hi : i1) : a.p.T;
+            for (long long t = s0; t < s1; ++t) {
+                const double v = nm_raw_at(a.p, r, t);
+                if (v != v) { flag = 1; break; }
+            }
+        }
+    }
+    a.flags[idx] = (unsigned char)flag;
+}
+
+// out[(row0 + w) * F + col] = NaN for every column listed for a flagged raw row
+struct NmNanFillArgs {
+    const unsigned char* flags;
+    int n_windows;
+    int C_all;
+    const int* col_ptr;  // [C_all + 1]
+    const int* cols;
+    double* out;
+    long long row0;
+    int F;
+};
+
+NM_GLOBAL void nm_nanfill_kernel(NmNanFillArgs a) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)a.n_windows * a.C_all) return;
+    if (!a.flags[idx]) return;
+    const int w = (int)(idx / a.C_all), r = (int)(idx - (long long)w * a.C_all);
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int k = a.col_ptr[r]; k < a.col_ptr[r + 1]; ++k) a.out[(size_t)(a.row0 + w) * a.F + a.cols[k]] = qnan;
+}

@@ -1,0 +1,70 @@
+"""Preprocessor chain (reference: ``processing/data_preprocessor.py``).
+
+The chain is executed in the fixed order of ``PREPROCESSOR_DICT`` -- NOT in the order of the
+``settings.preprocessing`` list -- exactly like the reference (data_preprocessor.py:44-52).
+In scope on the GPU: ``notch_filter``, ``re_referencing`` and ``raw_resampling`` when it is the
+identity (resample_freq_hz == sfreq).  ``preprocessing_filter``, ``raw_normalization`` and
+resampling with a ratio != 1 are "next" rows and raise NotImplementedError.
+"""
+
+from __future__ import annotations
+
+from typing import TYPE_CHECKING
+
+from ..utils.types import NMPreprocessor
+
+if TYPE_CHECKING:
+    import numpy as np
+
+    from ..stream.settings import NMSettings
+
+PREPROCESSOR_DICT: dict[str, str] = {
+    "preprocessing_filter": "PreprocessingFilter",
+    "notch_filter": "NotchFilter",
+    "raw_resampling": "Resampler",
+    "re_referencing": "ReReferencer",
+    "raw_normalization": "RawNormalizer",
+}
+
+
+def preprocessing_plan(settings: "NMSettings", sfreq: float) -> list[str]:
+    """Names of the preprocessors that actually do work, in execution order."""
+    for name in settings.preprocessing:
+        if name not in PREPROCESSOR_DICT:
+            raise ValueError(f"Invalid preprocessing method '{name}'. Must be one of {PREPROCESSOR_DICT.keys()}")
+    plan = []
+    for name in PREPROCESSOR_DICT:
+        if name not in settings.preprocessing:
+            continue
+        if name == "raw_resampling":
+            if settings.raw_resampling_settings.resample_freq_hz != sfreq:
+                raise NotImplementedError(
+                    f"raw_resampling from {sfreq} Hz to {settings.raw_resampling_settings.resample_freq_hz} Hz is not on the "
+                    "B200 path yet (SURVEY.md section 8f-2); set raw_resampling_settings.resample_freq_hz = sfreq or drop "
+                    "'raw_resampling' from settings.preprocessing"
+                )
+            continue  # identity, like the reference (processing/resample.py:36-38)
+        if name in ("preprocessing_filter", "raw_normalization"):
+            raise NotImplementedError(f"preprocessor '{name}' is not on the B200 path yet (SURVEY.md section 8f-3)")
+        plan.append(name)
+    return plan
+
+
+class DataPreprocessor:
+    """Holds ``NMPreprocessor`` instances with the reference's per-window ``process_data`` interface."""
+
+    def __init__(self, settings: "NMSettings", channels, sfreq: float, line_noise: float | None = None) -> None:
+        from ..filter.notch_filter import NotchFilter
+        from .rereference import ReReferencer
+
+        self.preprocessors: list[NMPreprocessor] = []
+        for name in preprocessing_plan(settings, sfreq):
+            if name == "notch_filter":
+                self.preprocessors.append(NotchFilter(sfreq=sfreq, line_noise=line_noise))
+            elif name == "re_referencing":
+                self.preprocessors.append(ReReferencer(sfreq=sfreq, channels=channels))
+
+    def process_data(self, data: "np.ndarray") -> "np.ndarray":
+        for pre in self.preprocessors:
+            data = pre.process(data)
+        return data

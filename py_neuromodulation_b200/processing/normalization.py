@@ -1,0 +1,54 @@
+"""Rolling normalisation settings + the feature normaliser (reference: ``processing/normalization.py``)."""
+
+from __future__ import annotations
+
+from typing import TYPE_CHECKING, get_args
+
+import numpy as np
+
+from ..utils.pydantic_extensions import NMField
+from ..utils.types import NORM_METHOD, NMBaseModel
+
+if TYPE_CHECKING:
+    from ..stream.settings import NMSettings
+
+GPU_NORM_METHODS = ("mean", "median", "zscore", "zscore-median")
+
+
+class NormalizationSettings(NMBaseModel):
+    normalization_time_s: float = NMField(30, gt=0, custom_metadata={"unit": "s"})
+    normalization_method: NORM_METHOD = NMField(default="zscore")
+    clip: float = NMField(default=3, ge=0, custom_metadata={"unit": "a.u."})
+
+    @staticmethod
+    def list_normalization_methods() -> list[str]:
+        return list(get_args(NORM_METHOD))
+
+
+class FeatureNormalizationSettings(NormalizationSettings):
+    normalize_psd: bool = False
+
+
+class FeatureNormalizer:
+    """Stand-alone feature normaliser with the reference's ``process(vector) -> vector`` interface.
+
+    History and arithmetic live on the GPU (``csrc/nm_norm.cuh``); inside ``DataProcessor`` the same kernel is
+    part of the fused pipeline instead.
+    """
+
+    def __init__(self, settings: "NMSettings") -> None:
+        self.settings = settings.feature_normalization_settings.validate()
+        self.method = self.settings.normalization_method
+        if self.method not in GPU_NORM_METHODS:
+            raise NotImplementedError(f"normalisation method '{self.method}' (scikit-learn transformer) is out of scope")
+        self.num_samples_normalize = int(self.settings.normalization_time_s * settings.sampling_rate_features_hz)
+        self._pipe = None
+
+    def process(self, data: np.ndarray) -> np.ndarray:
+        from .._pipeline import IdentityNormPipeline
+
+        v = np.asarray(data, dtype=np.float64).ravel()
+        if self._pipe is None:
+            self._pipe = IdentityNormPipeline(v.size, GPU_NORM_METHODS.index(self.method), float(self.settings.clip or 0.0),
+                                              self.num_samples_normalize)
+        return self._pipe.step(v)

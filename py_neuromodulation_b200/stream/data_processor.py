@@ -1,0 +1,296 @@
+"""Window processor (reference: ``stream/data_processor.py``).
+
+``DataProcessor.process(window)`` keeps the reference's one-window interface; ``process_windows`` is the
+batched entry used by ``Stream.run`` for offline arrays.  Both drive ONE fused GPU pipeline per window
+length: nan_to_num -> pick -> re-reference -> notch -> all enabled built-in features -> rolling
+normalisation -> NaN re-insertion.  Feature order = ``FeatureSelector`` field order (the reference's dict
+insertion order), then user-defined features.
+"""
+
+from __future__ import annotations
+
+from time import time
+from typing import TYPE_CHECKING
+
+import numpy as np
+
+from ..utils import io
+from ..utils.types import _PathLike
+from .settings import NMSettings
+
+if TYPE_CHECKING:
+    import pandas as pd
+
+_SCAN = {"raw_hjorth": "hjorth", "return_raw": "raw", "linelength": "linelength"}
+
+
+class _Plan:
+    """Everything that depends on the window length."""
+
+    def __init__(self, dp: "DataProcessor", window_samples: int, with_normalizer: bool) -> None:
+        from .._pipeline import BandpowerSpec, BurstsSpec, Pipeline, ScanSpec, SharpwaveSpec, SpectralSpec, band_items
+        from ..features.bursts import check_burst_bands
+        from ..features.feature_processor import OUT_OF_SCOPE
+
+        s, names, fs = dp.settings, dp.ch_names_used_features, dp.sfreq_raw
+        enabled = [f for f in s.features.get_enabled() if f not in dp.user_feature_names]
+        for f in enabled:
+            if f in OUT_OF_SCOPE:
+                raise NotImplementedError(f"feature '{f}' is outside the B200 hot path (SURVEY.md section 2 row 23)")
+        scan = ScanSpec(names, hjorth="raw_hjorth" in enabled, raw="return_raw" in enabled, linelength="linelength" in enabled)
+        specs: list = []
+        columns: list[str] = []
+        for f in enabled:
+            if f == "raw_hjorth":
+                columns += scan.keys_hjorth()
+            elif f == "return_raw":
+                columns += scan.keys_raw()
+            elif f == "linelength":
+                columns += scan.keys_linelength()
+            else:
+                if f in ("fft", "welch", "stft"):
+                    assert getattr(s, f"{f}_settings").windowlength_ms <= s.segment_length_features_ms
+                    spec = SpectralSpec(f, getattr(s, f"{f}_settings"), band_items(s), names, fs, window_samples)
+                elif f == "bandpass_filter":
+                    spec = BandpowerSpec(s.bandpass_filter_settings, band_items(s), names, fs)
+                elif f == "bursts":
+                    check_burst_bands(s)
+                    spec = BurstsSpec(s, names, fs)
+                elif f == "sharpwave_analysis":
+                    spec = SharpwaveSpec(s, names, fs)
+                else:  # pragma: no cover
+                    raise NotImplementedError(f)
+                specs.append(spec)
+                columns += spec.keys()
+        self.columns = columns
+        self.has_bursts = "bursts" in enabled
+        self.bool_columns = [i for i, k in enumerate(columns) if k.endswith("_in_burst")] if self.has_bursts else []
+        if not columns:
+            self.pipe = None
+            return
+        pipe = Pipeline(dp.n_raw_rows, len(names), window_samples, columns, device=dp.device)
+        pipe.set_pick(dp.feature_idx)
+        if "re_referencing" in dp.preproc_plan:
+            pipe.set_reref(dp.ref_matrix)
+        if "notch_filter" in dp.preproc_plan:
+            pipe.set_notch(dp.notch_taps)
+        if scan.hjorth or scan.raw or scan.linelength:
+            scan.attach(pipe)
+        for spec in specs:
+            spec.attach(pipe)
+        self.normalized = False
+        if with_normalizer and dp.normalize:
+            ns = s.feature_normalization_settings
+            cols = columns if ns.normalize_psd else [k for k in columns if "psd" not in k]
+            pipe.add_feature_normalizer(ns.normalization_method, ns.clip, dp.norm_keep, cols)
+            self.normalized = True
+        pipe.set_nan_columns(dp.nan_names_by_raw_row)
+        pipe.finalize()
+        self.pipe = pipe
+
+
+class DataProcessor:
+    def __init__(
+        self,
+        sfreq: float,
+        settings: NMSettings | _PathLike,
+        channels: "pd.DataFrame | _PathLike",
+        coord_names: list | None = None,
+        coord_list: list | None = None,
+        line_noise: float | None = None,
+        path_grids: _PathLike | None = None,
+        verbose: bool = True,
+        device: int = 0,
+    ) -> None:
+        from .. import user_features
+        from ..filter.notch_filter import NotchFilter
+        from ..processing.data_preprocessor import preprocessing_plan
+        from ..processing.normalization import GPU_NORM_METHODS
+        from ..processing.rereference import build_reference_matrix
+
+        self.settings = NMSettings.load(settings)
+        self.channels = io.load_channels(channels)
+        self.sfreq_features: float = self.settings.sampling_rate_features_hz
+        self._sfreq_raw_orig: float = sfreq
+        self.sfreq_raw: float = sfreq // 1
+        self.line_noise = line_noise
+        self.path_grids = path_grids
+        self.verbose = verbose
+        self.device = device
+        self.projection = None
+        if self.settings.postprocessing.project_cortex or self.settings.postprocessing.project_subcortex:
+            raise NotImplementedError("grid-point projection is outside the B200 hot path (SURVEY.md section 2 row 21)")
+
+        ch = self.channels
+        good_used = (ch["used"] == 1) & (ch["status"] == "good")
+        self.ch_names_used: list[str] = ch.loc[good_used, "new_name"].tolist()
+        self.feature_idx: list[int] = [
+            int(i) for i in np.where(ch["used"].astype(bool) & ~ch["target"].astype(bool))[0] if ch.loc[i, "status"] == "good"
+        ]
+        self.n_raw_rows = int(ch.shape[0])
+        # names of the rows that are actually processed (identical to ch_names_used unless a used channel is a target)
+        self.ch_names_used_features = [ch.loc[i, "new_name"] for i in self.feature_idx]
+        if len(self.ch_names_used) == len(self.ch_names_used_features):
+            self.ch_names_used_features = list(self.ch_names_used)
+        # NaN re-insertion indexes ch_names_used with a mask over ALL raw rows (reference quirk: lengths must agree)
+        self.nan_names_by_raw_row = [self.ch_names_used[r] if r < len(self.ch_names_used) else None for r in range(self.n_raw_rows)]
+
+        self.preproc_plan = preprocessing_plan(self.settings, self.sfreq_raw)
+        self.notch_taps = None
+        if "notch_filter" in self.preproc_plan:
+            self.notch_taps = NotchFilter(self.sfreq_raw, line_noise).filter_bank
+            if self.notch_taps is None:
+                self.preproc_plan.remove("notch_filter")
+        self.ref_matrix = None
+        if "re_referencing" in self.preproc_plan:
+            self.ref_matrix = build_reference_matrix(ch)
+            if self.ref_matrix is None:
+                self.preproc_plan.remove("re_referencing")
+
+        self.normalize = bool(self.settings.postprocessing.feature_normalization)
+        if self.normalize:
+            ns = self.settings.feature_normalization_settings.validate()
+            if ns.normalization_method not in GPU_NORM_METHODS:
+                raise NotImplementedError(f"normalisation method '{ns.normalization_method}' (scikit-learn) is out of scope")
+            self.norm_keep = int(ns.normalization_time_s * self.settings.sampling_rate_features_hz)
+
+        self.user_feature_names = list(user_features.keys())
+        self._user_plugins = {name: cls(self.settings, self.ch_names_used_features, self.sfreq_raw) for name, cls in user_features.items()}
+        self._user_norm = None
+        self._plans: dict[tuple[int, bool], _Plan] = {}
+        self.cnt_samples = 0
+        # validate the plug-in settings now (bands, filters, estimators) like the reference constructor does
+        self._probe = _ProbeOnly(self)
+
+    # ------------------------------------------------------------------ plans
+    def plan(self, window_samples: int, with_normalizer: bool = True) -> _Plan:
+        key = (int(window_samples), bool(with_normalizer))
+        if key not in self._plans:
+            self._plans[key] = _Plan(self, int(window_samples), with_normalizer)
+        return self._plans[key]
+
+    def reset_state(self) -> None:
+        for p in self._plans.values():
+            if p.pipe is not None:
+                p.pipe.reset_state()
+        self._user_norm = None
+
+    # ------------------------------------------------------------------ one window (reference interface)
+    def process(self, data: np.ndarray) -> dict[str, float]:
+        start_time = time()
+        data = np.asarray(data)
+        plan = self.plan(data.shape[1])
+        feats: dict = {}
+        if plan.pipe is not None:
+            values = plan.pipe.process_window(data.astype(np.float64, copy=False))
+            feats = dict(zip(plan.columns, values))
+            if not plan.normalized:
+                for i in plan.bool_columns:
+                    feats[plan.columns[i]] = bool(values[i])
+        if self._user_plugins:
+            feats.update(self._user_features(plan, data))
+        if self.verbose:
+            from .. import logger
+
+            logger.info("Last batch took: %.3f seconds to process", time() - start_time)
+        return feats
+
+    def _user_features(self, plan: _Plan, data: np.ndarray) -> dict:
+        """User-defined Python plugins see the same preprocessed window the GPU families see."""
+        from .._pipeline import IdentityNormPipeline
+        from ..processing.normalization import GPU_NORM_METHODS
+
+        pre_pipe = plan.pipe if plan.pipe is not None else self._preprocess_only(data.shape[1])
+        pre = pre_pipe.preprocess_window(data.astype(np.float64, copy=False))
+        out: dict = {}
+        for plugin in self._user_plugins.values():
+            out.update(plugin.calc_feature(pre))
+        if self.normalize and out:
+            ns = self.settings.feature_normalization_settings
+            keys = [k for k in out if ns.normalize_psd or "psd" not in k]
+            if keys:
+                if self._user_norm is None:
+                    self._user_norm = IdentityNormPipeline(len(keys), GPU_NORM_METHODS.index(ns.normalization_method),
+                                                           float(ns.clip or 0.0), self.norm_keep)
+                normed = self._user_norm.step(np.array([float(out[k]) for k in keys]))
+                out.update(zip(keys, normed))
+        nan_rows = np.isnan(data).any(axis=1)
+        if nan_rows.any():
+            for r in np.flatnonzero(nan_rows):
+                name = self.nan_names_by_raw_row[r]
+                if name is not None:
+                    for k in out:
+                        if name in k:
+                            out[k] = np.nan
+        return out
+
+    def _preprocess_only(self, window_samples: int):
+        from .._pipeline import Pipeline, ScanSpec
+
+        key = ("pre", window_samples)
+        if key not in self._plans:
+            names = self.ch_names_used_features
+            pipe = Pipeline(self.n_raw_rows, len(names), window_samples, ["_unused"], device=self.device)
+            pipe.set_pick(self.feature_idx)
+            if "re_referencing" in self.preproc_plan:
+                pipe.set_reref(self.ref_matrix)
+            if "notch_filter" in self.preproc_plan:
+                pipe.set_notch(self.notch_taps)
+            ScanSpec(names).attach(pipe)
+            pipe.finalize()
+            holder = _Plan.__new__(_Plan)
+            holder.pipe, holder.columns, holder.bool_columns, holder.normalized, holder.has_bursts = pipe, [], [], False, False
+            self._plans[key] = holder
+        return self._plans[key].pipe
+
+    # ------------------------------------------------------------------ batched offline entry
+    def process_windows(self, data: np.ndarray, starts: np.ndarray, window_samples: int, with_normalizer: bool = True,
+                        upload: bool = True, out: np.ndarray | None = None):
+        """All windows ``[starts[k], starts[k] + W)`` of a resident recording -> ``(columns, (n, F) float64)``."""
+        plan = self.plan(window_samples, with_normalizer)
+        if plan.pipe is None:
+            return [], np.empty((len(starts), 0))
+        if upload:
+            plan.pipe.upload(data)
+        return plan.columns, plan.pipe.run(starts, out=out)
+
+    # ------------------------------------------------------------------ side files
+    def save_sidecar(self, out_dir: _PathLike, prefix: str = "", additional_args: dict | None = None) -> None:
+        sidecar: dict = {"original_fs": self._sfreq_raw_orig, "final_fs": self.sfreq_raw, "sfreq": self.sfreq_features}
+        if additional_args is not None:
+            sidecar = sidecar | additional_args
+        io.save_sidecar(sidecar, out_dir, prefix)
+
+    def save_settings(self, out_dir: _PathLike, prefix: str = "") -> None:
+        self.settings.save(out_dir, prefix)
+
+    def save_channels(self, out_dir: _PathLike, prefix: str) -> None:
+        io.save_channels(self.channels, out_dir, prefix)
+
+    def save_features(self, feature_arr: "pd.DataFrame", out_dir: _PathLike = "", prefix: str = "") -> None:
+        io.save_features(feature_arr, out_dir, prefix)
+
+
+class _ProbeOnly:
+    """Runs the settings checks the reference plug-in constructors perform, without touching the GPU."""
+
+    def __init__(self, dp: DataProcessor) -> None:
+        from ..features.bursts import check_burst_bands
+        from ..features.feature_processor import OUT_OF_SCOPE
+
+        s = dp.settings
+        enabled = s.features.get_enabled()
+        for f in enabled:
+            if f in OUT_OF_SCOPE:
+                raise NotImplementedError(f"feature '{f}' is outside the B200 hot path (SURVEY.md section 2 row 23)")
+        for f in ("fft", "welch", "stft"):
+            if f in enabled:
+                assert getattr(s, f"{f}_settings").windowlength_ms <= s.segment_length_features_ms, (
+                    f"oscillatory feature windowlength_ms = ({getattr(s, f'{f}_settings').windowlength_ms})needs to be smaller than"
+                    f"settings['segment_length_features_ms'] = {s.segment_length_features_ms}"
+                )
+        if "bursts" in enabled:
+            check_burst_bands(s)
+        if "sharpwave_analysis" in enabled:
+            for fr in s.sharpwave_analysis_settings.filter_ranges_hz:
+                assert fr[1] < dp.sfreq_raw, f"Filter range has to be smaller than sfreq, got sfreq {dp.sfreq_raw} and filter range {fr}"
