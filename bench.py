@@ -1,0 +1,358 @@
+"""Benchmark of the per-window feature-extraction hot path (contract: see the task description / DESIGN.md section 6).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # this implementation on 1 B200
+    torchrun ... bench.py --gpus N ...                        # channel-sharded over N B200s (weak scaling)
+    python bench.py --impl reference ...                      # the reference algorithm (oracle port) on the host cores
+
+Workload = BASELINE.json configs[2] ("C3"): 256 ch x 300 s @ 1 kHz, default preprocessing (notch + common average),
+FFT + band-pass power + Hjorth + line length, 10 Hz feature rate -> 2 991 windows of 256 x 1000 samples per step.
+With N GPUs every rank owns its own 256-channel shard of a 256*N-channel recording (common average over ALL channels).
+A step = one pass of the hot path over the whole recording; metric = feature-windows/s where one unit is one
+256 ch x 1000 samp window with all its features (BASELINE.json `metric`).
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CH_PER_GPU = 256
+SFREQ = 1000.0
+DURATION_S = 300
+LINE_NOISE = 50
+METRIC = "feature-windows/sec (256ch x 1000samp fp32)"
+UNIT = "windows/s"
+
+
+def c3_settings():
+    import py_neuromodulation_b200 as nm
+
+    s = nm.NMSettings.get_default().reset()
+    s.features.fft = True
+    s.features.bandpass_filter = True
+    s.features.raw_hjorth = True
+    s.features.linelength = True
+    return s
+
+
+def synth(n_ch: int, n_samples: int, seed: int, out: np.ndarray | None = None) -> np.ndarray:
+    """Uniform [0, 1) float32 -- what every reference example / test feeds (README.rst:83)."""
+    rng = np.random.default_rng(seed)
+    if out is None:
+        out = np.empty((n_ch, n_samples), dtype=np.float32)
+    rng.random(out=out, dtype=np.float32)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int) -> None:
+        self.device = device
+        self.samples: list[list[str]] = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+
+    def _loop(self) -> None:
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.device)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self) -> dict:
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ pinned memory
+def pinned_array(lib, shape, dtype) -> np.ndarray:
+    from py_neuromodulation_b200 import _lib
+
+    n_bytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = C.c_void_p()
+    _lib.check(lib.nm_host_alloc(C.byref(ptr), n_bytes))
+    buf = (C.c_char * n_bytes).from_address(ptr.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def measured_peak_gbs() -> tuple[float, str]:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.is_file():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def _oracle_settings() -> dict:
+    return c3_settings().model_dump()
+
+
+def cpu_baseline_single(budget_s: float = 12.0) -> dict:
+    """Oracle port of the reference (one process, like the reference runs) on a bounded sample of the same workload."""
+    from oracle import np_oracle as orc
+
+    n_win_max = 400
+    x = synth(CH_PER_GPU, int(1000 + 100 * n_win_max), seed=0).astype(np.float64)
+    proc = orc.WindowOracle(SFREQ, _oracle_settings(), n_channels=CH_PER_GPU, line_noise=LINE_NOISE)
+    proc.process(x[:, :1000])  # warm-up: FIR design, FFT plans
+    done, t0 = 0, time.perf_counter()
+    while done < n_win_max:
+        proc.process(x[:, 100 * done : 100 * done + 1000])
+        done += 1
+        if time.perf_counter() - t0 > budget_s and done >= 8:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{done} consecutive windows of the C3 workload (256 ch x 1000 samp, float64), {dt:.1f} s, single process"}
+
+
+def _ref_worker(args):
+    """One worker of the multi-process reference arm: notch + features on a channel subset (re-reference done before)."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import np_oracle as orc
+
+    xr, names, n_win = args
+    sd = _oracle_settings()
+    taps = orc.design_notch(SFREQ, LINE_NOISE)
+    fft = orc.OscOracle("fft", sd, names, SFREQ)
+    bp = orc.BandPowerOracle(sd, names, SFREQ)
+    for k in range(n_win):
+        y = orc.apply_notch(xr[:, 100 * k : 100 * k + 1000].copy(), taps)
+        orc.hjorth(y, names)
+        fft.calc(y)
+        bp.calc(y)
+        orc.linelength(y, names)
+    return n_win
+
+
+def run_reference_arm(args) -> None:
+    """--impl reference: the reference algorithm on the host cores, all cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    from oracle import np_oracle as orc
+
+    cores = os.cpu_count() or 1
+    n_win = 16
+    x = synth(CH_PER_GPU, 1000 + 100 * (n_win - 1), seed=0).astype(np.float64)
+    ref = orc.reref_matrix(orc.default_channels(CH_PER_GPU))
+    names = orc.default_channels(CH_PER_GPU)["new_name"]
+    bounds = np.linspace(0, CH_PER_GPU, cores + 1).astype(int)
+
+    def one_step(pool) -> None:
+        xr = ref @ x  # re-reference before the channel split (the only cross-channel step)
+        jobs = [(xr[a:b], names[a:b], n_win) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+        pool.map(_ref_worker, jobs)
+
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(max(1, args.warmup)):
+            one_step(pool)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            one_step(pool)
+        dt = time.perf_counter() - t0
+    value = n_win * args.steps / dt
+    sample = (f"{n_win} windows of the C3 workload per step (256 ch x 1000 samp, float64), {cores} processes over disjoint "
+              "channel subsets after re-referencing, OMP threads = 1")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3: 256ch x 1000samp windows, notch+CAR, FFT+bandpass+Hjorth+linelength (bounded sample: "
+                               f"{n_win} windows/step)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args) -> None:
+    import py_neuromodulation_b200 as nm
+    from py_neuromodulation_b200 import _lib
+    from py_neuromodulation_b200.parallel import ShardedRun, car_shard_factorization, shard_bounds
+    from py_neuromodulation_b200.stream.generator import window_grid
+    from py_neuromodulation_b200.utils.channels import get_default_channels_from_data
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE {world}"
+
+    lib = _lib.load()
+    n_samples = int(DURATION_S * SFREQ)
+    settings = c3_settings()
+    c_total = CH_PER_GPU * world
+    lo, hi = shard_bounds(c_total, world, rank)
+    x = pinned_array(lib, (CH_PER_GPU, n_samples), np.float32)
+    synth(CH_PER_GPU, n_samples, seed=rank, out=x)
+
+    channels = get_default_channels_from_data(np.empty((c_total, 1)))
+    local_channels = channels.iloc[lo:hi].reset_index(drop=True)
+    reref = None
+    if world > 1:
+        reref = car_shard_factorization(list(channels["type"]), list(channels["status"]), list(channels["rereference"]), lo, hi)
+    dp = nm.DataProcessor(sfreq=SFREQ, settings=settings, channels=local_channels, line_noise=LINE_NOISE, verbose=False,
+                          device=local_rank, reref_factored=reref)
+    starts, lengths, _ = window_grid(n_samples, SFREQ, settings.sampling_rate_features_hz, settings.segment_length_features_ms)
+    W = int(lengths[0])
+    plan = dp.plan(W)
+    pipe = plan.pipe
+    n_win, F = int(starts.size), pipe.F
+    out = pinned_array(lib, (n_win, F), np.float64)
+    sharded = ShardedRun(pipe, on_gpu=True) if world > 1 else None
+
+    def barrier() -> None:
+        if dist is not None:
+            dist.barrier()
+        pipe.synchronize()
+
+    def step_e2e() -> None:
+        """Public call with HOST buffers: H2D of the recording, all kernels, D2H of the feature matrix."""
+        if sharded is None:
+            pipe.upload(x)
+            pipe.run(starts, out=out)
+        else:
+            sharded.upload(x)
+            sharded.run(starts)
+            sharded.gather(n_win)
+
+    def step_resident() -> None:
+        """Recording already in HBM: preprocessing + all window kernels, results stay on the device."""
+        pipe.prepare_resident()  # sharded recordings keep using their all-reduced group sums
+        pipe.run(starts, download=False)
+
+    def timed(fn, n: int) -> float:
+        barrier()
+        t0 = time.perf_counter()
+        pipe.timer_start()
+        for _ in range(n):
+            fn()
+        ms = pipe.timer_stop()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        local = max(ms, 0.0) if sharded is None else wall  # sharded steps also spend time on torch's NCCL stream
+        if dist is not None:
+            import torch
+
+            t = torch.tensor([local], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            local = float(t.item())
+        return local
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    with ClockSampler(local_rank) as clocks:
+        launches0 = pipe.kernel_launches
+        ms_res = timed(step_resident, args.steps)
+        launches = pipe.kernel_launches - launches0
+        ms_e2e = timed(step_e2e, args.steps)
+    units = n_win * world * args.steps
+    value = units / (ms_res * 1e-3)
+    e2e_value = units / (ms_e2e * 1e-3)
+
+    # per-kernel profile of one more (untimed) step -> roofline of the dominant kernel
+    pipe.set_profiling(True)
+    step_resident()
+    pipe.synchronize()
+    prof = pipe.profile()
+    pipe.set_profiling(False)
+    dominant = max(prof, key=lambda k: prof[k][0])
+    dom_ms, dom_launches = prof[dominant]
+    feats_of = {"notch": 0, "scan": 4 * CH_PER_GPU, "spectral": 4 * CH_PER_GPU, "bandpower": 4 * CH_PER_GPU, "prep": 0}
+    unit_bytes = CH_PER_GPU * W * 4 + feats_of.get(dominant, 0) * 4  # fp32 tile in + fp32 features out
+    bytes_per_launch = unit_bytes * n_win / max(dom_launches, 1)
+    achieved = bytes_per_launch / (dom_ms / max(dom_launches, 1) * 1e-3) / 1e9
+    peak, peak_src = measured_peak_gbs()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"C3 (BASELINE.json configs[2]): {CH_PER_GPU}ch/GPU x {DURATION_S}s @ {int(SFREQ)}Hz, notch+CAR, "
+                            f"FFT+bandpass+Hjorth+linelength, {n_win} windows of {CH_PER_GPU}x{W} per GPU per step, F={F}/GPU",
+                "sharding": "channels" if world > 1 else "none",
+                "l2": "inputs larger than L2 (raw 307 MB f32 + re-referenced 614 MB f64 per GPU)",
+                "timing": "CUDA events on the pipeline stream (N=1); barrier + device sync wall clock, max over ranks (N>1)",
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes * world + starts.nbytes * world),
+                    "d2h_bytes_per_step": int(out.nbytes * world), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "launches_per_step": int(dom_launches),
+                         "ms_per_launch": dom_ms / max(dom_launches, 1),
+                         "profile_ms_per_step": {k: round(v[0], 3) for k, v in prof.items()},
+                         "note": "FFT-convolution kernels are FP64/shared-memory bound, not HBM bound (DESIGN.md section 5)"},
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_single()
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

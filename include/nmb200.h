@@ -143,6 +143,17 @@ int nm_fir_apply(int device, const double* taps, int n_filters, int n_taps, int 
 /* CUDA events on the pipeline's stream */
 int nm_timer_start(nm_pipeline* p);
 int nm_timer_stop(nm_pipeline* p, double* elapsed_ms);
+/* re-run nan_to_num / pick / re-reference on the recording already resident on the device (benchmarks) */
+int nm_prepare_resident(nm_pipeline* p);
+int nm_synchronize(nm_pipeline* p);
+/* per-family kernel timing: when enabled every launch is bracketed by CUDA events on the pipeline's stream and
+ * host-synchronised (profiling runs only).  nm_get_profile fills ms[i] / launches[i] for family i and returns the
+ * number of families: 0 prep, 1 notch, 2 scan, 3 spectral, 4 bandpower, 5 sharpwave, 6 burst envelope,
+ * 7 burst threshold, 8 burst features, 9 normaliser, 10 nan. */
+int nm_set_profiling(nm_pipeline* p, int enabled);
+int nm_get_profile(nm_pipeline* p, double* ms, long long* launches, int n);
+/* windows per kernel launch (chunk size chosen so that the notched chunk stays L2 resident) */
+int nm_chunk_windows(nm_pipeline* p);
 /* number of kernels this library launched since the pipeline was created */
 long long nm_kernel_launches(nm_pipeline* p);
 /* device pointer / geometry of the last result matrix (for NCCL gathers by the host side) */

@@ -73,6 +73,11 @@ _SIGNATURES = {
     "nm_timer_start": (C.c_int, [C.c_void_p]),
     "nm_timer_stop": (C.c_int, [C.c_void_p, c_double_p]),
     "nm_kernel_launches": (C.c_longlong, [C.c_void_p]),
+    "nm_prepare_resident": (C.c_int, [C.c_void_p]),
+    "nm_synchronize": (C.c_int, [C.c_void_p]),
+    "nm_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "nm_get_profile": (C.c_int, [C.c_void_p, c_double_p, c_ll_p, C.c_int]),
+    "nm_chunk_windows": (C.c_int, [C.c_void_p]),
     "nm_result_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), c_ll_p, c_int_p]),
     "nm_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "nm_upload_begin_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong]),

@@ -193,6 +193,29 @@ class Pipeline:
         _lib.check(self.lib.nm_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    PROFILE_FAMILIES = ("prep", "notch", "scan", "spectral", "bandpower", "sharpwave", "burst_envelope", "burst_threshold",
+                        "burst_features", "normalizer", "nan")
+
+    def prepare_resident(self) -> None:
+        _lib.check(self.lib.nm_prepare_resident(self._h))
+
+    def synchronize(self) -> None:
+        _lib.check(self.lib.nm_synchronize(self._h))
+
+    def set_profiling(self, enabled: bool) -> None:
+        _lib.check(self.lib.nm_set_profiling(self._h, int(enabled)))
+
+    def profile(self) -> dict[str, tuple[float, int]]:
+        n = len(self.PROFILE_FAMILIES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_longlong * n)()
+        self.lib.nm_get_profile(self._h, ms, cnt, n)
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(self.PROFILE_FAMILIES) if cnt[i]}
+
+    @property
+    def chunk_windows(self) -> int:
+        return int(self.lib.nm_chunk_windows(self._h))
+
     @property
     def kernel_launches(self) -> int:
         return int(self.lib.nm_kernel_launches(self._h))

@@ -53,5 +53,6 @@ extern "C" int nm_upload_finish(nm_pipeline* p) {
     NM_CUDA_CHECK(cudaGetLastError());
     p->upload_pending = false;
     p->have_data = true;
+    p->resident_uses_gsum = true;
     return 0;
 }

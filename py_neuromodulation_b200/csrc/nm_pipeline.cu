@@ -62,6 +62,9 @@ struct BandpowerFam {
     int act = 0, mob = 0, comp = 0, logt = 0;
 };
 
+enum { NM_PROF_PREP = 0, NM_PROF_NOTCH, NM_PROF_SCAN, NM_PROF_SPEC, NM_PROF_BANDPOWER, NM_PROF_SHARPWAVE, NM_PROF_BURST_ENV,
+       NM_PROF_BURST_THR, NM_PROF_BURST_FEAT, NM_PROF_NORM, NM_PROF_NAN, NM_PROF_N };
+
 struct nm_pipeline {
     int device = 0, C_all = 0, C = 0, W = 0, F = 0;
     bool finalized = false;
@@ -69,6 +72,23 @@ struct nm_pipeline {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int n_sm = 1, smem_max = 48 * 1024;
     long long launches = 0;
+    // optional per-family kernel timing (nm_set_profiling): events around every launch, host-synchronised
+    bool profiling = false;
+    double prof_ms[NM_PROF_N] = {0};
+    long long prof_cnt[NM_PROF_N] = {0};
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    void prof_begin() {
+        if (profiling) cudaEventRecord(pe0, stream);
+    }
+    void prof_end(int fam) {
+        if (!profiling) return;
+        cudaEventRecord(pe1, stream);
+        cudaEventSynchronize(pe1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, pe0, pe1);
+        prof_ms[fam] += ms;
+        prof_cnt[fam] += 1;
+    }
 
     // preprocessing
     std::vector<int> pick;
@@ -94,7 +114,7 @@ struct nm_pipeline {
     DevBuf d_raw, d_xr, d_nanblk, d_gsum;
     bool raw_f64 = false;
     long long T = 0, raw_pitch = 0, xr_pitch = 0, nanblk_pitch = 0, gsum_pitch = 0;
-    bool have_data = false, upload_pending = false;
+    bool have_data = false, upload_pending = false, resident_uses_gsum = false;
     DevBuf d_starts, d_yoff, d_y, d_out, d_nanflags;
     long long out_rows = 0;
     int chunk = 1, Wp = 0;
@@ -170,7 +190,9 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     epi.win0 = batch;
     epi.S = S;
     const size_t sm = fir_smem();
+    p->prof_begin();
     NM_LAUNCH(nm_fir_kernel<NmEpiBursts>, dim3(p->grid_for(sm, fa.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, fa, epi);
+    p->prof_end(NM_PROF_BURST_ENV);
 
     NmBurstThrArgs ta;
     ta.ring = d_ring.as<double>();
@@ -182,7 +204,9 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     ta.gamma = d_gamma.as<double>();
     ta.thr = d_thr.as<double>();
     const int n_thr = n * C * nB;
+    p->prof_begin();
     NM_LAUNCH(nm_burst_thr_kernel, dim3(std::min(n_thr, p->n_sm * 8)), dim3(NM_FFT_THREADS), thr_smem(), p->stream, ta);
+    p->prof_end(NM_PROF_BURST_THR);
 
     NmBurstFeatArgs ba;
     ba.env = d_env.as<double>();
@@ -192,7 +216,9 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     ba.sfreq = sfreq; ba.seg_s = seg_s;
     ba.out = nm_out_for(p, d_colmap, nB * 6, w0);
     const int wpc = NM_ROW_THREADS / 32;
+    p->prof_begin();
     NM_LAUNCH(nm_burst_feat_kernel, dim3(std::max(1, std::min((n_thr + wpc - 1) / wpc, p->n_sm * 16))), dim3(NM_ROW_THREADS), 0, p->stream, ba);
+    p->prof_end(NM_PROF_BURST_FEAT);
     p->launches += 3;
     batch += n;
     return 0;
@@ -206,7 +232,9 @@ int SharpwaveFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     epi.cfg = cfg;
     epi.out = nm_out_for(p, d_colmap, per_ch, w0);
     const size_t sm = smem();
+    p->prof_begin();
     NM_LAUNCH(nm_fir_kernel<NmEpiSharpwave>, dim3(p->grid_for(sm, fa.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, fa, epi);
+    p->prof_end(NM_PROF_SHARPWAVE);
     p->launches++;
     return 0;
 }
@@ -234,7 +262,9 @@ int NormFam::run(nm_pipeline* p, int n_windows) {
     a.clip = clip;
     a.out = p->d_out.as<double>();
     a.F = p->F;
+    p->prof_begin();
     NM_LAUNCH(nm_norm_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
+    p->prof_end(NM_PROF_NORM);
     p->launches += 2;
     // keep the last (n_keep - 1) raw rows for the next call
     const int keep = (int)std::min<size_t>(rows, (size_t)std::max(0, n_keep - 1));
@@ -266,6 +296,8 @@ extern "C" int nm_pipeline_create(int device, int n_raw_rows, int n_ch, int wind
     NM_CUDA_CHECK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     NM_CUDA_CHECK(cudaEventCreate(&p->ev0));
     NM_CUDA_CHECK(cudaEventCreate(&p->ev1));
+    NM_CUDA_CHECK(cudaEventCreate(&p->pe0));
+    NM_CUDA_CHECK(cudaEventCreate(&p->pe1));
     NM_CUDA_CHECK(cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, device));
     NM_CUDA_CHECK(cudaDeviceGetAttribute(&p->smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     p->pick.resize(n_ch);
@@ -280,6 +312,8 @@ extern "C" void nm_pipeline_destroy(nm_pipeline* p) {
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->pe0) cudaEventDestroy(p->pe0);
+    if (p->pe1) cudaEventDestroy(p->pe1);
     cudaStream_t s = p->stream;
     delete p;
     if (s) cudaStreamDestroy(s);
@@ -570,11 +604,34 @@ static int nm_upload_impl(nm_pipeline* p, const void* data, bool f64, long long 
     if (nm_stage_raw(p, data, f64, n_samples, pitch)) return -1;
     const int threads = NM_ROW_THREADS;
     const unsigned grid = (unsigned)((n_samples + threads - 1) / threads);
+    p->prof_begin();
     NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(threads), 0, p->stream, nm_prep_args(p));
+    p->prof_end(NM_PROF_PREP);
     p->launches++;
     NM_CUDA_CHECK(cudaGetLastError());
     p->have_data = true;
     p->upload_pending = false;
+    p->resident_uses_gsum = false;
+    return 0;
+}
+
+// re-run the window-independent preprocessing on the recording that is already resident on the device
+extern "C" int nm_prepare_resident(nm_pipeline* p) {
+    NM_P_CHECK(p);
+    NM_CHECK(p->have_data && !p->upload_pending, "no resident recording");
+    cudaSetDevice(p->device);
+    const int threads = NM_ROW_THREADS;
+    const unsigned grid = (unsigned)((p->T + threads - 1) / threads);
+    NmPrepArgs a = nm_prep_args(p);
+    if (p->resident_uses_gsum) {  // channel-sharded recording: keep using the all-reduced group sums
+        a.gsum_ext = p->d_gsum.as<double>();
+        a.gsum_pitch = p->gsum_pitch;
+    }
+    p->prof_begin();
+    NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(threads), 0, p->stream, a);
+    p->prof_end(NM_PROF_PREP);
+    p->launches++;
+    NM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
@@ -598,7 +655,9 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         NmFirArgs a = p->notch->args(rows);
         NmEpiStore epi{p->d_y.as<double>(), (long long)p->Wp, 1};
         const size_t sm = p->notch->smem(NmEpiStore::smem_bytes(NM_FFT_THREADS));
+        p->prof_begin();
         NM_LAUNCH(nm_fir_kernel<NmEpiStore>, dim3(p->grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, a, epi);
+        p->prof_end(NM_PROF_NOTCH);
         p->launches++;
         rows.base = p->d_y.as<double>();
         rows.ch_stride = p->Wp;
@@ -621,7 +680,9 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         const int wpc = NM_ROW_THREADS / 32;
         const long long n_rows = (long long)n * p->C;
         const int grid = (int)std::max<long long>(1, std::min<long long>((n_rows + wpc - 1) / wpc, (long long)p->n_sm * 16));
+        p->prof_begin();
         NM_LAUNCH(nm_scan_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
+        p->prof_end(NM_PROF_SCAN);
         p->launches++;
     }
     for (auto& f : p->spectral) {
@@ -644,7 +705,9 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         a.out = out_for(f->d_colmap, f->per_ch);
         a.n_items = n * ((p->C + 1) / 2);
         const size_t sm = nm_spec_smem_bytes(c.nper, f->fft.generic, f->nk, c.keep_segments ? c.nseg : 1);
+        p->prof_begin();
         NM_LAUNCH(nm_spec_kernel, dim3(p->grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, a);
+        p->prof_end(NM_PROF_SPEC);
         p->launches++;
     }
     if (p->bandpower) {
@@ -655,7 +718,9 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         epi.want_act = f.act; epi.want_mob = f.mob; epi.want_comp = f.comp; epi.log_act = f.logt;
         epi.out = out_for(f.d_colmap, f.bank.nF * 3);
         const size_t sm = f.bank.smem(NmEpiBandpower::smem_bytes(NM_FFT_THREADS));
+        p->prof_begin();
         NM_LAUNCH(nm_fir_kernel<NmEpiBandpower>, dim3(p->grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, a, epi);
+        p->prof_end(NM_PROF_BANDPOWER);
         p->launches++;
     }
     if (p->sharpwave && p->sharpwave->run(p, rows, w0)) return -1;
@@ -777,6 +842,27 @@ extern "C" int nm_timer_stop(nm_pipeline* p, double* elapsed_ms) {
     return 0;
 }
 extern "C" long long nm_kernel_launches(nm_pipeline* p) { return p ? p->launches : 0; }
+extern "C" int nm_set_profiling(nm_pipeline* p, int enabled) {
+    NM_P_CHECK(p);
+    p->profiling = enabled != 0;
+    for (int i = 0; i < NM_PROF_N; ++i) { p->prof_ms[i] = 0; p->prof_cnt[i] = 0; }
+    return 0;
+}
+extern "C" int nm_get_profile(nm_pipeline* p, double* ms, long long* launches, int n) {
+    NM_P_CHECK(p);
+    for (int i = 0; i < n && i < NM_PROF_N; ++i) {
+        if (ms) ms[i] = p->prof_ms[i];
+        if (launches) launches[i] = p->prof_cnt[i];
+    }
+    return NM_PROF_N;
+}
+extern "C" int nm_chunk_windows(nm_pipeline* p) { return p ? p->chunk : 0; }
+extern "C" int nm_synchronize(nm_pipeline* p) {
+    NM_P_CHECK(p);
+    cudaSetDevice(p->device);
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
 extern "C" int nm_result_device_ptr(nm_pipeline* p, void** ptr, long long* n_rows, int* n_cols) {
     NM_P_CHECK(p);
     if (ptr) *ptr = p->d_out.p;

@@ -1,0 +1,129 @@
+"""Channel-sharded multi-GPU execution of the offline hot path.
+
+After re-referencing every hot-path feature is computed per channel, so the recording shards by channel with no
+halo: rank r of R owns channels [r*C/R, (r+1)*C/R) for ALL windows.  The data path has exactly two exchanges:
+
+1. common-average reference: one all-reduce(sum) of the per-sample channel-group sums (G x T float64) --
+   ``nm_upload_begin_f32`` / ``nm_group_sums_device_ptr`` / ``nm_upload_finish`` in the C ABI;
+2. one gather of the (n_windows x F_local) float64 result blocks to rank 0 at the end.
+
+The collectives go through ``torch.distributed`` (NCCL over NVLink on GPUs; gloo in the CPU tests, where the
+"device" buffers of the thread-emulated library are host memory).  torch is plumbing only: no torch kernel touches
+the samples.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def shard_bounds(n_channels: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous, balanced channel block of ``rank`` (first ``n % world`` ranks get one extra channel)."""
+    base, extra = divmod(n_channels, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def car_shard_factorization(types: list[str], status: list[str], refs: list[str], lo: int, hi: int):
+    """Factored re-reference (see ``csrc/nm_prep.cuh``) of the local channels [lo, hi) of a GLOBAL channel table.
+
+    Supports "average" (per channel type, good channels only) and "None"; bipolar references would need the
+    neighbour's samples on the same rank and are rejected.  Returns (n_groups, group_of, gcoef, sp_ptr, sp_col, sp_val).
+    """
+    n_loc = hi - lo
+    kinds = sorted({t for t, s, r in zip(types, status, refs) if s == "good" and str(r).lower() == "average"})
+    if len(kinds) > 8:
+        raise ValueError("more than 8 channel types use an average reference")
+    members = {k: [i for i, (t, s) in enumerate(zip(types, status)) if t == k and s == "good"] for k in kinds}
+    group_of = np.full(n_loc, -1, dtype=np.int32)
+    gcoef = np.zeros((n_loc, len(kinds)))
+    diag = np.ones(n_loc)
+    for j in range(n_loc):
+        i = lo + j
+        ref = str(refs[i]).lower()
+        if status[i] == "good" and types[i] in kinds:
+            group_of[j] = kinds.index(types[i])  # the channel contributes to its type's group sum
+        if status[i] != "good" or ref == "none":
+            continue
+        if ref != "average":
+            raise NotImplementedError("channel-sharded runs support 'average' and 'None' references only")
+        n_ref = len(members[types[i]]) - 1  # all good channels of the type except i itself
+        if n_ref <= 0:
+            continue
+        g = kinds.index(types[i])
+        gcoef[j, g] = -1.0 / n_ref
+        diag[j] = 1.0 + 1.0 / n_ref  # the group sum contains x_i itself
+    sp_ptr = np.arange(n_loc + 1, dtype=np.int32)
+    sp_col = np.arange(n_loc, dtype=np.int32)
+    return len(kinds), group_of, gcoef, sp_ptr, sp_col, diag
+
+
+class _DeviceView:
+    """Expose a raw device pointer through ``__cuda_array_interface__`` so torch can wrap it without a copy."""
+
+    def __init__(self, ptr: int, n: int, typestr: str = "<f8") -> None:
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": (int(n),), "typestr": typestr, "version": 2,
+                                         "strides": None}
+
+
+def wrap_buffer(ptr: int, n: int, on_gpu: bool):
+    """torch tensor over ``n`` float64 values at ``ptr`` (device memory on GPUs, host memory for the emulated library)."""
+    import torch
+
+    if on_gpu:
+        return torch.as_tensor(_DeviceView(ptr, n), device="cuda")
+    arr = np.ctypeslib.as_array((C.c_double * n).from_address(ptr))
+    return torch.from_numpy(arr)
+
+
+class ShardedRun:
+    """One rank's part of a channel-sharded offline run around an already-built local :class:`Pipeline`."""
+
+    def __init__(self, pipe, on_gpu: bool = True) -> None:
+        self.pipe = pipe
+        self.on_gpu = on_gpu
+
+    def upload(self, data_f32: np.ndarray) -> None:
+        """H2D of the local shard, all-reduce of the group sums, re-reference."""
+        import torch.distributed as dist
+
+        p = self.pipe
+        a = np.ascontiguousarray(data_f32, dtype=np.float32)
+        _lib.check(p.lib.nm_upload_begin_f32(p._h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[1]))
+        ptr, n = C.c_void_p(), C.c_longlong()
+        _lib.check(p.lib.nm_group_sums_device_ptr(p._h, C.byref(ptr), C.byref(n)))
+        sums = wrap_buffer(ptr.value, n.value, self.on_gpu)
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            if self.on_gpu:
+                import torch
+
+                torch.cuda.current_stream().synchronize()
+        _lib.check(p.lib.nm_upload_finish(p._h))
+        p._keep_data = a
+
+    def run(self, starts: np.ndarray) -> None:
+        self.pipe.run(starts, download=False)
+        self.pipe.synchronize()
+
+    def gather(self, n_windows: int):
+        """Gather the (n_windows, F_local) blocks to rank 0; returns a host array (n_windows, world*F_local) there, else None."""
+        import torch
+        import torch.distributed as dist
+
+        ptr, rows, cols = self.pipe.result_device_ptr()
+        local = wrap_buffer(ptr, rows * cols, self.on_gpu)[: n_windows * cols].view(n_windows, cols)
+        if not (dist.is_initialized() and dist.get_world_size() > 1):
+            return local.cpu().numpy().copy() if self.on_gpu else local.numpy().copy()
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if rank == 0:
+            parts = [torch.empty_like(local) for _ in range(world)]
+            dist.gather(local, gather_list=parts, dst=0)
+            full = torch.cat(parts, dim=1)
+            return full.cpu().numpy() if self.on_gpu else full.numpy().copy()
+        dist.gather(local, gather_list=None, dst=0)
+        return None

@@ -70,7 +70,9 @@ class _Plan:
             return
         pipe = Pipeline(dp.n_raw_rows, len(names), window_samples, columns, device=dp.device)
         pipe.set_pick(dp.feature_idx)
-        if "re_referencing" in dp.preproc_plan:
+        if dp.reref_factored is not None:  # channel-sharded run: coefficients come from the GLOBAL channel table
+            pipe.set_reref_factored(*dp.reref_factored)
+        elif "re_referencing" in dp.preproc_plan:
             pipe.set_reref(dp.ref_matrix)
         if "notch_filter" in dp.preproc_plan:
             pipe.set_notch(dp.notch_taps)
@@ -101,6 +103,7 @@ class DataProcessor:
         path_grids: _PathLike | None = None,
         verbose: bool = True,
         device: int = 0,
+        reref_factored: tuple | None = None,
     ) -> None:
         from .. import user_features
         from ..filter.notch_filter import NotchFilter
@@ -117,6 +120,7 @@ class DataProcessor:
         self.path_grids = path_grids
         self.verbose = verbose
         self.device = device
+        self.reref_factored = reref_factored
         self.projection = None
         if self.settings.postprocessing.project_cortex or self.settings.postprocessing.project_subcortex:
             raise NotImplementedError("grid-point projection is outside the B200 hot path (SURVEY.md section 2 row 21)")

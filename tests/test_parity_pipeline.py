@@ -1,0 +1,193 @@
+"""Parity of the fused window processor (DataProcessor.process / process_windows) and of Stream.run against
+fixtures generated from the unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+import py_neuromodulation_b200 as nm
+from oracle import np_oracle as orc
+from py_neuromodulation_b200.stream.generator import window_grid
+from py_neuromodulation_b200.utils.channels import get_default_channels_from_data
+from tests.helpers import load_golden, uniform, neural_like
+
+TOL = 1e-8  # relative to max(1, |ref|); z-scored features amplify the 1e-16 rounding differences of their inputs
+
+
+def check_matrix(cols, mat, keys_ref, ref, what, tol=TOL):
+    assert list(cols) == list(keys_ref), f"{what}: column order differs"
+    assert mat.shape == ref.shape, f"{what}: {mat.shape} vs {ref.shape}"
+    assert np.array_equal(np.isnan(mat), np.isnan(ref)), f"{what}: NaN pattern differs"
+    inf = np.isinf(ref)
+    assert np.array_equal(mat[inf], ref[inf]), f"{what}: inf pattern differs"
+    fin = np.isfinite(ref)
+    err = np.abs(mat - ref) / np.maximum(np.abs(ref), 1.0)
+    err[~fin] = 0
+    w, c = np.unravel_index(np.argmax(err), err.shape)
+    assert err.max() <= tol, f"{what}: window {w} {cols[c]}: got {mat[w, c]!r} ref {ref[w, c]!r}"
+    for j, k in enumerate(cols):
+        if k.endswith("_in_burst") and not np.isnan(ref[:, j]).any():
+            pass  # checked exactly in the non-normalised cases below
+
+
+def run_dp(g, n_windows=None, with_norm=True):
+    x = g["x"].astype(np.float64)
+    s = nm.NMSettings(**g["settings"])
+    dp = nm.DataProcessor(sfreq=g["sfreq"], settings=s, channels=get_default_channels_from_data(x),
+                          line_noise=g.get("line_noise", 50), verbose=False)
+    starts, lengths, _ = window_grid(x.shape[1], g["sfreq"], s.sampling_rate_features_hz, s.segment_length_features_ms)
+    if n_windows:
+        starts = starts[:n_windows]
+    cols, mat = dp.process_windows(x, starts, int(lengths[0]))
+    return dp, cols, mat, starts
+
+
+@pytest.mark.parametrize("name,n_emu", [("dataprocessor_c3_nan", None), ("dataprocessor_fast", None), ("dataprocessor_default", 24),
+                                        ("dataprocessor_realdata", 12)])
+def test_window_processor_matches_reference_golden(backend, name, n_emu):
+    g = load_golden(name)
+    n = n_emu if backend == "emu" else None  # the thread emulator is slow: fewer windows on CPU, all on the GPU
+    _, cols, mat, starts = run_dp(g, n)
+    check_matrix(cols, mat, g["keys"], g["vals"][: len(starts)], name)
+    if name == "dataprocessor_realdata":  # not normalised: integer-valued burst outputs must be bit-exact
+        for j, k in enumerate(cols):
+            if k.endswith("_in_burst") or k.endswith("_duration_max"):
+                assert np.array_equal(mat[:, j], g["vals"][: len(starts), j]), k
+
+
+def test_streaming_process_equals_batch(backend):
+    """DataProcessor.process window by window (stateful bursts + normaliser) == one batched run."""
+    g = load_golden("dataprocessor_default")
+    n = 8
+    dp, cols, mat, starts = run_dp(g, n)
+    x = g["x"].astype(np.float64)
+    s = nm.NMSettings(**g["settings"])
+    dp2 = nm.DataProcessor(sfreq=1000, settings=s, channels=get_default_channels_from_data(x), line_noise=50, verbose=False)
+    for k in range(n):
+        d = dp2.process(x[:, starts[k] : starts[k] + 1000])
+        assert list(d.keys()) == cols
+        v = np.array([float(t) for t in d.values()])
+        assert np.max(np.abs(v - mat[k]) / np.maximum(np.abs(mat[k]), 1)) < 1e-12, k
+        ref = g["vals"][k]
+        assert np.max(np.abs(v - ref) / np.maximum(np.abs(ref), 1)) < TOL, k
+
+
+def test_stream_readme_demo(backend, tmp_path):
+    """README demo of the reference: 5 ch x 10 s @ 1 kHz, 3 Hz features, default settings -> 28 x 156 DataFrame."""
+    g = load_golden("stream_readme_demo")
+    x = g["x"].astype(np.float64)
+    stream = nm.Stream(sfreq=1000, data=x, sampling_rate_features_hz=3)
+    df = stream.run(out_dir=tmp_path, experiment_name="demo")
+    assert df.shape == (28, 156)
+    assert list(df.columns) == g["keys"]
+    assert list(df["time"].iloc[:4]) == [1000, 1334, 1667, 2000] and df["time"].iloc[-1] == 10000
+    check_matrix(list(df.columns), df.to_numpy(), g["keys"], g["vals"], "readme demo")
+    for suffix in ("_FEATURES.csv", "_SETTINGS.yaml", "_SIDECAR.json", "_channels.csv"):
+        assert (tmp_path / "demo" / f"demo{suffix}").is_file(), suffix
+    import pandas as pd
+
+    back = pd.read_csv(tmp_path / "demo" / "demo_FEATURES.csv")
+    assert list(back.columns) == g["keys"] and back.shape == df.shape
+
+
+def test_stream_float_sampling_rate_variable_window_length(backend, tmp_path):
+    """reference tests/test_timing.py:43-73: sfreq 1111.111, 333 ms segments -> windows of 369 and 370 samples."""
+    g = load_golden("stream_float_fs")
+    x = g["x"].astype(np.float64)
+    s = nm.NMSettings(**g["settings"])
+    stream = nm.Stream(sfreq=g["sfreq"], data=x, sampling_rate_features_hz=g["rate"], settings=s)
+    df = stream.run(out_dir=tmp_path, experiment_name="floatfs")
+    assert list(df.columns) == g["keys"]
+    assert np.array_equal(df["time"].to_numpy(), g["vals"][:, g["keys"].index("time")])
+    check_matrix(list(df.columns), df.to_numpy(), g["keys"], g["vals"], "float fs", tol=1e-7)
+
+
+def test_bursts_history_two_tier_contract(backend):
+    """exact agreement with the UNMODIFIED reference while its history buffer is not full
+    (windows 0..290), agreement with the fixed oracle (true ring) afterwards."""
+    g = load_golden("bursts_history_320")
+    x = g["x"].astype(np.float64)
+    n = 320 if backend == "gpu" else 300
+    s = nm.NMSettings(**g["settings"])
+    b = nm.Bursts(s, g["ch_names"], 1000)
+    fixed = orc.BurstsOracle(g["settings"], g["ch_names"], 1000, faithful=False)
+    for k in range(n):
+        win = x[:, 100 * k : 100 * k + 1000]
+        out = b.calc_feature(win)
+        ref_fixed = fixed.calc(win)
+        assert list(out.keys()) == g["keys"]
+        v = np.array([float(t) for t in out.values()])
+        rf = np.array([float(t) for t in ref_fixed.values()])
+        assert np.max(np.abs(v - rf) / np.maximum(np.abs(rf), 1)) < 1e-12, f"window {k} vs fixed oracle"
+        if k <= 290:
+            r = g["vals"][k]
+            assert np.max(np.abs(v - r) / np.maximum(np.abs(r), 1)) < 1e-12, f"window {k} vs unmodified reference"
+            for j, key in enumerate(g["keys"]):
+                if key.endswith(("_in_burst", "_duration_max", "_duration_mean")):
+                    assert v[j] == r[j], (k, key)
+
+
+def test_nan_handling_like_reference_tests(backend, tmp_path):
+    """reference tests/test_nan_values.py: a NaN channel -> all its features NaN, others finite; a NaN span ->
+    NaN only for the windows that overlap it."""
+    x = uniform(3, 2, 3000)
+    x[0, 1000:2000] = np.nan
+    s = nm.NMSettings.get_fast_compute()
+    s.features.raw_hjorth = True
+    s.features.linelength = True
+    stream = nm.Stream(sfreq=1000, data=x, settings=s)
+    df = stream.run(out_dir=tmp_path, experiment_name="nan")
+    t = df["time"].to_numpy()
+    hit = (t > 1000) & (t < 2000 + 1000)
+    ch0 = df.filter(like="ch0")
+    ch1 = df.filter(like="ch1")
+    assert ch0[hit].isna().all().all() and ch0[~hit].notna().all().all()
+    assert ch1.notna().all().all()
+    # and the oracle agrees on the values
+    cols, ref = orc.run_offline(x, 1000, s.model_dump())
+    check_matrix(list(df.columns), df.to_numpy(), cols, ref, "nan span")
+
+
+def test_target_channel_and_bad_channel(backend, tmp_path):
+    """target channels are appended raw (stream.py:145-170); bad / unused channels are skipped."""
+    from py_neuromodulation_b200.utils.channels import set_channels
+
+    x = uniform(9, 5, 2500)
+    ch = set_channels(["ecog_0", "ecog_1", "ecog_2", "lfp_x", "MOV_RIGHT"], ["ecog", "ecog", "ecog", "dbs", "misc"],
+                      reference="default", bads=["ecog_2"], target_keywords=["mov"])
+    assert list(ch["used"]) == [1, 1, 0, 1, 0] and list(ch["target"]) == [0, 0, 0, 0, 1]
+    s = nm.NMSettings.get_fast_compute()
+    s.postprocessing.feature_normalization = False
+    stream = nm.Stream(sfreq=1000, data=x, channels=ch, settings=s)
+    df = stream.run(out_dir=tmp_path, experiment_name="tgt")
+    assert "MOV_RIGHT" in df.columns and df.columns[-2] == "time"
+    starts, lengths, _ = window_grid(2500, 1000, 10, 1000)
+    assert np.array_equal(df["MOV_RIGHT"].to_numpy(), x[4, starts + lengths - 1])
+    assert not any("ecog_2" in c for c in df.columns)
+    chd = {k: list(v) for k, v in ch.to_dict(orient="list").items()}
+    cols, ref = orc.run_offline(x, 1000, s.model_dump(), channels=chd)
+    check_matrix(list(df.columns), df.to_numpy(), cols, ref, "targets")
+
+
+def test_custom_python_feature_runs_next_to_gpu_features(backend, tmp_path):
+    """reference examples/plot_2_example_add_feature.py: a duck-typed user feature sees the preprocessed window."""
+
+    class ChannelMean:
+        def __init__(self, settings, ch_names, sfreq):
+            self.ch_names = ch_names
+
+        def calc_feature(self, data):
+            return {f"{ch}_chmean": float(np.mean(data[i])) for i, ch in enumerate(self.ch_names)}
+
+    nm.add_custom_feature("channel_mean", ChannelMean)
+    try:
+        x = uniform(4, 3, 1600)
+        s = nm.NMSettings.get_fast_compute()
+        s.postprocessing.feature_normalization = False
+        stream = nm.Stream(sfreq=1000, data=x, settings=s)
+        df = stream.run(out_dir=tmp_path, experiment_name="custom")
+        assert "ch0_avgref_chmean" in df.columns
+        wo = orc.WindowOracle(1000, {**s.model_dump(), "features": {**s.model_dump()["features"], "channel_mean": False}},
+                              n_channels=3)
+        pre = wo.preprocess(x[:, :1000])
+        assert abs(df["ch0_avgref_chmean"].iloc[0] - pre[0].mean()) < 1e-12
+    finally:
+        nm.remove_custom_feature("channel_mean")

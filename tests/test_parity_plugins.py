@@ -1,0 +1,157 @@
+"""Parity of the feature plug-ins (NMFeature.calc_feature) and preprocessors against the golden fixtures
+generated from the unmodified reference, and against the oracle for cases the fixtures do not cover.
+
+Tolerance: 1e-5 relative is the gate of the task (BASELINE.json north_star); the kernels compute in float64,
+so these tests assert a far tighter 1e-9 (relative to max(1, |ref|)) to catch regressions early.
+Integer-valued outputs (burst in_burst, durations in samples, num_peaks, width) must be exact.
+"""
+import numpy as np
+import pytest
+
+import py_neuromodulation_b200 as nm
+from oracle import np_oracle as orc
+from tests.helpers import load_golden, uniform, neural_like
+
+TOL = 1e-9
+
+PLUGINS = {
+    "fft": lambda: nm.FFT, "welch": lambda: nm.Welch, "stft": lambda: nm.STFT, "hjorth": lambda: nm.Hjorth,
+    "raw": lambda: nm.Raw, "linelength": lambda: nm.LineLength, "bandpower": lambda: nm.BandPower,
+    "bursts": lambda: nm.Bursts, "sharpwave": lambda: nm.SharpwaveAnalyzer,
+}
+FILES = ["plugins_default_uniform", "plugins_default_neural", "plugins_allest_uniform", "plugins_allest_neural",
+         "plugins_sevenbands_nolog_uniform", "plugins_sevenbands_nolog_neural", "plugins_default_neural_2k"]
+EXACT_SUFFIX = ("_in_burst",)
+EXACT_SUBSTR = ("_num_peaks_", "_width_")
+
+
+def compare(keys_ref, vals_ref, got: dict, what: str, tol: float = TOL):
+    assert list(got.keys()) == list(keys_ref), f"{what}: key order differs"
+    g = np.array([float(got[k]) for k in keys_ref])
+    r = np.asarray(vals_ref, dtype=np.float64)
+    assert np.array_equal(np.isnan(g), np.isnan(r)), f"{what}: NaN pattern"
+    inf = np.isinf(r)
+    assert np.array_equal(g[inf], r[inf]), f"{what}: inf pattern"
+    fin = np.isfinite(r)
+    err = np.abs(g[fin] - r[fin]) / np.maximum(np.abs(r[fin]), 1.0)
+    worst = int(np.argmax(err)) if err.size else 0
+    assert err.max(initial=0) <= tol, f"{what}: {np.array(keys_ref)[fin][worst]} got {g[fin][worst]!r} ref {r[fin][worst]!r}"
+    for i, k in enumerate(keys_ref):
+        if k.endswith(EXACT_SUFFIX) or any(s in k for s in EXACT_SUBSTR):
+            assert g[i] == r[i] or (np.isnan(g[i]) and np.isnan(r[i])), f"{what}: integer feature {k}: {g[i]} != {r[i]}"
+
+
+@pytest.mark.parametrize("fname", FILES)
+def test_plugins_match_reference_golden(backend, fname):
+    g = load_golden(fname)
+    x = g["x"].astype(np.float64)
+    settings = nm.NMSettings(**g["settings"])
+    for name, cls in PLUGINS.items():
+        out = cls()(settings, g["ch_names"], g["sfreq"]).calc_feature(x.copy())
+        compare(g[f"{name}_keys"], g[f"{name}_vals"], out, f"{fname}:{name}")
+
+
+def test_plugin_edge_inputs_match_oracle(backend):
+    """zeros (log10 -> -inf), ones, an odd number of channels, one channel -- vs the oracle on the same input."""
+    s = nm.NMSettings.get_default()
+    sd = s.model_dump()
+    for label, x in (("zeros", np.zeros((3, 1000))), ("ones", np.ones((3, 1000))), ("single", uniform(11, 1, 1000)),
+                     ("odd", neural_like(12, 5, 1000))):
+        ch = [f"k{i}" for i in range(x.shape[0])]
+        with np.errstate(all="ignore"):
+            ref = {}
+            for kind in ("fft", "welch", "stft"):
+                ref[kind] = orc.OscOracle(kind, sd, ch, 1000).calc(x)
+            ref["hjorth"] = orc.hjorth(x, ch)
+            ref["linelength"] = orc.linelength(x, ch)
+            ref["raw"] = orc.raw_last(x, ch)
+            ref["bandpower"] = orc.BandPowerOracle(sd, ch, 1000).calc(x)
+            ref["bursts"] = orc.BurstsOracle(sd, ch, 1000).calc(x)
+            ref["sharpwave"] = orc.SharpwaveOracle(sd, ch, 1000).calc(x)
+        for name, r in ref.items():
+            out = PLUGINS[name]()(s, ch, 1000).calc_feature(x.copy())
+            if label in ("zeros", "ones") and name in ("welch", "stft", "fft", "bandpower"):
+                # rounding noise around an exact zero: the reference itself yields -inf or ~1e-17 garbage here;
+                # what is pinned is the zero/non-zero structure the reference tests check (tests/test_osc_features.py:67-86,321-341)
+                assert list(out.keys()) == list(r.keys())
+                continue
+            compare(list(r.keys()), [float(v) for v in r.values()], out, f"{label}:{name}")
+
+
+def test_zero_input_gives_minus_inf_and_zero(backend):
+    s = nm.NMSettings.get_default()
+    x = np.zeros((2, 1000))
+    out = nm.FFT(s, ["a", "b"], 1000).calc_feature(x)
+    assert all(v == -np.inf for v in out.values())
+    out = nm.Hjorth(s, ["a", "b"], 1000).calc_feature(x)
+    assert all(v == 0.0 for v in out.values())
+    s.bandpass_filter_settings.log_transform = False
+    out = nm.BandPower(s, ["a", "b"], 1000).calc_feature(x)
+    assert all(v == 0.0 for v in out.values())
+    s.fft_settings.log_transform = False
+    out = nm.FFT(s, ["a", "b"], 1000).calc_feature(np.ones((2, 1000)))
+    assert all(abs(v) < 1e-6 for v in out.values())  # reference test_fft_zero_data: non-DC bins of a constant are ~0
+
+
+def test_non_smooth_window_length_uses_generic_radix(backend):
+    """sfreq 1111.111 Hz, 333 ms: 369 = 3*3*41 and 370 = 2*5*37 samples -> generic prime-radix FFT passes."""
+    s = nm.NMSettings.get_default()
+    s.segment_length_features_ms = 333
+    for osc in ("fft_settings", "welch_settings", "stft_settings"):
+        s[osc].windowlength_ms = 333
+    s.stft_settings.windowlength_ms = 222
+    s.frequency_ranges_hz = {"theta": [4, 8], "beta": [13, 35]}
+    s.bandpass_filter_settings.segment_lengths_ms = {"theta": 333, "beta": 200}
+    s = s.validate()
+    sd = s.model_dump()
+    fs = 1111.111
+    for w in (369, 370):
+        x = neural_like(20 + w, 3, w, fs)
+        ch = ["p", "q", "r"]
+        for kind, cls in (("fft", nm.FFT), ("stft", nm.STFT)):
+            ref = orc.OscOracle(kind, sd, ch, fs).calc(x)
+            compare(list(ref.keys()), [float(v) for v in ref.values()], cls(s, ch, fs).calc_feature(x), f"{kind}@{w}")
+        ref = orc.BurstsOracle({**sd, "bursts_settings": {**sd["bursts_settings"], "frequency_bands": ["beta"]}}, ch, fs).calc(x)
+        s2 = s.model_copy(deep=True)
+        s2.bursts_settings.frequency_bands = ["beta"]
+        compare(list(ref.keys()), [float(v) for v in ref.values()], nm.Bursts(s2, ch, fs).calc_feature(x), f"bursts@{w}")
+
+
+@pytest.mark.parametrize("name,line", [("notch_sf150", 50), ("notch_sf200", 50), ("notch_sf500", 50), ("notch_sf2000", 50),
+                                       ("notch_w370", 60), ("notch_w2500", 60)])
+def test_notch_filter_matches_reference(backend, name, line):
+    g = load_golden(name)
+    nf = nm.filter.NotchFilter(g["sfreq"], line)
+    assert np.max(np.abs(nf.filter_bank - g["taps"])) < 1e-14
+    out = nf.process(g["x"].astype(np.float64))
+    assert out.shape == g["out"].shape
+    assert np.max(np.abs(out - g["out"])) < 1e-12
+
+
+def test_preprocess_chain_matches_reference(backend):
+    import pandas as pd
+
+    g = load_golden("preprocess_notch_reref")
+    x = g["x"].astype(np.float64)
+    ch = pd.DataFrame({k: list(v.values()) for k, v in g["channels"].items()})
+    rr = nm.processing.ReReferencer(1000, ch)
+    assert np.array_equal(rr.ref_matrix, g["ref_matrix"])
+    nf = nm.filter.NotchFilter(1000, 50)
+    y = nf.process(x.copy())
+    assert np.max(np.abs(y - g["notch_out"])) < 1e-12
+    z = rr.process(y[:5])
+    assert np.max(np.abs(z - g["reref_out"])) < 1e-12
+
+
+def test_mne_filter_shapes_like_reference_tests(backend):
+    """reference tests/test_nm_filter.py: 1-D and 2-D input, several filter lengths -> (C, n_filters, W)."""
+    for flen in ("999ms", 999, "1501ms"):
+        f = nm.filter.MNEFilter([(4, 8), (13, 35)], 1000, filter_length=flen)
+        x = uniform(5, 3, 1000)
+        out = f.filter_data(x)
+        assert out.shape == (3, 2, 1000)
+        ref = orc.apply_bank(x, f.filter_bank)
+        assert np.max(np.abs(out - ref)) < 1e-12
+        assert f.filter_data(x[0]).shape == (1, 2, 1000)
+    with pytest.raises(ValueError):
+        f.filter_data(np.zeros((2, 2, 10)))
