@@ -17,6 +17,7 @@
 #include "nm_fir.cuh"
 
 struct NmEpiBursts {
+    static constexpr bool kRegs = false;
     NmFft<double> hfft;     // W-point transform
     int need_scratch;
     double* env;            // chunk envelopes (n_windows, n_ch, nB, Wp)

@@ -36,7 +36,22 @@ struct NmEpiStore {
     double* y;             // (n_windows, n_ch, nF, Wp)
     long long Wp;
     int nF;
+    static constexpr bool kRegs = true;   // nm_conv_kernel hands over the 16 outputs of each thread in registers
     static NM_HD size_t smem_bytes(int /*nt*/) { return 0; }
+    NM_DEV bool regs_ok() const { return true; }
+    // v[k] = filtered sample n = tid + nt*k of the (padded) row; the window occupies n in [o0, o0 + W)
+    NM_DEV void run_regs(const cx<double>* v, int o0, int W, int n_ch, int w, int c0, bool has2, int f,
+                         unsigned char* /*scratch*/, int tid, int nt) const {
+        double* r0 = y + (((size_t)w * n_ch + c0) * nF + f) * Wp;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int t = tid + nt * k - o0;
+            if (t >= 0 && t < W) {
+                r0[t] = v[k].re;
+                if (has2) r0[(size_t)nF * Wp + t] = v[k].im;
+            }
+        }
+    }
     NM_DEV void run(const cx<double>* buf, int o0, int W, int n_ch, int w, int c0, bool has2, int f,
                     unsigned char* /*scratch*/, int tid, int nt) const {
         double* r0 = y + (((size_t)w * n_ch + c0) * nF + f) * Wp;
@@ -53,7 +68,48 @@ struct NmEpiBandpower {
     const int* seglen;     // [nF] tail length in samples
     int want_act, want_mob, want_comp, log_act;
     NmOut out;             // per_ch = nF * 3  (activity, mobility, complexity)
+    static constexpr bool kRegs = true;
     static NM_HD size_t smem_bytes(int /*nt*/) { return 12 * 32 * sizeof(double); }
+    // the register path covers the default configuration (variance of the tail only); mobility / complexity need
+    // neighbouring samples and go through the shared-memory row
+    NM_DEV bool regs_ok() const { return !(want_mob || want_comp); }
+    NM_DEV void run_regs(const cx<double>* v, int o0, int W, int /*n_ch*/, int w, int c0, bool has2, int f,
+                         unsigned char* scratch, int tid, int nt) const {
+        double* red = reinterpret_cast<double*>(scratch);
+        int seg = nm_ldg(seglen + f);
+        if (seg > W) seg = W;
+        const int lo = o0 + W - seg, hi = o0 + W;
+        // band-pass outputs have (near) zero mean, so the one-pass moments lose nothing in float64
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int n = tid + nt * k;
+            if (n >= lo && n < hi) {
+                s[0] += v[k].re; s[1] += v[k].re * v[k].re;
+                s[2] += v[k].im; s[3] += v[k].im * v[k].im;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] = nm_warp_sum(s[i]);
+        const int lane = tid & 31, wid = tid >> 5, nw = (nt + 31) >> 5;
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) red[i * 32 + wid] = s[i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double tot[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int q = 0; q < nw; ++q)
+                for (int i = 0; i < 4; ++i) tot[i] += red[i * 32 + q];
+            const double n0 = seg;
+            for (int k = 0; k < (has2 ? 2 : 1); ++k) {
+                const double mean = tot[2 * k] / n0;
+                double v0 = tot[2 * k + 1] / n0 - mean * mean;
+                if (v0 < 0.0) v0 = 0.0;
+                if (want_act) nm_store(out, w, c0 + k, f * 3 + 0, nm_nan_to_num(log_act ? log10(v0) : v0));
+            }
+        }
+    }
     NM_DEV void run(const cx<double>* buf, int o0, int W, int /*n_ch*/, int w, int c0, bool has2, int f,
                     unsigned char* scratch, int tid, int nt) const {
         double* red = reinterpret_cast<double*>(scratch);

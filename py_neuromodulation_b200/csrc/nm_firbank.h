@@ -3,6 +3,7 @@
 
 #include <algorithm>
 
+#include "nm_conv.cuh"
 #include "nm_fir.cuh"
 #include "nm_host.h"
 
@@ -12,20 +13,42 @@ struct FirBank {
     int nF = 0, L = 0, Lh = 0, P = 0, mode = NM_FIR_SAME, E = 0;
     FftPlanHost fft;
     DevBuf d_hperm;
+    bool pow2 = false;  // register-blocked power-of-two kernel (nm_conv.cuh) vs generic mixed-radix kernel (nm_fir.cuh)
+    int pad = 3;
     int build(const double* taps, int nF_, int L_, int W, int mode_, cudaStream_t s) {
         nF = nF_; L = L_; Lh = (L - 1) / 2; mode = mode_;
+        int need;
         if (mode == NM_FIR_REFLECT) {
             // mne _overlap_add_filter: n_edge = max(min(len(h), len(x)) - 1, 0) reflected samples per side;
             // only the (L-1)/2 nearest ones can reach the W centre outputs
             const int n_edge = std::max(std::min(L, W) - 1, 0);
             E = std::min(n_edge, Lh);
-            P = nm_next_smooth(W + E + Lh);
+            need = W + E + Lh;
         } else {
             E = 0;
-            P = nm_next_smooth(W + Lh);
+            need = W + Lh;
         }
-        if (fft.build(P, s)) return -1;
-        NM_CHECK(!fft.generic, "internal: convolution length %d is not 5-smooth", P);
+        int p2 = 1;
+        while (p2 < need) p2 <<= 1;
+        pow2 = p2 >= 512 && p2 <= 16384;
+        if (pow2) {
+            P = p2;
+            std::vector<int> radices{16};
+            int rem = P / 16;
+            if (rem == 32) { radices.push_back(8); radices.push_back(4); rem = 1; }
+            if (rem == 64) { radices.push_back(8); radices.push_back(8); rem = 1; }
+            while (rem > 16) { radices.push_back(16); rem /= 16; }
+            if (rem > 1) radices.push_back(rem);
+            NM_CHECK((int)radices.size() <= NM_CONV_MAX_PASS && radices.size() >= 2, "internal: bad pass plan for P = %d", P);
+            int last = radices.back(), lg = 0;
+            while ((1 << lg) < last) ++lg;
+            pad = std::max(3, lg);
+            if (fft.build_with(P, radices, s)) return -1;
+        } else {
+            P = nm_next_smooth(need);
+            if (fft.build(P, s)) return -1;
+            NM_CHECK(!fft.generic, "internal: convolution length %d is not 5-smooth", P);
+        }
         std::vector<double> hperm;
         if (nm_build_hperm(taps, nF, L, fft, hperm)) return -1;
         return d_hperm.upload(hperm, s);
@@ -41,5 +64,27 @@ struct FirBank {
         a.n_items = in.n_windows * ((in.n_ch + 1) / 2);
         return a;
     }
-    size_t smem(size_t epi) const { return (size_t)P * sizeof(cx<double>) * (nF > 1 ? 2 : 1) + epi; }
+    NmConvArgs conv_args(const NmRows& in) const {
+        NmConvArgs a;
+        a.in = in;
+        a.fft.P = P;
+        a.fft.NT = P / 16;
+        a.fft.npass = (int)fft.radix.size();
+        for (int i = 0; i < a.fft.npass; ++i) { a.fft.radix[i] = fft.radix[i]; a.fft.len[i] = fft.len[i]; }
+        a.fft.pad = pad;
+        a.fft.tw = fft.d_tw.as<cx<double>>();
+        a.hperm = d_hperm.as<double>();
+        a.nF = nF;
+        a.mode = mode;
+        a.E = E;
+        a.n_items = in.n_windows * ((in.n_ch + 1) / 2);
+        a.scratch_in_tail = 0;
+        return a;
+    }
+    bool epi_fits_tail(size_t epi) const { return pow2 && epi > 0 && epi <= (nm_conv_buf_elems(P, pad) - (size_t)P) * sizeof(cx<double>); }
+    int threads() const { return pow2 ? P / 16 : NM_FFT_THREADS; }
+    size_t smem(size_t epi) const {
+        const size_t buf = pow2 ? nm_conv_buf_elems(P, pad) : (size_t)P;
+        return buf * sizeof(cx<double>) * (nF > 1 ? 2 : 1) + (epi_fits_tail(epi) ? 0 : epi);
+    }
 };

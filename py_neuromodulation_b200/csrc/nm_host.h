@@ -58,6 +58,14 @@ struct FftPlanHost {
     bool generic = false;
     DevBuf d_tw, d_pos;
 
+    // explicit radix list (power-of-two convolution plans)
+    int build_with(int n_, const std::vector<int>& radices, cudaStream_t s) {
+        n = n_;
+        radix = radices;
+        generic = false;
+        return finish(s);
+    }
+
     int build(int n_, cudaStream_t s) {
         n = n_;
         radix.clear();
@@ -79,7 +87,12 @@ struct FftPlanHost {
         for (int v : r2) radix.push_back(v);
         for (int v : r3) radix.push_back(v);
         for (int v : r5) radix.push_back(v);
+        return finish(s);
+    }
+
+    int finish(cudaStream_t s) {
         NM_CHECK((int)radix.size() <= NM_MAX_PASS, "FFT length %d has too many factors", n);
+        len.clear();
         int L = n;
         for (int v : radix) { len.push_back(L); L /= v; }
         pos.assign(n, 0);
@@ -95,7 +108,6 @@ struct FftPlanHost {
         }
         std::vector<cx<double>> tw(n);
         for (int k = 0; k < n; ++k) {
-            // exact octant reduction keeps cos/sin accurate to the last bit for large n
             const double ang = -2.0 * M_PI * (double)k / (double)n;
             tw[k] = {std::cos(ang), std::sin(ang)};
         }

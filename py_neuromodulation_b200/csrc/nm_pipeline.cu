@@ -138,6 +138,37 @@ static int nm_allow_smem(K kernel, size_t bytes, const nm_pipeline* p) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------- FIR launches
+template <class Epi>
+static int nm_allow_fir_smem(const FirBank& bank, size_t bytes, const nm_pipeline* p) {
+    if (bank.pow2) return nm_allow_smem(nm_conv_kernel<Epi>, bytes, p);
+    return nm_allow_smem(nm_fir_kernel<Epi>, bytes, p);
+}
+
+template <class K>
+static int nm_resident_grid(const nm_pipeline* p, K kernel, int threads, size_t smem_bytes, int n_items) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem_bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long long g = (long long)p->n_sm * per_sm;  // persistent: exactly one resident wave, items strided over it
+    return (int)std::max<long long>(1, std::min<long long>(g, n_items));
+}
+
+template <class Epi>
+static void nm_launch_fir(nm_pipeline* p, const FirBank& bank, const NmRows& rows, const Epi& epi, size_t smem_bytes, cudaStream_t stream,
+                          size_t epi_bytes = 0) {
+    const int threads = bank.threads();
+    if (bank.pow2) {
+        NmConvArgs a = bank.conv_args(rows);
+        a.scratch_in_tail = bank.epi_fits_tail(epi_bytes) ? 1 : 0;
+        const int grid = nm_resident_grid(p, nm_conv_kernel<Epi>, threads, smem_bytes, a.n_items);
+        NM_LAUNCH(nm_conv_kernel<Epi>, dim3(grid), dim3(threads), smem_bytes, stream, a, epi);
+    } else {
+        NmFirArgs a = bank.args(rows);
+        const int grid = nm_resident_grid(p, nm_fir_kernel<Epi>, threads, smem_bytes, a.n_items);
+        NM_LAUNCH(nm_fir_kernel<Epi>, dim3(grid), dim3(threads), smem_bytes, stream, a, epi);
+    }
+}
+
 // ------------------------------------------------------------------------------- family launches
 static NmOut nm_out_for(nm_pipeline* p, const DevBuf& colmap, int per_ch, int w0) {
     NmOut o;
@@ -150,7 +181,7 @@ static NmOut nm_out_for(nm_pipeline* p, const DevBuf& colmap, int per_ch, int w0
 }
 
 int BurstsFam::allow_smem(const nm_pipeline* p) {
-    if (nm_allow_smem(nm_fir_kernel<NmEpiBursts>, fir_smem(), p)) return -1;
+    if (nm_allow_fir_smem<NmEpiBursts>(bank, fir_smem(), p)) return -1;
     return nm_allow_smem(nm_burst_thr_kernel, thr_smem(), p);
 }
 
@@ -178,7 +209,6 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
         return -1;
     NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));  // the staging vectors above are temporaries
 
-    NmFirArgs fa = bank.args(rows);
     NmEpiBursts epi;
     epi.hfft = hfft.dev();
     epi.need_scratch = hfft.generic ? 1 : 0;
@@ -191,7 +221,7 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     epi.S = S;
     const size_t sm = fir_smem();
     p->prof_begin();
-    NM_LAUNCH(nm_fir_kernel<NmEpiBursts>, dim3(p->grid_for(sm, fa.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, fa, epi);
+    nm_launch_fir(p, bank, rows, epi, sm, p->stream);
     p->prof_end(NM_PROF_BURST_ENV);
 
     NmBurstThrArgs ta;
@@ -224,16 +254,15 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     return 0;
 }
 
-int SharpwaveFam::allow_smem(const nm_pipeline* p) { return nm_allow_smem(nm_fir_kernel<NmEpiSharpwave>, smem(), p); }
+int SharpwaveFam::allow_smem(const nm_pipeline* p) { return nm_allow_fir_smem<NmEpiSharpwave>(bank, smem(), p); }
 
 int SharpwaveFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
-    NmFirArgs fa = bank.args(rows);
     NmEpiSharpwave epi;
     epi.cfg = cfg;
     epi.out = nm_out_for(p, d_colmap, per_ch, w0);
     const size_t sm = smem();
     p->prof_begin();
-    NM_LAUNCH(nm_fir_kernel<NmEpiSharpwave>, dim3(p->grid_for(sm, fa.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, fa, epi);
+    nm_launch_fir(p, bank, rows, epi, sm, p->stream);
     p->prof_end(NM_PROF_SHARPWAVE);
     p->launches++;
     return 0;
@@ -522,7 +551,7 @@ extern "C" int nm_finalize(nm_pipeline* p) {
     p->Wp = (p->W + 1) & ~1;
     // chunk of windows whose notched copy (and burst envelopes) stays comfortably inside the 126 MB L2
     const size_t per_window = (size_t)p->C * p->Wp * sizeof(double) * (1 + (p->bursts ? p->bursts->nB : 0));
-    p->chunk = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)48 << 20) / per_window));
+    p->chunk = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)96 << 20) / per_window));
     std::vector<long long> yoff(p->chunk);
     for (int k = 0; k < p->chunk; ++k) yoff[k] = (long long)k * p->C * p->Wp;
     if (p->d_yoff.upload(yoff, p->stream)) return -1;
@@ -530,8 +559,8 @@ extern "C" int nm_finalize(nm_pipeline* p) {
     if (p->bursts && p->bursts->alloc_chunk(p->chunk, p->Wp)) return -1;
 
     // opt in to large dynamic shared memory once
-    if (p->notch && nm_allow_smem(nm_fir_kernel<NmEpiStore>, p->notch->smem(NmEpiStore::smem_bytes(NM_FFT_THREADS)), p)) return -1;
-    if (p->bandpower && nm_allow_smem(nm_fir_kernel<NmEpiBandpower>, p->bandpower->bank.smem(NmEpiBandpower::smem_bytes(NM_FFT_THREADS)), p)) return -1;
+    if (p->notch && nm_allow_fir_smem<NmEpiStore>(*p->notch, p->notch->smem(NmEpiStore::smem_bytes(NM_FFT_THREADS)), p)) return -1;
+    if (p->bandpower && nm_allow_fir_smem<NmEpiBandpower>(p->bandpower->bank, p->bandpower->bank.smem(NmEpiBandpower::smem_bytes(NM_FFT_THREADS)), p)) return -1;
     size_t spec_max = 0;
     for (auto& f : p->spectral)
         spec_max = std::max(spec_max, nm_spec_smem_bytes(f->cfg.nper, f->fft.generic, f->nk, f->cfg.keep_segments ? f->cfg.nseg : 1));
@@ -652,11 +681,10 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
     rows.W = p->W;
 
     if (p->notch) {
-        NmFirArgs a = p->notch->args(rows);
         NmEpiStore epi{p->d_y.as<double>(), (long long)p->Wp, 1};
         const size_t sm = p->notch->smem(NmEpiStore::smem_bytes(NM_FFT_THREADS));
         p->prof_begin();
-        NM_LAUNCH(nm_fir_kernel<NmEpiStore>, dim3(p->grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, a, epi);
+        nm_launch_fir(p, *p->notch, rows, epi, sm, p->stream);
         p->prof_end(NM_PROF_NOTCH);
         p->launches++;
         rows.base = p->d_y.as<double>();
@@ -712,14 +740,13 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
     }
     if (p->bandpower) {
         BandpowerFam& f = *p->bandpower;
-        NmFirArgs a = f.bank.args(rows);
         NmEpiBandpower epi;
         epi.seglen = f.d_seglen.as<int>();
         epi.want_act = f.act; epi.want_mob = f.mob; epi.want_comp = f.comp; epi.log_act = f.logt;
         epi.out = out_for(f.d_colmap, f.bank.nF * 3);
         const size_t sm = f.bank.smem(NmEpiBandpower::smem_bytes(NM_FFT_THREADS));
         p->prof_begin();
-        NM_LAUNCH(nm_fir_kernel<NmEpiBandpower>, dim3(p->grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, a, epi);
+        nm_launch_fir(p, f.bank, rows, epi, sm, p->stream, NmEpiBandpower::smem_bytes(NM_FFT_THREADS));
         p->prof_end(NM_PROF_BANDPOWER);
         p->launches++;
     }
@@ -808,10 +835,9 @@ extern "C" int nm_preprocess_window(nm_pipeline* p, const double* window, double
         rows.n_windows = 1;
         rows.n_ch = p->C;
         rows.W = p->W;
-        NmFirArgs a = p->notch->args(rows);
         NmEpiStore epi{p->d_y.as<double>(), (long long)p->Wp, 1};
         const size_t sm = p->notch->smem(NmEpiStore::smem_bytes(NM_FFT_THREADS));
-        NM_LAUNCH(nm_fir_kernel<NmEpiStore>, dim3(p->grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, a, epi);
+        nm_launch_fir(p, *p->notch, rows, epi, sm, p->stream);
         p->launches++;
         NM_CUDA_CHECK(cudaGetLastError());
         src = p->d_y.as<double>();
@@ -912,11 +938,10 @@ extern "C" int nm_fir_apply(int device, const double* taps, int n_filters, int n
             rows.n_windows = 1;
             rows.n_ch = n_ch;
             rows.W = n_samples;
-            NmFirArgs a = bank.args(rows);
             NmEpiStore epi{d_out.as<double>(), (long long)n_samples, n_filters};
             const size_t sm = bank.smem(0);
-            if (nm_allow_smem(nm_fir_kernel<NmEpiStore>, sm, &probe)) break;
-            NM_LAUNCH(nm_fir_kernel<NmEpiStore>, dim3(probe.grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, s, a, epi);
+            if (nm_allow_fir_smem<NmEpiStore>(bank, sm, &probe)) break;
+            nm_launch_fir(&probe, bank, rows, epi, sm, s);
             if (cudaGetLastError() != cudaSuccess) { nm_set_error("FIR kernel launch failed"); break; }
             if (cudaMemcpyAsync(out, d_out.p, (size_t)n_ch * n_filters * n_samples * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
                 cudaStreamSynchronize(s) != cudaSuccess) {
