@@ -62,6 +62,25 @@ def car_shard_factorization(types: list[str], status: list[str], refs: list[str]
     return len(kinds), group_of, gcoef, sp_ptr, sp_col, diag
 
 
+def merge_permutation(settings, global_names: list[str], sfreq: float, window_samples: int, world: int):
+    """Columns of the rank-major concatenation [rank 0 block | rank 1 block | ...] -> reference column order.
+
+    Returns (reference_columns, perm) with ``reference_matrix = gathered[:, perm]``.  Plug-ins such as FFT / Welch
+    order their keys band -> estimator -> channel (channel fastest), so the shards interleave in the reference order.
+    """
+    from .stream.data_processor import build_specs
+
+    ref_cols = build_specs(settings, global_names, sfreq, window_samples)[2]
+    concat: list[str] = []
+    for r in range(world):
+        lo, hi = shard_bounds(len(global_names), world, r)
+        concat += build_specs(settings, global_names[lo:hi], sfreq, window_samples)[2]
+    where = {k: i for i, k in enumerate(concat)}
+    if len(where) != len(concat) or set(where) != set(ref_cols):
+        raise ValueError("shard columns do not tile the reference columns")
+    return ref_cols, np.array([where[k] for k in ref_cols], dtype=np.int64)
+
+
 class _DeviceView:
     """Expose a raw device pointer through ``__cuda_array_interface__`` so torch can wrap it without a copy."""
 
@@ -120,10 +139,17 @@ class ShardedRun:
         if not (dist.is_initialized() and dist.get_world_size() > 1):
             return local.cpu().numpy().copy() if self.on_gpu else local.numpy().copy()
         world, rank = dist.get_world_size(), dist.get_rank()
+        # shards may differ by one channel: agree on the widest block, pad, gather, trim
+        widths = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
+        dist.all_gather(widths, torch.tensor([cols], dtype=torch.int64, device=local.device))
+        widths = [int(w.item()) for w in widths]
+        wmax = max(widths)
+        block = local if cols == wmax else torch.cat([local, local.new_zeros(n_windows, wmax - cols)], dim=1)
+        block = block.contiguous()
         if rank == 0:
-            parts = [torch.empty_like(local) for _ in range(world)]
-            dist.gather(local, gather_list=parts, dst=0)
-            full = torch.cat(parts, dim=1)
+            parts = [torch.empty_like(block) for _ in range(world)]
+            dist.gather(block, gather_list=parts, dst=0)
+            full = torch.cat([p[:, :w] for p, w in zip(parts, widths)], dim=1)
             return full.cpu().numpy() if self.on_gpu else full.numpy().copy()
-        dist.gather(local, gather_list=None, dst=0)
+        dist.gather(block, gather_list=None, dst=0)
         return None

@@ -24,47 +24,57 @@ if TYPE_CHECKING:
 _SCAN = {"raw_hjorth": "hjorth", "return_raw": "raw", "linelength": "linelength"}
 
 
+def build_specs(settings, names, sfreq, window_samples: int, user_feature_names=()):
+    """Feature-family specs + output columns in the reference's dict-insertion order.  No GPU involved."""
+    from .._pipeline import BandpowerSpec, BurstsSpec, ScanSpec, SharpwaveSpec, SpectralSpec, band_items
+    from ..features.bursts import check_burst_bands
+    from ..features.feature_processor import OUT_OF_SCOPE
+
+    s, fs = settings, sfreq
+    enabled = [f for f in s.features.get_enabled() if f not in user_feature_names]
+    for f in enabled:
+        if f in OUT_OF_SCOPE:
+            raise NotImplementedError(f"feature '{f}' is outside the B200 hot path (SURVEY.md section 2 row 23)")
+    scan = ScanSpec(names, hjorth="raw_hjorth" in enabled, raw="return_raw" in enabled, linelength="linelength" in enabled)
+    specs: list = []
+    columns: list[str] = []
+    for f in enabled:
+        if f == "raw_hjorth":
+            columns += scan.keys_hjorth()
+        elif f == "return_raw":
+            columns += scan.keys_raw()
+        elif f == "linelength":
+            columns += scan.keys_linelength()
+        else:
+            if f in ("fft", "welch", "stft"):
+                assert getattr(s, f"{f}_settings").windowlength_ms <= s.segment_length_features_ms
+                spec = SpectralSpec(f, getattr(s, f"{f}_settings"), band_items(s), names, fs, window_samples)
+            elif f == "bandpass_filter":
+                spec = BandpowerSpec(s.bandpass_filter_settings, band_items(s), names, fs)
+            elif f == "bursts":
+                check_burst_bands(s)
+                spec = BurstsSpec(s, names, fs)
+            elif f == "sharpwave_analysis":
+                spec = SharpwaveSpec(s, names, fs)
+            else:  # pragma: no cover
+                raise NotImplementedError(f)
+            specs.append(spec)
+            columns += spec.keys()
+    return scan, specs, columns, enabled
+
+
 class _Plan:
     """Everything that depends on the window length."""
 
     def __init__(self, dp: "DataProcessor", window_samples: int, with_normalizer: bool) -> None:
-        from .._pipeline import BandpowerSpec, BurstsSpec, Pipeline, ScanSpec, SharpwaveSpec, SpectralSpec, band_items
-        from ..features.bursts import check_burst_bands
-        from ..features.feature_processor import OUT_OF_SCOPE
+        from .._pipeline import Pipeline
 
-        s, names, fs = dp.settings, dp.ch_names_used_features, dp.sfreq_raw
-        enabled = [f for f in s.features.get_enabled() if f not in dp.user_feature_names]
-        for f in enabled:
-            if f in OUT_OF_SCOPE:
-                raise NotImplementedError(f"feature '{f}' is outside the B200 hot path (SURVEY.md section 2 row 23)")
-        scan = ScanSpec(names, hjorth="raw_hjorth" in enabled, raw="return_raw" in enabled, linelength="linelength" in enabled)
-        specs: list = []
-        columns: list[str] = []
-        for f in enabled:
-            if f == "raw_hjorth":
-                columns += scan.keys_hjorth()
-            elif f == "return_raw":
-                columns += scan.keys_raw()
-            elif f == "linelength":
-                columns += scan.keys_linelength()
-            else:
-                if f in ("fft", "welch", "stft"):
-                    assert getattr(s, f"{f}_settings").windowlength_ms <= s.segment_length_features_ms
-                    spec = SpectralSpec(f, getattr(s, f"{f}_settings"), band_items(s), names, fs, window_samples)
-                elif f == "bandpass_filter":
-                    spec = BandpowerSpec(s.bandpass_filter_settings, band_items(s), names, fs)
-                elif f == "bursts":
-                    check_burst_bands(s)
-                    spec = BurstsSpec(s, names, fs)
-                elif f == "sharpwave_analysis":
-                    spec = SharpwaveSpec(s, names, fs)
-                else:  # pragma: no cover
-                    raise NotImplementedError(f)
-                specs.append(spec)
-                columns += spec.keys()
+        s, names = dp.settings, dp.ch_names_used_features
+        scan, specs, columns, enabled = build_specs(s, names, dp.sfreq_raw, window_samples, dp.user_feature_names)
         self.columns = columns
         self.has_bursts = "bursts" in enabled
         self.bool_columns = [i for i, k in enumerate(columns) if k.endswith("_in_burst")] if self.has_bursts else []
+        self.normalized = False
         if not columns:
             self.pipe = None
             return
@@ -80,7 +90,6 @@ class _Plan:
             scan.attach(pipe)
         for spec in specs:
             spec.attach(pipe)
-        self.normalized = False
         if with_normalizer and dp.normalize:
             ns = s.feature_normalization_settings
             cols = columns if ns.normalize_psd else [k for k in columns if "psd" not in k]
