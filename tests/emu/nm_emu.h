@@ -2,14 +2,13 @@
 //
 // Lets the *unchanged* kernel sources under py_neuromodulation_b200/csrc/ be compiled by g++
 // (-DNM_EMULATE) so that indexing / synchronisation / algorithm bugs show up in the CPU test
-// suite of a container that has no GPU.  One std::thread per CUDA thread of a CTA; CTAs of a
-// launch run one after the other; __syncthreads() is a std::barrier.  Not shipped, not a
+// suite of a container that has no GPU.  One cooperative fiber per CUDA thread of a CTA (switching at
+// barriers / shuffles), CTAs of a launch spread over a few OS threads.  Not shipped, not a
 // fallback: the package never loads a library built this way.
 #pragma once
 
 #include <algorithm>
 #include <atomic>
-#include <barrier>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
@@ -43,55 +42,213 @@ struct float4 { float x, y, z, w; };
 inline double2 make_double2(double a, double b) { return {a, b}; }
 inline float2 make_float2(float a, float b) { return {a, b}; }
 
+// ---- execution model: one FIBER per CUDA thread -----------------------------------------------
+// Every CUDA thread of a CTA is a user-space fiber with its own stack; all fibers of a CTA live on one OS
+// thread and switch cooperatively at the synchronisation points (__syncthreads, __syncwarp, shuffles,
+// ballots), so a barrier costs a handful of register moves instead of a futex round trip.  CTAs of a launch
+// are spread over a few OS worker threads (they are independent on the GPU as well).
+extern "C" void nm_emu_swap(void** save_sp, void* load_sp);
+#if defined(__x86_64__)
+asm(R"(
+.text
+.globl nm_emu_swap
+.type nm_emu_swap,@function
+nm_emu_swap:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size nm_emu_swap,.-nm_emu_swap
+)");
+#else
+#error "tests/emu/nm_emu.h: the fiber switch is written for x86-64 only"
+#endif
+
 namespace nm_emu {
+constexpr size_t kStackBytes = 256 * 1024;
+
+struct Cta;
+struct Fiber {
+    dim3 tid;
+    unsigned lin = 0;
+    void* sp = nullptr;
+    bool done = false;
+    Cta* cta = nullptr;
+};
 struct WarpSlots {
-    std::unique_ptr<std::barrier<>> bar;
+    unsigned lanes = 0, arrived = 0, gen = 0;
     unsigned long long val[32];
 };
 struct Cta {
-    std::unique_ptr<std::barrier<>> bar;
+    dim3 bid, bdim, gdim;
+    unsigned nt = 0, alive = 0, arrived = 0, gen = 0;
+    std::vector<Fiber> fibers;
     std::vector<WarpSlots> warps;
-    std::vector<unsigned char> smem;
+    unsigned char* smem = nullptr;
+    const std::function<void()>* body = nullptr;
+    void* sched_sp = nullptr;
+    unsigned cur = 0;
 };
 struct Tls {
     dim3 tid, bid, bdim, gdim;
     unsigned char* smem = nullptr;
     Cta* cta = nullptr;
+    Fiber* fib = nullptr;
 };
 inline thread_local Tls tl;
 
+inline void enter(Fiber* f) {
+    Cta* c = f->cta;
+    tl.tid = f->tid;
+    tl.bid = c->bid;
+    tl.bdim = c->bdim;
+    tl.gdim = c->gdim;
+    tl.smem = c->smem;
+    tl.cta = c;
+    tl.fib = f;
+}
+
+// hand the OS thread to the next unfinished fiber of the CTA (round robin); returns when this fiber is resumed
+inline void yield() {
+    Fiber* me = tl.fib;
+    Cta* c = me->cta;
+    unsigned nxt = me->lin;
+    for (unsigned k = 0; k < c->nt; ++k) {
+        nxt = (nxt + 1 == c->nt) ? 0 : nxt + 1;
+        if (!c->fibers[nxt].done) break;
+    }
+    if (nxt == me->lin) {
+        if (me->done) nm_emu_swap(&me->sp, c->sched_sp);  // last fiber finished: back to the launcher
+        return;                                            // nobody else to run
+    }
+    Fiber* to = &c->fibers[nxt];
+    c->cur = nxt;
+    nm_emu_swap(&me->sp, to->sp);
+    enter(me);
+}
+
+inline void cta_release_if_complete(Cta* c) {
+    if (c->arrived && c->arrived >= c->alive) {
+        c->arrived = 0;
+        c->gen++;
+    }
+}
+
+[[noreturn]] inline void fiber_main() {
+    Fiber* me = tl.fib;
+    Cta* c = me->cta;
+    (*c->body)();
+    me->done = true;
+    c->alive--;
+    cta_release_if_complete(c);  // exited threads do not take part in later barriers
+    WarpSlots& w = c->warps[me->lin / 32];
+    w.lanes--;
+    if (w.arrived && w.arrived >= w.lanes) { w.arrived = 0; w.gen++; }
+    for (;;) yield();  // never resumed once every fiber is done (yield() returns to the launcher then)
+}
+extern "C" inline void nm_emu_trampoline() {
+    enter(tl.cta->fibers.data() + tl.cta->cur);
+    fiber_main();
+}
+
+struct Worker {
+    std::unique_ptr<unsigned char[]> stacks;  // not zero-filled: pages are committed only when a fiber touches them
+    size_t stack_cap = 0;
+    std::vector<unsigned char> smem;
+    void run_cta(dim3 grid, dim3 block, dim3 bid, size_t smem_bytes, const std::function<void()>& body) {
+        const unsigned nt = block.x * block.y * block.z;
+        if (stack_cap < (size_t)nt * kStackBytes) {
+            stack_cap = (size_t)nt * kStackBytes;
+            stacks.reset(new unsigned char[stack_cap]);
+        }
+        smem.assign(smem_bytes + 128, 0);
+        Cta cta;
+        cta.bid = bid; cta.bdim = block; cta.gdim = grid;
+        cta.nt = cta.alive = nt;
+        cta.body = &body;
+        unsigned char* sm = smem.data();
+        sm += (64 - (reinterpret_cast<uintptr_t>(sm) & 63)) & 63;
+        cta.smem = sm;
+        cta.fibers.resize(nt);
+        cta.warps.resize((nt + 31) / 32);
+        for (unsigned w = 0; w < cta.warps.size(); ++w) {
+            cta.warps[w].lanes = std::min(32u, nt - w * 32);
+            for (auto& v : cta.warps[w].val) v = 0;
+        }
+        for (unsigned t = 0; t < nt; ++t) {
+            Fiber& f = cta.fibers[t];
+            f.cta = &cta;
+            f.lin = t;
+            f.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+            uintptr_t top = reinterpret_cast<uintptr_t>(stacks.get() + (size_t)(t + 1) * kStackBytes);
+            top &= ~uintptr_t(15);
+            void** sp = reinterpret_cast<void**>(top);
+            *--sp = nullptr;                                           // keeps rsp = 8 (mod 16) at function entry
+            *--sp = reinterpret_cast<void*>(&nm_emu_trampoline);       // `ret` target
+            for (int r = 0; r < 6; ++r) *--sp = nullptr;               // rbp rbx r12 r13 r14 r15
+            f.sp = sp;
+        }
+        tl.cta = &cta;
+        cta.cur = 0;
+        nm_emu_swap(&cta.sched_sp, cta.fibers[0].sp);  // returns when every fiber has finished
+        tl = Tls{};
+    }
+};
+
+inline unsigned n_workers() {
+    static const unsigned n = [] {
+        const char* e = std::getenv("NM_EMU_WORKERS");
+        unsigned v = e ? (unsigned)std::atoi(e) : std::thread::hardware_concurrency();
+        return std::max(1u, std::min(v, 16u));
+    }();
+    return n;
+}
+
 inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
-    const unsigned nt = block.x * block.y * block.z;
-    Cta cta;
-    cta.bar = std::make_unique<std::barrier<>>(nt);
-    cta.smem.assign(smem_bytes + 64, 0);
-    cta.warps.resize((nt + 31) / 32);
-    for (unsigned w = 0; w < cta.warps.size(); ++w) {
-        unsigned lanes = std::min(32u, nt - w * 32);
-        cta.warps[w].bar = std::make_unique<std::barrier<>>(lanes);
-        for (auto& v : cta.warps[w].val) v = 0;
-    }
-    unsigned char* sm = cta.smem.data();
-    sm += (64 - (reinterpret_cast<uintptr_t>(sm) & 63)) & 63;
+    const unsigned long long n_cta = (unsigned long long)grid.x * grid.y * grid.z;
+    std::atomic<unsigned long long> next{0};
+    auto work = [&]() {
+        static thread_local Worker wk;
+        for (;;) {
+            const unsigned long long i = next.fetch_add(1);
+            if (i >= n_cta) break;
+            dim3 bid((unsigned)(i % grid.x), (unsigned)((i / grid.x) % grid.y), (unsigned)(i / ((unsigned long long)grid.x * grid.y)));
+            wk.run_cta(grid, block, bid, smem_bytes, body);
+        }
+    };
+    const unsigned nw = (unsigned)std::min<unsigned long long>(n_workers(), n_cta);
+    if (nw <= 1) { work(); return; }
     std::vector<std::thread> pool;
-    pool.reserve(nt);
-    for (unsigned t = 0; t < nt; ++t) {
-        pool.emplace_back([&, t]() {
-            tl.cta = &cta;
-            tl.smem = sm;
-            tl.bdim = block;
-            tl.gdim = grid;
-            tl.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-            for (unsigned bz = 0; bz < grid.z; ++bz)
-                for (unsigned by = 0; by < grid.y; ++by)
-                    for (unsigned bx = 0; bx < grid.x; ++bx) {
-                        tl.bid = dim3(bx, by, bz);
-                        body();
-                        cta.bar->arrive_and_wait();
-                    }
-        });
-    }
+    pool.reserve(nw);
+    for (unsigned t = 0; t < nw; ++t) pool.emplace_back(work);
     for (auto& th : pool) th.join();
+}
+
+inline void cta_barrier() {
+    Cta* c = tl.cta;
+    const unsigned g = c->gen;
+    c->arrived++;
+    cta_release_if_complete(c);
+    while (c->gen == g) yield();
+}
+inline void warp_barrier() {
+    Cta* c = tl.cta;
+    WarpSlots& w = c->warps[tl.fib->lin / 32];
+    const unsigned g = w.gen;
+    w.arrived++;
+    if (w.arrived >= w.lanes) { w.arrived = 0; w.gen++; }
+    while (w.gen == g) yield();
 }
 }  // namespace nm_emu
 
@@ -100,11 +257,8 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
 #define blockDim (nm_emu::tl.bdim)
 #define gridDim (nm_emu::tl.gdim)
 
-inline void __syncthreads() { nm_emu::tl.cta->bar->arrive_and_wait(); }
-inline void __syncwarp(unsigned = 0xffffffffu) {
-    unsigned lin = threadIdx.x + threadIdx.y * blockDim.x;
-    nm_emu::tl.cta->warps[lin / 32].bar->arrive_and_wait();
-}
+inline void __syncthreads() { nm_emu::cta_barrier(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { nm_emu::warp_barrier(); }
 
 template <typename T>
 inline T nm_emu_exchange(T v, int src_lane) {
@@ -115,9 +269,9 @@ inline T nm_emu_exchange(T v, int src_lane) {
     unsigned long long raw = 0;
     std::memcpy(&raw, &v, sizeof(T));
     w.val[lane] = raw;
-    w.bar->arrive_and_wait();
+    nm_emu::warp_barrier();
     unsigned long long got = w.val[(src_lane >= 0 && src_lane < 32) ? src_lane : lane];
-    w.bar->arrive_and_wait();
+    nm_emu::warp_barrier();
     T out;
     std::memcpy(&out, &got, sizeof(T));
     return out;
@@ -143,11 +297,11 @@ inline unsigned __ballot_sync(unsigned, int pred) {
     unsigned lin = threadIdx.x + threadIdx.y * blockDim.x;
     auto& w = nm_emu::tl.cta->warps[lin / 32];
     w.val[lin % 32] = pred ? 1ull : 0ull;
-    w.bar->arrive_and_wait();
+    nm_emu::warp_barrier();
     unsigned bits = 0;
     for (int l = 0; l < 32; ++l)
         if (w.val[l]) bits |= (1u << l);
-    w.bar->arrive_and_wait();
+    nm_emu::warp_barrier();
     return bits;
 }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
@@ -191,7 +345,7 @@ inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
-    *v = (a == cudaDevAttrMultiProcessorCount) ? 2 : 227 * 1024;
+    *v = (a == cudaDevAttrMultiProcessorCount) ? 4 : 227 * 1024;
     return cudaSuccess;
 }
 inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : 2; }
