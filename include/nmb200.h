@@ -154,6 +154,9 @@ int nm_set_profiling(nm_pipeline* p, int enabled);
 int nm_get_profile(nm_pipeline* p, double* ms, long long* launches, int n);
 /* windows per kernel launch (chunk size chosen so that the notched chunk stays L2 resident) */
 int nm_chunk_windows(nm_pipeline* p);
+/* text description of the launch plan (one line per family: kernel, transform size, threads, shared memory);
+ * writes at most n-1 characters + NUL into buf and returns the full length */
+int nm_describe_plan(nm_pipeline* p, char* buf, int n);
 /* number of kernels this library launched since the pipeline was created */
 long long nm_kernel_launches(nm_pipeline* p);
 /* device pointer / geometry of the last result matrix (for NCCL gathers by the host side) */

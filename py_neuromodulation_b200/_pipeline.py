@@ -216,6 +216,12 @@ class Pipeline:
     def chunk_windows(self) -> int:
         return int(self.lib.nm_chunk_windows(self._h))
 
+    def describe_plan(self) -> str:
+        """One line per family: which kernel serves it (specialised / runtime-plan / generic), sizes, shared memory."""
+        buf = C.create_string_buffer(4096)
+        self.lib.nm_describe_plan(self._h, buf, len(buf))
+        return buf.value.decode()
+
     @property
     def kernel_launches(self) -> int:
         return int(self.lib.nm_kernel_launches(self._h))

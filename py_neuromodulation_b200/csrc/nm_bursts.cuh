@@ -18,6 +18,7 @@
 
 struct NmEpiBursts {
     static constexpr bool kRegs = false;
+    static constexpr bool kRegsOnly = false, kReflectOk = false, kSameOk = true, kConvxOnly = false;  // nm_convx_kernel instantiation traits
     NmFft<double> hfft;     // W-point transform
     int need_scratch;
     double* env;            // chunk envelopes (n_windows, n_ch, nB, Wp)
@@ -361,7 +362,7 @@ struct BurstsFam {
         return 0;
     }
     void reset() { batch = 0; }
-    size_t fir_smem() const { return bank.smem(NmEpiBursts::smem_bytes_for(W, hfft.generic)); }
+    size_t epi_smem() const { return NmEpiBursts::smem_bytes_for(W, hfft.generic); }
     static size_t thr_smem() { return NM_SEL_BINS * sizeof(int) + NM_SEL_CAND * 8 + 8 * sizeof(int) + 2 * 8 + 2 * sizeof(int) + 64; }
     int allow_smem(const nm_pipeline* p);
     int run(nm_pipeline* p, const NmRows& rows, int w0);

@@ -3,7 +3,7 @@
 
 #include <algorithm>
 
-#include "nm_conv.cuh"
+#include "nm_convx.cuh"
 #include "nm_fir.cuh"
 #include "nm_host.h"
 
@@ -83,6 +83,10 @@ struct FirBank {
     }
     bool epi_fits_tail(size_t epi) const { return pow2 && epi > 0 && epi <= (nm_conv_buf_elems(P, pad) - (size_t)P) * sizeof(cx<double>); }
     int threads() const { return pow2 ? P / 16 : NM_FFT_THREADS; }
+    // nm_convx_kernel: reflect mode is single-filter (one buffer), 'same' mode always runs the bank code (two buffers)
+    size_t smem_x(size_t epi) const {
+        return nm_conv_buf_elems(P, pad) * sizeof(cx<double>) * (mode == NM_FIR_REFLECT ? 1 : 2) + NM_CX_RED_BYTES + (epi_fits_tail(epi) ? 0 : epi);
+    }
     size_t smem(size_t epi) const {
         const size_t buf = pow2 ? nm_conv_buf_elems(P, pad) : (size_t)P;
         return buf * sizeof(cx<double>) * (nF > 1 ? 2 : 1) + (epi_fits_tail(epi) ? 0 : epi);

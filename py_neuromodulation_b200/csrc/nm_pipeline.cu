@@ -11,6 +11,7 @@
 //   out (n_windows x F, f64) --D2H--> host
 #include <cstdarg>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "../../include/nmb200.h"
@@ -60,6 +61,8 @@ struct BandpowerFam {
     FirBank bank;
     DevBuf d_seglen, d_colmap;
     int act = 0, mob = 0, comp = 0, logt = 0;
+    // the register epilogue (activity only) keeps its reduction scratch inside the free `work` buffer
+    size_t epi_smem() const { return NmEpiBandpower::smem_bytes(NM_FFT_THREADS); }
 };
 
 enum { NM_PROF_PREP = 0, NM_PROF_NOTCH, NM_PROF_SCAN, NM_PROF_SPEC, NM_PROF_BANDPOWER, NM_PROF_SHARPWAVE, NM_PROF_BURST_ENV,
@@ -139,10 +142,52 @@ static int nm_allow_smem(K kernel, size_t bytes, const nm_pipeline* p) {
 }
 
 // ------------------------------------------------------------------------------- FIR launches
+// Three kernels implement the same contract; the most specialised one that covers the bank is used:
+//   nm_convx_kernel  P in {1024, 2048, 4096}, compile-time plan (nm_convx.cuh)   <- every default configuration
+//   nm_conv_kernel   other powers of two in [512, 16384], runtime plan (nm_conv.cuh)
+//   nm_fir_kernel    5-smooth sizes, generic mixed radix (nm_fir.cuh)
 template <class Epi>
-static int nm_allow_fir_smem(const FirBank& bank, size_t bytes, const nm_pipeline* p) {
-    if (bank.pow2) return nm_allow_smem(nm_conv_kernel<Epi>, bytes, p);
-    return nm_allow_smem(nm_fir_kernel<Epi>, bytes, p);
+using NmConvKernel = void (*)(NmConvArgs, Epi);
+
+template <class Epi>
+static NmConvKernel<Epi> nm_convx_pick(const FirBank& b) {
+    if (!b.pow2 || !nm_convx_supported(b.P)) return nullptr;
+    if (b.mode == NM_FIR_REFLECT) {
+        if constexpr (Epi::kReflectOk) {
+            if (b.nF != 1) return nullptr;
+            switch (b.P) {
+                case 1024: return nm_convx_kernel<1024, true, false, Epi>;
+                case 2048: return nm_convx_kernel<2048, true, false, Epi>;
+                default: return nm_convx_kernel<4096, true, false, Epi>;
+            }
+        }
+    } else {
+        if constexpr (Epi::kSameOk) {
+            switch (b.P) {
+                case 1024: return nm_convx_kernel<1024, false, true, Epi>;
+                case 2048: return nm_convx_kernel<2048, false, true, Epi>;
+                default: return nm_convx_kernel<4096, false, true, Epi>;
+            }
+        }
+    }
+    return nullptr;
+}
+
+// dynamic shared memory of the kernel that nm_launch_fir will pick for (bank, Epi)
+template <class Epi>
+static size_t nm_fir_smem(const FirBank& bank, size_t epi_bytes) {
+    if (nm_convx_pick<Epi>(bank)) return bank.smem_x(epi_bytes);
+    return bank.smem(epi_bytes);
+}
+
+template <class Epi>
+static int nm_allow_fir_smem(const FirBank& bank, size_t epi_bytes, const nm_pipeline* p) {
+    if (auto k = nm_convx_pick<Epi>(bank)) return nm_allow_smem(k, bank.smem_x(epi_bytes), p);
+    if constexpr (!Epi::kConvxOnly) {
+        if (bank.pow2) return nm_allow_smem(nm_conv_kernel<Epi>, bank.smem(epi_bytes), p);
+        return nm_allow_smem(nm_fir_kernel<Epi>, bank.smem(epi_bytes), p);
+    }
+    return 0;
 }
 
 template <class K>
@@ -154,19 +199,49 @@ static int nm_resident_grid(const nm_pipeline* p, K kernel, int threads, size_t 
 }
 
 template <class Epi>
-static void nm_launch_fir(nm_pipeline* p, const FirBank& bank, const NmRows& rows, const Epi& epi, size_t smem_bytes, cudaStream_t stream,
-                          size_t epi_bytes = 0) {
+static void nm_launch_fir(nm_pipeline* p, const FirBank& bank, const NmRows& rows, const Epi& epi, cudaStream_t stream, size_t epi_bytes) {
     const int threads = bank.threads();
-    if (bank.pow2) {
+    if (auto k = nm_convx_pick<Epi>(bank)) {
         NmConvArgs a = bank.conv_args(rows);
         a.scratch_in_tail = bank.epi_fits_tail(epi_bytes) ? 1 : 0;
-        const int grid = nm_resident_grid(p, nm_conv_kernel<Epi>, threads, smem_bytes, a.n_items);
-        NM_LAUNCH(nm_conv_kernel<Epi>, dim3(grid), dim3(threads), smem_bytes, stream, a, epi);
+        const size_t sm = bank.smem_x(epi_bytes);
+        const int grid = nm_resident_grid(p, k, threads, sm, a.n_items);
+        NM_LAUNCH(k, dim3(grid), dim3(threads), sm, stream, a, epi);
+        return;
+    }
+    if constexpr (Epi::kConvxOnly) return;
+    else if (bank.pow2) {
+        NmConvArgs a = bank.conv_args(rows);
+        a.scratch_in_tail = bank.epi_fits_tail(epi_bytes) ? 1 : 0;
+        const size_t sm = bank.smem(epi_bytes);
+        const int grid = nm_resident_grid(p, nm_conv_kernel<Epi>, threads, sm, a.n_items);
+        NM_LAUNCH(nm_conv_kernel<Epi>, dim3(grid), dim3(threads), sm, stream, a, epi);
     } else {
         NmFirArgs a = bank.args(rows);
-        const int grid = nm_resident_grid(p, nm_fir_kernel<Epi>, threads, smem_bytes, a.n_items);
-        NM_LAUNCH(nm_fir_kernel<Epi>, dim3(grid), dim3(threads), smem_bytes, stream, a, epi);
+        const size_t sm = bank.smem(epi_bytes);
+        const int grid = nm_resident_grid(p, nm_fir_kernel<Epi>, threads, sm, a.n_items);
+        NM_LAUNCH(nm_fir_kernel<Epi>, dim3(grid), dim3(threads), sm, stream, a, epi);
     }
+}
+
+// Notch of one batch of windows: rows -> y (and, on the specialised kernel, the scan features of the notched rows).
+// Returns true when the scan family has been computed by the notch kernel's epilogue.
+static bool nm_launch_notch(nm_pipeline* p, const NmRows& rows, double* y, const NmOut* scan_out, cudaStream_t stream) {
+    const FirBank& bank = *p->notch;
+    if (nm_convx_pick<NmEpiStoreScan>(bank)) {
+        NmEpiStoreScan epi;
+        epi.y = y;
+        epi.Wp = p->Wp;
+        epi.want_scan = scan_out ? 1 : 0;
+        epi.want_hjorth = p->scan_h; epi.want_raw = p->scan_r; epi.want_ll = p->scan_l;
+        if (scan_out) epi.out = *scan_out;
+        else epi.out = NmOut{nullptr, 0, 0, nullptr, 0};
+        nm_launch_fir(p, bank, rows, epi, stream, 0);
+        return scan_out != nullptr;
+    }
+    NmEpiStore epi{y, (long long)p->Wp, 1};
+    nm_launch_fir(p, bank, rows, epi, stream, 0);
+    return false;
 }
 
 // ------------------------------------------------------------------------------- family launches
@@ -181,7 +256,7 @@ static NmOut nm_out_for(nm_pipeline* p, const DevBuf& colmap, int per_ch, int w0
 }
 
 int BurstsFam::allow_smem(const nm_pipeline* p) {
-    if (nm_allow_fir_smem<NmEpiBursts>(bank, fir_smem(), p)) return -1;
+    if (nm_allow_fir_smem<NmEpiBursts>(bank, epi_smem(), p)) return -1;
     return nm_allow_smem(nm_burst_thr_kernel, thr_smem(), p);
 }
 
@@ -219,9 +294,8 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     epi.cap = cap;
     epi.win0 = batch;
     epi.S = S;
-    const size_t sm = fir_smem();
     p->prof_begin();
-    nm_launch_fir(p, bank, rows, epi, sm, p->stream);
+    nm_launch_fir(p, bank, rows, epi, p->stream, epi_smem());
     p->prof_end(NM_PROF_BURST_ENV);
 
     NmBurstThrArgs ta;
@@ -254,15 +328,14 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     return 0;
 }
 
-int SharpwaveFam::allow_smem(const nm_pipeline* p) { return nm_allow_fir_smem<NmEpiSharpwave>(bank, smem(), p); }
+int SharpwaveFam::allow_smem(const nm_pipeline* p) { return nm_allow_fir_smem<NmEpiSharpwave>(bank, epi_smem(), p); }
 
 int SharpwaveFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     NmEpiSharpwave epi;
     epi.cfg = cfg;
     epi.out = nm_out_for(p, d_colmap, per_ch, w0);
-    const size_t sm = smem();
     p->prof_begin();
-    nm_launch_fir(p, bank, rows, epi, sm, p->stream);
+    nm_launch_fir(p, bank, rows, epi, p->stream, epi_smem());
     p->prof_end(NM_PROF_SHARPWAVE);
     p->launches++;
     return 0;
@@ -559,8 +632,8 @@ extern "C" int nm_finalize(nm_pipeline* p) {
     if (p->bursts && p->bursts->alloc_chunk(p->chunk, p->Wp)) return -1;
 
     // opt in to large dynamic shared memory once
-    if (p->notch && nm_allow_fir_smem<NmEpiStore>(*p->notch, p->notch->smem(NmEpiStore::smem_bytes(NM_FFT_THREADS)), p)) return -1;
-    if (p->bandpower && nm_allow_fir_smem<NmEpiBandpower>(p->bandpower->bank, p->bandpower->bank.smem(NmEpiBandpower::smem_bytes(NM_FFT_THREADS)), p)) return -1;
+    if (p->notch && (nm_allow_fir_smem<NmEpiStore>(*p->notch, 0, p) || nm_allow_fir_smem<NmEpiStoreScan>(*p->notch, 0, p))) return -1;
+    if (p->bandpower && nm_allow_fir_smem<NmEpiBandpower>(p->bandpower->bank, p->bandpower->epi_smem(), p)) return -1;
     size_t spec_max = 0;
     for (auto& f : p->spectral)
         spec_max = std::max(spec_max, nm_spec_smem_bytes(f->cfg.nper, f->fft.generic, f->nk, f->cfg.keep_segments ? f->cfg.nseg : 1));
@@ -680,17 +753,6 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
     rows.n_ch = p->C;
     rows.W = p->W;
 
-    if (p->notch) {
-        NmEpiStore epi{p->d_y.as<double>(), (long long)p->Wp, 1};
-        const size_t sm = p->notch->smem(NmEpiStore::smem_bytes(NM_FFT_THREADS));
-        p->prof_begin();
-        nm_launch_fir(p, *p->notch, rows, epi, sm, p->stream);
-        p->prof_end(NM_PROF_NOTCH);
-        p->launches++;
-        rows.base = p->d_y.as<double>();
-        rows.ch_stride = p->Wp;
-        rows.off = p->d_yoff.as<long long>();
-    }
     auto out_for = [&](const DevBuf& colmap, int per_ch) {
         NmOut o;
         o.out = p->d_out.as<double>();
@@ -700,7 +762,20 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         o.per_ch = per_ch;
         return o;
     };
-    if (p->has_scan) {
+    bool scan_done = false;
+    if (p->notch) {
+        const bool y_needed = !p->spectral.empty() || p->bandpower || p->sharpwave || p->bursts;
+        NmOut so;
+        if (p->has_scan) so = out_for(p->d_scan_colmap, 5);
+        p->prof_begin();
+        scan_done = nm_launch_notch(p, rows, y_needed || !p->has_scan ? p->d_y.as<double>() : nullptr, p->has_scan ? &so : nullptr, p->stream);
+        p->prof_end(NM_PROF_NOTCH);
+        p->launches++;
+        rows.base = p->d_y.as<double>();
+        rows.ch_stride = p->Wp;
+        rows.off = p->d_yoff.as<long long>();
+    }
+    if (p->has_scan && !scan_done) {
         NmScanArgs a;
         a.in = rows;
         a.want_hjorth = p->scan_h; a.want_raw = p->scan_r; a.want_ll = p->scan_l;
@@ -744,9 +819,8 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         epi.seglen = f.d_seglen.as<int>();
         epi.want_act = f.act; epi.want_mob = f.mob; epi.want_comp = f.comp; epi.log_act = f.logt;
         epi.out = out_for(f.d_colmap, f.bank.nF * 3);
-        const size_t sm = f.bank.smem(NmEpiBandpower::smem_bytes(NM_FFT_THREADS));
         p->prof_begin();
-        nm_launch_fir(p, f.bank, rows, epi, sm, p->stream, NmEpiBandpower::smem_bytes(NM_FFT_THREADS));
+        nm_launch_fir(p, f.bank, rows, epi, p->stream, f.epi_smem());
         p->prof_end(NM_PROF_BANDPOWER);
         p->launches++;
     }
@@ -835,9 +909,7 @@ extern "C" int nm_preprocess_window(nm_pipeline* p, const double* window, double
         rows.n_windows = 1;
         rows.n_ch = p->C;
         rows.W = p->W;
-        NmEpiStore epi{p->d_y.as<double>(), (long long)p->Wp, 1};
-        const size_t sm = p->notch->smem(NmEpiStore::smem_bytes(NM_FFT_THREADS));
-        nm_launch_fir(p, *p->notch, rows, epi, sm, p->stream);
+        nm_launch_notch(p, rows, p->d_y.as<double>(), nullptr, p->stream);
         p->launches++;
         NM_CUDA_CHECK(cudaGetLastError());
         src = p->d_y.as<double>();
@@ -883,6 +955,41 @@ extern "C" int nm_get_profile(nm_pipeline* p, double* ms, long long* launches, i
     return NM_PROF_N;
 }
 extern "C" int nm_chunk_windows(nm_pipeline* p) { return p ? p->chunk : 0; }
+
+template <class Epi>
+static void nm_describe_fir(std::string& s, const char* family, const FirBank& b, size_t epi_bytes) {
+    char line[256];
+    const bool x = nm_convx_pick<Epi>(b) != nullptr;
+    snprintf(line, sizeof(line), "%s: %s P=%d filters=%d taps=%d threads=%d smem=%zu\n", family,
+             x ? "nm_convx_kernel" : (b.pow2 ? "nm_conv_kernel" : "nm_fir_kernel"), b.P, b.nF, b.L, b.threads(), nm_fir_smem<Epi>(b, epi_bytes));
+    s += line;
+}
+
+extern "C" int nm_describe_plan(nm_pipeline* p, char* buf, int n) {
+    if (!p || !p->finalized) return 0;
+    std::string s;
+    char line[256];
+    snprintf(line, sizeof(line), "window=%d channels=%d features=%d chunk=%d\n", p->W, p->C, p->F, p->chunk);
+    s += line;
+    if (p->notch) {
+        if (nm_convx_pick<NmEpiStoreScan>(*p->notch)) nm_describe_fir<NmEpiStoreScan>(s, p->has_scan ? "notch+scan" : "notch", *p->notch, 0);
+        else nm_describe_fir<NmEpiStore>(s, "notch", *p->notch, 0);
+    }
+    if (p->has_scan && !(p->notch && nm_convx_pick<NmEpiStoreScan>(*p->notch))) s += "scan: nm_scan_kernel\n";
+    for (auto& f : p->spectral) {
+        snprintf(line, sizeof(line), "spectral: nm_spec_kernel nper=%d nseg=%d bins=%d\n", f->cfg.nper, f->cfg.nseg, f->nk);
+        s += line;
+    }
+    if (p->bandpower) nm_describe_fir<NmEpiBandpower>(s, "bandpower", p->bandpower->bank, p->bandpower->epi_smem());
+    if (p->sharpwave) nm_describe_fir<NmEpiSharpwave>(s, "sharpwave", p->sharpwave->bank, p->sharpwave->epi_smem());
+    if (p->bursts) nm_describe_fir<NmEpiBursts>(s, "bursts", p->bursts->bank, p->bursts->epi_smem());
+    if (buf && n > 0) {
+        const size_t m = std::min<size_t>(s.size(), (size_t)n - 1);
+        memcpy(buf, s.data(), m);
+        buf[m] = 0;
+    }
+    return (int)s.size();
+}
 extern "C" int nm_synchronize(nm_pipeline* p) {
     NM_P_CHECK(p);
     cudaSetDevice(p->device);
@@ -939,9 +1046,8 @@ extern "C" int nm_fir_apply(int device, const double* taps, int n_filters, int n
             rows.n_ch = n_ch;
             rows.W = n_samples;
             NmEpiStore epi{d_out.as<double>(), (long long)n_samples, n_filters};
-            const size_t sm = bank.smem(0);
-            if (nm_allow_fir_smem<NmEpiStore>(bank, sm, &probe)) break;
-            nm_launch_fir(&probe, bank, rows, epi, sm, s);
+            if (nm_allow_fir_smem<NmEpiStore>(bank, 0, &probe)) break;
+            nm_launch_fir(&probe, bank, rows, epi, s, 0);
             if (cudaGetLastError() != cudaSuccess) { nm_set_error("FIR kernel launch failed"); break; }
             if (cudaMemcpyAsync(out, d_out.p, (size_t)n_ch * n_filters * n_samples * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
                 cudaStreamSynchronize(s) != cudaSuccess) {

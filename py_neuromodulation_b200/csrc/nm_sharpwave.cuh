@@ -285,6 +285,7 @@ NM_DEV double nm_sw_join(int est, double a, double b) {
 
 struct NmEpiSharpwave {
     static constexpr bool kRegs = false;
+    static constexpr bool kRegsOnly = false, kReflectOk = false, kSameOk = true, kConvxOnly = false;  // nm_convx_kernel instantiation traits
     NmSwCfg cfg;
     NmOut out;  // per_ch = nF * (n_combo + 1) * 2 ; slot (f*(n_combo+1) + combo)*2 + polarity
     static NM_HD size_t smem_bytes_for(int maxn, int n_combo) {
@@ -356,7 +357,7 @@ struct SharpwaveFam {
         per_ch = nF * (n_combo + 1) * 2;
         return d_colmap.upload(colmap, (size_t)C * per_ch, s);
     }
-    size_t smem() const { return bank.smem(NmEpiSharpwave::smem_bytes_for(cfg.maxn, cfg.n_combo)); }
+    size_t epi_smem() const { return NmEpiSharpwave::smem_bytes_for(cfg.maxn, cfg.n_combo); }
     int allow_smem(const nm_pipeline* p);
     int run(nm_pipeline* p, const NmRows& rows, int w0);
 };
