@@ -67,6 +67,29 @@ NM_DEV int nm_warp_sum_i(int v) {
     return v;
 }
 
+// Warp-wide sums of NV (power of two, <= 8) values with a halving exchange: in every step a lane keeps one half of
+// its values and trades the other half with a partner, so NV values cost NV - 1 + (5 - log2 NV) shuffles instead of
+// 5 * NV.  On return the total of value i sits in v[0] of every lane whose index has bits (4, 3, ..) == bits of i,
+// i.e. value i is held by lanes with  (lane >> (5 - log2 NV)) == i.
+template <int NV>
+NM_DEV void nm_warp_sum_multi(double* v, int lane) {
+    static_assert(NV == 1 || NV == 2 || NV == 4 || NV == 8, "NV must be a power of two <= 8");
+    int bit = 16;
+#pragma unroll
+    for (int n = NV; n > 1; n >>= 1) {
+        const bool upper = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const double keep = upper ? v[i + n / 2] : v[i];
+            const double give = upper ? v[i] : v[i + n / 2];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, give, bit);
+        }
+        bit >>= 1;
+    }
+#pragma unroll
+    for (int o = bit; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+}
+
 // Sum NV values over the whole CTA; every thread receives the totals.  `red` needs
 // NV * 32 doubles of shared memory.  Contains two barriers.
 template <int NV>

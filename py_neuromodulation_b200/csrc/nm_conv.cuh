@@ -32,6 +32,7 @@ struct NmConvArgs {
     NmRows in;
     NmConv fft;
     const double* hperm;  // [nF][P] real spectra in slot order, scaled by 1/P
+    const double* hx;     // same values in nm_convx_kernel's per-thread order (nm_cx_load_h), or nullptr
     int nF, mode, E, n_items;
     int scratch_in_tail;  // epilogue scratch aliases the unused padding tail of `work` (linear output only uses [0, P))
 };

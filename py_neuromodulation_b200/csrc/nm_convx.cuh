@@ -32,7 +32,10 @@ struct NmCxPlan {
     static constexpr int B1 = NT * R1 + ((NT * R1) >> PAD);
     static constexpr int B2 = NT * R2 + ((NT * R2) >> PAD);
     static constexpr int NBUF = P + (P >> PAD) + 2;
-    static constexpr int MINB = (NT >= 256) ? 2 : (NT == 128 ? 4 : 8);  // 128 registers per thread
+    // resident CTAs per SM the register allocation is tuned for: single-filter kernels run at 128 registers,
+    // bank kernels (shared-memory limited anyway) at ~168 so that the prefetched filter spectrum stays in registers
+    static constexpr int MINB1 = (NT >= 256) ? 2 : (NT == 128 ? 4 : 8);
+    static constexpr int MINBK = (NT >= 256) ? 1 : (NT == 128 ? 3 : 6);
     static_assert(R2 == (1 << PAD), "padding unit must equal the last radix");
     static_assert(M1 % R2 == 0 && NT % R2 == 0, "strides must be multiples of the padding unit");
     static_assert(R1 * R2 * 16 == P, "three-pass plan");
@@ -82,38 +85,76 @@ NM_DEV void nm_cx_pass1(cx<double>* sm, const cx<double> w1, int tid) {
 #pragma unroll
         for (int t = 0; t < R; ++t) v[t] = p[i * PL::B1 + t * PL::S1];
         if (INV) {
-            if (j != 0) nm_twiddle_w1<R, true>(v, w1);
+            nm_twiddle_w1<R, true>(v, w1);  // j == 0 multiplies by exactly 1
             nm_bflyR<R, true>(v);
         } else {
             nm_bflyR<R, false>(v);
-            if (j != 0) nm_twiddle_w1<R, false>(v, w1);
+            nm_twiddle_w1<R, false>(v, w1);
         }
 #pragma unroll
         for (int t = 0; t < R; ++t) p[i * PL::B1 + t * PL::S1] = v[t];
     }
 }
 
+// The 16 filter-spectrum values a thread multiplies with in the last pass are slots (tid + NT*i)*R2 + t -- the same for
+// every item.  The host stores them thread-interleaved (`hx`, nm_cx_hx_index) so that a warp's 128-bit loads are
+// contiguous (4 L1 tag requests per instruction instead of 16 for the slot-ordered table); they are fetched one
+// phase ahead of their use.
+template <class PL>
+static NM_HD int nm_cx_hx_index(int tid, int i, int t) {  // position of slot (tid + NT*i)*R2 + t inside one filter's hx block
+    return ((i * (PL::R2 / 2) + (t >> 1)) * PL::NT + tid) * 2 + (t & 1);
+}
+
+template <class PL>
+NM_DEV void nm_cx_load_h(double* hv, const double* NM_RESTRICT hx, int tid) {
+    constexpr int R = PL::R2;
+#pragma unroll
+    for (int i = 0; i < 16 / R; ++i) {
+#ifdef NM_EMULATE
+#pragma unroll
+        for (int t = 0; t < R; ++t) hv[i * R + t] = hx[nm_cx_hx_index<PL>(tid, i, t)];
+#else
+        const double2* p = reinterpret_cast<const double2*>(hx) + (i * (R / 2)) * PL::NT + tid;
+#pragma unroll
+        for (int t = 0; t < R / 2; ++t) {
+            const double2 d = __ldg(p + t * PL::NT);
+            hv[i * R + 2 * t] = d.x;
+            hv[i * R + 2 * t + 1] = d.y;
+        }
+#endif
+    }
+}
+
+// host side: slot-ordered spectrum block (P values) -> thread-interleaved block
+template <int P>
+static inline void nm_cx_interleave_h(const double* h, double* hx) {
+    using PL = NmCxPlan<P>;
+    for (int tid = 0; tid < PL::NT; ++tid)
+        for (int i = 0; i < 16 / PL::R2; ++i)
+            for (int t = 0; t < PL::R2; ++t) hx[nm_cx_hx_index<PL>(tid, i, t)] = h[(tid + PL::NT * i) * PL::R2 + t];
+}
+static inline void nm_cx_interleave_h(int P, const double* h, double* hx) {
+    if (P == 1024) nm_cx_interleave_h<1024>(h, hx);
+    else if (P == 2048) nm_cx_interleave_h<2048>(h, hx);
+    else nm_cx_interleave_h<4096>(h, hx);
+}
+
 // last forward pass (unit stride).  MODE 0: forward butterfly only (bank: spectrum stays in `src`).
 // MODE 1: forward butterfly, * H, inverse butterfly in place (single filter).
 // MODE 2: load the spectrum from `src`, * H, inverse butterfly, store to `dst` (one filter of a bank).
 template <class PL, int MODE>
-NM_DEV void nm_cx_pass2(cx<double>* dst, const cx<double>* src, const double* NM_RESTRICT h, int tid) {
+NM_DEV void nm_cx_pass2(cx<double>* dst, const cx<double>* src, const double* hv, int tid) {
     constexpr int R = PL::R2;
     const int off = tid * (R + 1);  // tid*R + ((tid*R) >> PAD)
 #pragma unroll
     for (int i = 0; i < 16 / R; ++i) {
         cx<double> v[R];
-        double hv[R];
-        if (MODE != 0) {
-#pragma unroll
-            for (int t = 0; t < R; ++t) hv[t] = nm_ldg(h + (tid + PL::NT * i) * R + t);
-        }
 #pragma unroll
         for (int t = 0; t < R; ++t) v[t] = src[off + i * PL::B2 + t];
         if (MODE != 2) nm_bflyR<R, false>(v);
         if (MODE != 0) {
 #pragma unroll
-            for (int t = 0; t < R; ++t) v[t] = {v[t].re * hv[t], v[t].im * hv[t]};
+            for (int t = 0; t < R; ++t) v[t] = {v[t].re * hv[i * R + t], v[t].im * hv[i * R + t]};
             nm_bflyR<R, true>(v);
         }
 #pragma unroll
@@ -121,17 +162,15 @@ NM_DEV void nm_cx_pass2(cx<double>* dst, const cx<double>* src, const double* NM
     }
 }
 
-// compact CTA-wide sum of NV values; `red` needs NV * (NT/32) doubles; result valid in every thread.  Two barriers.
+// compact CTA-wide sum of NV (power of two <= 8) values; `red` needs NV * NW doubles; result valid in every thread.
+// Two barriers; the warp stage is the halving exchange of nm_warp_sum_multi.
 template <int NV, int NW>
 NM_DEV void nm_cx_block_sum(double* v, double* red, int tid) {
     const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = nm_warp_sum(v[i]);
+    constexpr int SH = (NV == 8) ? 2 : (NV == 4 ? 3 : (NV == 2 ? 4 : 5));  // value i lives in lanes with lane >> SH == i
+    nm_warp_sum_multi<NV>(v, lane);
     __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) red[i * NW + wid] = v[i];
-    }
+    if ((lane & ((1 << SH) - 1)) == 0) red[(lane >> SH) * NW + wid] = v[0];
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -154,15 +193,20 @@ struct NmEpiStoreScan {
     NmOut out;  // per_ch = 5: activity, mobility, complexity, raw, linelength
     static constexpr bool kRegs = true;
     static constexpr bool kRegsOnly = true, kReflectOk = true, kSameOk = false, kConvxOnly = true;
+    static constexpr bool kSyncsInside = false;  // (not on every path) -> the kernel adds the trailing barrier
     static NM_HD size_t smem_bytes(int /*nt*/) { return 0; }  // reductions use the padding tail of `work`
     NM_DEV bool regs_ok() const { return true; }
-    static constexpr bool kSyncsInside = false;  // (not on every path) -> the kernel adds the trailing barrier
+    struct State {};
 
+    // window sample u lives at work[u + (u >> 3)]: threads then walk chunks of CH = ceil(W / NT) consecutive samples
+    // (8 for the default sizes), which this padding makes bank-conflict free
+    static NM_HD int phys(int u) { return u + (u >> 3); }
+
+    // part 1: needs the registers -- store the rows, lay the window out in natural order
     template <class PL>
-    NM_DEV void run_x(const cx<double>* v, cx<double>* work, double* /*red*/, int o0, int W, int n_ch, int w, int c0, bool has2, int /*f*/,
-                      int tid) const {
-        constexpr int NT = PL::NT, NW = (PL::NT + 31) / 32;
-        static_assert((size_t)14 * NW * sizeof(double) <= (size_t)(PL::NBUF - PL::P) * sizeof(cx<double>), "reduction scratch must fit the tail");
+    NM_DEV void consume(const cx<double>* v, cx<double>* work, double* /*red*/, State& /*st*/, int o0, int W, int n_ch, int w, int c0,
+                        bool has2, int /*f*/, int tid) const {
+        constexpr int NT = PL::NT;
         if (y) {
             double* r0 = y + ((size_t)w * n_ch + c0) * Wp;
 #pragma unroll
@@ -175,59 +219,68 @@ struct NmEpiStoreScan {
             }
         }
         if (!want_scan) return;
-        double* red = reinterpret_cast<double*>(work + PL::P);
-        // natural-order copy so that every thread can see the two samples after each of its own
         __syncthreads();  // every thread has read its pass-0 inputs from `work`
 #pragma unroll
-        for (int k = 0; k < 16; ++k) work[tid + NT * k] = v[k];
-        __syncthreads();
-        const cx<double>* x = work + o0;
-        double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per row: sum x, sum d, sum dd, sum |d|
-#pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const int t = tid + NT * k - o0;
-            if (t >= 0 && t < W) {
-                s[0] += v[k].re; s[4] += v[k].im;
-                if (t + 1 < W) {
-                    const cx<double> b = x[t + 1];
-                    const double da = b.re - v[k].re, db = b.im - v[k].im;
+            const int u = tid + NT * k - o0;
+            if (u >= 0 && u < W) work[phys(u)] = v[k];
+        }
+    }
+
+    // part 2: two-pass moments (numpy.var semantics) over chunks of consecutive samples, each sample loaded once per pass
+    template <class PL>
+    NM_DEV void finish(cx<double>* work, double* /*red*/, State& /*st*/, int /*o0*/, int W, int /*n_ch*/, int w, int c0, bool has2, int /*f*/,
+                       int tid) const {
+        constexpr int NT = PL::NT, NW = (PL::NT + 31) / 32;
+        static_assert((size_t)16 * NW * sizeof(double) <= (size_t)(PL::NBUF - PL::P) * sizeof(cx<double>), "reduction scratch must fit the tail");
+        if (!want_scan) return;
+        double* red = reinterpret_cast<double*>(work + PL::P);  // W + W/8 <= P for every supported plan
+        __syncthreads();
+        const int CH = (W + NT - 1) / NT;
+        const int u0 = tid * CH, u1 = min(W, u0 + CH);
+        double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per row: sum x, sum d, sum dd, sum |d|
+        if (u0 < W) {
+            cx<double> xa = work[phys(u0)], xb = (u0 + 1 < W) ? work[phys(u0 + 1)] : cx<double>{0.0, 0.0};
+            for (int u = u0; u < u1; ++u) {
+                const cx<double> xc = (u + 2 < W) ? work[phys(u + 2)] : cx<double>{0.0, 0.0};
+                s[0] += xa.re; s[4] += xa.im;
+                if (u + 1 < W) {
+                    const double da = xb.re - xa.re, db = xb.im - xa.im;
                     s[1] += da; s[5] += db;
                     s[3] += fabs(da); s[7] += fabs(db);
-                    if (t + 2 < W) {
-                        const cx<double> c = x[t + 2];
-                        s[2] += (c.re - b.re) - da;
-                        s[6] += (c.im - b.im) - db;
+                    if (u + 2 < W) {
+                        s[2] += (xc.re - xb.re) - da;
+                        s[6] += (xc.im - xb.im) - db;
                     }
                 }
+                xa = xb; xb = xc;
             }
         }
         nm_cx_block_sum<8, NW>(s, red, tid);
         const double n0 = W, n1 = W - 1, n2 = W - 2;
-        double q[6] = {0, 0, 0, 0, 0, 0};
+        double q[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // 6 used; 8 for the power-of-two exchange reduction
         if (want_hjorth) {
             const double m0a = s[0] / n0, m1a = s[1] / n1, m2a = s[2] / n2;
             const double m0b = s[4] / n0, m1b = s[5] / n1, m2b = s[6] / n2;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int t = tid + NT * k - o0;
-                if (t >= 0 && t < W) {
-                    const cx<double> a = x[t];  // re-read instead of keeping v[] live across the reduction (registers)
-                    double e = a.re - m0a; q[0] += e * e;
-                    e = a.im - m0b; q[3] += e * e;
-                    if (t + 1 < W) {
-                        const cx<double> b = x[t + 1];
-                        const double da = b.re - a.re, db = b.im - a.im;
+            if (u0 < W) {
+                cx<double> xa = work[phys(u0)], xb = (u0 + 1 < W) ? work[phys(u0 + 1)] : cx<double>{0.0, 0.0};
+                for (int u = u0; u < u1; ++u) {
+                    const cx<double> xc = (u + 2 < W) ? work[phys(u + 2)] : cx<double>{0.0, 0.0};
+                    double e = xa.re - m0a; q[0] += e * e;
+                    e = xa.im - m0b; q[3] += e * e;
+                    if (u + 1 < W) {
+                        const double da = xb.re - xa.re, db = xb.im - xa.im;
                         e = da - m1a; q[1] += e * e;
                         e = db - m1b; q[4] += e * e;
-                        if (t + 2 < W) {
-                            const cx<double> c = x[t + 2];
-                            e = ((c.re - b.re) - da) - m2a; q[2] += e * e;
-                            e = ((c.im - b.im) - db) - m2b; q[5] += e * e;
+                        if (u + 2 < W) {
+                            e = ((xc.re - xb.re) - da) - m2a; q[2] += e * e;
+                            e = ((xc.im - xb.im) - db) - m2b; q[5] += e * e;
                         }
                     }
+                    xa = xb; xb = xc;
                 }
             }
-            nm_cx_block_sum<6, NW>(q, red + 8 * NW, tid);
+            nm_cx_block_sum<8, NW>(q, red + 8 * NW, tid);
         }
         if (tid < (has2 ? 2 : 1)) {
             const bool k = tid != 0;  // selects by predicate: no dynamically indexed local arrays
@@ -239,7 +292,7 @@ struct NmEpiStoreScan {
                 nm_store(out, w, c, 1, mob);
                 nm_store(out, w, c, 2, nm_nan_to_num(sqrt(v2 / v1) / mob));
             }
-            const cx<double> last = x[W - 1];
+            const cx<double> last = work[phys(W - 1)];
             if (want_raw) nm_store(out, w, c, 3, k ? last.im : last.re);
             // mean(|dx| / (W-1)) over W-1 samples: the reference divides by (W-1) twice
             if (want_ll) nm_store(out, w, c, 4, ((k ? s[7] : s[3]) / n1) / n1);
@@ -248,9 +301,48 @@ struct NmEpiStoreScan {
 };
 
 // ---------------------------------------------------------------- the kernel
-// MODE_REFLECT: NM_FIR_REFLECT (notch) or NM_FIR_SAME;  BANK: more than one filter shares the forward transform.
+// REFLECT: NM_FIR_REFLECT (notch) or NM_FIR_SAME;  BANK: the filters of a bank share the forward transform.
+//
+// Register epilogues come in two parts: consume() reads the 16 outputs a thread holds, finish() does whatever is left
+// (reductions, final formulas).  Between the two the kernel already issues the global loads of the NEXT item into the
+// freed registers, so their latency overlaps the reductions / barriers instead of stalling the next pass 0.
+template <int P, bool REFLECT>
+NM_DEV void nm_cx_load_item(cx<double>* v, const NmConvArgs& a, int item, int npair, int tid, int& w, int& c0, bool& has2) {
+    constexpr int NT = NmCxPlan<P>::NT;
+    const int W = a.in.W, E = a.E;
+    w = item / npair;
+    c0 = (item - w * npair) * 2;
+    has2 = c0 + 1 < a.in.n_ch;
+    const double* NM_RESTRICT r0 = a.in.base + (size_t)c0 * a.in.ch_stride + nm_ldg(a.in.off + w);
+    const double* NM_RESTRICT r1 = r0 + (has2 ? a.in.ch_stride : 0);
+    if (REFLECT) {
+        // odd reflection about both end samples, branch-free: value = c + s * row[idx] with (c, s, idx) selected per
+        // region, so all 32 loads of a thread are issued back to back (c - x == fma(-1, x, c): same rounding)
+        const double a0 = 2.0 * r0[0], b0 = 2.0 * r1[0], a1 = 2.0 * r0[W - 1], b1 = 2.0 * r1[W - 1];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int n = tid + NT * t;
+            const bool left = n < E, mid = !left && n < E + W, right = !left && !mid && n < W + 2 * E;
+            int idx = left ? E - n : (mid ? n - E : 2 * W + E - 2 - n);  // right: W-1-k with k = n-(E+W)+1
+            idx = (left || mid || right) ? idx : 0;
+            const double sgn = mid ? 1.0 : ((left || right) ? -1.0 : 0.0);
+            const double ca = left ? a0 : (right ? a1 : 0.0), cb = left ? b0 : (right ? b1 : 0.0);
+            const double va = fma(sgn, r0[idx], ca), vb = fma(sgn, r1[idx], cb);
+            v[t] = {va, has2 ? vb : 0.0};
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int n = tid + NT * t;
+            const int idx = n < W ? n : 0;
+            const double va = r0[idx], vb = r1[idx];
+            v[t] = {n < W ? va : 0.0, (has2 && n < W) ? vb : 0.0};
+        }
+    }
+}
+
 template <int P, bool REFLECT, bool BANK, class Epi>
-NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, NmCxPlan<P>::MINB) nm_convx_kernel(NmConvArgs a, Epi epi) {
+NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, BANK ? NmCxPlan<P>::MINBK : NmCxPlan<P>::MINB1) nm_convx_kernel(NmConvArgs a, Epi epi) {
     using PL = NmCxPlan<P>;
     constexpr int NT = PL::NT;
     NM_SHARED_BYTES(smem);
@@ -260,54 +352,36 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, NmCxPlan<P>::MINB) nm_convx_ker
     unsigned char* scratch = a.scratch_in_tail ? reinterpret_cast<unsigned char*>(work + P)
                                                : reinterpret_cast<unsigned char*>(red) + NM_CX_RED_BYTES;
     const int tid = threadIdx.x;
-    const int W = a.in.W, E = a.E;
+    const int W = a.in.W;
     const int npair = (a.in.n_ch + 1) >> 1;
-    const int o0 = REFLECT ? E : 0;
+    const int o0 = REFLECT ? a.E : 0;
+    const int nF = BANK ? a.nF : 1;
     const cx<double>* NM_RESTRICT tw = a.fft.tw;
     cx<double>* const p0w = work + tid + (tid >> PL::PAD);
     cx<double>* const p0s = spec + tid + (tid >> PL::PAD);
-    const cx<double> wA = nm_ldg(tw + tid);                          // exp(-2*pi*i*tid/P): pass-0 twiddle generator
-    const cx<double> wB = nm_ldg(tw + (tid & (PL::M1 - 1)) * 16);    // exp(-2*pi*i*j/NT): pass-1 generator (table stride P/NT)
+    // twiddle generators; tid == 0 / j == 0 multiply by exactly 1, so no thread needs a special case
+    const cx<double> wA = nm_ldg(tw + tid);                          // exp(-2*pi*i*tid/P): pass 0
+    const cx<double> wB = nm_ldg(tw + (tid & (PL::M1 - 1)) * 16);    // exp(-2*pi*i*j/NT): pass 1 (table stride P/NT)
 
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-        const int w = item / npair;
-        const int c0 = (item - w * npair) * 2;
-        const bool has2 = c0 + 1 < a.in.n_ch;
-        const double* NM_RESTRICT r0 = a.in.base + (size_t)c0 * a.in.ch_stride + nm_ldg(a.in.off + w);
-        const double* NM_RESTRICT r1 = r0 + (has2 ? a.in.ch_stride : 0);
+    cx<double> v[16];
+    double hv[16];
+    int item = blockIdx.x, w = 0, c0 = 0;
+    bool has2 = false;
+    if (item >= a.n_items) return;
+    nm_cx_load_item<P, REFLECT>(v, a, item, npair, tid, w, c0, has2);
+    if (BANK) nm_cx_load_h<PL>(hv, a.hx, tid);
 
-        // ---- pass 0 fused with the load of the (odd-reflected / zero padded) window
-        cx<double> v[16];
-        if (REFLECT) {
-            const double a0 = 2.0 * r0[0], b0 = 2.0 * r1[0], a1 = 2.0 * r0[W - 1], b1 = 2.0 * r1[W - 1];
-#pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const int n = tid + NT * t;
-                double va = 0.0, vb = 0.0;
-                if (n < E) {
-                    va = a0 - r0[E - n]; vb = b0 - r1[E - n];
-                } else if (n < E + W) {
-                    va = r0[n - E]; vb = r1[n - E];
-                } else if (n < W + 2 * E) {
-                    const int k = n - (E + W) + 1;
-                    va = a1 - r0[W - 1 - k]; vb = b1 - r1[W - 1 - k];
-                }
-                v[t] = {va, has2 ? vb : 0.0};
-            }
-        } else {
-#pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const int n = tid + NT * t;
-                double va = 0.0, vb = 0.0;
-                if (n < W) { va = r0[n]; vb = r1[n]; }
-                v[t] = {va, has2 ? vb : 0.0};
-            }
-        }
+    while (item < a.n_items) {
+        const int next = item + gridDim.x;
+        int nw = 0, nc0 = 0;
+        bool nhas2 = false;
+        // ---- pass 0 on the window that is already in registers
         nm_bfly16<false>(v);
-        if (tid != 0) nm_twiddle_w1<16, false>(v, wA);
+        nm_twiddle_w1<16, false>(v, wA);
 #pragma unroll
         for (int t = 0; t < 16; ++t) p0s[t * PL::S0] = v[t];
         __syncthreads();
+        if (!BANK) nm_cx_load_h<PL>(hv, a.hx, tid);  // (L1 resident) lands while pass 1 computes
         nm_cx_pass1<PL, false>(spec, wB, tid);
         __syncthreads();
         if (BANK) {
@@ -315,17 +389,22 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, NmCxPlan<P>::MINB) nm_convx_ker
             __syncthreads();
         }
 
-        for (int fi = 0; fi < (BANK ? a.nF : 1); ++fi) {
-            const double* NM_RESTRICT h = a.hperm + (size_t)fi * P;
-            if (BANK) nm_cx_pass2<PL, 2>(work, spec, h, tid);
-            else nm_cx_pass2<PL, 1>(work, work, h, tid);
+        for (int fi = 0; fi < nF; ++fi) {
+            const bool last = fi + 1 == nF;
+            if (BANK) {
+                nm_cx_pass2<PL, 2>(work, spec, hv, tid);
+                // prefetch the next filter's spectrum (wrapping to filter 0 for the next item) one phase ahead
+                nm_cx_load_h<PL>(hv, a.hx + (size_t)(last ? 0 : fi + 1) * P, tid);
+            } else {
+                nm_cx_pass2<PL, 1>(work, work, hv, tid);
+            }
             __syncthreads();
             nm_cx_pass1<PL, true>(work, wB, tid);
             __syncthreads();
             // ---- final inverse pass: padded slots -> registers, natural order n = tid + NT * t
 #pragma unroll
             for (int t = 0; t < 16; ++t) v[t] = p0w[t * PL::S0];
-            if (tid != 0) nm_twiddle_w1<16, true>(v, wA);
+            nm_twiddle_w1<16, true>(v, wA);
             nm_bfly16<true>(v);
             // `work` may still be read by slower threads: an epilogue (or the next filter's pass) must not write it
             // before a barrier.  Register epilogues either synchronise inside (kSyncsInside) or get a trailing barrier.
@@ -333,7 +412,10 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, NmCxPlan<P>::MINB) nm_convx_ker
             if constexpr (Epi::kRegs && !Epi::kRegsOnly) in_regs = epi.regs_ok();
             if (in_regs) {
                 if constexpr (Epi::kRegs) {
-                    epi.template run_x<PL>(v, work, red, o0, W, a.in.n_ch, w, c0, has2, fi, tid);
+                    typename Epi::State st;
+                    epi.template consume<PL>(v, work, red, st, o0, W, a.in.n_ch, w, c0, has2, fi, tid);
+                    if (last && next < a.n_items) nm_cx_load_item<P, REFLECT>(v, a, next, npair, tid, nw, nc0, nhas2);
+                    epi.template finish<PL>(work, red, st, o0, W, a.in.n_ch, w, c0, has2, fi, tid);
                     if constexpr (!Epi::kSyncsInside) __syncthreads();
                 }
             } else {
@@ -342,10 +424,12 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, NmCxPlan<P>::MINB) nm_convx_ker
 #pragma unroll
                     for (int t = 0; t < 16; ++t) work[tid + NT * t] = v[t];
                     __syncthreads();
+                    if (last && next < a.n_items) nm_cx_load_item<P, REFLECT>(v, a, next, npair, tid, nw, nc0, nhas2);
                     epi.run(work, o0, W, a.in.n_ch, w, c0, has2, fi, scratch, tid, NT);
                     __syncthreads();
                 }
             }
         }
+        item = next; w = nw; c0 = nc0; has2 = nhas2;
     }
 }

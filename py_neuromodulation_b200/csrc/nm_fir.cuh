@@ -41,11 +41,15 @@ struct NmEpiStore {
     static NM_HD size_t smem_bytes(int /*nt*/) { return 0; }
     NM_DEV bool regs_ok() const { return true; }
     static constexpr bool kSyncsInside = false;
+    struct State {};
     template <class PL>
-    NM_DEV void run_x(const cx<double>* v, cx<double>* /*work*/, double* /*red*/, int o0, int W, int n_ch, int w, int c0, bool has2, int f,
-                      int tid) const {
+    NM_DEV void consume(const cx<double>* v, cx<double>* /*work*/, double* /*red*/, State& /*st*/, int o0, int W, int n_ch, int w, int c0,
+                        bool has2, int f, int tid) const {
         run_regs(v, o0, W, n_ch, w, c0, has2, f, nullptr, tid, PL::NT);
     }
+    template <class PL>
+    NM_DEV void finish(cx<double>* /*work*/, double* /*red*/, State& /*st*/, int /*o0*/, int /*W*/, int /*n_ch*/, int /*w*/, int /*c0*/,
+                       bool /*has2*/, int /*f*/, int /*tid*/) const {}
     // v[k] = filtered sample n = tid + nt*k of the (padded) row; the window occupies n in [o0, o0 + W)
     NM_DEV void run_regs(const cx<double>* v, int o0, int W, int n_ch, int w, int c0, bool has2, int f,
                          unsigned char* /*scratch*/, int tid, int nt) const {
@@ -81,30 +85,33 @@ struct NmEpiBandpower {
     // nm_convx_kernel register epilogue: tail moments from the registers, one barrier, then ONE warp (rotating with the
     // filter index) finishes the two channels on two lanes while the other warps already run the next filter.
     static constexpr bool kSyncsInside = true;
+    struct State { double s[4]; int seg; };
     template <class PL>
-    NM_DEV void run_x(const cx<double>* v, cx<double>* /*work*/, double* red, int o0, int W, int /*n_ch*/, int w, int c0, bool has2, int f,
-                      int tid) const {
-        constexpr int NT = PL::NT, NW = (PL::NT + 31) / 32;
+    NM_DEV void consume(const cx<double>* v, cx<double>* /*work*/, double* /*red*/, State& st, int o0, int W, int /*n_ch*/, int /*w*/, int /*c0*/,
+                        bool /*has2*/, int f, int tid) const {
+        constexpr int NT = PL::NT;
         int seg = nm_ldg(seglen + f);
         if (seg > W) seg = W;
+        st.seg = seg;
         const int lo = o0 + W - seg, hi = o0 + W;
         // band-pass outputs have (near) zero mean, so the one-pass moments lose nothing in float64
-        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        st.s[0] = st.s[1] = st.s[2] = st.s[3] = 0.0;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const int n = tid + NT * k;
             if (n >= lo && n < hi) {
-                s[0] += v[k].re; s[1] += v[k].re * v[k].re;
-                s[2] += v[k].im; s[3] += v[k].im * v[k].im;
+                st.s[0] += v[k].re; st.s[1] += v[k].re * v[k].re;
+                st.s[2] += v[k].im; st.s[3] += v[k].im * v[k].im;
             }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s[i] = nm_warp_sum(s[i]);
+    }
+    template <class PL>
+    NM_DEV void finish(cx<double>* /*work*/, double* red, State& st, int /*o0*/, int /*W*/, int /*n_ch*/, int w, int c0, bool has2, int f,
+                       int tid) const {
+        constexpr int NW = (PL::NT + 31) / 32;
         const int lane = tid & 31, wid = tid >> 5;
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) red[i * NW + wid] = s[i];
-        }
+        nm_warp_sum_multi<4>(st.s, lane);  // value i ends up in the lanes with lane >> 3 == i
+        if ((lane & 7) == 0) red[(lane >> 3) * NW + wid] = st.s[0];
         __syncthreads();
         if (wid == (f & (NW - 1)) && lane < (has2 ? 2 : 1)) {
             double t0 = 0.0, t1 = 0.0;
@@ -113,7 +120,7 @@ struct NmEpiBandpower {
                 t0 += red[(2 * lane) * NW + q];
                 t1 += red[(2 * lane + 1) * NW + q];
             }
-            const double n0 = seg, mean = t0 / n0;
+            const double n0 = st.seg, mean = t0 / n0;
             double v0 = t1 / n0 - mean * mean;
             if (v0 < 0.0) v0 = 0.0;
             if (want_act) nm_store(out, w, c0 + lane, f * 3 + 0, nm_nan_to_num(log_act ? log10(v0) : v0));

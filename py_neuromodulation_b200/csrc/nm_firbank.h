@@ -12,7 +12,7 @@ struct nm_pipeline;
 struct FirBank {
     int nF = 0, L = 0, Lh = 0, P = 0, mode = NM_FIR_SAME, E = 0;
     FftPlanHost fft;
-    DevBuf d_hperm;
+    DevBuf d_hperm, d_hx;
     bool pow2 = false;  // register-blocked power-of-two kernel (nm_conv.cuh) vs generic mixed-radix kernel (nm_fir.cuh)
     int pad = 3;
     int build(const double* taps, int nF_, int L_, int W, int mode_, cudaStream_t s) {
@@ -51,6 +51,11 @@ struct FirBank {
         }
         std::vector<double> hperm;
         if (nm_build_hperm(taps, nF, L, fft, hperm)) return -1;
+        if (pow2 && nm_convx_supported(P)) {
+            std::vector<double> hx(hperm.size());
+            for (int f = 0; f < nF; ++f) nm_cx_interleave_h(P, hperm.data() + (size_t)f * P, hx.data() + (size_t)f * P);
+            if (d_hx.upload(hx, s)) return -1;
+        }
         return d_hperm.upload(hperm, s);
     }
     NmFirArgs args(const NmRows& in) const {
@@ -74,6 +79,7 @@ struct FirBank {
         a.fft.pad = pad;
         a.fft.tw = fft.d_tw.as<cx<double>>();
         a.hperm = d_hperm.as<double>();
+        a.hx = d_hx.as<double>();
         a.nF = nF;
         a.mode = mode;
         a.E = E;
