@@ -154,6 +154,12 @@ int nm_set_profiling(nm_pipeline* p, int enabled);
 int nm_get_profile(nm_pipeline* p, double* ms, long long* launches, int n);
 /* windows per kernel launch (chunk size chosen so that the notched chunk stays L2 resident) */
 int nm_chunk_windows(nm_pipeline* p);
+/* burst thresholds: 1 (default) = incremental sliding order statistics, 0 = re-select from the whole history for every
+ * window (slower reference implementation of the same kernel; results are identical).  Resets the burst state. */
+int nm_set_burst_threshold_mode(nm_pipeline* p, int incremental);
+/* statistics of the incremental thresholds since the last reset, summed over (channel, band) rows: bracket rebuilds
+ * and windows that fell back to the direct selection */
+int nm_burst_threshold_stats(nm_pipeline* p, long long* rebuilds, long long* direct_windows);
 /* text description of the launch plan (one line per family: kernel, transform size, threads, shared memory);
  * writes at most n-1 characters + NUL into buf and returns the full length */
 int nm_describe_plan(nm_pipeline* p, char* buf, int n);

@@ -78,6 +78,8 @@ _SIGNATURES = {
     "nm_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "nm_get_profile": (C.c_int, [C.c_void_p, c_double_p, c_ll_p, C.c_int]),
     "nm_chunk_windows": (C.c_int, [C.c_void_p]),
+    "nm_set_burst_threshold_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "nm_burst_threshold_stats": (C.c_int, [C.c_void_p, c_ll_p, c_ll_p]),
     "nm_describe_plan": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "nm_result_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), c_ll_p, c_int_p]),
     "nm_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -216,6 +216,16 @@ class Pipeline:
     def chunk_windows(self) -> int:
         return int(self.lib.nm_chunk_windows(self._h))
 
+    def set_burst_threshold_mode(self, incremental: bool) -> None:
+        """Incremental sliding quantile (default) or per-window re-selection from the whole history (same results)."""
+        _lib.check(self.lib.nm_set_burst_threshold_mode(self._h, int(incremental)))
+
+    def burst_threshold_stats(self) -> tuple[int, int]:
+        """(bracket rebuilds, windows served by the direct selection) summed over rows since the last reset."""
+        a, b = C.c_longlong(), C.c_longlong()
+        _lib.check(self.lib.nm_burst_threshold_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def describe_plan(self) -> str:
         """One line per family: which kernel serves it (specialised / runtime-plan / generic), sizes, shared memory."""
         buf = C.create_string_buffer(4096)

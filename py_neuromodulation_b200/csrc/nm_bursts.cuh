@@ -71,6 +71,33 @@ struct NmEpiBursts {
 };
 
 // ------------------------------------------------------------------ pass 2: thresholds
+// threshold = numpy.quantile(history, q) with the 'linear' rule: order statistics k_lo, k_hi of the last n envelope
+// samples and a lerp (host supplies k_lo, k_hi, gamma per window).  Envelopes are >= 0, so the float64 bit patterns
+// ("keys") order like the values and all selection is done on unsigned 64-bit keys -- exact, no tolerance.
+//
+// The history slides by S samples per window (S = 100 of 30 000 at defaults), so the threshold is maintained
+// INCREMENTALLY per (channel, band) row instead of re-selecting from the whole ring for every window:
+//
+//   bracket [lo_key, hi_key)   a key interval around the current quantile holding <= NM_BQ_CAP history samples
+//   cnt_below                  number of history samples with key < lo_key
+//   queue                      the history samples inside the bracket, in TIME order (FIFO: they enter and expire
+//                              in time order), with their logical sample index
+//
+// A window step classifies only the S entering and S expiring samples (cnt_below +-, queue append / pop) and selects
+// rank k_lo - cnt_below among the queue entries (<= 2048 keys in shared memory).  When the target rank leaves the
+// bracket, the queue overflows or there is no valid state (first window, reset), the bracket is rebuilt from the ring
+// with a two-level radix histogram (the former per-window algorithm, which also remains the fallback when a single
+// 2^-12-binade sub-bin holds more samples than the queue, e.g. an all-zero signal).
+// One CTA owns one row and walks the windows of the chunk in order; the state persists in global memory between
+// launches (chunks, streamed windows).
+struct NmBurstQRow {
+    unsigned long long lo_key, hi_key;
+    long long e_prev, first_prev;  // the state describes the history [first_prev, e_prev)
+    int cnt_below, count, valid;
+    int rebuilds, directs;  // statistics since the last reset: bracket rebuilds, windows served by the direct selection
+    int pad;
+};
+
 struct NmBurstThrArgs {
     const double* ring;
     long long cap;
@@ -81,152 +108,477 @@ struct NmBurstThrArgs {
     const int* k_hi;
     const double* gamma;     // [n_windows]
     double* thr;             // (n_windows, n_ch, nB)
+    NmBurstQRow* qrow;       // [n_ch * nB]
+    unsigned long long* qkey;  // [n_ch * nB][NM_BQ_CAP]
+    unsigned* qidx;            // [n_ch * nB][NM_BQ_CAP] low 32 bits of the logical sample index
+    int incremental;         // 0: re-select from the ring for every window (reference implementation of this kernel)
 };
 
 #define NM_SEL_BINS 4096
 #define NM_SEL_CAND 1024
+#define NM_BQ_CAP 2048
+#define NM_BQ_MASK (NM_BQ_CAP - 1)
+#define NM_BQ_HALF 448
+#define NM_BQ_SLACK 128
+#define NM_BQ_THREADS 128
+
+struct NmBqSmem {
+    int* hist;                  // NM_SEL_BINS
+    unsigned long long* qk;     // NM_BQ_CAP (also the candidate list of the direct selection)
+    unsigned* qi;               // NM_BQ_CAP
+    int* ctl;                   // 16
+    unsigned long long* res;    // 4
+    int* wcnt;                  // 32
+};
+
+static NM_HD size_t nm_bq_smem_bytes() {
+    return NM_SEL_BINS * sizeof(int) + NM_BQ_CAP * 8 + NM_BQ_CAP * 4 + 16 * sizeof(int) + 4 * 8 + 32 * sizeof(int) + 64;
+}
+
+NM_DEV unsigned long long nm_bq_key(const double* rrow, long long cap, long long i) {
+    return (unsigned long long)__double_as_longlong(rrow[i % cap]);
+}
+
+// locate the bin that holds 0-based rank `rank` in hist[0, nbins): ctl[0] = bin, ctl[1] = count below it, ctl[2] = its count.
+// Executed by warp 0; nbins is a multiple of 32.  Callers place barriers around it.
+NM_DEV void nm_bq_find_bin(const int* hist, int nbins, int rank, int* ctl, int tid) {
+    if (tid < 32) {
+        const int lane = tid, per = nbins / 32;
+        int s = 0;
+        for (int i = 0; i < per; ++i) s += hist[lane * per + i];
+        int incl = s;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        const int excl = incl - s;
+        if (rank >= excl && rank < incl) {
+            int run = excl;
+            for (int i = 0; i < per; ++i) {
+                const int h = hist[lane * per + i];
+                if (rank < run + h) {
+                    ctl[0] = lane * per + i;
+                    ctl[1] = run;
+                    ctl[2] = h;
+                    break;
+                }
+                run += h;
+            }
+        }
+    }
+}
+
+// Exact order statistics straight from the ring (radix select, 12-bit digits, candidate gather): returns the
+// interpolated threshold.  All threads of the CTA call it; result valid in every thread.
+NM_DEV double nm_bq_select_direct(const double* rrow, long long cap, long long first, int n, int k_lo, int k_hi, double gamma,
+                                  const NmBqSmem& sm, int tid, int nt) {
+    const int lane = tid & 31;
+    int rank = k_lo;
+    unsigned long long prefix = 0ull, mask = 0ull;
+    int shift = 52, width = 12;
+    bool resolved = false;
+    const long long first_mod = first % cap;
+    while (true) {
+        for (int i = tid; i < NM_SEL_BINS; i += nt) sm.hist[i] = 0;
+        __syncthreads();
+        const unsigned long long dm = (1ull << width) - 1ull;
+        for (int i = tid; i < n; i += nt) {
+            long long p = first_mod + i;
+            if (p >= cap) p -= cap;
+            const unsigned long long key = (unsigned long long)__double_as_longlong(rrow[p]);
+            if ((key & mask) == prefix) atomicAdd(&sm.hist[(int)((key >> shift) & dm)], 1);
+        }
+        __syncthreads();
+        nm_bq_find_bin(sm.hist, NM_SEL_BINS, rank, sm.ctl, tid);
+        __syncthreads();
+        const int digit = sm.ctl[0], below = sm.ctl[1], cnt = sm.ctl[2];
+        rank -= below;
+        prefix |= ((unsigned long long)digit) << shift;
+        mask |= dm << shift;
+        __syncthreads();
+        if (shift == 0) { resolved = true; break; }
+        if (cnt <= NM_SEL_CAND) break;
+        if (shift >= 16) { shift -= 12; width = 12; }
+        else { width = shift; shift = 0; }   // final 4 bits
+    }
+    unsigned long long a_key = prefix;
+    if (!resolved) {
+        if (tid == 0) sm.ctl[3] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += nt) {
+            long long p = first_mod + i;
+            if (p >= cap) p -= cap;
+            const unsigned long long key = (unsigned long long)__double_as_longlong(rrow[p]);
+            if ((key & mask) == prefix) {
+                const int slot = atomicAdd(&sm.ctl[3], 1);
+                if (slot < NM_SEL_CAND) sm.qk[slot] = key;
+            }
+        }
+        __syncthreads();
+        const int m = sm.ctl[3] < NM_SEL_CAND ? sm.ctl[3] : NM_SEL_CAND;
+        for (int i = tid; i < m; i += nt) {
+            const unsigned long long x = sm.qk[i];
+            int r = 0;
+            for (int j = 0; j < m; ++j) {
+                const unsigned long long y = sm.qk[j];
+                r += (y < x || (y == x && j < i)) ? 1 : 0;
+            }
+            if (r == rank) sm.res[0] = x;
+        }
+        __syncthreads();
+        a_key = sm.res[0];
+    }
+    // second order statistic: a again if duplicated far enough, else the smallest larger value
+    const double av = __longlong_as_double((long long)a_key);
+    double thr = av;
+    if (k_hi != k_lo) {
+        if (tid == 0) { sm.ctl[4] = 0; sm.ctl[5] = 0; }
+        __syncthreads();
+        int less = 0, eq = 0;
+        unsigned long long mg = ~0ull;
+        for (int i = tid; i < n; i += nt) {
+            long long p = first_mod + i;
+            if (p >= cap) p -= cap;
+            const unsigned long long key = (unsigned long long)__double_as_longlong(rrow[p]);
+            less += key < a_key;
+            eq += key == a_key;
+            if (key > a_key && key < mg) mg = key;
+        }
+        less = nm_warp_sum_i(less);
+        eq = nm_warp_sum_i(eq);
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long u = __shfl_xor_sync(0xffffffffu, mg, o);
+            mg = u < mg ? u : mg;
+        }
+        if (lane == 0) {
+            atomicAdd(&sm.ctl[4], less);
+            atomicAdd(&sm.ctl[5], eq);
+            sm.qk[tid >> 5] = mg;  // per-warp minima (the candidate list is no longer needed)
+        }
+        __syncthreads();
+        unsigned long long best = ~0ull;
+        for (int q = 0; q < ((nt + 31) >> 5); ++q) best = sm.qk[q] < best ? sm.qk[q] : best;
+        const double bv = (k_hi < sm.ctl[4] + sm.ctl[5]) ? av : __longlong_as_double((long long)best);
+        const double diff = bv - av;
+        double lerp = av + diff * gamma;
+        if (gamma >= 0.5) lerp = bv - diff * (1.0 - gamma);
+        thr = (diff == 0.0) ? av : lerp;
+        __syncthreads();
+    }
+    return thr;
+}
+
+// (Re)build the bracket around rank k_lo of the history [first, first + n) and fill the queue in time order.
+// Returns false (uniformly) when no bracket fits the queue; the caller then falls back to the direct selection.
+NM_DEV bool nm_bq_rebuild(const double* rrow, long long cap, long long first, int n, int k_lo, const NmBqSmem& sm, unsigned long long& lo_key,
+                          unsigned long long& hi_key, int& cnt_below, int& head, int& count, int tid, int nt) {
+    const int lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
+    // level 1: sign + exponent
+    for (int i = tid; i < NM_SEL_BINS; i += nt) sm.hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) atomicAdd(&sm.hist[(int)(nm_bq_key(rrow, cap, first + i) >> 52)], 1);
+    __syncthreads();
+    nm_bq_find_bin(sm.hist, NM_SEL_BINS, k_lo, sm.ctl, tid);
+    __syncthreads();
+    const unsigned long long d1 = (unsigned long long)sm.ctl[0];
+    const int below1 = sm.ctl[1];
+    __syncthreads();
+    // level 2: the top 12 mantissa bits inside that binade
+    for (int i = tid; i < NM_SEL_BINS; i += nt) sm.hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        const unsigned long long key = nm_bq_key(rrow, cap, first + i);
+        if ((key >> 52) == d1) atomicAdd(&sm.hist[(int)((key >> 40) & 0xfffull)], 1);
+    }
+    __syncthreads();
+    nm_bq_find_bin(sm.hist, NM_SEL_BINS, k_lo - below1, sm.ctl, tid);
+    __syncthreads();
+    if (tid == 0) {
+        const int d2 = sm.ctl[0], below2 = sm.ctl[1];
+        const int budget = NM_BQ_CAP - NM_BQ_SLACK;
+        int total = sm.ctl[2], lo_sub = d2, hi_sub = d2, acc_lo = 0, acc_hi = 0;
+        while (lo_sub > 0 && acc_lo < NM_BQ_HALF && total + sm.hist[lo_sub - 1] <= budget) {
+            --lo_sub;
+            acc_lo += sm.hist[lo_sub];
+            total += sm.hist[lo_sub];
+        }
+        while (hi_sub < NM_SEL_BINS - 1 && acc_hi < NM_BQ_HALF && total + sm.hist[hi_sub + 1] <= budget) {
+            ++hi_sub;
+            acc_hi += sm.hist[hi_sub];
+            total += sm.hist[hi_sub];
+        }
+        sm.ctl[6] = lo_sub;
+        sm.ctl[7] = hi_sub;
+        sm.ctl[8] = total;
+        sm.ctl[9] = below1 + below2 - acc_lo;
+    }
+    __syncthreads();
+    const int total = sm.ctl[8];
+    if (total > NM_BQ_CAP - NM_BQ_SLACK) {  // a single sub-bin does not fit (massive ties)
+        __syncthreads();
+        return false;
+    }
+    lo_key = (d1 << 52) | ((unsigned long long)sm.ctl[6] << 40);
+    hi_key = (d1 << 52) + (((unsigned long long)sm.ctl[7] + 1ull) << 40);
+    cnt_below = sm.ctl[9];
+    // gather in time order: warp `wid` owns the contiguous segment [wid*seg, (wid+1)*seg) of the history
+    const int seg = (n + nwarp - 1) / nwarp;
+    const int s0 = min(n, wid * seg), s1 = min(n, s0 + seg);
+    int mine = 0;
+    for (int i = s0 + lane; i < s1; i += 32) {
+        const unsigned long long key = nm_bq_key(rrow, cap, first + i);
+        mine += (key >= lo_key && key < hi_key) ? 1 : 0;
+    }
+    mine = nm_warp_sum_i(mine);
+    __syncthreads();
+    if (lane == 0) sm.wcnt[wid] = mine;
+    __syncthreads();
+    int off = 0;
+    for (int q = 0; q < wid; ++q) off += sm.wcnt[q];
+    for (int i0 = s0; i0 < s1; i0 += 32) {
+        const int i = i0 + lane;
+        unsigned long long key = 0ull;
+        bool in = false;
+        if (i < s1) {
+            key = nm_bq_key(rrow, cap, first + i);
+            in = key >= lo_key && key < hi_key;
+        }
+        const unsigned bm = __ballot_sync(0xffffffffu, in);
+        if (in) {
+            const int pos = off + __popc(bm & ((1u << lane) - 1u));
+            sm.qk[pos] = key;
+            sm.qi[pos] = (unsigned)(first + i);
+        }
+        off += __popc(bm);
+    }
+    head = 0;
+    count = total;
+    __syncthreads();
+    return true;
+}
+
+// rank-`r` key (0-based) among the queue entries, plus (when wanted) the next order statistic: res[0] = a, res[1] = b.
+// Requires 0 <= r and r + (want_next ? 1 : 0) < count.
+NM_DEV void nm_bq_select_queue(const NmBqSmem& sm, int head, int count, unsigned long long lo_key, unsigned long long hi_key, int r,
+                               bool want_next, int tid, int nt) {
+    const int lane = tid & 31;
+    unsigned long long lo = lo_key, range = hi_key - lo_key;
+    int rr = r;
+    unsigned long long a_key = 0ull;
+    while (true) {
+        int sh = 0;
+        while (((range - 1ull) >> sh) > 255ull) ++sh;
+        for (int i = tid; i < 256; i += nt) sm.hist[i] = 0;
+        __syncthreads();
+        for (int j = tid; j < count; j += nt) {
+            const unsigned long long key = sm.qk[(head + j) & NM_BQ_MASK];
+            if (key >= lo && key - lo < range) atomicAdd(&sm.hist[(int)((key - lo) >> sh)], 1);
+        }
+        __syncthreads();
+        nm_bq_find_bin(sm.hist, 256, rr, sm.ctl, tid);
+        __syncthreads();
+        const int tb = sm.ctl[0], below = sm.ctl[1], cnt = sm.ctl[2];
+        __syncthreads();
+        lo += (unsigned long long)tb << sh;
+        range = 1ull << sh;
+        rr -= below;
+        if (sh == 0) { a_key = lo; break; }  // every key of the bin equals lo
+        if (cnt <= 256) {
+            // gather the bin's members (order irrelevant) and rank them by counting
+            if (tid == 0) sm.ctl[3] = 0;
+            __syncthreads();
+            unsigned long long* mem = reinterpret_cast<unsigned long long*>(sm.hist + 256);
+            for (int j = tid; j < count; j += nt) {
+                const unsigned long long key = sm.qk[(head + j) & NM_BQ_MASK];
+                if (key >= lo && key - lo < range) mem[atomicAdd(&sm.ctl[3], 1)] = key;
+            }
+            __syncthreads();
+            for (int i = tid; i < cnt; i += nt) {
+                const unsigned long long x = mem[i];
+                int q = 0;
+                for (int j = 0; j < cnt; ++j) {
+                    const unsigned long long y = mem[j];
+                    q += (y < x || (y == x && j < i)) ? 1 : 0;
+                }
+                if (q == rr) sm.res[0] = x;
+            }
+            __syncthreads();
+            a_key = sm.res[0];
+            break;
+        }
+    }
+    if (tid == 0) { sm.res[0] = a_key; sm.ctl[4] = 0; sm.ctl[5] = 0; }
+    __syncthreads();
+    if (want_next) {
+        int less = 0, eq = 0;
+        unsigned long long mg = ~0ull;
+        for (int j = tid; j < count; j += nt) {
+            const unsigned long long key = sm.qk[(head + j) & NM_BQ_MASK];
+            less += key < a_key;
+            eq += key == a_key;
+            if (key > a_key && key < mg) mg = key;
+        }
+        less = nm_warp_sum_i(less);
+        eq = nm_warp_sum_i(eq);
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long u = __shfl_xor_sync(0xffffffffu, mg, o);
+            mg = u < mg ? u : mg;
+        }
+        if (lane == 0) {
+            atomicAdd(&sm.ctl[4], less);
+            atomicAdd(&sm.ctl[5], eq);
+            reinterpret_cast<unsigned long long*>(sm.hist)[tid >> 5] = mg;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long best = ~0ull;
+            for (int q = 0; q < ((nt + 31) >> 5); ++q) {
+                const unsigned long long u = reinterpret_cast<unsigned long long*>(sm.hist)[q];
+                best = u < best ? u : best;
+            }
+            sm.res[1] = (r + 1 < sm.ctl[4] + sm.ctl[5]) ? a_key : best;
+        }
+        __syncthreads();
+    }
+}
 
 NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
     NM_SHARED_BYTES(smem);
-    int* hist = reinterpret_cast<int*>(smem);                                 // NM_SEL_BINS
-    unsigned long long* cand = reinterpret_cast<unsigned long long*>(hist + NM_SEL_BINS);  // NM_SEL_CAND
-    int* ctl = reinterpret_cast<int*>(cand + NM_SEL_CAND);                    // [0] digit [1] below [2] count [3] ncand
-    unsigned long long* res = reinterpret_cast<unsigned long long*>(ctl + 8); // [0] a  [1] min greater
-    int* cnts = reinterpret_cast<int*>(res + 2);                              // [0] less [1] equal
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    NmBqSmem sm;
+    sm.hist = reinterpret_cast<int*>(smem);
+    sm.qk = reinterpret_cast<unsigned long long*>(sm.hist + NM_SEL_BINS);
+    sm.qi = reinterpret_cast<unsigned*>(sm.qk + NM_BQ_CAP);
+    sm.ctl = reinterpret_cast<int*>(sm.qi + NM_BQ_CAP);
+    sm.res = reinterpret_cast<unsigned long long*>(sm.ctl + 16);
+    sm.wcnt = reinterpret_cast<int*>(sm.res + 4);
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
+    const int n_rows = a.n_ch * a.nB;
 
-    const long long n_items = (long long)a.n_windows * a.n_ch * a.nB;
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int w = (int)(item / ((long long)a.n_ch * a.nB));
-        const int cb = (int)(item - (long long)w * a.n_ch * a.nB);
-        const double* rrow = a.ring + (size_t)cb * a.cap;
-        const int n = a.n_hist[w];
-        const long long first = a.e_end[w] - n;
-        const long long first_mod = first % a.cap;
-        int rank = a.k_lo[w];
-        unsigned long long prefix = 0ull, mask = 0ull;
-        int shift = 52, width = 12;
-        bool resolved = false;
-        while (true) {
-            for (int i = tid; i < NM_SEL_BINS; i += nt) hist[i] = 0;
-            __syncthreads();
-            const unsigned long long dm = (1ull << width) - 1ull;
-            for (int i = tid; i < n; i += nt) {
-                long long p = first_mod + i;
-                if (p >= a.cap) p -= a.cap;
-                const unsigned long long key = (unsigned long long)__double_as_longlong(rrow[p]);
-                if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & dm)], 1);
+    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const double* rrow = a.ring + (size_t)row * a.cap;
+        NmBurstQRow st = a.qrow[row];
+        unsigned long long lo_key = st.lo_key, hi_key = st.hi_key;
+        long long e_prev = st.e_prev, first_prev = st.first_prev;
+        int cnt_below = st.cnt_below, count = st.count, head = 0;
+        int n_rebuild = st.rebuilds, n_direct = st.directs;
+        bool valid = a.incremental && st.valid != 0;
+        if (valid) {
+            for (int j = tid; j < count; j += nt) {
+                sm.qk[j] = a.qkey[(size_t)row * NM_BQ_CAP + j];
+                sm.qi[j] = a.qidx[(size_t)row * NM_BQ_CAP + j];
             }
-            __syncthreads();
-            if (tid < 32) {
-                const int per = NM_SEL_BINS / 32;
-                int s = 0;
-                for (int i = 0; i < per; ++i) s += hist[lane * per + i];
-                int incl = s;
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += u;
-                }
-                const int excl = incl - s;
-                if (rank >= excl && rank < incl) {
-                    int run = excl;
-                    for (int i = 0; i < per; ++i) {
-                        const int h = hist[lane * per + i];
-                        if (rank < run + h) {
-                            ctl[0] = lane * per + i;
-                            ctl[1] = run;
-                            ctl[2] = h;
-                            break;
-                        }
-                        run += h;
+        }
+        __syncthreads();
+
+        for (int w = 0; w < a.n_windows; ++w) {
+            const long long e = a.e_end[w];
+            const int n = a.n_hist[w];
+            const long long first = e - n;
+            const int k_lo = a.k_lo[w], k_hi = a.k_hi[w];
+            const bool want_next = k_hi != k_lo;
+            if (valid && (e < e_prev || first < first_prev || e - e_prev > a.cap / 2)) valid = false;
+            if (valid) {
+                // ---- slide: expiring samples [first_prev, first), entering samples [e_prev, e)
+                if (tid == 0) { sm.ctl[10] = 0; sm.ctl[11] = 0; }
+                __syncthreads();
+                int delta = 0;
+                for (long long i = first_prev + tid; i < first; i += nt) delta -= (nm_bq_key(rrow, a.cap, i) < lo_key) ? 1 : 0;
+                int nexp = 0;
+                for (int j = tid; j < count; j += nt) nexp += ((int)(sm.qi[(head + j) & NM_BQ_MASK] - (unsigned)first) < 0) ? 1 : 0;
+                nexp = nm_warp_sum_i(nexp);
+                if (lane == 0 && nexp) atomicAdd(&sm.ctl[11], nexp);
+                __syncthreads();
+                nexp = sm.ctl[11];
+                head = (head + nexp) & NM_BQ_MASK;
+                count -= nexp;
+                const int n_enter = (int)(e - e_prev);
+                for (int base = 0; base < n_enter && valid; base += nt) {
+                    const int i = base + tid;
+                    unsigned long long key = 0ull;
+                    bool in = false;
+                    if (i < n_enter) {
+                        key = nm_bq_key(rrow, a.cap, e_prev + i);
+                        if (key < lo_key) delta += 1;
+                        else in = key < hi_key;
                     }
+                    const unsigned bm = __ballot_sync(0xffffffffu, in);
+                    if (lane == 0) sm.wcnt[wid] = __popc(bm);
+                    __syncthreads();
+                    int off = 0, tot = 0;
+                    for (int q = 0; q < nwarp; ++q) {
+                        const int c = sm.wcnt[q];
+                        if (q < wid) off += c;
+                        tot += c;
+                    }
+                    if (count + tot > NM_BQ_CAP) {
+                        valid = false;  // uniform: queue overflow -> rebuild below
+                    } else {
+                        if (in) {
+                            const int pos = (head + count + off + __popc(bm & ((1u << lane) - 1u))) & NM_BQ_MASK;
+                            sm.qk[pos] = key;
+                            sm.qi[pos] = (unsigned)(e_prev + i);
+                        }
+                        count += tot;
+                    }
+                    __syncthreads();
+                }
+                delta = nm_warp_sum_i(delta);
+                if (lane == 0 && delta) atomicAdd(&sm.ctl[10], delta);
+                __syncthreads();
+                cnt_below += sm.ctl[10];
+                const int r = k_lo - cnt_below;
+                if (r < 0 || r + (want_next ? 1 : 0) >= count) valid = false;
+                __syncthreads();
+            }
+            double thr;
+            bool have = false;
+            if (!valid && a.incremental) {
+                ++n_rebuild;
+                valid = nm_bq_rebuild(rrow, a.cap, first, n, k_lo, sm, lo_key, hi_key, cnt_below, head, count, tid, nt);
+                if (valid) {
+                    const int r = k_lo - cnt_below;
+                    if (r < 0 || r + (want_next ? 1 : 0) >= count) valid = false;  // bracket clipped at a binade edge
                 }
             }
+            if (valid) {
+                nm_bq_select_queue(sm, head, count, lo_key, hi_key, k_lo - cnt_below, want_next, tid, nt);
+                const double av = __longlong_as_double((long long)sm.res[0]);
+                thr = av;
+                if (want_next) {
+                    const double bv = __longlong_as_double((long long)sm.res[1]);
+                    const double g = a.gamma[w];
+                    const double diff = bv - av;
+                    double lerp = av + diff * g;
+                    if (g >= 0.5) lerp = bv - diff * (1.0 - g);
+                    thr = (diff == 0.0) ? av : lerp;
+                }
+                have = true;
+                __syncthreads();
+            }
+            if (!have) ++n_direct;
+            if (!have) thr = nm_bq_select_direct(rrow, a.cap, first, n, k_lo, k_hi, a.gamma[w], sm, tid, nt);
+            if (tid == 0) a.thr[(size_t)w * n_rows + row] = thr;
+            e_prev = e;
+            first_prev = first;
             __syncthreads();
-            const int digit = ctl[0], below = ctl[1], cnt = ctl[2];
-            rank -= below;
-            prefix |= ((unsigned long long)digit) << shift;
-            mask |= dm << shift;
-            __syncthreads();
-            if (shift == 0) { resolved = true; break; }
-            if (cnt <= NM_SEL_CAND) break;
-            if (shift >= 16) { shift -= 12; width = 12; }
-            else { width = shift; shift = 0; }   // final 4 bits
         }
-        unsigned long long a_key = prefix;
-        if (!resolved) {
-            if (tid == 0) ctl[3] = 0;
-            __syncthreads();
-            for (int i = tid; i < n; i += nt) {
-                long long p = first_mod + i;
-                if (p >= a.cap) p -= a.cap;
-                const unsigned long long key = (unsigned long long)__double_as_longlong(rrow[p]);
-                if ((key & mask) == prefix) {
-                    const int slot = atomicAdd(&ctl[3], 1);
-                    if (slot < NM_SEL_CAND) cand[slot] = key;
+        // ---- persist the state of this row
+        if (a.incremental) {
+            if (valid) {
+                for (int j = tid; j < count; j += nt) {
+                    a.qkey[(size_t)row * NM_BQ_CAP + j] = sm.qk[(head + j) & NM_BQ_MASK];
+                    a.qidx[(size_t)row * NM_BQ_CAP + j] = sm.qi[(head + j) & NM_BQ_MASK];
                 }
             }
-            __syncthreads();
-            const int m = ctl[3] < NM_SEL_CAND ? ctl[3] : NM_SEL_CAND;
-            for (int i = tid; i < m; i += nt) {
-                const unsigned long long x = cand[i];
-                int r = 0;
-                for (int j = 0; j < m; ++j) {
-                    const unsigned long long y = cand[j];
-                    r += (y < x || (y == x && j < i)) ? 1 : 0;
-                }
-                if (r == rank) res[0] = x;
-            }
-            __syncthreads();
-            a_key = res[0];
-        }
-        // second order statistic: a again if duplicated far enough, else the smallest larger value
-        double thr;
-        const double av = __longlong_as_double((long long)a_key);
-        if (a.k_hi[w] == a.k_lo[w]) {
-            thr = av;
-        } else {
-            if (tid == 0) { cnts[0] = 0; cnts[1] = 0; res[1] = ~0ull; }
-            __syncthreads();
-            int less = 0, eq = 0;
-            unsigned long long mg = ~0ull;
-            for (int i = tid; i < n; i += nt) {
-                long long p = first_mod + i;
-                if (p >= a.cap) p -= a.cap;
-                const unsigned long long key = (unsigned long long)__double_as_longlong(rrow[p]);
-                less += key < a_key;
-                eq += key == a_key;
-                if (key > a_key && key < mg) mg = key;
-            }
-            less = nm_warp_sum_i(less);
-            eq = nm_warp_sum_i(eq);
-            for (int o = 16; o > 0; o >>= 1) {
-                const unsigned long long u = __shfl_xor_sync(0xffffffffu, mg, o);
-                mg = u < mg ? u : mg;
-            }
-            if (lane == 0) {
-                atomicAdd(&cnts[0], less);
-                atomicAdd(&cnts[1], eq);
-                // 64-bit min via two-step: serialised by warp count (<= 32 warps), done with a spin-free CAS-less loop below
-            }
-            __syncthreads();
-            // reduce the per-warp minima through shared memory (cand[] is free now)
-            if (lane == 0) cand[tid >> 5] = mg;
-            __syncthreads();
             if (tid == 0) {
-                unsigned long long best = ~0ull;
-                for (int q = 0; q < ((nt + 31) >> 5); ++q) best = cand[q] < best ? cand[q] : best;
-                res[1] = best;
+                NmBurstQRow o;
+                o.lo_key = lo_key; o.hi_key = hi_key;
+                o.e_prev = e_prev; o.first_prev = first_prev;
+                o.cnt_below = cnt_below; o.count = count; o.valid = valid ? 1 : 0;
+                o.rebuilds = n_rebuild; o.directs = n_direct; o.pad = 0;
+                a.qrow[row] = o;
             }
-            __syncthreads();
-            const double bv = (a.k_hi[w] < cnts[0] + cnts[1]) ? av : __longlong_as_double((long long)res[1]);
-            const double g = a.gamma[w];
-            const double diff = bv - av;
-            double lerp = av + diff * g;
-            if (g >= 0.5) lerp = bv - diff * (1.0 - g);
-            thr = (diff == 0.0) ? av : lerp;
         }
-        if (tid == 0) a.thr[item] = thr;
         __syncthreads();
     }
 }
@@ -340,7 +692,8 @@ NM_GLOBAL void nm_burst_feat_kernel(NmBurstFeatArgs a) {
 struct BurstsFam {
     FirBank bank;
     FftPlanHost hfft;
-    DevBuf d_env, d_ring, d_thr, d_colmap, d_e_end, d_n, d_lo, d_hi, d_gamma;
+    DevBuf d_env, d_ring, d_thr, d_colmap, d_e_end, d_n, d_lo, d_hi, d_gamma, d_qrow, d_qkey, d_qidx;
+    int incremental = 1;  // nm_set_burst_threshold_mode(0) selects the per-window re-selection (reference of the kernel)
     int nB = 0, C = 0, W = 0, S = 0, ring_n = 0, chunk = 0;
     long long cap = 0, Wp = 0, batch = 0;
     double q = 0.75, sfreq = 1000, seg_s = 1;
@@ -359,11 +712,17 @@ struct BurstsFam {
         if (d_env.ensure((size_t)chunk * C * nB * Wp * sizeof(double))) return -1;
         if (d_ring.ensure((size_t)C * nB * cap * sizeof(double))) return -1;
         if (d_thr.ensure((size_t)chunk * C * nB * sizeof(double))) return -1;
+        const size_t rows = (size_t)C * nB;
+        if (d_qrow.ensure(rows * sizeof(NmBurstQRow)) || d_qkey.ensure(rows * NM_BQ_CAP * 8) || d_qidx.ensure(rows * NM_BQ_CAP * 4)) return -1;
+        NM_CUDA_CHECK(cudaMemset(d_qrow.p, 0, rows * sizeof(NmBurstQRow)));
         return 0;
     }
-    void reset() { batch = 0; }
+    void reset() {
+        batch = 0;
+        if (d_qrow.p) cudaMemset(d_qrow.p, 0, (size_t)C * nB * sizeof(NmBurstQRow));  // valid = 0 for every row
+    }
     size_t epi_smem() const { return NmEpiBursts::smem_bytes_for(W, hfft.generic); }
-    static size_t thr_smem() { return NM_SEL_BINS * sizeof(int) + NM_SEL_CAND * 8 + 8 * sizeof(int) + 2 * 8 + 2 * sizeof(int) + 64; }
+    static size_t thr_smem() { return nm_bq_smem_bytes(); }
     int allow_smem(const nm_pipeline* p);
     int run(nm_pipeline* p, const NmRows& rows, int w0);
 };

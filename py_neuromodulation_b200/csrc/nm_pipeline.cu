@@ -307,9 +307,13 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     ta.k_lo = d_lo.as<int>(); ta.k_hi = d_hi.as<int>();
     ta.gamma = d_gamma.as<double>();
     ta.thr = d_thr.as<double>();
+    ta.qrow = d_qrow.as<NmBurstQRow>();
+    ta.qkey = d_qkey.as<unsigned long long>();
+    ta.qidx = d_qidx.as<unsigned>();
+    ta.incremental = incremental;
     const int n_thr = n * C * nB;
     p->prof_begin();
-    NM_LAUNCH(nm_burst_thr_kernel, dim3(std::min(n_thr, p->n_sm * 8)), dim3(NM_FFT_THREADS), thr_smem(), p->stream, ta);
+    NM_LAUNCH(nm_burst_thr_kernel, dim3(C * nB), dim3(NM_BQ_THREADS), thr_smem(), p->stream, ta);
     p->prof_end(NM_PROF_BURST_THR);
 
     NmBurstFeatArgs ba;
@@ -955,6 +959,31 @@ extern "C" int nm_get_profile(nm_pipeline* p, double* ms, long long* launches, i
     return NM_PROF_N;
 }
 extern "C" int nm_chunk_windows(nm_pipeline* p) { return p ? p->chunk : 0; }
+extern "C" int nm_burst_threshold_stats(nm_pipeline* p, long long* rebuilds, long long* direct_windows) {
+    NM_P_CHECK(p);
+    long long r = 0, d = 0;
+    if (p->bursts && p->bursts->d_qrow.p) {
+        cudaSetDevice(p->device);
+        NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+        std::vector<NmBurstQRow> rows((size_t)p->bursts->C * p->bursts->nB);
+        NM_CUDA_CHECK(cudaMemcpy(rows.data(), p->bursts->d_qrow.p, rows.size() * sizeof(NmBurstQRow), cudaMemcpyDeviceToHost));
+        for (const auto& q : rows) { r += q.rebuilds; d += q.directs; }
+    }
+    if (rebuilds) *rebuilds = r;
+    if (direct_windows) *direct_windows = d;
+    return 0;
+}
+extern "C" int nm_set_burst_threshold_mode(nm_pipeline* p, int incremental) {
+    NM_P_CHECK(p);
+    NM_CHECK(p->finalized, "call nm_finalize first");
+    if (p->bursts) {
+        cudaSetDevice(p->device);
+        NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+        p->bursts->incremental = incremental ? 1 : 0;
+        p->bursts->reset();
+    }
+    return 0;
+}
 
 template <class Epi>
 static void nm_describe_fir(std::string& s, const char* family, const FirBank& b, size_t epi_bytes) {

@@ -306,6 +306,7 @@ inline unsigned __ballot_sync(unsigned, int pred) {
 }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz(unsigned(v)); }
+inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 
 template <typename T>

@@ -191,3 +191,68 @@ def test_custom_python_feature_runs_next_to_gpu_features(backend, tmp_path):
         assert abs(df["ch0_avgref_chmean"].iloc[0] - pre[0].mean()) < 1e-12
     finally:
         nm.remove_custom_feature("channel_mean")
+
+
+def _burst_stress_signal(seed, c, t):
+    """Amplitude jumps (bracket rebuilds), an exactly constant stretch (ties -> direct selection), slow drift."""
+    rng = np.random.default_rng(seed)
+    tt = np.arange(t) / 1000.0
+    x = rng.standard_normal((c, t)) * 0.1
+    x += np.sin(2 * np.pi * 17 * tt) * (0.2 + 2.0 * ((tt % 7.0) > 5.0))      # strong beta episodes
+    x *= 1.0 + 0.5 * np.sin(2 * np.pi * 0.05 * tt)                             # slow amplitude drift
+    x[:, 12000:16500] = 0.0                                                    # flat line: envelope ties at 0
+    x[:, 30000:31000] *= 50.0                                                  # artefact
+    return x.astype(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("duration_s,n_windows", [(3.0, 420), (30.0, 150)])
+def test_burst_thresholds_incremental_equals_direct(backend, duration_s, n_windows):
+    """The sliding order-statistic state (bracket + FIFO queue) must reproduce the per-window re-selection bit for
+    bit: short history (constant expiry), chunk boundaries, streamed single windows, rebuilds, ties."""
+    x = _burst_stress_signal(3, 3, 46000)
+    s = nm.NMSettings.get_default().reset()
+    s.features.bursts = True
+    s.bursts_settings.time_duration_s = duration_s
+    s.postprocessing.feature_normalization = False
+    s.preprocessing = []
+    outs = []
+    for incremental in (True, False):
+        dp = nm.DataProcessor(sfreq=1000, settings=s, channels=get_default_channels_from_data(x), line_noise=50, verbose=False)
+        starts, lengths, _ = window_grid(x.shape[1], 1000, s.sampling_rate_features_hz, s.segment_length_features_ms)
+        starts = starts[:n_windows]
+        plan = dp.plan(int(lengths[0]))
+        plan.pipe.set_burst_threshold_mode(incremental)
+        cols, mat = dp.process_windows(x, starts, int(lengths[0]))
+        outs.append(mat)
+        if incremental:  # the sliding path must carry most windows: 6 rows x n_windows row-windows in total
+            rebuilds, direct = plan.pipe.burst_threshold_stats()
+            print(f"burst thresholds: {rebuilds} rebuilds, {direct} direct windows of {6 * n_windows}")
+            assert rebuilds + direct < 0.35 * 6 * n_windows
+    assert np.array_equal(outs[0], outs[1]), np.argwhere(outs[0] != outs[1])[:5]
+    # and against the oracle (true-ring variant) on the same windows
+    ref_cols, ref = orc.run_offline(x, 1000, s.model_dump(), max_windows=n_windows)  # faithful_bursts=False: true ring
+    ref = ref[:, : len(cols)]
+    check_matrix(cols, outs[0], ref_cols[: len(cols)], ref, "burst stress")
+    for j, k in enumerate(cols):
+        if k.endswith("_in_burst") or k.endswith("_duration_max"):
+            assert np.array_equal(outs[0][:, j], ref[:, j]), k
+
+
+def test_burst_thresholds_streaming_equals_batch(backend):
+    """One window per call (state saved / restored around every launch) == one batched run."""
+    x = _burst_stress_signal(5, 2, 20000)
+    s = nm.NMSettings.get_default().reset()
+    s.features.bursts = True
+    s.bursts_settings.time_duration_s = 2.0
+    s.postprocessing.feature_normalization = False
+    s.preprocessing = []
+    ch = get_default_channels_from_data(x)
+    dp = nm.DataProcessor(sfreq=1000, settings=s, channels=ch, line_noise=50, verbose=False)
+    starts, lengths, _ = window_grid(x.shape[1], 1000, s.sampling_rate_features_hz, s.segment_length_features_ms)
+    starts = starts[:120]
+    cols, mat = dp.process_windows(x, starts, 1000)
+    dp2 = nm.DataProcessor(sfreq=1000, settings=s, channels=ch, line_noise=50, verbose=False)
+    for k, st in enumerate(starts):
+        d = dp2.process(x[:, st : st + 1000])
+        v = np.array([float(t) for t in d.values()])
+        assert np.array_equal(v, mat[k]), k
