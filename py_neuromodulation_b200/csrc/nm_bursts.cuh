@@ -120,7 +120,7 @@ struct NmBurstThrArgs {
 #define NM_BQ_MASK (NM_BQ_CAP - 1)
 #define NM_BQ_HALF 448
 #define NM_BQ_SLACK 128
-#define NM_BQ_THREADS 128
+#define NM_BQ_THREADS 256
 
 struct NmBqSmem {
     int* hist;                  // NM_SEL_BINS
@@ -137,6 +137,31 @@ static NM_HD size_t nm_bq_smem_bytes() {
 
 NM_DEV unsigned long long nm_bq_key(const double* rrow, long long cap, long long i) {
     return (unsigned long long)__double_as_longlong(rrow[i % cap]);
+}
+
+// Visit the history samples i = i0 + lane_or_tid + k * step (i < i1) of the ring row: f(i, key).  `pos0` is the ring
+// position of sample 0 of the history (already reduced mod cap); positions wrap at most once.  Four independent loads
+// are in flight per thread -- these passes are latency bound otherwise (one CTA streams 240 kB out of L2).
+template <class F>
+NM_DEV void nm_bq_for_each(const double* NM_RESTRICT rrow, long long cap, long long pos0, int i0, int i1, int first_i, int step, F f) {
+    int i = i0 + first_i;
+    for (; i + 3 * step < i1; i += 4 * step) {
+        long long p0 = pos0 + i, p1 = p0 + step, p2 = p1 + step, p3 = p2 + step;
+        if (p0 >= cap) p0 -= cap;
+        if (p1 >= cap) p1 -= cap;
+        if (p2 >= cap) p2 -= cap;
+        if (p3 >= cap) p3 -= cap;
+        const double v0 = rrow[p0], v1 = rrow[p1], v2 = rrow[p2], v3 = rrow[p3];
+        f(i, (unsigned long long)__double_as_longlong(v0));
+        f(i + step, (unsigned long long)__double_as_longlong(v1));
+        f(i + 2 * step, (unsigned long long)__double_as_longlong(v2));
+        f(i + 3 * step, (unsigned long long)__double_as_longlong(v3));
+    }
+    for (; i < i1; i += step) {
+        long long p = pos0 + i;
+        if (p >= cap) p -= cap;
+        f(i, (unsigned long long)__double_as_longlong(rrow[p]));
+    }
 }
 
 // locate the bin that holds 0-based rank `rank` in hist[0, nbins): ctl[0] = bin, ctl[1] = count below it, ctl[2] = its count.
@@ -182,12 +207,9 @@ NM_DEV double nm_bq_select_direct(const double* rrow, long long cap, long long f
         for (int i = tid; i < NM_SEL_BINS; i += nt) sm.hist[i] = 0;
         __syncthreads();
         const unsigned long long dm = (1ull << width) - 1ull;
-        for (int i = tid; i < n; i += nt) {
-            long long p = first_mod + i;
-            if (p >= cap) p -= cap;
-            const unsigned long long key = (unsigned long long)__double_as_longlong(rrow[p]);
+        nm_bq_for_each(rrow, cap, first_mod, 0, n, tid, nt, [&](int, unsigned long long key) {
             if ((key & mask) == prefix) atomicAdd(&sm.hist[(int)((key >> shift) & dm)], 1);
-        }
+        });
         __syncthreads();
         nm_bq_find_bin(sm.hist, NM_SEL_BINS, rank, sm.ctl, tid);
         __syncthreads();
@@ -205,15 +227,12 @@ NM_DEV double nm_bq_select_direct(const double* rrow, long long cap, long long f
     if (!resolved) {
         if (tid == 0) sm.ctl[3] = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += nt) {
-            long long p = first_mod + i;
-            if (p >= cap) p -= cap;
-            const unsigned long long key = (unsigned long long)__double_as_longlong(rrow[p]);
+        nm_bq_for_each(rrow, cap, first_mod, 0, n, tid, nt, [&](int, unsigned long long key) {
             if ((key & mask) == prefix) {
                 const int slot = atomicAdd(&sm.ctl[3], 1);
                 if (slot < NM_SEL_CAND) sm.qk[slot] = key;
             }
-        }
+        });
         __syncthreads();
         const int m = sm.ctl[3] < NM_SEL_CAND ? sm.ctl[3] : NM_SEL_CAND;
         for (int i = tid; i < m; i += nt) {
@@ -236,14 +255,11 @@ NM_DEV double nm_bq_select_direct(const double* rrow, long long cap, long long f
         __syncthreads();
         int less = 0, eq = 0;
         unsigned long long mg = ~0ull;
-        for (int i = tid; i < n; i += nt) {
-            long long p = first_mod + i;
-            if (p >= cap) p -= cap;
-            const unsigned long long key = (unsigned long long)__double_as_longlong(rrow[p]);
+        nm_bq_for_each(rrow, cap, first_mod, 0, n, tid, nt, [&](int, unsigned long long key) {
             less += key < a_key;
             eq += key == a_key;
             if (key > a_key && key < mg) mg = key;
-        }
+        });
         less = nm_warp_sum_i(less);
         eq = nm_warp_sum_i(eq);
         for (int o = 16; o > 0; o >>= 1) {
@@ -276,7 +292,8 @@ NM_DEV bool nm_bq_rebuild(const double* rrow, long long cap, long long first, in
     // level 1: sign + exponent
     for (int i = tid; i < NM_SEL_BINS; i += nt) sm.hist[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += nt) atomicAdd(&sm.hist[(int)(nm_bq_key(rrow, cap, first + i) >> 52)], 1);
+    const long long first_mod = first % cap;
+    nm_bq_for_each(rrow, cap, first_mod, 0, n, tid, nt, [&](int, unsigned long long key) { atomicAdd(&sm.hist[(int)(key >> 52)], 1); });
     __syncthreads();
     nm_bq_find_bin(sm.hist, NM_SEL_BINS, k_lo, sm.ctl, tid);
     __syncthreads();
@@ -286,10 +303,9 @@ NM_DEV bool nm_bq_rebuild(const double* rrow, long long cap, long long first, in
     // level 2: the top 12 mantissa bits inside that binade
     for (int i = tid; i < NM_SEL_BINS; i += nt) sm.hist[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += nt) {
-        const unsigned long long key = nm_bq_key(rrow, cap, first + i);
+    nm_bq_for_each(rrow, cap, first_mod, 0, n, tid, nt, [&](int, unsigned long long key) {
         if ((key >> 52) == d1) atomicAdd(&sm.hist[(int)((key >> 40) & 0xfffull)], 1);
-    }
+    });
     __syncthreads();
     nm_bq_find_bin(sm.hist, NM_SEL_BINS, k_lo - below1, sm.ctl, tid);
     __syncthreads();
@@ -325,10 +341,7 @@ NM_DEV bool nm_bq_rebuild(const double* rrow, long long cap, long long first, in
     const int seg = (n + nwarp - 1) / nwarp;
     const int s0 = min(n, wid * seg), s1 = min(n, s0 + seg);
     int mine = 0;
-    for (int i = s0 + lane; i < s1; i += 32) {
-        const unsigned long long key = nm_bq_key(rrow, cap, first + i);
-        mine += (key >= lo_key && key < hi_key) ? 1 : 0;
-    }
+    nm_bq_for_each(rrow, cap, first_mod, s0, s1, lane, 32, [&](int, unsigned long long key) { mine += (key >= lo_key && key < hi_key) ? 1 : 0; });
     mine = nm_warp_sum_i(mine);
     __syncthreads();
     if (lane == 0) sm.wcnt[wid] = mine;
@@ -340,7 +353,9 @@ NM_DEV bool nm_bq_rebuild(const double* rrow, long long cap, long long first, in
         unsigned long long key = 0ull;
         bool in = false;
         if (i < s1) {
-            key = nm_bq_key(rrow, cap, first + i);
+            long long p = first_mod + i;
+            if (p >= cap) p -= cap;
+            key = (unsigned long long)__double_as_longlong(rrow[p]);
             in = key >= lo_key && key < hi_key;
         }
         const unsigned bm = __ballot_sync(0xffffffffu, in);
@@ -366,8 +381,8 @@ NM_DEV void nm_bq_select_queue(const NmBqSmem& sm, int head, int count, unsigned
     int rr = r;
     unsigned long long a_key = 0ull;
     while (true) {
-        int sh = 0;
-        while (((range - 1ull) >> sh) > 255ull) ++sh;
+        int sh = 56 - __clzll((long long)((range - 1ull) | 1ull));  // smallest shift with (range - 1) >> sh <= 255
+        if (sh < 0) sh = 0;
         for (int i = tid; i < 256; i += nt) sm.hist[i] = 0;
         __syncthreads();
         for (int j = tid; j < count; j += nt) {
@@ -482,7 +497,8 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
                 if (tid == 0) { sm.ctl[10] = 0; sm.ctl[11] = 0; }
                 __syncthreads();
                 int delta = 0;
-                for (long long i = first_prev + tid; i < first; i += nt) delta -= (nm_bq_key(rrow, a.cap, i) < lo_key) ? 1 : 0;
+                nm_bq_for_each(rrow, a.cap, first_prev % a.cap, 0, (int)(first - first_prev), tid, nt,
+                               [&](int, unsigned long long key) { delta -= (key < lo_key) ? 1 : 0; });
                 int nexp = 0;
                 for (int j = tid; j < count; j += nt) nexp += ((int)(sm.qi[(head + j) & NM_BQ_MASK] - (unsigned)first) < 0) ? 1 : 0;
                 nexp = nm_warp_sum_i(nexp);
@@ -492,12 +508,15 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
                 head = (head + nexp) & NM_BQ_MASK;
                 count -= nexp;
                 const int n_enter = (int)(e - e_prev);
+                const long long enter_mod = e_prev % a.cap;
                 for (int base = 0; base < n_enter && valid; base += nt) {
                     const int i = base + tid;
                     unsigned long long key = 0ull;
                     bool in = false;
                     if (i < n_enter) {
-                        key = nm_bq_key(rrow, a.cap, e_prev + i);
+                        long long p = enter_mod + i;
+                        if (p >= a.cap) p -= a.cap;
+                        key = (unsigned long long)__double_as_longlong(rrow[p]);
                         if (key < lo_key) delta += 1;
                         else in = key < hi_key;
                     }
