@@ -19,7 +19,7 @@
 #include "nm_prep.cuh"
 #include "nm_firbank.h"
 #include "nm_scan.cuh"
-#include "nm_spec.cuh"
+#include "nm_specx.cuh"
 #include "nm_bursts.cuh"
 #include "nm_sharpwave.cuh"
 #include "nm_norm.cuh"
@@ -55,6 +55,17 @@ struct SpectralFam {
     FftPlanHost fft;
     DevBuf d_win, d_lo, d_hi, d_colmap;
     int k0 = 0, nk = 0, per_ch = 0;
+    bool fast = false;  // register-blocked three-pass plan (nm_specx.cuh) instead of the generic mixed-radix kernel
+    int nsegv() const { return cfg.keep_segments ? cfg.nseg : 1; }
+    int nbuf() const { return cfg.nper == 1000 ? NmSx1000::NBUF : (cfg.nper == 2000 ? NmSx2000::NBUF : NmSx500::NBUF); }
+    int threads() const { return !fast ? NM_FFT_THREADS : (cfg.nper == 500 ? NmSx500::NT : NmSx1000::NT); }
+    size_t smem() const { return fast ? nm_specx_smem_bytes(nbuf(), nk, nsegv()) : nm_spec_smem_bytes(cfg.nper, fft.generic, nk, nsegv()); }
+    void (*kernel() const)(NmSpecArgs) {
+        if (!fast) return nm_spec_kernel;
+        if (cfg.nper == 1000) return nm_specx_kernel<NmSx1000>;
+        if (cfg.nper == 2000) return nm_specx_kernel<NmSx2000>;
+        return nm_specx_kernel<NmSx500>;
+    }
 };
 
 struct BandpowerFam {
@@ -532,7 +543,14 @@ extern "C" int nm_add_spectral(nm_pipeline* p, const nm_spectral_cfg* cfg) {
     if (kmax <= kmin) { kmin = 0; kmax = 1; }
     f->k0 = kmin;
     f->nk = kmax - kmin;
-    if (f->fft.build(cfg->nper, p->stream)) return -1;
+    f->fast = nm_specx_supported(cfg->nper);
+    if (f->fast) {
+        const std::vector<int> radices = cfg->nper == 1000 ? std::vector<int>{10, 10, 10}
+                                         : (cfg->nper == 2000 ? std::vector<int>{20, 10, 10} : std::vector<int>{10, 10, 5});
+        if (f->fft.build_with(cfg->nper, radices, p->stream)) return -1;
+    } else if (f->fft.build(cfg->nper, p->stream)) {
+        return -1;
+    }
     if (cfg->win && f->d_win.upload(cfg->win, (size_t)cfg->nper, p->stream)) return -1;
     if (f->d_lo.upload(cfg->band_lo, (size_t)cfg->n_bands, p->stream)) return -1;
     if (f->d_hi.upload(cfg->band_hi, (size_t)cfg->n_bands, p->stream)) return -1;
@@ -640,8 +658,10 @@ extern "C" int nm_finalize(nm_pipeline* p) {
     if (p->bandpower && nm_allow_fir_smem<NmEpiBandpower>(p->bandpower->bank, p->bandpower->epi_smem(), p)) return -1;
     size_t spec_max = 0;
     for (auto& f : p->spectral)
-        spec_max = std::max(spec_max, nm_spec_smem_bytes(f->cfg.nper, f->fft.generic, f->nk, f->cfg.keep_segments ? f->cfg.nseg : 1));
-    if (!p->spectral.empty() && nm_allow_smem(nm_spec_kernel, spec_max, p)) return -1;
+        if (!f->fast) spec_max = std::max(spec_max, f->smem());
+    if (spec_max && nm_allow_smem(nm_spec_kernel, spec_max, p)) return -1;
+    for (auto& f : p->spectral)
+        if (f->fast && nm_allow_smem(f->kernel(), f->smem(), p)) return -1;
     if (p->bursts && p->bursts->allow_smem(p)) return -1;
     if (p->sharpwave && p->sharpwave->allow_smem(p)) return -1;
     NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
@@ -811,9 +831,14 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         a.want_spectrum = c.want_spectrum;
         a.out = out_for(f->d_colmap, f->per_ch);
         a.n_items = n * ((p->C + 1) / 2);
-        const size_t sm = nm_spec_smem_bytes(c.nper, f->fft.generic, f->nk, c.keep_segments ? c.nseg : 1);
+        const size_t sm = f->smem();
         p->prof_begin();
-        NM_LAUNCH(nm_spec_kernel, dim3(p->grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, a);
+        if (f->fast) {
+            auto k = f->kernel();
+            NM_LAUNCH(k, dim3(nm_resident_grid(p, k, f->threads(), sm, a.n_items)), dim3(f->threads()), sm, p->stream, a);
+        } else {
+            NM_LAUNCH(nm_spec_kernel, dim3(p->grid_for(sm, a.n_items, NM_FFT_THREADS)), dim3(NM_FFT_THREADS), sm, p->stream, a);
+        }
         p->prof_end(NM_PROF_SPEC);
         p->launches++;
     }
@@ -1006,7 +1031,8 @@ extern "C" int nm_describe_plan(nm_pipeline* p, char* buf, int n) {
     }
     if (p->has_scan && !(p->notch && nm_convx_pick<NmEpiStoreScan>(*p->notch))) s += "scan: nm_scan_kernel\n";
     for (auto& f : p->spectral) {
-        snprintf(line, sizeof(line), "spectral: nm_spec_kernel nper=%d nseg=%d bins=%d\n", f->cfg.nper, f->cfg.nseg, f->nk);
+        snprintf(line, sizeof(line), "spectral: %s nper=%d nseg=%d bins=%d threads=%d smem=%zu\n", f->fast ? "nm_specx_kernel" : "nm_spec_kernel",
+                 f->cfg.nper, f->cfg.nseg, f->nk, f->threads(), f->smem());
         s += line;
     }
     if (p->bandpower) nm_describe_fir<NmEpiBandpower>(s, "bandpower", p->bandpower->bank, p->bandpower->epi_smem());
