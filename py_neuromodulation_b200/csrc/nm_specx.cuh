@@ -112,14 +112,26 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(PL::NT, 4) nm_specx_kernel(NmSpecArgs a) {
             cx<double> v[R0];
             double sum[2] = {0.0, 0.0};
             if (active) {
+                if (base >= 0 && base + N <= W) {  // segment inside the window (FFT, Welch): plain coalesced loads
+#pragma unroll
+                    for (int t = 0; t < R0; ++t) {
+                        const int n = base + tid + NA * t;
+                        const double va = r0[n], vb = r1[n];
+                        v[t] = {va, has2 ? vb : 0.0};
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < R0; ++t) {
+                        const int n = tid + NA * t;
+                        const double va = nm_spec_sample(r0, base + n, W, a.ext_even, a.ext_len);
+                        const double vb = has2 ? nm_spec_sample(r1, base + n, W, a.ext_even, a.ext_len) : 0.0;
+                        v[t] = {va, vb};
+                    }
+                }
 #pragma unroll
                 for (int t = 0; t < R0; ++t) {
-                    const int n = tid + NA * t;
-                    const double va = nm_spec_sample(r0, base + n, W, a.ext_even, a.ext_len);
-                    const double vb = has2 ? nm_spec_sample(r1, base + n, W, a.ext_even, a.ext_len) : 0.0;
-                    v[t] = {va, vb};
-                    sum[0] += va;
-                    sum[1] += vb;
+                    sum[0] += v[t].re;
+                    sum[1] += v[t].im;
                 }
             }
             if (a.detrend) {
