@@ -424,9 +424,10 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, BANK ? NmCxPlan<P>::MINBK : NmC
 #pragma unroll
                     for (int t = 0; t < 16; ++t) work[tid + NT * t] = v[t];
                     __syncthreads();
-                    if (last && next < a.n_items) nm_cx_load_item<P, REFLECT>(v, a, next, npair, tid, nw, nc0, nhas2);
                     epi.run(work, o0, W, a.in.n_ch, w, c0, has2, fi, scratch, tid, NT);
                     __syncthreads();
+                    // (no early prefetch here: these epilogues are register hungry and long enough to hide nothing)
+                    if (last && next < a.n_items) nm_cx_load_item<P, REFLECT>(v, a, next, npair, tid, nw, nc0, nhas2);
                 }
             }
         }

@@ -25,6 +25,7 @@ struct NmSwCfg {
     int pair_est;        // apply the estimator between the Peak and Trough passes
     int want_num_peaks;
     int maxn;            // capacity of the per-row peak lists (W/2 + 2)
+    int tmp_in_tail;     // the median scratch (4 x maxn doubles) lives behind the filtered rows in the transform buffer
 };
 
 struct NmSwLists {
@@ -33,10 +34,12 @@ struct NmSwLists {
     double* tmp;
 };
 
-static NM_HD size_t nm_sw_row_bytes(int maxn) {
-    size_t b = (size_t)6 * maxn * sizeof(unsigned short) + (size_t)maxn;
-    b = (b + 7) & ~(size_t)7;
-    return b + (size_t)maxn * sizeof(double);
+static NM_HD size_t nm_sw_list_bytes(int maxn) {
+    const size_t b = (size_t)6 * maxn * sizeof(unsigned short) + (size_t)maxn;
+    return (b + 7) & ~(size_t)7;
+}
+static NM_HD size_t nm_sw_row_bytes(int maxn, int tmp_in_tail) {
+    return nm_sw_list_bytes(maxn) + (tmp_in_tail ? 0 : (size_t)maxn * sizeof(double));
 }
 
 NM_DEV double nm_sw_v(const cx<double>* x, int comp, double sign, int t) { return sign * (comp ? x[t].im : x[t].re); }
@@ -168,10 +171,10 @@ NM_DEV bool nm_sw_feature(const cx<double>* x, int comp, double sign, int W, con
 }
 
 // one warp: full analysis of one row; results[combo] and results[n_combo] = num_peaks
-NM_DEV void nm_sw_analyze(const cx<double>* x, int comp, double sign, int W, const NmSwCfg& c, const NmSwLists& l, double* results,
-                          int lane) {
-    const int nP0 = nm_sw_local_maxima(x, comp, sign, W, l.rawP, lane);
-    const int nT0 = nm_sw_local_maxima(x, comp, -sign, W, l.rawT, lane);
+// nP0 / nT0: local maxima of sign*x in l.rawP and of -sign*x in l.rawT (the latter is the OTHER polarity's rawP list:
+// the two passes of a channel share their local-maxima scans)
+NM_DEV void nm_sw_analyze(const cx<double>* x, int comp, double sign, int W, const NmSwCfg& c, const NmSwLists& l, int nP0, int nT0,
+                          double* results, int lane) {
     const int nP = nm_sw_select(x, comp, sign, l.rawP, nP0, c.D_pk, l.st, l.KP, lane);
     const int nT = nm_sw_select(x, comp, -sign, l.rawT, nT0, c.D_tr, l.st, l.KT, lane);
 
@@ -288,28 +291,48 @@ struct NmEpiSharpwave {
     static constexpr bool kRegsOnly = false, kReflectOk = false, kSameOk = true, kConvxOnly = false;  // nm_convx_kernel instantiation traits
     NmSwCfg cfg;
     NmOut out;  // per_ch = nF * (n_combo + 1) * 2 ; slot (f*(n_combo+1) + combo)*2 + polarity
-    static NM_HD size_t smem_bytes_for(int maxn, int n_combo) {
-        return 4 * nm_sw_row_bytes(maxn) + (size_t)4 * (n_combo + 1) * sizeof(double) + 16;
+    static NM_HD size_t smem_bytes_for(int maxn, int n_combo, int tmp_in_tail) {
+        return 4 * nm_sw_row_bytes(maxn, tmp_in_tail) + (size_t)4 * (n_combo + 1) * sizeof(double) + 4 * sizeof(int) + 16;
+    }
+    NM_DEV void lists_for(NmSwLists& l, unsigned char* scratch, const cx<double>* tail, int ar) const {
+        unsigned char* base = scratch + (size_t)ar * nm_sw_row_bytes(cfg.maxn, cfg.tmp_in_tail);
+        l.rawP = reinterpret_cast<unsigned short*>(base);
+        l.rawT = l.rawP + cfg.maxn;
+        l.KP = l.rawT + cfg.maxn;
+        l.KT = l.KP + cfg.maxn;
+        l.Lp = l.KT + cfg.maxn;
+        l.Rp = l.Lp + cfg.maxn;
+        l.st = reinterpret_cast<unsigned char*>(l.Rp + cfg.maxn);
+        l.tmp = cfg.tmp_in_tail ? const_cast<double*>(reinterpret_cast<const double*>(tail)) + (size_t)ar * cfg.maxn
+                                : reinterpret_cast<double*>(base + nm_sw_list_bytes(cfg.maxn));
     }
     NM_DEV void run(const cx<double>* buf, int o0, int W, int /*n_ch*/, int w, int c0, bool has2, int f, unsigned char* scratch,
                     int tid, int nt) const {
         const int lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
-        const size_t rb = nm_sw_row_bytes(cfg.maxn);
+        const size_t rb = nm_sw_row_bytes(cfg.maxn, cfg.tmp_in_tail);
         double* results = reinterpret_cast<double*>(scratch + 4 * rb);
+        int* nraw = reinterpret_cast<int*>(results + (size_t)4 * (cfg.n_combo + 1));  // local-maxima counts of the 4 rows
+        const cx<double>* x = buf + o0;
+        const cx<double>* tail = x + W;  // free part of the transform buffer (host checked the capacity: tmp_in_tail)
+        // phase 1: analysis row (comp, pol) scans the local maxima of (pol ? -x : x) into its rawP list
         for (int ar = wid; ar < 4; ar += nwarp) {
             const int comp = ar >> 1, pol = ar & 1;
             if (comp == 1 && !has2) continue;
-            unsigned char* base = scratch + (size_t)ar * rb;
             NmSwLists l;
-            l.rawP = reinterpret_cast<unsigned short*>(base);
-            l.rawT = l.rawP + cfg.maxn;
-            l.KP = l.rawT + cfg.maxn;
-            l.KT = l.KP + cfg.maxn;
-            l.Lp = l.KT + cfg.maxn;
-            l.Rp = l.Lp + cfg.maxn;
-            l.st = reinterpret_cast<unsigned char*>(l.Rp + cfg.maxn);
-            l.tmp = reinterpret_cast<double*>(base + (((size_t)6 * cfg.maxn * sizeof(unsigned short) + cfg.maxn + 7) & ~(size_t)7));
-            nm_sw_analyze(buf + o0, comp, pol ? -1.0 : 1.0, W, cfg, l, results + (size_t)ar * (cfg.n_combo + 1), lane);
+            lists_for(l, scratch, tail, ar);
+            const int n = nm_sw_local_maxima(x, comp, pol ? -1.0 : 1.0, W, l.rawP, lane);
+            if (lane == 0) nraw[ar] = n;
+        }
+        __syncthreads();
+        // phase 2: the other polarity's list serves as this row's trough candidates
+        for (int ar = wid; ar < 4; ar += nwarp) {
+            const int comp = ar >> 1, pol = ar & 1;
+            if (comp == 1 && !has2) continue;
+            NmSwLists l, other;
+            lists_for(l, scratch, tail, ar);
+            lists_for(other, scratch, tail, ar ^ 1);
+            l.rawT = other.rawP;
+            nm_sw_analyze(x, comp, pol ? -1.0 : 1.0, W, cfg, l, nraw[ar], nraw[ar ^ 1], results + (size_t)ar * (cfg.n_combo + 1), lane);
         }
         __syncthreads();
         const int per_f = (cfg.n_combo + 1) * 2;
@@ -354,10 +377,12 @@ struct SharpwaveFam {
         cfg.pair_est = pair_est;
         cfg.want_num_peaks = want_num_peaks;
         cfg.maxn = W / 2 + 2;
+        // the transform buffer holds P >= W + (L-1)/2 elements; whatever follows the W filtered samples is free
+        cfg.tmp_in_tail = ((size_t)(bank.P - W) * sizeof(cx<double>) >= (size_t)4 * cfg.maxn * sizeof(double)) ? 1 : 0;
         per_ch = nF * (n_combo + 1) * 2;
         return d_colmap.upload(colmap, (size_t)C * per_ch, s);
     }
-    size_t epi_smem() const { return NmEpiSharpwave::smem_bytes_for(cfg.maxn, cfg.n_combo); }
+    size_t epi_smem() const { return NmEpiSharpwave::smem_bytes_for(cfg.maxn, cfg.n_combo, cfg.tmp_in_tail); }
     int allow_smem(const nm_pipeline* p);
     int run(nm_pipeline* p, const NmRows& rows, int w0);
 };

@@ -130,7 +130,11 @@ class ShardedRun:
         self.pipe.synchronize()
 
     def gather(self, n_windows: int):
-        """Gather the (n_windows, F_local) blocks to rank 0; returns a host array (n_windows, world*F_local) there, else None."""
+        """Gather the (n_windows, F_local) blocks to rank 0; returns a host array (n_windows, sum F_local) there, else None.
+
+        Device staging blocks and the pinned host matrix are allocated once and reused (the returned array is a view
+        of that pinned buffer: copy it if it must survive the next call).
+        """
         import torch
         import torch.distributed as dist
 
@@ -139,17 +143,32 @@ class ShardedRun:
         if not (dist.is_initialized() and dist.get_world_size() > 1):
             return local.cpu().numpy().copy() if self.on_gpu else local.numpy().copy()
         world, rank = dist.get_world_size(), dist.get_rank()
-        # shards may differ by one channel: agree on the widest block, pad, gather, trim
-        widths = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
-        dist.all_gather(widths, torch.tensor([cols], dtype=torch.int64, device=local.device))
-        widths = [int(w.item()) for w in widths]
-        wmax = max(widths)
-        block = local if cols == wmax else torch.cat([local, local.new_zeros(n_windows, wmax - cols)], dim=1)
-        block = block.contiguous()
-        if rank == 0:
-            parts = [torch.empty_like(block) for _ in range(world)]
-            dist.gather(block, gather_list=parts, dst=0)
-            full = torch.cat([p[:, :w] for p, w in zip(parts, widths)], dim=1)
-            return full.cpu().numpy() if self.on_gpu else full.numpy().copy()
-        dist.gather(block, gather_list=None, dst=0)
-        return None
+        key = (n_windows, cols)
+        if getattr(self, "_gather_key", None) != key:
+            # shards may differ by one channel: agree on the widest block once, pad, gather, trim
+            widths = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
+            dist.all_gather(widths, torch.tensor([cols], dtype=torch.int64, device=local.device))
+            self._widths = [int(w.item()) for w in widths]
+            wmax = max(self._widths)
+            self._block = None if cols == wmax else local.new_zeros(n_windows, wmax)
+            self._parts = [local.new_empty(n_windows, wmax) for _ in range(world)] if rank == 0 else None
+            self._host = None
+            if rank == 0:
+                self._host = torch.empty((n_windows, sum(self._widths)), dtype=local.dtype, pin_memory=self.on_gpu)
+            self._gather_key = key
+        if self._block is None:
+            block = local if local.is_contiguous() else local.contiguous()
+        else:
+            self._block[:, :cols].copy_(local)
+            block = self._block
+        if rank != 0:
+            dist.gather(block, gather_list=None, dst=0)
+            return None
+        dist.gather(block, gather_list=self._parts, dst=0)
+        off = 0
+        for part, w in zip(self._parts, self._widths):
+            self._host[:, off : off + w].copy_(part[:, :w], non_blocking=True)
+            off += w
+        if self.on_gpu:
+            torch.cuda.current_stream().synchronize()
+        return self._host.numpy()
