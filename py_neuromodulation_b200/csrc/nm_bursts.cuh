@@ -95,7 +95,7 @@ struct NmBurstQRow {
     long long e_prev, first_prev;  // the state describes the history [first_prev, e_prev)
     int cnt_below, count, valid;
     int rebuilds, directs;  // statistics since the last reset: bracket rebuilds, windows served by the direct selection
-    int pad;
+    int pad;                // (statistics) brackets re-centred without a histogram rebuild
 };
 
 struct NmBurstThrArgs {
@@ -284,11 +284,62 @@ NM_DEV double nm_bq_select_direct(const double* rrow, long long cap, long long f
     return thr;
 }
 
+// Fill the queue, in time order, with the history samples of [first, first + n) whose key lies in [lo_key, hi_key) and
+// count the samples below lo_key.  Two passes without atomics: warp `wid` owns a contiguous time segment, counts its
+// matches, and after a prefix over the warps writes them at its offset.  Returns false (uniformly) if they do not fit.
+NM_DEV bool nm_bq_gather(const double* rrow, long long cap, long long first, int n, unsigned long long lo_key, unsigned long long hi_key,
+                         const NmBqSmem& sm, int& cnt_below, int& head, int& count, int tid, int nt) {
+    const int lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
+    const long long first_mod = first % cap;
+    const int seg = (n + nwarp - 1) / nwarp;
+    const int s0 = min(n, wid * seg), s1 = min(n, s0 + seg);
+    int mine = 0, below = 0;
+    nm_bq_for_each(rrow, cap, first_mod, s0, s1, lane, 32, [&](int, unsigned long long key) {
+        mine += (key >= lo_key && key < hi_key) ? 1 : 0;
+        below += (key < lo_key) ? 1 : 0;
+    });
+    mine = nm_warp_sum_i(mine);
+    below = nm_warp_sum_i(below);
+    __syncthreads();
+    if (lane == 0) { sm.wcnt[wid] = mine; sm.hist[wid] = below; }
+    __syncthreads();
+    int off = 0, total = 0, nb = 0;
+    for (int q = 0; q < nwarp; ++q) {
+        if (q < wid) off += sm.wcnt[q];
+        total += sm.wcnt[q];
+        nb += sm.hist[q];
+    }
+    __syncthreads();
+    if (total > NM_BQ_CAP - NM_BQ_SLACK) return false;
+    for (int i0 = s0; i0 < s1; i0 += 32) {
+        const int i = i0 + lane;
+        unsigned long long key = 0ull;
+        bool in = false;
+        if (i < s1) {
+            long long p = first_mod + i;
+            if (p >= cap) p -= cap;
+            key = (unsigned long long)__double_as_longlong(rrow[p]);
+            in = key >= lo_key && key < hi_key;
+        }
+        const unsigned bm = __ballot_sync(0xffffffffu, in);
+        if (in) {
+            const int pos = off + __popc(bm & ((1u << lane) - 1u));
+            sm.qk[pos] = key;
+            sm.qi[pos] = (unsigned)(first + i);
+        }
+        off += __popc(bm);
+    }
+    head = 0;
+    count = total;
+    cnt_below = nb;
+    __syncthreads();
+    return true;
+}
+
 // (Re)build the bracket around rank k_lo of the history [first, first + n) and fill the queue in time order.
 // Returns false (uniformly) when no bracket fits the queue; the caller then falls back to the direct selection.
 NM_DEV bool nm_bq_rebuild(const double* rrow, long long cap, long long first, int n, int k_lo, const NmBqSmem& sm, unsigned long long& lo_key,
                           unsigned long long& hi_key, int& cnt_below, int& head, int& count, int tid, int nt) {
-    const int lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
     // level 1: sign + exponent
     for (int i = tid; i < NM_SEL_BINS; i += nt) sm.hist[i] = 0;
     __syncthreads();
@@ -329,47 +380,14 @@ NM_DEV bool nm_bq_rebuild(const double* rrow, long long cap, long long first, in
         sm.ctl[9] = below1 + below2 - acc_lo;
     }
     __syncthreads();
-    const int total = sm.ctl[8];
-    if (total > NM_BQ_CAP - NM_BQ_SLACK) {  // a single sub-bin does not fit (massive ties)
+    if (sm.ctl[8] > NM_BQ_CAP - NM_BQ_SLACK) {  // a single sub-bin does not fit (massive ties)
         __syncthreads();
         return false;
     }
     lo_key = (d1 << 52) | ((unsigned long long)sm.ctl[6] << 40);
     hi_key = (d1 << 52) + (((unsigned long long)sm.ctl[7] + 1ull) << 40);
-    cnt_below = sm.ctl[9];
-    // gather in time order: warp `wid` owns the contiguous segment [wid*seg, (wid+1)*seg) of the history
-    const int seg = (n + nwarp - 1) / nwarp;
-    const int s0 = min(n, wid * seg), s1 = min(n, s0 + seg);
-    int mine = 0;
-    nm_bq_for_each(rrow, cap, first_mod, s0, s1, lane, 32, [&](int, unsigned long long key) { mine += (key >= lo_key && key < hi_key) ? 1 : 0; });
-    mine = nm_warp_sum_i(mine);
     __syncthreads();
-    if (lane == 0) sm.wcnt[wid] = mine;
-    __syncthreads();
-    int off = 0;
-    for (int q = 0; q < wid; ++q) off += sm.wcnt[q];
-    for (int i0 = s0; i0 < s1; i0 += 32) {
-        const int i = i0 + lane;
-        unsigned long long key = 0ull;
-        bool in = false;
-        if (i < s1) {
-            long long p = first_mod + i;
-            if (p >= cap) p -= cap;
-            key = (unsigned long long)__double_as_longlong(rrow[p]);
-            in = key >= lo_key && key < hi_key;
-        }
-        const unsigned bm = __ballot_sync(0xffffffffu, in);
-        if (in) {
-            const int pos = off + __popc(bm & ((1u << lane) - 1u));
-            sm.qk[pos] = key;
-            sm.qi[pos] = (unsigned)(first + i);
-        }
-        off += __popc(bm);
-    }
-    head = 0;
-    count = total;
-    __syncthreads();
-    return true;
+    return nm_bq_gather(rrow, cap, first, n, lo_key, hi_key, sm, cnt_below, head, count, tid, nt);
 }
 
 // rank-`r` key (0-based) among the queue entries, plus (when wanted) the next order statistic: res[0] = a, res[1] = b.
@@ -475,7 +493,7 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
         unsigned long long lo_key = st.lo_key, hi_key = st.hi_key;
         long long e_prev = st.e_prev, first_prev = st.first_prev;
         int cnt_below = st.cnt_below, count = st.count, head = 0;
-        int n_rebuild = st.rebuilds, n_direct = st.directs;
+        int n_rebuild = st.rebuilds, n_direct = st.directs, n_recentre = st.pad;
         bool valid = a.incremental && st.valid != 0;
         if (valid) {
             for (int j = tid; j < count; j += nt) {
@@ -546,8 +564,22 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
                 __syncthreads();
                 cnt_below += sm.ctl[10];
                 const int r = k_lo - cnt_below;
-                if (r < 0 || r + (want_next ? 1 : 0) >= count) valid = false;
                 __syncthreads();
+                if (valid && (r < 0 || r + (want_next ? 1 : 0) >= count)) {
+                    // the quantile has just drifted past an edge of the bracket: re-centre a bracket of the same key
+                    // width on that edge (two atomic-free passes) before falling back to the histogram rebuild
+                    const unsigned long long hw = (hi_key - lo_key) >> 1;
+                    const unsigned long long c = (r < 0) ? lo_key : hi_key;
+                    const unsigned long long nlo = c > hw ? c - hw : 0ull, nhi = c + hw;
+                    ++n_recentre;
+                    valid = nhi > nlo && nm_bq_gather(rrow, a.cap, first, n, nlo, nhi, sm, cnt_below, head, count, tid, nt);
+                    if (valid) {
+                        lo_key = nlo;
+                        hi_key = nhi;
+                        const int r2 = k_lo - cnt_below;
+                        if (r2 < 0 || r2 + (want_next ? 1 : 0) >= count) valid = false;
+                    }
+                }
             }
             double thr;
             bool have = false;
@@ -594,7 +626,7 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
                 o.lo_key = lo_key; o.hi_key = hi_key;
                 o.e_prev = e_prev; o.first_prev = first_prev;
                 o.cnt_below = cnt_below; o.count = count; o.valid = valid ? 1 : 0;
-                o.rebuilds = n_rebuild; o.directs = n_direct; o.pad = 0;
+                o.rebuilds = n_rebuild; o.directs = n_direct; o.pad = n_recentre;
                 a.qrow[row] = o;
             }
         }

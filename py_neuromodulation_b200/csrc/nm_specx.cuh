@@ -116,8 +116,8 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(PL::NT, 4) nm_specx_kernel(NmSpecArgs a) {
 #pragma unroll
                     for (int t = 0; t < R0; ++t) {
                         const int n = base + tid + NA * t;
-                        const double va = r0[n], vb = r1[n];
-                        v[t] = {va, has2 ? vb : 0.0};
+                        v[t].re = r0[n];
+                        v[t].im = has2 ? r1[n] : 0.0;
                     }
                 } else {
 #pragma unroll
