@@ -646,7 +646,9 @@ extern "C" int nm_finalize(nm_pipeline* p) {
     p->Wp = (p->W + 1) & ~1;
     // chunk of windows whose notched copy (and burst envelopes) stays comfortably inside the 126 MB L2
     const size_t per_window = (size_t)p->C * p->Wp * sizeof(double) * (1 + (p->bursts ? p->bursts->nB : 0));
-    p->chunk = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)96 << 20) / per_window));
+    size_t chunk_mb = 96;
+    if (const char* e = getenv("NMB200_CHUNK_MB")) chunk_mb = (size_t)std::max(1, atoi(e));  // tuning knob (profiling only)
+    p->chunk = (int)std::max<size_t>(1, std::min<size_t>(64, (chunk_mb << 20) / per_window));
     std::vector<long long> yoff(p->chunk);
     for (int k = 0; k < p->chunk; ++k) yoff[k] = (long long)k * p->C * p->Wp;
     if (p->d_yoff.upload(yoff, p->stream)) return -1;
