@@ -117,11 +117,16 @@ int nm_add_feature_normalizer(nm_pipeline* p, int method, double clip, int n_kee
 
 /* ---- data path ------------------------------------------------------------------------------ */
 /* Recording (n_raw_rows, n_samples), row pitch in elements; copies host -> device and runs the
- * window-independent preprocessing (nan_to_num, pick, re-reference). */
+ * window-independent preprocessing (nan_to_num, pick, re-reference).  Recordings of >= 65 536 samples are copied
+ * ASYNCHRONOUSLY in time slices on a second stream (each slice is re-referenced right before the first chunk of
+ * windows that needs it, so the transfer overlaps the window kernels): `data` must stay valid and unchanged until
+ * the next nm_run_windows / nm_synchronize on this pipeline has returned. */
 int nm_upload_f32(nm_pipeline* p, const float* data, long long n_samples, long long pitch);
 int nm_upload_f64(nm_pipeline* p, const double* data, long long n_samples, long long pitch);
 /* RawDataGenerator windows (stream/generator.py:41-53): window k = samples [starts[k], starts[k]+W).
- * out_host may be NULL (results stay on the device; use nm_download). */
+ * out_host may be NULL (results stay on the device; use nm_download).  With out_host and no feature normaliser the
+ * rows of every finished chunk are copied back while the next chunk computes; the call returns when all rows are
+ * on the host. */
 int nm_run_windows(nm_pipeline* p, const long long* starts, int n_windows, double* out_host);
 int nm_download(nm_pipeline* p, double* out_host, int n_windows);
 /* DataProcessor.process for one (n_raw_rows, W) float64 window; keeps cross-window state. */

@@ -84,6 +84,13 @@ struct nm_pipeline {
     bool finalized = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // copy engine overlap: H2D of the recording in time slices and D2H of finished chunks run on `copy_stream` while the
+    // window kernels run on `stream`; slices are re-referenced lazily, right before the first chunk that needs them
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_sync = nullptr;
+    std::vector<cudaEvent_t> slice_ev, chunk_ev;
+    long long slice_len = 0;
+    int n_slices = 0, slices_prepped = 0;
     int n_sm = 1, smem_max = 48 * 1024;
     long long launches = 0;
     // optional per-family kernel timing (nm_set_profiling): events around every launch, host-synchronised
@@ -411,6 +418,8 @@ extern "C" int nm_pipeline_create(int device, int n_raw_rows, int n_ch, int wind
     p->W = window_samples;
     p->F = n_features;
     NM_CUDA_CHECK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    NM_CUDA_CHECK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    NM_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_sync, cudaEventDisableTiming));
     NM_CUDA_CHECK(cudaEventCreate(&p->ev0));
     NM_CUDA_CHECK(cudaEventCreate(&p->ev1));
     NM_CUDA_CHECK(cudaEventCreate(&p->pe0));
@@ -431,9 +440,14 @@ extern "C" void nm_pipeline_destroy(nm_pipeline* p) {
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->pe0) cudaEventDestroy(p->pe0);
     if (p->pe1) cudaEventDestroy(p->pe1);
-    cudaStream_t s = p->stream;
+    if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
+    if (p->ev_sync) cudaEventDestroy(p->ev_sync);
+    for (auto e : p->slice_ev) cudaEventDestroy(e);
+    for (auto e : p->chunk_ev) cudaEventDestroy(e);
+    cudaStream_t s = p->stream, cs = p->copy_stream;
     delete p;
     if (s) cudaStreamDestroy(s);
+    if (cs) cudaStreamDestroy(cs);
 }
 
 extern "C" int nm_set_pick(nm_pipeline* p, const int* pick) {
@@ -700,11 +714,39 @@ static NmPrepArgs nm_prep_args(nm_pipeline* p) {
     a.nanblk_pitch = p->nanblk_pitch;
     a.gsum_ext = nullptr;
     a.gsum_pitch = 0;
+    a.t0 = 0;
+    a.t1 = p->T;
     return a;
+}
+
+#define NM_UPLOAD_SLICES 8
+#define NM_UPLOAD_MIN_PIPELINED (1 << 16)  // samples; shorter recordings are copied and re-referenced in one go
+
+// re-reference every uploaded time slice that holds samples below `upto` and has not been processed yet
+static int nm_ensure_prepped(nm_pipeline* p, long long upto) {
+    while (p->slices_prepped < p->n_slices && (long long)p->slices_prepped * p->slice_len < upto) {
+        const int k = p->slices_prepped;
+        NM_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->slice_ev[k], 0));
+        NmPrepArgs a = nm_prep_args(p);
+        a.t0 = (long long)k * p->slice_len;
+        a.t1 = std::min<long long>(p->T, a.t0 + p->slice_len);
+        const int threads = NM_ROW_THREADS;
+        const unsigned grid = (unsigned)((a.t1 - a.t0 + threads - 1) / threads);
+        p->prof_begin();
+        NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(threads), 0, p->stream, a);
+        p->prof_end(NM_PROF_PREP);
+        p->launches++;
+        p->slices_prepped++;
+    }
+    NM_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 static int nm_stage_raw(nm_pipeline* p, const void* data, bool f64, long long n_samples, long long pitch) {
     const size_t esz = f64 ? 8 : 4;
+    p->n_slices = 0;
+    p->slices_prepped = 0;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->copy_stream));  // a pipelined upload / download may still use the buffers
     p->raw_f64 = f64;
     p->T = n_samples;
     p->raw_pitch = (n_samples + 3) & ~3LL;
@@ -729,14 +771,46 @@ static int nm_upload_impl(nm_pipeline* p, const void* data, bool f64, long long 
     NM_CHECK(data && n_samples >= p->W && pitch >= n_samples, "bad recording geometry (n_samples %lld, pitch %lld, W %d)", n_samples,
              pitch, p->W);
     cudaSetDevice(p->device);
-    if (nm_stage_raw(p, data, f64, n_samples, pitch)) return -1;
-    const int threads = NM_ROW_THREADS;
-    const unsigned grid = (unsigned)((n_samples + threads - 1) / threads);
-    p->prof_begin();
-    NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(threads), 0, p->stream, nm_prep_args(p));
-    p->prof_end(NM_PROF_PREP);
-    p->launches++;
-    NM_CUDA_CHECK(cudaGetLastError());
+    p->n_slices = 0;
+    p->slices_prepped = 0;
+    if (n_samples >= NM_UPLOAD_MIN_PIPELINED) {
+        // pipelined upload: time slices on the copy stream, each followed by an event; nm_ensure_prepped() makes the compute
+        // stream wait for (and re-reference) a slice only when a chunk of windows first needs it
+        const size_t esz = f64 ? 8 : 4;
+        p->raw_f64 = f64;
+        p->T = n_samples;
+        p->raw_pitch = (n_samples + 3) & ~3LL;
+        p->xr_pitch = (n_samples + 1) & ~1LL;
+        p->nanblk_pitch = (n_samples + 31) / 32;
+        if (p->d_raw.ensure((size_t)p->C_all * p->raw_pitch * esz)) return -1;
+        if (p->d_xr.ensure((size_t)p->C * p->xr_pitch * sizeof(double))) return -1;
+        if (p->d_nanblk.ensure((size_t)p->C_all * p->nanblk_pitch)) return -1;
+        p->slice_len = ((n_samples + NM_UPLOAD_SLICES - 1) / NM_UPLOAD_SLICES + 255) & ~255LL;
+        p->n_slices = (int)((n_samples + p->slice_len - 1) / p->slice_len);
+        while ((int)p->slice_ev.size() < p->n_slices) {
+            cudaEvent_t e;
+            NM_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            p->slice_ev.push_back(e);
+        }
+        // kernels of the previous run may still read the buffers that are about to be overwritten
+        NM_CUDA_CHECK(cudaEventRecord(p->ev_sync, p->stream));
+        NM_CUDA_CHECK(cudaStreamWaitEvent(p->copy_stream, p->ev_sync, 0));
+        for (int k = 0; k < p->n_slices; ++k) {
+            const long long t0 = (long long)k * p->slice_len, len = std::min<long long>(p->slice_len, n_samples - t0);
+            NM_CUDA_CHECK(cudaMemcpy2DAsync((char*)p->d_raw.p + (size_t)t0 * esz, (size_t)p->raw_pitch * esz, (const char*)data + (size_t)t0 * esz,
+                                            (size_t)pitch * esz, (size_t)len * esz, (size_t)p->C_all, cudaMemcpyHostToDevice, p->copy_stream));
+            NM_CUDA_CHECK(cudaEventRecord(p->slice_ev[k], p->copy_stream));
+        }
+    } else {
+        if (nm_stage_raw(p, data, f64, n_samples, pitch)) return -1;
+        const int threads = NM_ROW_THREADS;
+        const unsigned grid = (unsigned)((n_samples + threads - 1) / threads);
+        p->prof_begin();
+        NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(threads), 0, p->stream, nm_prep_args(p));
+        p->prof_end(NM_PROF_PREP);
+        p->launches++;
+        NM_CUDA_CHECK(cudaGetLastError());
+    }
     p->have_data = true;
     p->upload_pending = false;
     p->resident_uses_gsum = false;
@@ -748,6 +822,7 @@ extern "C" int nm_prepare_resident(nm_pipeline* p) {
     NM_P_CHECK(p);
     NM_CHECK(p->have_data && !p->upload_pending, "no resident recording");
     cudaSetDevice(p->device);
+    if (nm_ensure_prepped(p, p->T)) return -1;  // (a pipelined upload may still be in flight)
     const int threads = NM_ROW_THREADS;
     const unsigned grid = (unsigned)((p->T + threads - 1) / threads);
     NmPrepArgs a = nm_prep_args(p);
@@ -873,34 +948,64 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
     if (p->d_out.ensure((size_t)n_windows * p->F * sizeof(double))) return -1;
     p->out_rows = n_windows;
     NM_CUDA_CHECK(cudaMemsetAsync(p->d_out.p, 0, (size_t)n_windows * p->F * sizeof(double), p->stream));
-    for (int w0 = 0; w0 < n_windows; w0 += p->chunk)
-        if (nm_run_chunk(p, w0, std::min(p->chunk, n_windows - w0))) return -1;
-    if (p->norm && p->norm->run(p, n_windows)) return -1;
-    if (p->has_nan_cols) {
-        if (p->d_nanflags.ensure((size_t)n_windows * p->C_all)) return -1;
+    const bool per_chunk = !p->norm;  // without the (sequential) normaliser a chunk's rows are final when its kernels end
+    if (p->has_nan_cols && p->d_nanflags.ensure((size_t)n_windows * p->C_all)) return -1;
+    auto nan_fill = [&](int w0, int n) {
         NmNanArgs na;
         na.p = nm_prep_args(p);
-        na.start = p->d_starts.as<long long>();
-        na.n_windows = n_windows;
+        na.start = p->d_starts.as<long long>() + w0;
+        na.n_windows = n;
         na.W = p->W;
-        na.flags = p->d_nanflags.as<unsigned char>();
-        const long long tot = (long long)n_windows * p->C_all;
+        na.flags = p->d_nanflags.as<unsigned char>() + (size_t)w0 * p->C_all;
+        const long long tot = (long long)n * p->C_all;
         const unsigned grid = (unsigned)((tot + NM_ROW_THREADS - 1) / NM_ROW_THREADS);
         NM_LAUNCH(nm_nanflag_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, na);
         NmNanFillArgs nf;
         nf.flags = na.flags;
-        nf.n_windows = n_windows;
+        nf.n_windows = n;
         nf.C_all = p->C_all;
         nf.col_ptr = p->d_nan_ptr.as<int>();
         nf.cols = p->d_nan_cols.as<int>();
         nf.out = p->d_out.as<double>();
-        nf.row0 = 0;
+        nf.row0 = w0;
         nf.F = p->F;
         NM_LAUNCH(nm_nanfill_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, nf);
         p->launches += 2;
+    };
+    int n_ev = 0;
+    for (int w0 = 0; w0 < n_windows; w0 += p->chunk) {
+        const int n = std::min(p->chunk, n_windows - w0);
+        long long upto = 0;
+        for (int k = 0; k < n; ++k) upto = std::max(upto, starts[w0 + k] + p->W);
+        if (nm_ensure_prepped(p, upto)) return -1;
+        if (nm_run_chunk(p, w0, n)) return -1;
+        if (per_chunk) {
+            if (p->has_nan_cols) nan_fill(w0, n);
+            if (out_host) {  // ship the finished rows while the next chunk computes
+                if ((int)p->chunk_ev.size() <= n_ev) {
+                    cudaEvent_t e;
+                    NM_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    p->chunk_ev.push_back(e);
+                }
+                NM_CUDA_CHECK(cudaEventRecord(p->chunk_ev[n_ev], p->stream));
+                NM_CUDA_CHECK(cudaStreamWaitEvent(p->copy_stream, p->chunk_ev[n_ev], 0));
+                NM_CUDA_CHECK(cudaMemcpyAsync(out_host + (size_t)w0 * p->F, p->d_out.as<double>() + (size_t)w0 * p->F,
+                                              (size_t)n * p->F * sizeof(double), cudaMemcpyDeviceToHost, p->copy_stream));
+                ++n_ev;
+            }
+        }
+    }
+    if (nm_ensure_prepped(p, p->T)) return -1;  // leave no slice event un-consumed (nm_prepare_resident, NaN maps)
+    if (!per_chunk) {
+        if (p->norm->run(p, n_windows)) return -1;
+        if (p->has_nan_cols) nan_fill(0, n_windows);
     }
     NM_CUDA_CHECK(cudaGetLastError());
-    if (out_host) return nm_download(p, out_host, n_windows);
+    if (out_host) {
+        if (!per_chunk) return nm_download(p, out_host, n_windows);
+        NM_CUDA_CHECK(cudaStreamSynchronize(p->copy_stream));
+        NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    }
     return 0;
 }
 
@@ -1050,6 +1155,7 @@ extern "C" int nm_describe_plan(nm_pipeline* p, char* buf, int n) {
 extern "C" int nm_synchronize(nm_pipeline* p) {
     NM_P_CHECK(p);
     cudaSetDevice(p->device);
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->copy_stream));
     NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
     return 0;
 }

@@ -39,6 +39,7 @@ struct NmPrepArgs {
     // the host between nm_gsum_kernel and nm_prep_kernel; nullptr = sum the local channels in-kernel
     const double* gsum_ext;
     long long gsum_pitch;
+    long long t0, t1;      // samples [t0, t1) are processed by this launch (time slices of a pipelined upload)
 };
 
 NM_DEV double nm_raw_at(const NmPrepArgs& a, int row, long long t) {
@@ -47,8 +48,8 @@ NM_DEV double nm_raw_at(const NmPrepArgs& a, int row, long long t) {
 }
 
 NM_GLOBAL void nm_prep_kernel(NmPrepArgs a) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = t < a.T;
+    const long long t = a.t0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // t0 is a multiple of 32 (NaN block map)
+    const bool active = t < a.t1;
     const int lane = threadIdx.x & 31;
 
     for (int r = 0; r < a.C_all; ++r) {
