@@ -948,7 +948,8 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
     if (p->d_out.ensure((size_t)n_windows * p->F * sizeof(double))) return -1;
     p->out_rows = n_windows;
     NM_CUDA_CHECK(cudaMemsetAsync(p->d_out.p, 0, (size_t)n_windows * p->F * sizeof(double), p->stream));
-    const bool per_chunk = !p->norm;  // without the (sequential) normaliser a chunk's rows are final when its kernels end
+    // without the (sequential) normaliser a chunk's rows are final when its kernels end: ship them chunk by chunk
+    const bool per_chunk = !p->norm && out_host != nullptr;
     if (p->has_nan_cols && p->d_nanflags.ensure((size_t)n_windows * p->C_all)) return -1;
     auto nan_fill = [&](int w0, int n) {
         NmNanArgs na;
