@@ -642,6 +642,74 @@ class FeatureNormalizerOracle:
         return np.nan_to_num(out)
 
 
+# ----------------------------------------------------------------------------- 8f-3: preprocessing filter, raw normaliser
+PREFILTER_ORDER = ["bandstop_filter", "bandpass_filter", "lowpass_filter", "highpass_filter"]
+
+
+def design_prefilters(settings: dict, sfreq: float) -> list[np.ndarray]:
+    """processing/filter_preprocessing.py:44-77: one single-filter MNEFilter per enabled stage, filter_length = sfreq - 1;
+    the band stages first (in FilterSettings field order), then low-pass, then high-pass.  Note that the reference hands
+    the 'bandstop' range to create_filter as (l_freq, h_freq) = (low, high), i.e. it designs a band-PASS there."""
+    cfg = settings["preprocessing_filter"]
+    enabled = [k for k in PREFILTER_ORDER if cfg.get(k) is True]
+    ranges = []
+    for name in enabled:
+        if name in ("bandstop_filter", "bandpass_filter"):
+            ranges.append(_band_tuple(cfg[name + "_settings"]))
+    if "lowpass_filter" in enabled:
+        ranges.append((None, cfg["lowpass_filter_cutoff_hz"]))
+    if "highpass_filter" in enabled:
+        ranges.append((cfg["highpass_filter_cutoff_hz"], None))
+    return [design_bank([r], sfreq, filter_length=int(sfreq - 1)) for r in ranges]
+
+
+def apply_prefilters(x: np.ndarray, banks: list[np.ndarray]) -> np.ndarray:
+    """processing/filter_preprocessing.py:79-94: the stages are applied one after the other ('same' FFT convolution)."""
+    for b in banks:
+        x = apply_bank(x, b)[:, 0, :]
+    return x
+
+
+class RawNormalizerOracle:
+    """processing/normalization.py:30-111 ('raw' type; numpy methods only): window 0 passes through and seeds the history;
+    window k >= 1 appends its last int(sfreq / rate) samples, is normalised against the WHOLE history (its own new
+    samples included), clipped, and the history is trimmed to normalization_time_s * sfreq - 1 samples."""
+
+    def __init__(self, settings: dict, sfreq: float):
+        cfg = settings["raw_normalization_settings"]
+        self.method = cfg["normalization_method"]
+        self.clip = cfg["clip"]
+        self.add = int(sfreq / settings["sampling_rate_features_hz"])
+        self.n_keep = int(cfg["normalization_time_s"] * sfreq)
+        self.prev = np.empty((0, 0))
+
+    def process(self, data: np.ndarray) -> np.ndarray:
+        if self.prev.size == 0:
+            self.prev = data.T
+            return data
+        d = data.T
+        self.prev = np.vstack((self.prev, d[-self.add:]))
+        has_nan = np.any(np.isnan(sum(self.prev)))
+        mean = (np.nanmean if has_nan else np.mean)(self.prev, axis=0)
+        with np.errstate(all="ignore"):
+            if self.method == "mean":
+                out = (d - mean) / mean
+            elif self.method == "median":
+                med = (np.nanmedian if has_nan else np.median)(self.prev, axis=0)
+                out = (d - med) / med
+            elif self.method in ("zscore", "zscore-median"):
+                std = (np.nanstd if has_nan else np.std)(self.prev, axis=0)
+                std[std == 0] = 1
+                centre = mean if self.method == "zscore" else (np.nanmedian if has_nan else np.median)(self.prev, axis=0)
+                out = (d - centre) / std
+            else:
+                raise NotImplementedError(f"sklearn normaliser '{self.method}' is out of scope")
+        if self.clip:
+            out = out.clip(min=-self.clip, max=self.clip)
+        self.prev = self.prev[-self.n_keep + 1:]
+        return np.nan_to_num(out).T
+
+
 # ----------------------------------------------------------------------------- a2/a3/a6: window processor
 class WindowOracle:
     """stream/data_processor.py:19-90,238-311 + processing/data_preprocessor.py:21-84 +
@@ -659,9 +727,17 @@ class WindowOracle:
         pre = [p for p in PREPROC_ORDER if p in settings["preprocessing"]]
         self.notch = None
         self.ref = None
+        self.prefilters = None
+        self.rawnorm = None
         self.pre = []
         for p in pre:
-            if p == "notch_filter":
+            if p == "preprocessing_filter":
+                self.prefilters = design_prefilters(settings, self.sfreq)
+                self.pre.append(p)
+            elif p == "raw_normalization":
+                self.rawnorm = RawNormalizerOracle(settings, self.sfreq)
+                self.pre.append(p)
+            elif p == "notch_filter":
                 self.notch = design_notch(self.sfreq, line_noise)
                 self.pre.append(p)
             elif p == "re_referencing":
@@ -671,7 +747,7 @@ class WindowOracle:
                 if settings["raw_resampling_settings"]["resample_freq_hz"] != self.sfreq:
                     raise NotImplementedError("resampling with ratio != 1 is a 'next' row (SURVEY.md section 8f-2)")
             else:
-                raise NotImplementedError(f"preprocessor {p} is a 'next' row (SURVEY.md section 8f-3)")
+                raise NotImplementedError(f"unknown preprocessor {p}")
         self.plugins = []
         for f in _enabled(settings["features"], FEATURE_ORDER):
             if f not in self.IN_SCOPE_FEATURES:
@@ -699,8 +775,12 @@ class WindowOracle:
     def preprocess(self, data: np.ndarray) -> np.ndarray:
         d = np.nan_to_num(data)[self.feature_idx, :]
         for p in self.pre:
-            if p == "notch_filter":
+            if p == "preprocessing_filter":
+                d = apply_prefilters(d, self.prefilters)
+            elif p == "notch_filter":
                 d = apply_notch(d, self.notch)
+            elif p == "raw_normalization":
+                d = self.rawnorm.process(d)
             elif self.ref is not None:
                 d = self.ref @ d
         return d

@@ -198,6 +198,56 @@ def window_processor_cases(nm):
          vals=np.array(rows), sfreq=1000.0)
 
 
+def _run_windows(nm, st, x, line_noise=50):
+    ch = nm.utils.channels.get_default_channels_from_data(x)
+    dp = nm.DataProcessor(sfreq=1000, settings=st, channels=ch, line_noise=line_noise, verbose=False)
+    gen = nm.RawDataGenerator(x, 1000, st.sampling_rate_features_hz, st.segment_length_features_ms)
+    rows, keys = [], None
+    for _, batch in gen:
+        d = dp.process(batch)
+        if keys is None:
+            keys = list(d.keys())
+        rows.append([float(d[k]) for k in keys])
+    return keys, np.array(rows)
+
+
+def next_row_cases(nm):
+    """PreprocessingFilter (processing/filter_preprocessing.py) and RawNormalizer
+    (processing/normalization.py) in front of a small feature set, unmodified reference through the shim."""
+    def base():
+        st = nm.NMSettings.get_default().reset()
+        for f in ("fft", "raw_hjorth", "linelength", "return_raw"):
+            st.features[f] = True
+        st.postprocessing.feature_normalization = False
+        return st
+
+    x = neural_like(21, 4, 1000 + 100 * 24)
+    st = base()
+    st.preprocessing = ["preprocessing_filter", "notch_filter", "re_referencing"]  # default FilterSettings: all four stages
+    keys, vals = _run_windows(nm, st, x)
+    save("dataprocessor_prefilter_default", x=x.astype(np.float32), settings=dump_settings(st), keys=json.dumps(keys), vals=vals, sfreq=1000.0)
+
+    st = base()
+    st.preprocessing = ["preprocessing_filter", "re_referencing"]
+    st.preprocessing_filter.bandstop_filter = False
+    st.preprocessing_filter.bandpass_filter = False
+    st.preprocessing_filter.lowpass_filter_cutoff_hz = 90
+    st.preprocessing_filter.highpass_filter_cutoff_hz = 5
+    keys, vals = _run_windows(nm, st, x)
+    save("dataprocessor_prefilter_lphp", x=x.astype(np.float32), settings=dump_settings(st), keys=json.dumps(keys), vals=vals, sfreq=1000.0)
+
+    x = neural_like(22, 4, 1000 + 100 * 44)
+    for method in ("zscore", "mean", "median", "zscore-median"):
+        st = base()
+        st.preprocessing = ["notch_filter", "re_referencing", "raw_normalization"]
+        st.raw_normalization_settings.normalization_time_s = 2.5   # history is trimmed inside the run
+        st.raw_normalization_settings.normalization_method = method
+        st.raw_normalization_settings.clip = 2.0 if method == "zscore" else 3.0
+        keys, vals = _run_windows(nm, st, x)
+        save(f"dataprocessor_rawnorm_{method.replace('-', '_')}", x=x.astype(np.float32), settings=dump_settings(st), keys=json.dumps(keys),
+             vals=vals, sfreq=1000.0)
+
+
 def stream_cases():
     nm = load_reference_stream()
     import tempfile
@@ -268,6 +318,9 @@ def real_data_case(nm):
 
 if __name__ == "__main__":
     nm = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "next":  # only the SURVEY 8f "next row" fixtures
+        next_row_cases(nm)
+        raise SystemExit(0)
     plugin_cases(nm)
     preprocess_cases(nm)
     window_processor_cases(nm)

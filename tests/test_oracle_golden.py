@@ -108,7 +108,12 @@ def test_notch_shapes(name, line):
     assert np.max(np.abs(out - g["out"])) < 1e-12
 
 
-@pytest.mark.parametrize("name", ["dataprocessor_default", "dataprocessor_fast", "dataprocessor_c3_nan", "dataprocessor_realdata"])
+NEXT_ROW_FIXTURES = ["dataprocessor_prefilter_default", "dataprocessor_prefilter_lphp", "dataprocessor_rawnorm_zscore",
+                     "dataprocessor_rawnorm_mean", "dataprocessor_rawnorm_median", "dataprocessor_rawnorm_zscore_median"]
+
+
+@pytest.mark.parametrize("name", ["dataprocessor_default", "dataprocessor_fast", "dataprocessor_c3_nan", "dataprocessor_realdata"]
+                         + NEXT_ROW_FIXTURES)
 def test_window_processor_matches_reference(name):
     g = load_golden(name)
     x = g["x"].astype(np.float64)
