@@ -58,6 +58,11 @@ int nm_set_reref(nm_pipeline* p, int n_groups, const int* group_of, const double
                  const int* sp_ptr, const int* sp_col, const double* sp_val);
 /* NotchFilter.process: zero-phase FIR with reflect-limited padding (filter/notch_filter.py:78-93) */
 int nm_set_notch(nm_pipeline* p, const double* taps, int n_taps);
+/* PreprocessingFilter (processing/filter_preprocessing.py:44-94): appends one single 'same' FIR stage (odd-length,
+ * symmetric taps; stages may differ in length); the stages are applied in the order added to every window before
+ * the notch. */
+int nm_add_prefilter(nm_pipeline* p, const double* taps, int n_taps);
+
 /* NaN re-insertion (stream/data_processor.py:297-306): columns [col_ptr[r], col_ptr[r+1]) of `cols`
  * become NaN in every window where raw row r contains a NaN */
 int nm_set_nan_columns(nm_pipeline* p, const int* col_ptr, const int* cols);

@@ -117,6 +117,12 @@ class Pipeline:
         a = _f64(taps)
         _lib.check(self.lib.nm_set_notch(self._h, _ptr(a, C.c_double), int(a.size)))
 
+    def set_prefilters(self, stages: Sequence[np.ndarray] | None) -> None:
+        """PreprocessingFilter stages (one tap vector each, possibly of different lengths), applied in order before the notch."""
+        for taps in stages or []:
+            a = _f64(np.ravel(taps))
+            _lib.check(self.lib.nm_add_prefilter(self._h, _ptr(a, C.c_double), int(a.size)))
+
     def set_nan_columns(self, names_by_raw_row: Sequence[str | None]) -> None:
         """names_by_raw_row[r] = channel name whose features become NaN when raw row r holds a NaN (or None).
 

@@ -118,6 +118,10 @@ struct nm_pipeline {
     bool has_reref = false;
     std::unique_ptr<FirBank> notch;
     std::vector<double> notch_taps;
+    // PreprocessingFilter (processing/filter_preprocessing.py): single-filter 'same' FIR stages applied one after the
+    // other to every window BEFORE the notch; stage outputs ping-pong between two chunk buffers
+    std::vector<std::unique_ptr<FirBank>> prefilters;
+    DevBuf d_pre[2];
     DevBuf d_nan_ptr, d_nan_cols;
     bool has_nan_cols = false;
 
@@ -503,6 +507,18 @@ extern "C" int nm_set_notch(nm_pipeline* p, const double* taps, int n_taps) {
     return 0;
 }
 
+extern "C" int nm_add_prefilter(nm_pipeline* p, const double* taps, int n_taps) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    NM_CHECK(taps && n_taps > 0, "bad prefilter taps");
+    cudaSetDevice(p->device);
+    auto b = std::make_unique<FirBank>();
+    if (b->build(taps, 1, n_taps, p->W, NM_FIR_SAME, p->stream)) return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    p->prefilters.push_back(std::move(b));
+    return 0;
+}
+
 extern "C" int nm_set_nan_columns(nm_pipeline* p, const int* col_ptr, const int* cols) {
     NM_P_CHECK(p);
     NM_CHECK(col_ptr && col_ptr[0] == 0, "col_ptr must start at 0");
@@ -667,6 +683,10 @@ extern "C" int nm_finalize(nm_pipeline* p) {
     for (int k = 0; k < p->chunk; ++k) yoff[k] = (long long)k * p->C * p->Wp;
     if (p->d_yoff.upload(yoff, p->stream)) return -1;
     if (p->notch && p->d_y.ensure((size_t)p->chunk * p->C * p->Wp * sizeof(double))) return -1;
+    for (size_t i = 0; i < std::min<size_t>(2, p->prefilters.size()); ++i)
+        if (p->d_pre[i].ensure((size_t)p->chunk * p->C * p->Wp * sizeof(double))) return -1;
+    for (auto& b : p->prefilters)
+        if (nm_allow_fir_smem<NmEpiStore>(*b, 0, p)) return -1;
     if (p->bursts && p->bursts->alloc_chunk(p->chunk, p->Wp)) return -1;
 
     // opt in to large dynamic shared memory once
@@ -845,6 +865,21 @@ extern "C" int nm_upload_f64(nm_pipeline* p, const double* data, long long n_sam
     return nm_upload_impl(p, data, true, n_samples, pitch);
 }
 
+// PreprocessingFilter stages of one batch of windows; on return `rows` describes the last stage's output buffer
+static void nm_run_prefilters(nm_pipeline* p, NmRows& rows) {
+    for (size_t i = 0; i < p->prefilters.size(); ++i) {
+        double* dst = p->d_pre[i & 1].as<double>();
+        NmEpiStore epi{dst, (long long)p->Wp, 1};
+        p->prof_begin();
+        nm_launch_fir(p, *p->prefilters[i], rows, epi, p->stream, 0);
+        p->prof_end(NM_PROF_NOTCH);
+        p->launches++;
+        rows.base = dst;
+        rows.ch_stride = p->Wp;
+        rows.off = p->d_yoff.as<long long>();
+    }
+}
+
 static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
     NmRows rows;
     rows.base = p->d_xr.as<double>();
@@ -863,6 +898,7 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         o.per_ch = per_ch;
         return o;
     };
+    nm_run_prefilters(p, rows);
     bool scan_done = false;
     if (p->notch) {
         const bool y_needed = !p->spectral.empty() || p->bandpower || p->sharpwave || p->bursts;
@@ -1036,22 +1072,23 @@ extern "C" int nm_preprocess_window(nm_pipeline* p, const double* window, double
     if (nm_upload_impl(p, window, true, p->W, p->W)) return -1;
     const long long zero = 0;
     if (p->d_starts.upload(&zero, 1, p->stream)) return -1;
-    const double* src = p->d_xr.as<double>();
-    long long pitch = p->xr_pitch;
+    NmRows rows;
+    rows.base = p->d_xr.as<double>();
+    rows.ch_stride = p->xr_pitch;
+    rows.off = p->d_starts.as<long long>();
+    rows.n_windows = 1;
+    rows.n_ch = p->C;
+    rows.W = p->W;
+    nm_run_prefilters(p, rows);
     if (p->notch) {
-        NmRows rows;
-        rows.base = p->d_xr.as<double>();
-        rows.ch_stride = p->xr_pitch;
-        rows.off = p->d_starts.as<long long>();
-        rows.n_windows = 1;
-        rows.n_ch = p->C;
-        rows.W = p->W;
         nm_launch_notch(p, rows, p->d_y.as<double>(), nullptr, p->stream);
         p->launches++;
-        NM_CUDA_CHECK(cudaGetLastError());
-        src = p->d_y.as<double>();
-        pitch = p->Wp;
+        rows.base = p->d_y.as<double>();
+        rows.ch_stride = p->Wp;
     }
+    NM_CUDA_CHECK(cudaGetLastError());
+    const double* src = rows.base;
+    const long long pitch = rows.ch_stride;
     for (int c = 0; c < p->C; ++c)
         NM_CUDA_CHECK(cudaMemcpyAsync(out_rows + (size_t)c * p->W, src + (size_t)c * pitch, (size_t)p->W * sizeof(double),
                                       cudaMemcpyDeviceToHost, p->stream));
@@ -1133,6 +1170,7 @@ extern "C" int nm_describe_plan(nm_pipeline* p, char* buf, int n) {
     char line[256];
     snprintf(line, sizeof(line), "window=%d channels=%d features=%d chunk=%d\n", p->W, p->C, p->F, p->chunk);
     s += line;
+    for (auto& b : p->prefilters) nm_describe_fir<NmEpiStore>(s, "prefilter", *b, 0);
     if (p->notch) {
         if (nm_convx_pick<NmEpiStoreScan>(*p->notch)) nm_describe_fir<NmEpiStoreScan>(s, p->has_scan ? "notch+scan" : "notch", *p->notch, 0);
         else nm_describe_fir<NmEpiStore>(s, "notch", *p->notch, 0);

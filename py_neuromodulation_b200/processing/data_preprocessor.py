@@ -2,9 +2,9 @@
 
 The chain is executed in the fixed order of ``PREPROCESSOR_DICT`` -- NOT in the order of the
 ``settings.preprocessing`` list -- exactly like the reference (data_preprocessor.py:44-52).
-In scope on the GPU: ``notch_filter``, ``re_referencing`` and ``raw_resampling`` when it is the
-identity (resample_freq_hz == sfreq).  ``preprocessing_filter``, ``raw_normalization`` and
-resampling with a ratio != 1 are "next" rows and raise NotImplementedError.
+In scope on the GPU: ``preprocessing_filter``, ``notch_filter``, ``re_referencing`` and ``raw_resampling`` when it
+is the identity (resample_freq_hz == sfreq).  ``raw_normalization`` and resampling with a ratio != 1 are "next" rows
+ and raise NotImplementedError.
 """
 
 from __future__ import annotations
@@ -44,7 +44,7 @@ def preprocessing_plan(settings: "NMSettings", sfreq: float) -> list[str]:
                     "'raw_resampling' from settings.preprocessing"
                 )
             continue  # identity, like the reference (processing/resample.py:36-38)
-        if name in ("preprocessing_filter", "raw_normalization"):
+        if name == "raw_normalization":
             raise NotImplementedError(f"preprocessor '{name}' is not on the B200 path yet (SURVEY.md section 8f-3)")
         plan.append(name)
     return plan
@@ -55,11 +55,14 @@ class DataPreprocessor:
 
     def __init__(self, settings: "NMSettings", channels, sfreq: float, line_noise: float | None = None) -> None:
         from ..filter.notch_filter import NotchFilter
+        from .filter_preprocessing import PreprocessingFilter
         from .rereference import ReReferencer
 
         self.preprocessors: list[NMPreprocessor] = []
         for name in preprocessing_plan(settings, sfreq):
-            if name == "notch_filter":
+            if name == "preprocessing_filter":
+                self.preprocessors.append(PreprocessingFilter(settings=settings, sfreq=sfreq))
+            elif name == "notch_filter":
                 self.preprocessors.append(NotchFilter(sfreq=sfreq, line_noise=line_noise))
             elif name == "re_referencing":
                 self.preprocessors.append(ReReferencer(sfreq=sfreq, channels=channels))

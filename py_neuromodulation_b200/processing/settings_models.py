@@ -35,7 +35,8 @@ class FilterSettings(BoolSelector):
 
     def get_filter_tuple(self, filter_name: str):
         if filter_name == "bandstop_filter":
-            return (self.bandstop_filter_settings.frequency_high_hz, self.bandstop_filter_settings.frequency_low_hz)
+            # like the reference (filter_preprocessing.py:27-29): the range is returned as (low, high)
+            return (self.bandstop_filter_settings.frequency_low_hz, self.bandstop_filter_settings.frequency_high_hz)
         if filter_name == "bandpass_filter":
             return (self.bandpass_filter_settings.frequency_low_hz, self.bandpass_filter_settings.frequency_high_hz)
         if filter_name == "lowpass_filter":

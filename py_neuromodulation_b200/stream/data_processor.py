@@ -84,6 +84,7 @@ class _Plan:
             pipe.set_reref_factored(*dp.reref_factored)
         elif "re_referencing" in dp.preproc_plan:
             pipe.set_reref(dp.ref_matrix)
+        pipe.set_prefilters(dp.prefilter_taps)
         if "notch_filter" in dp.preproc_plan:
             pipe.set_notch(dp.notch_taps)
         if scan.hjorth or scan.raw or scan.linelength:
@@ -154,6 +155,13 @@ class DataProcessor:
             self.notch_taps = NotchFilter(self.sfreq_raw, line_noise).filter_bank
             if self.notch_taps is None:
                 self.preproc_plan.remove("notch_filter")
+        self.prefilter_taps = None
+        if "preprocessing_filter" in self.preproc_plan:
+            from ..processing.filter_preprocessing import PreprocessingFilter
+
+            self.prefilter_taps = PreprocessingFilter(self.settings, self.sfreq_raw).stage_taps()
+            if self.prefilter_taps is None:
+                self.preproc_plan.remove("preprocessing_filter")
         self.ref_matrix = None
         if "re_referencing" in self.preproc_plan:
             self.ref_matrix = build_reference_matrix(ch)
@@ -247,6 +255,7 @@ class DataProcessor:
             pipe.set_pick(self.feature_idx)
             if "re_referencing" in self.preproc_plan:
                 pipe.set_reref(self.ref_matrix)
+            pipe.set_prefilters(self.prefilter_taps)
             if "notch_filter" in self.preproc_plan:
                 pipe.set_notch(self.notch_taps)
             ScanSpec(names).attach(pipe)

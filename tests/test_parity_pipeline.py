@@ -41,7 +41,8 @@ def run_dp(g, n_windows=None, with_norm=True):
 
 
 @pytest.mark.parametrize("name,n_emu", [("dataprocessor_c3_nan", None), ("dataprocessor_fast", None), ("dataprocessor_default", 24),
-                                        ("dataprocessor_realdata", 12)])
+                                        ("dataprocessor_realdata", 12), ("dataprocessor_prefilter_default", None),
+                                        ("dataprocessor_prefilter_lphp", None)])
 def test_window_processor_matches_reference_golden(backend, name, n_emu):
     g = load_golden(name)
     n = n_emu if backend == "emu" else None  # the thread emulator is slow: fewer windows on CPU, all on the GPU
@@ -283,3 +284,17 @@ def test_pipelined_upload_and_chunked_download(backend):
     # a second run on the same pipeline (buffers reused, events re-recorded) gives the same matrix
     cols2, mat2 = dp.process_windows(x, starts, 1000)
     assert np.array_equal(mat, mat2, equal_nan=True)
+
+
+def test_standalone_preprocessing_filter_matches_oracle(backend):
+    """PreprocessingFilter.process outside a DataProcessor (reference class of the same name and signature)."""
+    from py_neuromodulation_b200.processing import PreprocessingFilter
+
+    x = neural_like(31, 3, 1000)
+    s = nm.NMSettings.get_default()
+    pf = PreprocessingFilter(s, 1000)
+    assert len(pf.filters) == 4
+    got = pf.process(x)
+    ref = orc.apply_prefilters(x, orc.design_prefilters(s.model_dump(), 1000))
+    assert got.shape == ref.shape == x.shape
+    assert np.max(np.abs(got - ref)) <= 1e-11 * max(1.0, np.max(np.abs(ref)))
