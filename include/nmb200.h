@@ -58,6 +58,12 @@ int nm_set_reref(nm_pipeline* p, int n_groups, const int* group_of, const double
                  const int* sp_ptr, const int* sp_col, const double* sp_val);
 /* NotchFilter.process: zero-phase FIR with reflect-limited padding (filter/notch_filter.py:78-93) */
 int nm_set_notch(nm_pipeline* p, const double* taps, int n_taps);
+/* RawNormalizer (processing/normalization.py:30-111, type "raw"): window 0 passes through and seeds the per-channel
+ * history; window g >= 1 appends its last add_samples = int(sfreq / rate) preprocessed samples, is normalised against the
+ * whole history (method 0 mean, 2 zscore), clipped (clip == 0: off) and the history is trimmed to n_keep - 1 samples
+ * (n_keep = int(normalization_time_s * sfreq)).  Runs after the notch / re-reference, before every feature. */
+int nm_set_raw_normalizer(nm_pipeline* p, int method, double clip, int n_keep, int add_samples);
+
 /* PreprocessingFilter (processing/filter_preprocessing.py:44-94): appends one single 'same' FIR stage (odd-length,
  * symmetric taps; stages may differ in length); the stages are applied in the order added to every window before
  * the notch. */

@@ -23,6 +23,7 @@
 #include "nm_bursts.cuh"
 #include "nm_sharpwave.cuh"
 #include "nm_norm.cuh"
+#include "nm_rawnorm.cuh"
 
 // ------------------------------------------------------------------------------- errors
 static thread_local char g_err[1024] = "";
@@ -134,6 +135,7 @@ struct nm_pipeline {
     std::unique_ptr<BurstsFam> bursts;
     std::unique_ptr<SharpwaveFam> sharpwave;
     std::unique_ptr<NormFam> norm;
+    std::unique_ptr<RawNormFam> rawnorm;
 
     // data
     DevBuf d_raw, d_xr, d_nanblk, d_gsum;
@@ -364,6 +366,52 @@ int SharpwaveFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     nm_launch_fir(p, bank, rows, epi, p->stream, epi_smem());
     p->prof_end(NM_PROF_SHARPWAVE);
     p->launches++;
+    return 0;
+}
+
+int RawNormFam::run(nm_pipeline* p, NmRows& rows) {
+    const int n = rows.n_windows;
+    // history bookkeeping per window (processing/normalization.py:92-107): statistics range [lo, end of block g)
+    std::vector<long long> lo(n, 0);
+    for (int k = 0; k < n; ++k) {
+        const long long g = batch + k;
+        if (g == 0) {
+            len_prev = W;
+            continue;
+        }
+        const long long hist = len_prev + add;
+        const long long end = (long long)W + g * add;
+        lo[k] = end - hist;
+        len_prev = (n_keep > 1) ? std::min<long long>(hist, n_keep - 1) : hist;  // previous[-n_keep + 1:] keeps everything for n_keep == 1
+    }
+    NM_CHECK(n_keep > 1 || (long long)W + (batch + n) * add < cap, "raw normalisation history exceeds the ring (normalization_time_s * sfreq == 1)");
+    if (d_lo.upload(lo, p->stream)) return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));  // `lo` is a temporary
+    NmRawNormArgs a;
+    a.in = rows;
+    a.out = d_out.as<double>();
+    a.Wp = Wp;
+    a.ring = d_ring.as<double>();
+    a.cap = cap;
+    a.blk = d_blk.as<double>();
+    a.blk_cap = blk_cap;
+    a.g0 = batch;
+    a.add = add;
+    a.lo = d_lo.as<long long>();
+    a.method = method;
+    a.clip = clip;
+    const int wpc = NM_ROW_THREADS / 32;
+    const long long n_rows = (long long)n * C;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n_rows + wpc - 1) / wpc, (long long)p->n_sm * 16));
+    p->prof_begin();
+    NM_LAUNCH(nm_rawnorm_append_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
+    NM_LAUNCH(nm_rawnorm_apply_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
+    p->prof_end(NM_PROF_NOTCH);
+    p->launches += 2;
+    batch += n;
+    rows.base = d_out.as<double>();
+    rows.ch_stride = Wp;
+    rows.off = p->d_yoff.as<long long>();
     return 0;
 }
 
@@ -658,6 +706,17 @@ extern "C" int nm_add_feature_normalizer(nm_pipeline* p, int method, double clip
     return 0;
 }
 
+extern "C" int nm_set_raw_normalizer(nm_pipeline* p, int method, double clip, int n_keep, int add_samples) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    NM_CHECK(method == 0 || method == 2, "raw normalisation on the GPU supports 'mean' (0) and 'zscore' (2); got %d", method);
+    NM_CHECK(n_keep >= 1 && add_samples >= 1 && clip >= 0.0, "bad raw normaliser configuration");
+    auto f = std::make_unique<RawNormFam>();
+    if (f->build(method, clip, n_keep, add_samples, p->C, p->W)) return -1;
+    p->rawnorm = std::move(f);
+    return 0;
+}
+
 extern "C" int nm_finalize(nm_pipeline* p) {
     NM_P_CHECK(p);
     NM_CHECK(!p->finalized, "pipeline already finalized");
@@ -688,6 +747,7 @@ extern "C" int nm_finalize(nm_pipeline* p) {
     for (auto& b : p->prefilters)
         if (nm_allow_fir_smem<NmEpiStore>(*b, 0, p)) return -1;
     if (p->bursts && p->bursts->alloc_chunk(p->chunk, p->Wp)) return -1;
+    if (p->rawnorm && p->rawnorm->alloc_chunk(p->chunk, p->Wp)) return -1;
 
     // opt in to large dynamic shared memory once
     if (p->notch && (nm_allow_fir_smem<NmEpiStore>(*p->notch, 0, p) || nm_allow_fir_smem<NmEpiStoreScan>(*p->notch, 0, p))) return -1;
@@ -709,6 +769,7 @@ extern "C" int nm_reset_state(nm_pipeline* p) {
     NM_P_CHECK(p);
     if (p->bursts) p->bursts->reset();
     if (p->norm) p->norm->reset();
+    if (p->rawnorm) p->rawnorm->reset();
     return 0;
 }
 
@@ -901,17 +962,19 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
     nm_run_prefilters(p, rows);
     bool scan_done = false;
     if (p->notch) {
-        const bool y_needed = !p->spectral.empty() || p->bandpower || p->sharpwave || p->bursts;
+        const bool y_needed = !p->spectral.empty() || p->bandpower || p->sharpwave || p->bursts || p->rawnorm;
+        const bool fuse_scan = p->has_scan && !p->rawnorm;  // the scan features are taken from the NORMALISED rows otherwise
         NmOut so;
-        if (p->has_scan) so = out_for(p->d_scan_colmap, 5);
+        if (fuse_scan) so = out_for(p->d_scan_colmap, 5);
         p->prof_begin();
-        scan_done = nm_launch_notch(p, rows, y_needed || !p->has_scan ? p->d_y.as<double>() : nullptr, p->has_scan ? &so : nullptr, p->stream);
+        scan_done = nm_launch_notch(p, rows, y_needed || !p->has_scan ? p->d_y.as<double>() : nullptr, fuse_scan ? &so : nullptr, p->stream);
         p->prof_end(NM_PROF_NOTCH);
         p->launches++;
         rows.base = p->d_y.as<double>();
         rows.ch_stride = p->Wp;
         rows.off = p->d_yoff.as<long long>();
     }
+    if (p->rawnorm && p->rawnorm->run(p, rows)) return -1;
     if (p->has_scan && !scan_done) {
         NmScanArgs a;
         a.in = rows;
@@ -1034,7 +1097,7 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
     }
     if (nm_ensure_prepped(p, p->T)) return -1;  // leave no slice event un-consumed (nm_prepare_resident, NaN maps)
     if (!per_chunk) {
-        if (p->norm->run(p, n_windows)) return -1;
+        if (p->norm && p->norm->run(p, n_windows)) return -1;
         if (p->has_nan_cols) nan_fill(0, n_windows);
     }
     NM_CUDA_CHECK(cudaGetLastError());
@@ -1086,6 +1149,7 @@ extern "C" int nm_preprocess_window(nm_pipeline* p, const double* window, double
         rows.base = p->d_y.as<double>();
         rows.ch_stride = p->Wp;
     }
+    if (p->rawnorm && p->rawnorm->run(p, rows)) return -1;
     NM_CUDA_CHECK(cudaGetLastError());
     const double* src = rows.base;
     const long long pitch = rows.ch_stride;

@@ -1,0 +1,169 @@
+// nm_rawnorm.cuh -- RawNormalizer (processing/normalization.py:30-111, type "raw"), SURVEY.md 8f-3.
+//
+// Reference semantics per window g (counted since the processor was built), per channel, on the PREPROCESSED rows d_g
+// (filter -> notch -> re-reference of that very window):
+//   g == 0 : d_0 is returned unchanged and becomes the history
+//   g >= 1 : the last `add` = int(sfreq / rate) samples of d_g are appended to the history, d_g is normalised against the
+//            WHOLE history (those new samples included), clipped to +-clip, nan_to_num'ed, and the history is trimmed to
+//            its last n_keep - 1 samples.
+// The history is a stream of blocks -- block 0 = the W samples of window 0, block g = the `add` tail samples of window g --
+// kept in a per-channel ring; every block also leaves (n, mean, M2) behind, so that the mean / variance a window needs are
+// Chan-combined from <= ~300 block records plus one partially expired block read from the ring, instead of two passes over
+// 30 000 samples per (window, channel).  Histories hold un-normalised samples, so the windows of a chunk are independent
+// once their blocks are appended: kernel 1 appends (warp per (window, channel)), kernel 2 combines and normalises.
+// Methods: 0 mean, 2 zscore (the median variants need a sliding order statistic and are not on the GPU path yet).
+#pragma once
+
+#include "nm_common.cuh"
+
+struct NmRawNormArgs {
+    NmRows in;              // preprocessed rows of the chunk
+    double* out;            // (n_windows, n_ch, Wp) normalised rows
+    long long Wp;
+    double* ring;           // (n_ch, cap) history samples by stream position
+    long long cap;
+    double* blk;            // (n_ch, blk_cap, 3): n, mean, M2 of block j at [j % blk_cap]
+    int blk_cap;
+    long long g0;           // global index of the chunk's first window
+    int add;                // min(int(sfreq / rate), W)
+    const long long* lo;    // [n_windows] first stream position of the statistics range of window k (unused for g == 0)
+    int method;
+    double clip;
+};
+
+struct NmStat { double n, mean, m2; };
+
+NM_DEV NmStat nm_stat_merge(NmStat a, NmStat b) {
+    if (b.n == 0.0) return a;
+    if (a.n == 0.0) return b;
+    const double n = a.n + b.n, d = b.mean - a.mean;
+    return {n, a.mean + d * (b.n / n), a.m2 + b.m2 + d * d * (a.n * b.n / n)};
+}
+
+NM_DEV NmStat nm_stat_warp(NmStat s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        NmStat t;
+        t.n = __shfl_xor_sync(0xffffffffu, s.n, o);
+        t.mean = __shfl_xor_sync(0xffffffffu, s.mean, o);
+        t.m2 = __shfl_xor_sync(0xffffffffu, s.m2, o);
+        s = nm_stat_merge(s, t);
+    }
+    return s;
+}
+
+// stream geometry: block 0 = [0, W), block j >= 1 = [W + (j-1)*add, W + j*add)
+NM_DEV long long nm_rn_block_start(long long j, int W, int add) { return j == 0 ? 0 : (long long)W + (j - 1) * add; }
+
+// kernel 1: append the block of every window of the chunk (samples -> ring, two-pass block statistics -> blk)
+NM_GLOBAL void nm_rawnorm_append_kernel(NmRawNormArgs a) {
+    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const long long n_rows = (long long)a.in.n_windows * a.in.n_ch;
+    const int W = a.in.W;
+    for (long long row = (long long)blockIdx.x * wpc + (threadIdx.x >> 5); row < n_rows; row += (long long)gridDim.x * wpc) {
+        const int k = (int)(row / a.in.n_ch), c = (int)(row - (long long)k * a.in.n_ch);
+        const long long g = a.g0 + k;
+        const double* x = a.in.base + (size_t)c * a.in.ch_stride + nm_ldg(a.in.off + k);
+        const int len = (g == 0) ? W : a.add;
+        const double* src = x + (W - len);
+        const long long s0 = nm_rn_block_start(g, W, a.add);
+        double* ring = a.ring + (size_t)c * a.cap;
+        double sum = 0.0;
+        for (int t = lane; t < len; t += 32) {
+            const double v = src[t];
+            ring[(s0 + t) % a.cap] = v;
+            sum += v;
+        }
+        const double mean = nm_warp_sum(sum) / len;
+        double q = 0.0;
+        for (int t = lane; t < len; t += 32) {
+            const double e = src[t] - mean;
+            q += e * e;
+        }
+        q = nm_warp_sum(q);
+        if (lane == 0) {
+            double* b = a.blk + ((size_t)c * a.blk_cap + (size_t)(g % a.blk_cap)) * 3;
+            b[0] = (double)len;
+            b[1] = mean;
+            b[2] = q;
+        }
+    }
+}
+
+// kernel 2: statistics of the history range [lo, end of block g) and normalisation of the window
+NM_GLOBAL void nm_rawnorm_apply_kernel(NmRawNormArgs a) {
+    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const long long n_rows = (long long)a.in.n_windows * a.in.n_ch;
+    const int W = a.in.W;
+    for (long long row = (long long)blockIdx.x * wpc + (threadIdx.x >> 5); row < n_rows; row += (long long)gridDim.x * wpc) {
+        const int k = (int)(row / a.in.n_ch), c = (int)(row - (long long)k * a.in.n_ch);
+        const long long g = a.g0 + k;
+        const double* x = a.in.base + (size_t)c * a.in.ch_stride + nm_ldg(a.in.off + k);
+        double* y = a.out + ((size_t)k * a.in.n_ch + c) * a.Wp;
+        if (g == 0) {
+            for (int t = lane; t < W; t += 32) y[t] = x[t];
+            continue;
+        }
+        const long long lo = nm_ldg(a.lo + k);
+        // first block that lies completely inside the range
+        long long jf = (lo <= 0) ? 0 : ((lo <= W) ? 1 : (lo - W + a.add - 1) / a.add + 1);
+        const long long jf_start = nm_rn_block_start(jf, W, a.add);
+        NmStat s = {0.0, 0.0, 0.0};
+        // partially expired block jf - 1: samples [lo, jf_start) straight from the ring (Welford per lane)
+        const double* ring = a.ring + (size_t)c * a.cap;
+        for (long long i = lo + lane; i < jf_start; i += 32) {
+            const double v = ring[i % a.cap];
+            s.n += 1.0;
+            const double d = v - s.mean;
+            s.mean += d / s.n;
+            s.m2 += d * (v - s.mean);
+        }
+        const double* blk = a.blk + (size_t)c * a.blk_cap * 3;
+        for (long long j = jf + lane; j <= g; j += 32) {
+            const double* b = blk + (size_t)(j % a.blk_cap) * 3;
+            s = nm_stat_merge(s, NmStat{b[0], b[1], b[2]});
+        }
+        s = nm_stat_warp(s);
+        const double mean = s.mean;
+        double scale = mean;
+        if (a.method == 2) {
+            scale = sqrt(s.m2 / s.n);
+            if (scale == 0.0) scale = 1.0;  // same behaviour as the reference (and sklearn)
+        }
+        for (int t = lane; t < W; t += 32) {
+            double v = (x[t] - mean) / scale;
+            if (a.clip != 0.0) {  // (NaN compares false both ways and survives the clip like numpy.clip)
+                if (v > a.clip) v = a.clip;
+                if (v < -a.clip) v = -a.clip;
+            }
+            y[t] = nm_nan_to_num(v);
+        }
+    }
+}
+
+struct nm_pipeline;
+
+struct RawNormFam {
+    int method = 2, n_keep = 30000, add = 100, C = 0, W = 0, chunk = 0, blk_cap = 0;
+    double clip = 3.0;
+    long long cap = 0, Wp = 0, batch = 0, len_prev = 0;  // len_prev: history length after the last processed window
+    DevBuf d_ring, d_blk, d_out, d_lo;
+    int build(int method_, double clip_, int n_keep_, int add_, int C_, int W_) {
+        method = method_; clip = clip_; n_keep = n_keep_; C = C_; W = W_;
+        add = std::max(1, std::min(add_, W));
+        return 0;
+    }
+    int alloc_chunk(int chunk_, long long Wp_) {
+        chunk = chunk_;
+        Wp = Wp_;
+        const long long max_hist = std::max<long long>(W, n_keep > 1 ? n_keep - 1 : (1LL << 22)) + add;
+        cap = max_hist + (long long)chunk * add + W;
+        blk_cap = (int)(max_hist / add + chunk + 8);
+        if (d_ring.ensure((size_t)C * cap * sizeof(double))) return -1;
+        if (d_blk.ensure((size_t)C * blk_cap * 3 * sizeof(double))) return -1;
+        if (d_out.ensure((size_t)chunk * C * Wp * sizeof(double))) return -1;
+        return 0;
+    }
+    void reset() { batch = 0; len_prev = 0; }
+    int run(nm_pipeline* p, NmRows& rows);
+};

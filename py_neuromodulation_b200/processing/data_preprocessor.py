@@ -3,8 +3,8 @@
 The chain is executed in the fixed order of ``PREPROCESSOR_DICT`` -- NOT in the order of the
 ``settings.preprocessing`` list -- exactly like the reference (data_preprocessor.py:44-52).
 In scope on the GPU: ``preprocessing_filter``, ``notch_filter``, ``re_referencing`` and ``raw_resampling`` when it
-is the identity (resample_freq_hz == sfreq).  ``raw_normalization`` and resampling with a ratio != 1 are "next" rows
- and raise NotImplementedError.
+is the identity (resample_freq_hz == sfreq) and ``raw_normalization`` with the 'mean' / 'zscore' methods.  Resampling with a
+ratio != 1 and the median / scikit-learn raw normalisers raise NotImplementedError.
 """
 
 from __future__ import annotations
@@ -45,7 +45,10 @@ def preprocessing_plan(settings: "NMSettings", sfreq: float) -> list[str]:
                 )
             continue  # identity, like the reference (processing/resample.py:36-38)
         if name == "raw_normalization":
-            raise NotImplementedError(f"preprocessor '{name}' is not on the B200 path yet (SURVEY.md section 8f-3)")
+            method = settings.raw_normalization_settings.normalization_method
+            if method not in ("mean", "zscore"):
+                raise NotImplementedError(
+                    f"raw_normalization with method '{method}' is not on the B200 path (mean and zscore are; SURVEY.md section 8f-3)")
         plan.append(name)
     return plan
 
@@ -56,6 +59,7 @@ class DataPreprocessor:
     def __init__(self, settings: "NMSettings", channels, sfreq: float, line_noise: float | None = None) -> None:
         from ..filter.notch_filter import NotchFilter
         from .filter_preprocessing import PreprocessingFilter
+        from .normalization import RawNormalizer
         from .rereference import ReReferencer
 
         self.preprocessors: list[NMPreprocessor] = []
@@ -66,6 +70,8 @@ class DataPreprocessor:
                 self.preprocessors.append(NotchFilter(sfreq=sfreq, line_noise=line_noise))
             elif name == "re_referencing":
                 self.preprocessors.append(ReReferencer(sfreq=sfreq, channels=channels))
+            elif name == "raw_normalization":
+                self.preprocessors.append(RawNormalizer(sfreq=sfreq, settings=settings))
 
     def process_data(self, data: "np.ndarray") -> "np.ndarray":
         for pre in self.preprocessors:

@@ -52,3 +52,39 @@ class FeatureNormalizer:
             self._pipe = IdentityNormPipeline(v.size, GPU_NORM_METHODS.index(self.method), float(self.settings.clip or 0.0),
                                               self.num_samples_normalize)
         return self._pipe.step(v)
+
+
+class RawNormalizer:
+    """Rolling normalisation of the preprocessed samples (reference class of the same name, ``process(data) -> data``).
+
+    Stateful like the reference: window 0 passes through and seeds the history, later windows append their last
+    ``int(sfreq / sampling_rate_features_hz)`` samples and are normalised against the whole history
+    (``csrc/nm_rawnorm.cuh``).  'mean' and 'zscore' run on the GPU; the median variants and the scikit-learn
+    transformers raise ``NotImplementedError``.
+    """
+
+    GPU_METHODS = ("mean", "zscore")
+
+    def __init__(self, sfreq: float, settings: "NMSettings", **kwargs) -> None:
+        self.settings = settings.raw_normalization_settings.validate()
+        self.method = self.settings.normalization_method
+        if self.method not in self.GPU_METHODS:
+            raise NotImplementedError(
+                f"raw normalisation method '{self.method}' is not on the B200 path (supported: {', '.join(self.GPU_METHODS)})")
+        self.add_samples = int(sfreq / settings.sampling_rate_features_hz)
+        self.num_samples_normalize = int(self.settings.normalization_time_s * sfreq)
+        self._pipes: dict = {}
+
+    def process(self, data: np.ndarray) -> np.ndarray:
+        from .._pipeline import Pipeline, ScanSpec
+
+        data = np.asarray(data, dtype=np.float64)
+        n_ch, w = data.shape
+        pipe = self._pipes.get((n_ch, w))
+        if pipe is None:
+            pipe = Pipeline(n_ch, n_ch, w, ["_unused"])
+            pipe.set_raw_normalizer(self.method, self.settings.clip, self.num_samples_normalize, self.add_samples)
+            ScanSpec([f"_c{i}" for i in range(n_ch)]).attach(pipe)
+            pipe.finalize()
+            self._pipes[(n_ch, w)] = pipe
+        return pipe.preprocess_window(data)

@@ -87,6 +87,8 @@ class _Plan:
         pipe.set_prefilters(dp.prefilter_taps)
         if "notch_filter" in dp.preproc_plan:
             pipe.set_notch(dp.notch_taps)
+        if dp.rawnorm_cfg is not None:
+            pipe.set_raw_normalizer(*dp.rawnorm_cfg)
         if scan.hjorth or scan.raw or scan.linelength:
             scan.attach(pipe)
         for spec in specs:
@@ -162,6 +164,11 @@ class DataProcessor:
             self.prefilter_taps = PreprocessingFilter(self.settings, self.sfreq_raw).stage_taps()
             if self.prefilter_taps is None:
                 self.preproc_plan.remove("preprocessing_filter")
+        self.rawnorm_cfg = None
+        if "raw_normalization" in self.preproc_plan:
+            rs = self.settings.raw_normalization_settings.validate()
+            self.rawnorm_cfg = (rs.normalization_method, rs.clip, int(rs.normalization_time_s * self.sfreq_raw),
+                                int(self.sfreq_raw / self.settings.sampling_rate_features_hz))
         self.ref_matrix = None
         if "re_referencing" in self.preproc_plan:
             self.ref_matrix = build_reference_matrix(ch)
@@ -258,6 +265,8 @@ class DataProcessor:
             pipe.set_prefilters(self.prefilter_taps)
             if "notch_filter" in self.preproc_plan:
                 pipe.set_notch(self.notch_taps)
+            if self.rawnorm_cfg is not None:
+                pipe.set_raw_normalizer(*self.rawnorm_cfg)
             ScanSpec(names).attach(pipe)
             pipe.finalize()
             holder = _Plan.__new__(_Plan)

@@ -163,7 +163,8 @@ def test_out_of_scope_requests_fail_loudly():
     with pytest.raises(NotImplementedError):
         nm.Stream(sfreq=1000, data=x, settings=s)
     s = nm.NMSettings.get_default()
-    s.preprocessing = ["preprocessing_filter", "notch_filter"]
+    s.preprocessing = ["raw_normalization", "notch_filter"]
+    s.raw_normalization_settings.normalization_method = "quantile"  # scikit-learn transformer: out of scope
     with pytest.raises(NotImplementedError):
         nm.Stream(sfreq=1000, data=x, settings=s)
     s = nm.NMSettings.get_default()  # default resampling to 1 kHz of a 2 kHz recording: 'next' row 8f-2

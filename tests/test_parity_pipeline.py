@@ -42,7 +42,8 @@ def run_dp(g, n_windows=None, with_norm=True):
 
 @pytest.mark.parametrize("name,n_emu", [("dataprocessor_c3_nan", None), ("dataprocessor_fast", None), ("dataprocessor_default", 24),
                                         ("dataprocessor_realdata", 12), ("dataprocessor_prefilter_default", None),
-                                        ("dataprocessor_prefilter_lphp", None)])
+                                        ("dataprocessor_prefilter_lphp", None), ("dataprocessor_rawnorm_zscore", None),
+                                        ("dataprocessor_rawnorm_mean", None)])
 def test_window_processor_matches_reference_golden(backend, name, n_emu):
     g = load_golden(name)
     n = n_emu if backend == "emu" else None  # the thread emulator is slow: fewer windows on CPU, all on the GPU
@@ -298,3 +299,32 @@ def test_standalone_preprocessing_filter_matches_oracle(backend):
     ref = orc.apply_prefilters(x, orc.design_prefilters(s.model_dump(), 1000))
     assert got.shape == ref.shape == x.shape
     assert np.max(np.abs(got - ref)) <= 1e-11 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_raw_normalizer_streaming_and_standalone(backend):
+    """RawNormalizer state across calls: window-by-window DataProcessor.process == batched run == stand-alone class ==
+    oracle; the median variants are refused loudly."""
+    from py_neuromodulation_b200.processing import RawNormalizer
+
+    g = load_golden("dataprocessor_rawnorm_zscore")
+    x = g["x"].astype(np.float64)
+    s = nm.NMSettings(**g["settings"])
+    ch = get_default_channels_from_data(x)
+    dp = nm.DataProcessor(sfreq=1000, settings=s, channels=ch, line_noise=50, verbose=False)
+    starts, _, _ = window_grid(x.shape[1], 1000, s.sampling_rate_features_hz, s.segment_length_features_ms)
+    for k in range(30):
+        d = dp.process(x[:, starts[k] : starts[k] + 1000])
+        v = np.array([float(d[c]) for c in g["keys"]])
+        ref = g["vals"][k]
+        assert np.max(np.abs(v - ref) / np.maximum(np.abs(ref), 1.0)) < TOL, k
+    # stand-alone class on raw windows (no other preprocessing) against the oracle's restatement
+    rn = RawNormalizer(sfreq=1000, settings=s)
+    ora = orc.RawNormalizerOracle(s.model_dump(), 1000)
+    for k in range(30):
+        w = x[:, starts[k] : starts[k] + 1000]
+        got, ref = rn.process(w), ora.process(w)
+        assert np.max(np.abs(got - ref)) < 1e-10, k
+    s2 = nm.NMSettings(**g["settings"])
+    s2.raw_normalization_settings.normalization_method = "median"
+    with pytest.raises(NotImplementedError):
+        nm.DataProcessor(sfreq=1000, settings=s2, channels=ch, line_noise=50, verbose=False)
