@@ -153,6 +153,7 @@ class ShardedRun:
             self._block = None if cols == wmax else local.new_zeros(n_windows, wmax)
             self._parts = [local.new_empty(n_windows, wmax) for _ in range(world)] if rank == 0 else None
             self._host = None
+            self._full = None
             if rank == 0:
                 self._host = torch.empty((n_windows, sum(self._widths)), dtype=local.dtype, pin_memory=self.on_gpu)
             self._gather_key = key
@@ -165,10 +166,12 @@ class ShardedRun:
             dist.gather(block, gather_list=None, dst=0)
             return None
         dist.gather(block, gather_list=self._parts, dst=0)
-        off = 0
-        for part, w in zip(self._parts, self._widths):
-            self._host[:, off : off + w].copy_(part[:, :w], non_blocking=True)
-            off += w
+        # concatenate the column blocks ON THE DEVICE (one pass at HBM speed), then a single contiguous D2H into the
+        # pinned matrix: a strided device->host copy per block goes through a slow path (87 ms instead of 3 ms for 147 MB)
+        if self._full is None:
+            self._full = local.new_empty(n_windows, sum(self._widths))
+        torch.cat([part[:, :w] for part, w in zip(self._parts, self._widths)], dim=1, out=self._full)
+        self._host.copy_(self._full, non_blocking=True)
         if self.on_gpu:
             torch.cuda.current_stream().synchronize()
         return self._host.numpy()
