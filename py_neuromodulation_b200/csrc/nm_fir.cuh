@@ -75,8 +75,10 @@ struct NmEpiStore {
 };
 
 // ---------------------------------------------------------------- epilogue: band power (features/bandpower.py:165-207)
+#define NM_BP_MAX_INLINE 16
 struct NmEpiBandpower {
-    const int* seglen;     // [nF] tail length in samples
+    const int* seglen;     // [nF] tail length in samples (device array, shared-memory epilogue)
+    int seglen_k[NM_BP_MAX_INLINE];  // the same values in the kernel parameter space (register epilogue: no global load per band)
     int want_act, want_mob, want_comp, log_act;
     NmOut out;             // per_ch = nF * 3  (activity, mobility, complexity)
     static constexpr bool kRegs = true;
@@ -90,7 +92,7 @@ struct NmEpiBandpower {
     NM_DEV void consume(const cx<double>* v, cx<double>* /*work*/, double* /*red*/, State& st, int o0, int W, int /*n_ch*/, int /*w*/, int /*c0*/,
                         bool /*has2*/, int f, int tid) const {
         constexpr int NT = PL::NT;
-        int seg = nm_ldg(seglen + f);
+        int seg = (f < NM_BP_MAX_INLINE) ? seglen_k[f] : nm_ldg(seglen + f);
         if (seg > W) seg = W;
         st.seg = seg;
         const int lo = o0 + W - seg, hi = o0 + W;

@@ -72,6 +72,7 @@ struct SpectralFam {
 struct BandpowerFam {
     FirBank bank;
     DevBuf d_seglen, d_colmap;
+    std::vector<int> h_seglen;
     int act = 0, mob = 0, comp = 0, logt = 0;
     // the register epilogue (activity only) keeps its reduction scratch inside the free `work` buffer
     size_t epi_smem() const { return NmEpiBandpower::smem_bytes(NM_FFT_THREADS); }
@@ -650,6 +651,7 @@ extern "C" int nm_add_bandpower(nm_pipeline* p, int n_bands, const double* taps,
     if (f->bank.build(taps, n_bands, n_taps, p->W, NM_FIR_SAME, p->stream)) return -1;
     for (int b = 0; b < n_bands; ++b) NM_CHECK(seglen[b] >= 1, "segment length must be >= 1 sample");
     if (f->d_seglen.upload(seglen, (size_t)n_bands, p->stream)) return -1;
+    f->h_seglen.assign(seglen, seglen + n_bands);
     if (f->d_colmap.upload(colmap, (size_t)p->C * n_bands * 3, p->stream)) return -1;
     NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
     f->act = activity; f->mob = mobility; f->comp = complexity; f->logt = log_transform;
@@ -1022,6 +1024,7 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         BandpowerFam& f = *p->bandpower;
         NmEpiBandpower epi;
         epi.seglen = f.d_seglen.as<int>();
+        for (int b = 0; b < NM_BP_MAX_INLINE; ++b) epi.seglen_k[b] = b < (int)f.h_seglen.size() ? f.h_seglen[b] : 1;
         epi.want_act = f.act; epi.want_mob = f.mob; epi.want_comp = f.comp; epi.log_act = f.logt;
         epi.out = out_for(f.d_colmap, f.bank.nF * 3);
         p->prof_begin();
