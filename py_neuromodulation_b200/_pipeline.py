@@ -118,9 +118,9 @@ class Pipeline:
         _lib.check(self.lib.nm_set_notch(self._h, _ptr(a, C.c_double), int(a.size)))
 
     def set_raw_normalizer(self, method: str, clip: float, n_keep: int, add_samples: int) -> None:
-        """RawNormalizer in front of the features ('mean' / 'zscore'; the median variants are not on the GPU path yet)."""
-        if method not in ("mean", "zscore"):
-            raise NotImplementedError(f"raw normalisation method '{method}' is not on the B200 path yet (mean and zscore are)")
+        """RawNormalizer in front of the features (mean / median / zscore / zscore-median; scikit-learn methods are out of scope)."""
+        if method not in NORM_METHODS:
+            raise NotImplementedError(f"raw normalisation method '{method}' (scikit-learn transformer) is out of scope")
         _lib.check(self.lib.nm_set_raw_normalizer(self._h, NORM_METHODS.index(method), float(clip or 0.0), int(n_keep), int(add_samples)))
 
     def set_prefilters(self, stages: Sequence[np.ndarray] | None) -> None:

@@ -135,9 +135,17 @@ static NM_HD size_t nm_bq_smem_bytes() {
     return NM_SEL_BINS * sizeof(int) + NM_BQ_CAP * 8 + NM_BQ_CAP * 4 + 16 * sizeof(int) + 4 * 8 + 32 * sizeof(int) + 64;
 }
 
-NM_DEV unsigned long long nm_bq_key(const double* rrow, long long cap, long long i) {
-    return (unsigned long long)__double_as_longlong(rrow[i % cap]);
+// order-preserving map double -> unsigned 64-bit key (all finite values, either sign) and back: the sliding order
+// statistics serve the burst envelopes (>= 0) and the raw-normaliser medians (signed samples) with the same code
+NM_DEV unsigned long long nm_key_of(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
+NM_DEV double nm_val_of(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+NM_DEV unsigned long long nm_bq_key(const double* rrow, long long cap, long long i) { return nm_key_of(rrow[i % cap]); }
 
 // Visit the history samples i = i0 + lane_or_tid + k * step (i < i1) of the ring row: f(i, key).  `pos0` is the ring
 // position of sample 0 of the history (already reduced mod cap); positions wrap at most once.  Four independent loads
@@ -152,15 +160,15 @@ NM_DEV void nm_bq_for_each(const double* NM_RESTRICT rrow, long long cap, long l
         if (p2 >= cap) p2 -= cap;
         if (p3 >= cap) p3 -= cap;
         const double v0 = rrow[p0], v1 = rrow[p1], v2 = rrow[p2], v3 = rrow[p3];
-        f(i, (unsigned long long)__double_as_longlong(v0));
-        f(i + step, (unsigned long long)__double_as_longlong(v1));
-        f(i + 2 * step, (unsigned long long)__double_as_longlong(v2));
-        f(i + 3 * step, (unsigned long long)__double_as_longlong(v3));
+        f(i, nm_key_of(v0));
+        f(i + step, nm_key_of(v1));
+        f(i + 2 * step, nm_key_of(v2));
+        f(i + 3 * step, nm_key_of(v3));
     }
     for (; i < i1; i += step) {
         long long p = pos0 + i;
         if (p >= cap) p -= cap;
-        f(i, (unsigned long long)__double_as_longlong(rrow[p]));
+        f(i, nm_key_of(rrow[p]));
     }
 }
 
@@ -248,7 +256,7 @@ NM_DEV double nm_bq_select_direct(const double* rrow, long long cap, long long f
         a_key = sm.res[0];
     }
     // second order statistic: a again if duplicated far enough, else the smallest larger value
-    const double av = __longlong_as_double((long long)a_key);
+    const double av = nm_val_of(a_key);
     double thr = av;
     if (k_hi != k_lo) {
         if (tid == 0) { sm.ctl[4] = 0; sm.ctl[5] = 0; }
@@ -274,7 +282,7 @@ NM_DEV double nm_bq_select_direct(const double* rrow, long long cap, long long f
         __syncthreads();
         unsigned long long best = ~0ull;
         for (int q = 0; q < ((nt + 31) >> 5); ++q) best = sm.qk[q] < best ? sm.qk[q] : best;
-        const double bv = (k_hi < sm.ctl[4] + sm.ctl[5]) ? av : __longlong_as_double((long long)best);
+        const double bv = (k_hi < sm.ctl[4] + sm.ctl[5]) ? av : nm_val_of(best);
         const double diff = bv - av;
         double lerp = av + diff * gamma;
         if (gamma >= 0.5) lerp = bv - diff * (1.0 - gamma);
@@ -318,7 +326,7 @@ NM_DEV bool nm_bq_gather(const double* rrow, long long cap, long long first, int
         if (i < s1) {
             long long p = first_mod + i;
             if (p >= cap) p -= cap;
-            key = (unsigned long long)__double_as_longlong(rrow[p]);
+            key = nm_key_of(rrow[p]);
             in = key >= lo_key && key < hi_key;
         }
         const unsigned bm = __ballot_sync(0xffffffffu, in);
@@ -534,7 +542,7 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
                     if (i < n_enter) {
                         long long p = enter_mod + i;
                         if (p >= a.cap) p -= a.cap;
-                        key = (unsigned long long)__double_as_longlong(rrow[p]);
+                        key = nm_key_of(rrow[p]);
                         if (key < lo_key) delta += 1;
                         else in = key < hi_key;
                     }
@@ -593,10 +601,10 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
             }
             if (valid) {
                 nm_bq_select_queue(sm, head, count, lo_key, hi_key, k_lo - cnt_below, want_next, tid, nt);
-                const double av = __longlong_as_double((long long)sm.res[0]);
+                const double av = nm_val_of(sm.res[0]);
                 thr = av;
                 if (want_next) {
-                    const double bv = __longlong_as_double((long long)sm.res[1]);
+                    const double bv = nm_val_of(sm.res[1]);
                     const double g = a.gamma[w];
                     const double diff = bv - av;
                     double lerp = av + diff * g;

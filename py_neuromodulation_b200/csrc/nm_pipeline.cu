@@ -373,17 +373,25 @@ int SharpwaveFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
 int RawNormFam::run(nm_pipeline* p, NmRows& rows) {
     const int n = rows.n_windows;
     // history bookkeeping per window (processing/normalization.py:92-107): statistics range [lo, end of block g)
-    std::vector<long long> lo(n, 0);
+    std::vector<long long> lo(n, 0), e_end(n, 0);
+    std::vector<int> nh(n, 0), klo(n, 0), khi(n, 0);
+    std::vector<double> gam(n, 0.0);
     for (int k = 0; k < n; ++k) {
         const long long g = batch + k;
+        long long hist = W;
+        e_end[k] = (long long)W + g * add;
         if (g == 0) {
             len_prev = W;
-            continue;
+        } else {
+            hist = len_prev + add;
+            lo[k] = e_end[k] - hist;
+            len_prev = (n_keep > 1) ? std::min<long long>(hist, n_keep - 1) : hist;  // previous[-n_keep + 1:] keeps everything for n_keep == 1
         }
-        const long long hist = len_prev + add;
-        const long long end = (long long)W + g * add;
-        lo[k] = end - hist;
-        len_prev = (n_keep > 1) ? std::min<long long>(hist, n_keep - 1) : hist;  // previous[-n_keep + 1:] keeps everything for n_keep == 1
+        // numpy.median == 'linear' quantile at 0.5: order statistics (hist - 1) / 2 rounded down / up, averaged
+        nh[k] = (int)hist;
+        klo[k] = (int)((hist - 1) / 2);
+        khi[k] = (int)(hist / 2);
+        gam[k] = (hist % 2 == 0) ? 0.5 : 0.0;
     }
     NM_CHECK(n_keep > 1 || (long long)W + (batch + n) * add < cap, "raw normalisation history exceeds the ring (normalization_time_s * sfreq == 1)");
     if (d_lo.upload(lo, p->stream)) return -1;
@@ -401,11 +409,33 @@ int RawNormFam::run(nm_pipeline* p, NmRows& rows) {
     a.lo = d_lo.as<long long>();
     a.method = method;
     a.clip = clip;
+    a.med = need_median() ? d_med.as<double>() : nullptr;
     const int wpc = NM_ROW_THREADS / 32;
     const long long n_rows = (long long)n * C;
     const int grid = (int)std::max<long long>(1, std::min<long long>((n_rows + wpc - 1) / wpc, (long long)p->n_sm * 16));
     p->prof_begin();
     NM_LAUNCH(nm_rawnorm_append_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
+    if (need_median()) {
+        if (d_e_end.upload(e_end, p->stream) || d_n.upload(nh, p->stream) || d_klo.upload(klo, p->stream) || d_khi.upload(khi, p->stream) ||
+            d_gamma.upload(gam, p->stream))
+            return -1;
+        NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+        NmBurstThrArgs ta;
+        ta.ring = d_ring.as<double>();
+        ta.cap = cap;
+        ta.n_ch = C; ta.nB = 1; ta.n_windows = n;
+        ta.e_end = d_e_end.as<long long>();
+        ta.n_hist = d_n.as<int>();
+        ta.k_lo = d_klo.as<int>(); ta.k_hi = d_khi.as<int>();
+        ta.gamma = d_gamma.as<double>();
+        ta.thr = d_med.as<double>();
+        ta.qrow = d_qrow.as<NmBurstQRow>();
+        ta.qkey = d_qkey.as<unsigned long long>();
+        ta.qidx = d_qidx.as<unsigned>();
+        ta.incremental = 1;
+        NM_LAUNCH(nm_burst_thr_kernel, dim3(C), dim3(NM_BQ_THREADS), BurstsFam::thr_smem(), p->stream, ta);
+        p->launches++;
+    }
     NM_LAUNCH(nm_rawnorm_apply_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
     p->prof_end(NM_PROF_NOTCH);
     p->launches += 2;
@@ -711,7 +741,7 @@ extern "C" int nm_add_feature_normalizer(nm_pipeline* p, int method, double clip
 extern "C" int nm_set_raw_normalizer(nm_pipeline* p, int method, double clip, int n_keep, int add_samples) {
     NM_P_CHECK(p);
     NM_CHECK(!p->finalized, "pipeline already finalized");
-    NM_CHECK(method == 0 || method == 2, "raw normalisation on the GPU supports 'mean' (0) and 'zscore' (2); got %d", method);
+    NM_CHECK(method >= 0 && method <= 3, "raw normalisation method must be 0..3 (mean, median, zscore, zscore-median); got %d", method);
     NM_CHECK(n_keep >= 1 && add_samples >= 1 && clip >= 0.0, "bad raw normaliser configuration");
     auto f = std::make_unique<RawNormFam>();
     if (f->build(method, clip, n_keep, add_samples, p->C, p->W)) return -1;
@@ -750,6 +780,7 @@ extern "C" int nm_finalize(nm_pipeline* p) {
         if (nm_allow_fir_smem<NmEpiStore>(*b, 0, p)) return -1;
     if (p->bursts && p->bursts->alloc_chunk(p->chunk, p->Wp)) return -1;
     if (p->rawnorm && p->rawnorm->alloc_chunk(p->chunk, p->Wp)) return -1;
+    if (p->rawnorm && p->rawnorm->need_median() && nm_allow_smem(nm_burst_thr_kernel, BurstsFam::thr_smem(), p)) return -1;
 
     // opt in to large dynamic shared memory once
     if (p->notch && (nm_allow_fir_smem<NmEpiStore>(*p->notch, 0, p) || nm_allow_fir_smem<NmEpiStoreScan>(*p->notch, 0, p))) return -1;

@@ -11,10 +11,11 @@
 // Chan-combined from <= ~300 block records plus one partially expired block read from the ring, instead of two passes over
 // 30 000 samples per (window, channel).  Histories hold un-normalised samples, so the windows of a chunk are independent
 // once their blocks are appended: kernel 1 appends (warp per (window, channel)), kernel 2 combines and normalises.
-// Methods: 0 mean, 2 zscore (the median variants need a sliding order statistic and are not on the GPU path yet).
+// Methods: 0 mean, 2 zscore; 1 median and 3 zscore-median take the median of the same history from the sliding
+// order-statistic kernel of the burst thresholds (nm_burst_thr_kernel on signed keys, q = 0.5) between the two kernels.
 #pragma once
 
-#include "nm_common.cuh"
+#include "nm_bursts.cuh"
 
 struct NmRawNormArgs {
     NmRows in;              // preprocessed rows of the chunk
@@ -29,6 +30,7 @@ struct NmRawNormArgs {
     const long long* lo;    // [n_windows] first stream position of the statistics range of window k (unused for g == 0)
     int method;
     double clip;
+    const double* med;      // (n_windows, n_ch) medians of the histories (methods 1 and 3), else nullptr
 };
 
 struct NmStat { double n, mean, m2; };
@@ -124,14 +126,16 @@ NM_GLOBAL void nm_rawnorm_apply_kernel(NmRawNormArgs a) {
             s = nm_stat_merge(s, NmStat{b[0], b[1], b[2]});
         }
         s = nm_stat_warp(s);
-        const double mean = s.mean;
-        double scale = mean;
-        if (a.method == 2) {
+        // centre / scale per method: mean -> (mean, mean); median -> (med, med); zscore -> (mean, std); zscore-median -> (med, std)
+        double centre = s.mean;
+        if (a.method == 1 || a.method == 3) centre = nm_ldg(a.med + (size_t)k * a.in.n_ch + c);
+        double scale = centre;
+        if (a.method >= 2) {
             scale = sqrt(s.m2 / s.n);
             if (scale == 0.0) scale = 1.0;  // same behaviour as the reference (and sklearn)
         }
         for (int t = lane; t < W; t += 32) {
-            double v = (x[t] - mean) / scale;
+            double v = (x[t] - centre) / scale;
             if (a.clip != 0.0) {  // (NaN compares false both ways and survives the clip like numpy.clip)
                 if (v > a.clip) v = a.clip;
                 if (v < -a.clip) v = -a.clip;
@@ -148,6 +152,9 @@ struct RawNormFam {
     double clip = 3.0;
     long long cap = 0, Wp = 0, batch = 0, len_prev = 0;  // len_prev: history length after the last processed window
     DevBuf d_ring, d_blk, d_out, d_lo;
+    // sliding median (methods 1, 3): per-window bookkeeping + persistent state of nm_burst_thr_kernel, one row per channel
+    DevBuf d_e_end, d_n, d_klo, d_khi, d_gamma, d_med, d_qrow, d_qkey, d_qidx;
+    bool need_median() const { return method == 1 || method == 3; }
     int build(int method_, double clip_, int n_keep_, int add_, int C_, int W_) {
         method = method_; clip = clip_; n_keep = n_keep_; C = C_; W = W_;
         add = std::max(1, std::min(add_, W));
@@ -162,8 +169,17 @@ struct RawNormFam {
         if (d_ring.ensure((size_t)C * cap * sizeof(double))) return -1;
         if (d_blk.ensure((size_t)C * blk_cap * 3 * sizeof(double))) return -1;
         if (d_out.ensure((size_t)chunk * C * Wp * sizeof(double))) return -1;
+        if (need_median()) {
+            if (d_med.ensure((size_t)chunk * C * sizeof(double))) return -1;
+            if (d_qrow.ensure((size_t)C * sizeof(NmBurstQRow)) || d_qkey.ensure((size_t)C * NM_BQ_CAP * 8) || d_qidx.ensure((size_t)C * NM_BQ_CAP * 4)) return -1;
+            NM_CUDA_CHECK(cudaMemset(d_qrow.p, 0, (size_t)C * sizeof(NmBurstQRow)));
+        }
         return 0;
     }
-    void reset() { batch = 0; len_prev = 0; }
+    void reset() {
+        batch = 0;
+        len_prev = 0;
+        if (d_qrow.p) cudaMemset(d_qrow.p, 0, (size_t)C * sizeof(NmBurstQRow));
+    }
     int run(nm_pipeline* p, NmRows& rows);
 };

@@ -3,8 +3,8 @@
 The chain is executed in the fixed order of ``PREPROCESSOR_DICT`` -- NOT in the order of the
 ``settings.preprocessing`` list -- exactly like the reference (data_preprocessor.py:44-52).
 In scope on the GPU: ``preprocessing_filter``, ``notch_filter``, ``re_referencing`` and ``raw_resampling`` when it
-is the identity (resample_freq_hz == sfreq) and ``raw_normalization`` with the 'mean' / 'zscore' methods.  Resampling with a
-ratio != 1 and the median / scikit-learn raw normalisers raise NotImplementedError.
+is the identity (resample_freq_hz == sfreq) and ``raw_normalization`` (mean / median / zscore / zscore-median).  Resampling
+with a ratio != 1 and the scikit-learn raw normalisers raise NotImplementedError.
 """
 
 from __future__ import annotations
@@ -46,9 +46,8 @@ def preprocessing_plan(settings: "NMSettings", sfreq: float) -> list[str]:
             continue  # identity, like the reference (processing/resample.py:36-38)
         if name == "raw_normalization":
             method = settings.raw_normalization_settings.normalization_method
-            if method not in ("mean", "zscore"):
-                raise NotImplementedError(
-                    f"raw_normalization with method '{method}' is not on the B200 path (mean and zscore are; SURVEY.md section 8f-3)")
+            if method not in ("mean", "median", "zscore", "zscore-median"):
+                raise NotImplementedError(f"raw_normalization with the scikit-learn method '{method}' is out of scope")
         plan.append(name)
     return plan
 

@@ -59,11 +59,11 @@ class RawNormalizer:
 
     Stateful like the reference: window 0 passes through and seeds the history, later windows append their last
     ``int(sfreq / sampling_rate_features_hz)`` samples and are normalised against the whole history
-    (``csrc/nm_rawnorm.cuh``).  'mean' and 'zscore' run on the GPU; the median variants and the scikit-learn
-    transformers raise ``NotImplementedError``.
+    (``csrc/nm_rawnorm.cuh``; the medians come from the sliding order-statistic kernel of the burst thresholds).
+    The scikit-learn transformers raise ``NotImplementedError``.
     """
 
-    GPU_METHODS = ("mean", "zscore")
+    GPU_METHODS = GPU_NORM_METHODS
 
     def __init__(self, sfreq: float, settings: "NMSettings", **kwargs) -> None:
         self.settings = settings.raw_normalization_settings.validate()

@@ -43,7 +43,8 @@ def run_dp(g, n_windows=None, with_norm=True):
 @pytest.mark.parametrize("name,n_emu", [("dataprocessor_c3_nan", None), ("dataprocessor_fast", None), ("dataprocessor_default", 24),
                                         ("dataprocessor_realdata", 12), ("dataprocessor_prefilter_default", None),
                                         ("dataprocessor_prefilter_lphp", None), ("dataprocessor_rawnorm_zscore", None),
-                                        ("dataprocessor_rawnorm_mean", None)])
+                                        ("dataprocessor_rawnorm_mean", None), ("dataprocessor_rawnorm_median", None),
+                                        ("dataprocessor_rawnorm_zscore_median", None)])
 def test_window_processor_matches_reference_golden(backend, name, n_emu):
     g = load_golden(name)
     n = n_emu if backend == "emu" else None  # the thread emulator is slow: fewer windows on CPU, all on the GPU
@@ -303,7 +304,7 @@ def test_standalone_preprocessing_filter_matches_oracle(backend):
 
 def test_raw_normalizer_streaming_and_standalone(backend):
     """RawNormalizer state across calls: window-by-window DataProcessor.process == batched run == stand-alone class ==
-    oracle; the median variants are refused loudly."""
+    oracle; the scikit-learn variants are refused loudly."""
     from py_neuromodulation_b200.processing import RawNormalizer
 
     g = load_golden("dataprocessor_rawnorm_zscore")
@@ -325,6 +326,6 @@ def test_raw_normalizer_streaming_and_standalone(backend):
         got, ref = rn.process(w), ora.process(w)
         assert np.max(np.abs(got - ref)) < 1e-10, k
     s2 = nm.NMSettings(**g["settings"])
-    s2.raw_normalization_settings.normalization_method = "median"
+    s2.raw_normalization_settings.normalization_method = "robust"  # scikit-learn transformer
     with pytest.raises(NotImplementedError):
         nm.DataProcessor(sfreq=1000, settings=s2, channels=ch, line_noise=50, verbose=False)
