@@ -783,5 +783,7 @@ struct BurstsFam {
     size_t epi_smem() const { return NmEpiBursts::smem_bytes_for(W, hfft.generic); }
     static size_t thr_smem() { return nm_bq_smem_bytes(); }
     int allow_smem(const nm_pipeline* p);
+    long long run_base = 0;  // `batch` at the time prepare() ran
+    int prepare(nm_pipeline* p, int n_windows);
     int run(nm_pipeline* p, const NmRows& rows, int w0);
 };

@@ -90,6 +90,10 @@ struct nm_pipeline {
     // window kernels run on `stream`; slices are re-referenced lazily, right before the first chunk that needs them
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_sync = nullptr;
+    // independent feature families of a chunk (spectral + band power | sharp waves | bursts) run on side streams between a
+    // fork after the notch and a join before the next chunk: their kernels are latency / occupancy limited in different ways
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> slice_ev, chunk_ev;
     long long slice_len = 0;
     int n_slices = 0, slices_prepped = 0;
@@ -285,9 +289,9 @@ int BurstsFam::allow_smem(const nm_pipeline* p) {
     return nm_allow_smem(nm_burst_thr_kernel, thr_smem(), p);
 }
 
-int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
-    const int n = rows.n_windows;
-    // numpy 'linear' quantile bookkeeping per window (numpy/lib/_function_base_impl.py _quantile, alpha = beta = 1)
+// numpy 'linear' quantile bookkeeping (numpy/lib/_function_base_impl.py _quantile, alpha = beta = 1) for ALL windows of a
+// run, uploaded once: the chunk launches then only offset into these arrays (no host synchronisation per chunk)
+int BurstsFam::prepare(nm_pipeline* p, int n) {
     std::vector<long long> e_end(n);
     std::vector<int> nh(n), klo(n), khi(n);
     std::vector<double> gam(n);
@@ -308,6 +312,14 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
         d_gamma.upload(gam, p->stream))
         return -1;
     NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));  // the staging vectors above are temporaries
+    run_base = batch;
+    return 0;
+}
+
+int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
+    const int n = rows.n_windows;
+    const long long k0 = batch - run_base;  // offset of this chunk inside the arrays prepared for the run
+    (void)w0;
 
     NmEpiBursts epi;
     epi.hfft = hfft.dev();
@@ -327,10 +339,10 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     ta.ring = d_ring.as<double>();
     ta.cap = cap;
     ta.n_ch = C; ta.nB = nB; ta.n_windows = n;
-    ta.e_end = d_e_end.as<long long>();
-    ta.n_hist = d_n.as<int>();
-    ta.k_lo = d_lo.as<int>(); ta.k_hi = d_hi.as<int>();
-    ta.gamma = d_gamma.as<double>();
+    ta.e_end = d_e_end.as<long long>() + k0;
+    ta.n_hist = d_n.as<int>() + k0;
+    ta.k_lo = d_lo.as<int>() + k0; ta.k_hi = d_hi.as<int>() + k0;
+    ta.gamma = d_gamma.as<double>() + k0;
     ta.thr = d_thr.as<double>();
     ta.qrow = d_qrow.as<NmBurstQRow>();
     ta.qkey = d_qkey.as<unsigned long long>();
@@ -503,6 +515,11 @@ extern "C" int nm_pipeline_create(int device, int n_raw_rows, int n_ch, int wind
     NM_CUDA_CHECK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     NM_CUDA_CHECK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
     NM_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_sync, cudaEventDisableTiming));
+    NM_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    for (int b = 0; b < 3; ++b) {
+        NM_CUDA_CHECK(cudaStreamCreateWithFlags(&p->side[b], cudaStreamNonBlocking));
+        NM_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_join[b], cudaEventDisableTiming));
+    }
     NM_CUDA_CHECK(cudaEventCreate(&p->ev0));
     NM_CUDA_CHECK(cudaEventCreate(&p->ev1));
     NM_CUDA_CHECK(cudaEventCreate(&p->pe0));
@@ -525,6 +542,11 @@ extern "C" void nm_pipeline_destroy(nm_pipeline* p) {
     if (p->pe1) cudaEventDestroy(p->pe1);
     if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
     if (p->ev_sync) cudaEventDestroy(p->ev_sync);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    for (int b = 0; b < 3; ++b) {
+        if (p->side[b]) { cudaStreamSynchronize(p->side[b]); cudaStreamDestroy(p->side[b]); }
+        if (p->ev_join[b]) cudaEventDestroy(p->ev_join[b]);
+    }
     for (auto e : p->slice_ev) cudaEventDestroy(e);
     for (auto e : p->chunk_ev) cudaEventDestroy(e);
     cudaStream_t s = p->stream, cs = p->copy_stream;
@@ -1021,6 +1043,23 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         p->prof_end(NM_PROF_SCAN);
         p->launches++;
     }
+    // ---- fork: the families below only read `rows` and write disjoint columns of `out`
+    cudaStream_t const main_stream = p->stream;
+    const int n_branches = ((!p->spectral.empty() || p->bandpower) ? 1 : 0) + (p->sharpwave ? 1 : 0) + (p->bursts ? 1 : 0);
+    const bool fork = !p->profiling && n_branches >= 2;
+    if (fork) NM_CUDA_CHECK(cudaEventRecord(p->ev_fork, main_stream));
+    auto branch_begin = [&](int b) {
+        if (!fork) return;
+        cudaStreamWaitEvent(p->side[b], p->ev_fork, 0);
+        p->stream = p->side[b];
+    };
+    auto branch_end = [&](int b) {
+        if (!fork) return;
+        cudaEventRecord(p->ev_join[b], p->side[b]);
+        p->stream = main_stream;
+        cudaStreamWaitEvent(main_stream, p->ev_join[b], 0);
+    };
+    branch_begin(0);
     for (auto& f : p->spectral) {
         NmSpecArgs a;
         const nm_spectral_cfg& c = f->cfg;
@@ -1063,8 +1102,15 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         p->prof_end(NM_PROF_BANDPOWER);
         p->launches++;
     }
-    if (p->sharpwave && p->sharpwave->run(p, rows, w0)) return -1;
-    if (p->bursts && p->bursts->run(p, rows, w0)) return -1;
+    branch_end(0);
+    int rc = 0;
+    branch_begin(1);
+    if (p->sharpwave) rc |= p->sharpwave->run(p, rows, w0);
+    branch_end(1);
+    branch_begin(2);
+    if (p->bursts) rc |= p->bursts->run(p, rows, w0);
+    branch_end(2);
+    if (rc) return -1;
     NM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -1106,6 +1152,7 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
         NM_LAUNCH(nm_nanfill_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, nf);
         p->launches += 2;
     };
+    if (p->bursts && p->bursts->prepare(p, n_windows)) return -1;
     int n_ev = 0;
     for (int w0 = 0; w0 < n_windows; w0 += p->chunk) {
         const int n = std::min(p->chunk, n_windows - w0);
