@@ -151,3 +151,57 @@ def test_batch_equals_streaming_at_scale(gpu):
         d = dp2.process(x[:, starts[k] : starts[k] + 1000])
         v = np.array([float(t) for t in d.values()])
         assert rel(v, mat[k]) < 1e-12, k
+
+
+def test_burst_thresholds_long_run_incremental_vs_direct_and_oracle(gpu):
+    """Sliding order statistics far beyond the ring fill: 64 ch x 120 s (1 191 windows) incremental == direct selection bit
+    for bit; 8 ch x 100 s against the oracle's true-ring quantile on every window."""
+    s = nm.NMSettings.get_default().reset()
+    s.features.bursts = True
+    s.postprocessing.feature_normalization = False
+    x = neural_like(9, 64, 120_000).astype(np.float32)
+    starts, _, _ = window_grid(x.shape[1], 1000, 10, 1000)
+    outs = []
+    for incremental in (True, False):
+        dp = nm.DataProcessor(sfreq=1000, settings=s, channels=get_default_channels_from_data(x), line_noise=50, verbose=False)
+        dp.plan(1000).pipe.set_burst_threshold_mode(incremental)
+        cols, mat = dp.process_windows(x, starts, 1000)
+        outs.append(mat)
+        if incremental:
+            rebuilds, direct = dp.plan(1000).pipe.burst_threshold_stats()
+            assert rebuilds + direct < 0.1 * 128 * starts.size, (rebuilds, direct)
+    assert np.array_equal(outs[0], outs[1])
+    x8 = x[:8, :100_000]
+    starts8, _, _ = window_grid(x8.shape[1], 1000, 10, 1000)
+    dp = nm.DataProcessor(sfreq=1000, settings=s, channels=get_default_channels_from_data(x8), line_noise=50, verbose=False)
+    cols, mat = dp.process_windows(x8, starts8, 1000)
+    ref_cols, ref = orc.run_offline(x8.astype(np.float64), 1000, s.model_dump())
+    assert ref_cols[: len(cols)] == cols
+    ref = ref[:, : len(cols)]
+    assert rel(mat, ref) < 1e-9
+    for j, key in enumerate(cols):
+        if key.endswith(("_in_burst", "_duration_max")):
+            assert np.array_equal(mat[:, j], ref[:, j]), key
+
+
+def test_next_rows_at_scale_prefilter_and_raw_normalizer(gpu):
+    """SURVEY 8f-3 at 256 channels: PreprocessingFilter + notch + CAR + RawNormalizer (zscore-median) in front of the C3
+    feature set; the oracle walks the stateful normaliser from window 0."""
+    x = neural_like(10, 256, 4000).astype(np.float32)
+    s = c3_settings()
+    s.preprocessing = ["preprocessing_filter", "notch_filter", "re_referencing", "raw_normalization"]
+    s.preprocessing_filter.bandstop_filter = False
+    s.raw_normalization_settings.normalization_time_s = 1.5
+    s.raw_normalization_settings.normalization_method = "zscore-median"
+    s.postprocessing.feature_normalization = False
+    dp = nm.DataProcessor(sfreq=1000, settings=s, channels=get_default_channels_from_data(x), line_noise=50, verbose=False)
+    starts, _, _ = window_grid(x.shape[1], 1000, 10, 1000)
+    cols, mat = dp.process_windows(x, starts, 1000)
+    assert "nm_convx_kernel" in dp.plan(1000).pipe.describe_plan()
+    wo = orc.WindowOracle(1000, s.model_dump(), n_channels=256, line_noise=50)
+    xd = x.astype(np.float64)
+    for k in range(starts.size):
+        ref = wo.process(xd[:, starts[k] : starts[k] + 1000])
+        if k == 0:
+            assert list(ref.keys()) == cols
+        assert rel(mat[k], np.array([float(v) for v in ref.values()])) < 1e-8, k
