@@ -1,0 +1,76 @@
+"""Randomised configuration sweep: window processor vs oracle over sampling rates, window lengths, channel counts (odd counts
+exercise the half-empty channel pair), feature subsets, preprocessing chains and NaN spans.  Every case runs on the emulated
+kernels (CPU suite) and on the GPU (-m gpu).  Transform sizes covered: FIR 1024 / 2048 / 4096 (specialised kernel), other
+powers of two and 5-smooth sizes (runtime-plan / generic kernels), segment DFTs 500 / 1000 / 2000 (register plans) and
+generic lengths."""
+import numpy as np
+import pytest
+
+import py_neuromodulation_b200 as nm
+from oracle import np_oracle as orc
+from py_neuromodulation_b200.stream.generator import window_grid
+from py_neuromodulation_b200.utils.channels import get_default_channels_from_data
+from tests.helpers import neural_like
+
+FEATURES = ["raw_hjorth", "return_raw", "bandpass_filter", "stft", "fft", "welch", "sharpwave_analysis", "bursts", "linelength"]
+
+
+def _case(seed: int):
+    rng = np.random.default_rng(1000 + seed)
+    sfreq = float(rng.choice([500, 1000, 1000, 2000]))
+    seg_ms = int(rng.choice([1000, 1000, 600, 1300]))
+    n_ch = int(rng.choice([1, 2, 3, 5, 6]))
+    rate = float(rng.choice([10, 10, 4, 7]))
+    n_win = 5
+    W = int(sfreq * seg_ms / 1000)
+    T = W + int(sfreq / rate * (n_win - 1)) + 3
+    x = neural_like(seed, n_ch, T, sfreq)
+    s = nm.NMSettings.get_default().reset()
+    s.sampling_rate_features_hz = rate
+    s.segment_length_features_ms = seg_ms
+    s.raw_resampling_settings.resample_freq_hz = sfreq
+    k = int(rng.integers(2, 5))
+    feats = list(rng.choice(FEATURES, size=k, replace=False))
+    if seg_ms < 1000:  # plug-in windows must fit the segment (the reference asserts the same)
+        feats = [f for f in feats if f not in ("stft", "welch", "bursts", "bandpass_filter")] or ["fft"]
+        s.fft_settings.windowlength_ms = seg_ms
+    for f in feats:
+        s.features[f] = True
+    pre = []
+    if rng.random() < 0.8:
+        pre.append("notch_filter")
+    if n_ch > 1 and rng.random() < 0.8:
+        pre.append("re_referencing")
+    if rng.random() < 0.3 and seg_ms >= 1000:
+        pre.append("preprocessing_filter")
+        s.preprocessing_filter.bandstop_filter = False
+    if rng.random() < 0.3:
+        pre.append("raw_normalization")
+        s.raw_normalization_settings.normalization_method = str(rng.choice(["zscore", "mean", "median", "zscore-median"]))
+        s.raw_normalization_settings.normalization_time_s = 1.5
+    s.preprocessing = pre
+    s.postprocessing.feature_normalization = bool(rng.random() < 0.4)
+    if rng.random() < 0.3 and n_ch > 1:
+        c = int(rng.integers(0, n_ch))
+        i0 = int(rng.integers(0, T - 20))
+        x[c, i0 : i0 + 10] = np.nan
+    return sfreq, x, s
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_configuration_matches_oracle(backend, seed):
+    sfreq, x, s = _case(seed)
+    line = 50 if "notch_filter" in s.preprocessing else None
+    dp = nm.DataProcessor(sfreq=sfreq, settings=s, channels=get_default_channels_from_data(x), line_noise=line, verbose=False)
+    starts, lengths, _ = window_grid(x.shape[1], sfreq, s.sampling_rate_features_hz, s.segment_length_features_ms)
+    cols, mat = dp.process_windows(x, starts, int(lengths[0]))
+    ref_cols, ref = orc.run_offline(x, sfreq, s.model_dump(), line_noise=line)
+    assert ref_cols[: len(cols)] == cols, (s.features.get_enabled(), s.preprocessing)
+    ref = ref[:, : len(cols)]
+    assert np.array_equal(np.isnan(mat), np.isnan(ref)), dp.plan(int(lengths[0])).pipe.describe_plan()
+    fin = np.isfinite(ref)
+    assert np.array_equal(mat[~fin & ~np.isnan(ref)], ref[~fin & ~np.isnan(ref)])
+    err = np.abs(mat[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0)
+    # z-scored features divide by a rolling std that can be tiny: 1e-7 there, 1e-9 otherwise (gate of the task: 1e-5)
+    tol = 1e-7 if (s.postprocessing.feature_normalization or "raw_normalization" in s.preprocessing) else 1e-9
+    assert err.max() < tol, (float(err.max()), s.features.get_enabled(), s.preprocessing, dp.plan(int(lengths[0])).pipe.describe_plan())
