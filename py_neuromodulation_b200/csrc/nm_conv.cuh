@@ -229,7 +229,7 @@ NM_DEV void nm_conv_last_dispatch(cx<double>* dst, const cx<double>* src, const 
 static NM_HD size_t nm_conv_buf_elems(int P, int pad) { return (size_t)P + ((size_t)P >> pad) + 2; }
 
 template <class Epi>
-NM_GLOBAL void NM_LAUNCH_BOUNDS(256, 2) nm_conv_kernel(NmConvArgs a, Epi epi) {
+NM_GLOBAL void NM_LAUNCH_BOUNDS(512, 1) nm_conv_kernel(NmConvArgs a, Epi epi) {  // NT = P/16 <= 512 (P <= 8192)
     NM_SHARED_BYTES(smem);
     const NmConv& f = a.fft;
     const int P = f.P, NT = f.NT;

@@ -30,7 +30,7 @@ struct FirBank {
         }
         int p2 = 1;
         while (p2 < need) p2 <<= 1;
-        pow2 = p2 >= 512 && p2 <= 16384;
+        pow2 = p2 >= 512 && p2 <= 8192;  // P/16 threads per CTA: 32 .. 512 (larger transforms use the generic kernel)
         if (pow2) {
             P = p2;
             std::vector<int> radices{16};

@@ -173,7 +173,7 @@ static int nm_allow_smem(K kernel, size_t bytes, const nm_pipeline* p) {
 // ------------------------------------------------------------------------------- FIR launches
 // Three kernels implement the same contract; the most specialised one that covers the bank is used:
 //   nm_convx_kernel  P in {1024, 2048, 4096}, compile-time plan (nm_convx.cuh)   <- every default configuration
-//   nm_conv_kernel   other powers of two in [512, 16384], runtime plan (nm_conv.cuh)
+//   nm_conv_kernel   other powers of two in [512, 8192], runtime plan (nm_conv.cuh)
 //   nm_fir_kernel    5-smooth sizes, generic mixed radix (nm_fir.cuh)
 template <class Epi>
 using NmConvKernel = void (*)(NmConvArgs, Epi);
