@@ -566,8 +566,10 @@ class SharpwaveSpec:
         else:
             for ch in self.ch_names:
                 for fname, _ in self.filters:
-                    for pol in ("Peak", "Trough"):
-                        for ft, e in self.combos:
+                    # the reference flattens {key: {"Peak": v, "Trough": v}} in key-insertion order (features/sharpwaves.py:323-326):
+                    # both polarities of a key are adjacent, num_peaks sits at its position among the enabled features
+                    for ft, e in self.combos:
+                        for pol in ("Peak", "Trough"):
                             k = (f"{ch}_Sharpwave_num_peaks_{fname}" if ft == "num_peaks"
                                  else f"{ch}_Sharpwave_{e.title()}_{ft}_{fname}") + "_analyze_" + pol
                             if k not in out:

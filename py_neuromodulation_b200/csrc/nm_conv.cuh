@@ -34,6 +34,7 @@ struct NmConvArgs {
     const double* hperm;  // [nF][P] real spectra in slot order, scaled by 1/P
     const double* hx;     // same values in nm_convx_kernel's per-thread order (nm_cx_load_h), or nullptr
     int nF, mode, E, n_items;
+    int f0;               // index of the first filter of this launch inside its bank (banks too large for shared memory run filter by filter)
     int scratch_in_tail;  // epilogue scratch aliases the unused padding tail of `work` (linear output only uses [0, P))
 };
 
@@ -308,13 +309,13 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(512, 1) nm_conv_kernel(NmConvArgs a, Epi epi) { 
             bool in_regs = false;
             if constexpr (Epi::kRegs) in_regs = epi.regs_ok();
             if (in_regs) {
-                if constexpr (Epi::kRegs) epi.run_regs(v, o0, W, a.in.n_ch, w, c0, has2, fi, scratch, tid, NT);
+                if constexpr (Epi::kRegs) epi.run_regs(v, o0, W, a.in.n_ch, w, c0, has2, fi + a.f0, scratch, tid, NT);
             } else {
                 __syncthreads();
 #pragma unroll
                 for (int t = 0; t < 16; ++t) work[tid + NT * t] = v[t];
                 __syncthreads();
-                epi.run(work, o0, W, a.in.n_ch, w, c0, has2, fi, scratch, tid, NT);
+                epi.run(work, o0, W, a.in.n_ch, w, c0, has2, fi + a.f0, scratch, tid, NT);
             }
             __syncthreads();
         }

@@ -29,6 +29,7 @@ struct NmFirArgs {
     int mode;
     int E;                 // samples of odd-reflected extension on each side (reflect mode)
     int n_items;           // n_windows * ceil(n_ch / 2)
+    int f0;                // index of the first filter of this launch inside its bank
 };
 
 // ---------------------------------------------------------------- epilogue: store filtered rows
@@ -275,7 +276,7 @@ NM_GLOBAL void nm_fir_kernel(NmFirArgs a, Epi epi) {
             }
             __syncthreads();
             nm_fft_inverse<double>(work, nullptr, a.fft, tid, nt);
-            epi.run(work, o0, W, a.in.n_ch, w, c0, has2, f, scratch, tid, nt);
+            epi.run(work, o0, W, a.in.n_ch, w, c0, has2, f + a.f0, scratch, tid, nt);
             __syncthreads();
         }
     }

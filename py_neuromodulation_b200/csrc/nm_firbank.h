@@ -58,18 +58,20 @@ struct FirBank {
         }
         return d_hperm.upload(hperm, s);
     }
-    NmFirArgs args(const NmRows& in) const {
+    // args / conv_args(in, f0, n): the launch serves filters [f0, f0 + n) of the bank (n < 0: all of them)
+    NmFirArgs args(const NmRows& in, int f0 = 0, int n = -1) const {
         NmFirArgs a;
         a.in = in;
         a.fft = fft.dev();
-        a.hperm = d_hperm.as<double>();
-        a.nF = nF;
+        a.hperm = d_hperm.as<double>() + (size_t)f0 * P;
+        a.nF = n < 0 ? nF : n;
+        a.f0 = f0;
         a.mode = mode;
         a.E = E;
         a.n_items = in.n_windows * ((in.n_ch + 1) / 2);
         return a;
     }
-    NmConvArgs conv_args(const NmRows& in) const {
+    NmConvArgs conv_args(const NmRows& in, int f0 = 0, int n = -1) const {
         NmConvArgs a;
         a.in = in;
         a.fft.P = P;
@@ -78,9 +80,10 @@ struct FirBank {
         for (int i = 0; i < a.fft.npass; ++i) { a.fft.radix[i] = fft.radix[i]; a.fft.len[i] = fft.len[i]; }
         a.fft.pad = pad;
         a.fft.tw = fft.d_tw.as<cx<double>>();
-        a.hperm = d_hperm.as<double>();
+        a.hperm = d_hperm.as<double>() + (size_t)f0 * P;
         a.hx = d_hx.as<double>();
-        a.nF = nF;
+        a.nF = n < 0 ? nF : n;
+        a.f0 = f0;
         a.mode = mode;
         a.E = E;
         a.n_items = in.n_windows * ((in.n_ch + 1) / 2);
@@ -93,8 +96,8 @@ struct FirBank {
     size_t smem_x(size_t epi) const {
         return nm_conv_buf_elems(P, pad) * sizeof(cx<double>) * (mode == NM_FIR_REFLECT ? 1 : 2) + NM_CX_RED_BYTES + (epi_fits_tail(epi) ? 0 : epi);
     }
-    size_t smem(size_t epi) const {
+    size_t smem(size_t epi, int n_filters = -1) const {
         const size_t buf = pow2 ? nm_conv_buf_elems(P, pad) : (size_t)P;
-        return buf * sizeof(cx<double>) * (nF > 1 ? 2 : 1) + (epi_fits_tail(epi) ? 0 : epi);
+        return buf * sizeof(cx<double>) * ((n_filters < 0 ? nF : n_filters) > 1 ? 2 : 1) + (epi_fits_tail(epi) ? 0 : epi);
     }
 };

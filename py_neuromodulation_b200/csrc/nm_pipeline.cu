@@ -202,6 +202,14 @@ static NmConvKernel<Epi> nm_convx_pick(const FirBank& b) {
     return nullptr;
 }
 
+// a bank whose spectrum + work buffers do not fit the shared memory of one CTA (long filters at high sampling rates: P = 8192
+// and more than one filter) runs filter by filter: the forward transform is repeated, the buffers are not
+template <class Epi>
+static bool nm_fir_split(const FirBank& bank, size_t epi_bytes, const nm_pipeline* p) {
+    if (nm_convx_pick<Epi>(bank)) return false;
+    return bank.nF > 1 && bank.smem(epi_bytes) > (size_t)p->smem_max && bank.smem(epi_bytes, 1) <= (size_t)p->smem_max;
+}
+
 // dynamic shared memory of the kernel that nm_launch_fir will pick for (bank, Epi)
 template <class Epi>
 static size_t nm_fir_smem(const FirBank& bank, size_t epi_bytes) {
@@ -213,8 +221,9 @@ template <class Epi>
 static int nm_allow_fir_smem(const FirBank& bank, size_t epi_bytes, const nm_pipeline* p) {
     if (auto k = nm_convx_pick<Epi>(bank)) return nm_allow_smem(k, bank.smem_x(epi_bytes), p);
     if constexpr (!Epi::kConvxOnly) {
-        if (bank.pow2) return nm_allow_smem(nm_conv_kernel<Epi>, bank.smem(epi_bytes), p);
-        return nm_allow_smem(nm_fir_kernel<Epi>, bank.smem(epi_bytes), p);
+        const size_t sm = bank.smem(epi_bytes, nm_fir_split<Epi>(bank, epi_bytes, p) ? 1 : -1);
+        if (bank.pow2) return nm_allow_smem(nm_conv_kernel<Epi>, sm, p);
+        return nm_allow_smem(nm_fir_kernel<Epi>, sm, p);
     }
     return 0;
 }
@@ -239,17 +248,22 @@ static void nm_launch_fir(nm_pipeline* p, const FirBank& bank, const NmRows& row
         return;
     }
     if constexpr (Epi::kConvxOnly) return;
-    else if (bank.pow2) {
-        NmConvArgs a = bank.conv_args(rows);
-        a.scratch_in_tail = bank.epi_fits_tail(epi_bytes) ? 1 : 0;
-        const size_t sm = bank.smem(epi_bytes);
-        const int grid = nm_resident_grid(p, nm_conv_kernel<Epi>, threads, sm, a.n_items);
-        NM_LAUNCH(nm_conv_kernel<Epi>, dim3(grid), dim3(threads), sm, stream, a, epi);
-    } else {
-        NmFirArgs a = bank.args(rows);
-        const size_t sm = bank.smem(epi_bytes);
-        const int grid = nm_resident_grid(p, nm_fir_kernel<Epi>, threads, sm, a.n_items);
-        NM_LAUNCH(nm_fir_kernel<Epi>, dim3(grid), dim3(threads), sm, stream, a, epi);
+    else {
+        const bool split = nm_fir_split<Epi>(bank, epi_bytes, p);
+        const int n_launch = split ? bank.nF : 1, per = split ? 1 : bank.nF;
+        for (int l = 0; l < n_launch; ++l) {
+            const size_t sm = bank.smem(epi_bytes, per);
+            if (bank.pow2) {
+                NmConvArgs a = bank.conv_args(rows, l * per, per);
+                a.scratch_in_tail = bank.epi_fits_tail(epi_bytes) ? 1 : 0;
+                const int grid = nm_resident_grid(p, nm_conv_kernel<Epi>, threads, sm, a.n_items);
+                NM_LAUNCH(nm_conv_kernel<Epi>, dim3(grid), dim3(threads), sm, stream, a, epi);
+            } else {
+                NmFirArgs a = bank.args(rows, l * per, per);
+                const int grid = nm_resident_grid(p, nm_fir_kernel<Epi>, threads, sm, a.n_items);
+                NM_LAUNCH(nm_fir_kernel<Epi>, dim3(grid), dim3(threads), sm, stream, a, epi);
+            }
+        }
     }
 }
 

@@ -57,7 +57,7 @@ def _case(seed: int):
     return sfreq, x, s
 
 
-@pytest.mark.parametrize("seed", range(48))
+@pytest.mark.parametrize("seed", range(72))
 def test_random_configuration_matches_oracle(backend, seed):
     sfreq, x, s = _case(seed)
     line = 50 if "notch_filter" in s.preprocessing else None
@@ -74,3 +74,85 @@ def test_random_configuration_matches_oracle(backend, seed):
     # z-scored features divide by a rolling std that can be tiny: 1e-7 there, 1e-9 otherwise (gate of the task: 1e-5)
     tol = 1e-7 if (s.postprocessing.feature_normalization or "raw_normalization" in s.preprocessing) else 1e-9
     assert err.max() < tol, (float(err.max()), s.features.get_enabled(), s.preprocessing, dp.plan(int(lengths[0])).pipe.describe_plan())
+
+
+SW_FEATS = ["peak_left", "peak_right", "num_peaks", "trough", "width", "prominence", "interval", "decay_time", "rise_time", "sharpness",
+            "rise_steepness", "decay_steepness", "slope_ratio"]
+
+
+def _option_case(seed: int):
+    """Feature OPTIONS rather than geometry: estimators, spectra, Hjorth on the band-pass rows, sharp-wave feature /
+    estimator combinations, burst thresholds and durations, normalisation methods, bad / bipolar channels."""
+    rng = np.random.default_rng(5000 + seed)
+    n_ch = int(rng.choice([2, 3, 4]))
+    n_win = int(rng.choice([4, 7]))
+    x = neural_like(100 + seed, n_ch, 1000 + 100 * (n_win - 1))
+    s = nm.NMSettings.get_default().reset()
+    kind = seed % 6
+    if kind == 0:  # oscillatory estimators + spectra
+        for f in ("fft", "welch", "stft"):
+            s.features[f] = True
+            st = getattr(s, f + "_settings")
+            st.log_transform = bool(rng.random() < 0.5)
+            st.return_spectrum = bool(rng.random() < 0.5)
+            for e in ("mean", "median", "std", "max"):
+                setattr(st.features, e, bool(rng.random() < 0.6))
+            if not any(getattr(st.features, e) for e in ("mean", "median", "std", "max")):
+                st.features.mean = True
+    elif kind == 1:  # band power with mobility / complexity (shared-memory epilogue) and all seven class-default bands
+        s.features.bandpass_filter = True
+        s.bandpass_filter_settings.bandpower_features.mobility = bool(rng.random() < 0.7)
+        s.bandpass_filter_settings.bandpower_features.complexity = bool(rng.random() < 0.7)
+        s.bandpass_filter_settings.log_transform = bool(rng.random() < 0.5)
+    elif kind == 2:  # sharp waves: random feature / estimator table
+        s.features.sharpwave_analysis = True
+        sw = s.sharpwave_analysis_settings
+        chosen = list(rng.choice(SW_FEATS, size=int(rng.integers(2, 7)), replace=False))
+        for f in SW_FEATS:
+            setattr(sw.sharpwave_features, f, f in chosen)
+        table = {e: [] for e in ("mean", "median", "max", "min", "var")}
+        for f in chosen:  # (the reference demands an estimator entry for every enabled feature, num_peaks included)
+            for e in rng.choice(list(table), size=int(rng.integers(1, 3)), replace=False):
+                table[str(e)].append(f)
+        for e, v in table.items():
+            setattr(sw.estimator, e, v)
+        sw.apply_estimator_between_peaks_and_troughs = bool(rng.random() < 0.7)
+    elif kind == 3:  # bursts: threshold / history / feature selection
+        s.features.bursts = True
+        s.bursts_settings.threshold = float(rng.choice([50, 75, 90, 99.5]))
+        s.bursts_settings.time_duration_s = float(rng.choice([1.2, 5, 30]))
+        s.bursts_settings.frequency_bands = list(rng.choice(["theta", "alpha", "low_beta", "high_beta"], size=2, replace=False))
+    elif kind == 4:  # feature normalisation methods incl. PSD columns
+        for f in ("fft", "raw_hjorth", "linelength"):
+            s.features[f] = True
+        s.fft_settings.return_spectrum = True
+        s.postprocessing.feature_normalization = True
+        s.feature_normalization_settings.normalization_method = str(rng.choice(["mean", "median", "zscore", "zscore-median"]))
+        s.feature_normalization_settings.normalization_time_s = float(rng.choice([0.35, 30]))
+        s.feature_normalization_settings.normalize_psd = bool(rng.random() < 0.5)
+        s.feature_normalization_settings.clip = float(rng.choice([0, 1.5, 3]))
+    else:  # everything the README demo computes
+        s = nm.NMSettings.get_default()
+        s.postprocessing.feature_normalization = False
+    ch = get_default_channels_from_data(x)
+    if n_ch >= 3 and rng.random() < 0.5:  # one bad channel, one bipolar reference
+        ch.loc[0, "status"] = "bad"
+        ch.loc[1, "rereference"] = ch.loc[2, "name"]
+    return x, s, ch
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_feature_options_match_oracle(backend, seed):
+    x, s, ch = _option_case(seed)
+    dp = nm.DataProcessor(sfreq=1000, settings=s, channels=ch, line_noise=50, verbose=False)
+    starts, lengths, _ = window_grid(x.shape[1], 1000, s.sampling_rate_features_hz, s.segment_length_features_ms)
+    cols, mat = dp.process_windows(x, starts, 1000)
+    ref_cols, ref = orc.run_offline(x, 1000, s.model_dump(), channels={k: list(ch[k]) for k in ch.columns})
+    assert ref_cols[: len(cols)] == cols
+    ref = ref[:, : len(cols)]
+    assert np.array_equal(np.isnan(mat), np.isnan(ref))
+    fin = np.isfinite(ref)
+    assert np.array_equal(mat[~fin & ~np.isnan(ref)], ref[~fin & ~np.isnan(ref)])
+    err = np.abs(mat[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0)
+    tol = 1e-7 if s.postprocessing.feature_normalization else 1e-9
+    assert err.max() < tol, (float(err.max()), cols[int(np.argmax(np.abs(np.where(fin, mat - ref, 0)).max(axis=0)))])
