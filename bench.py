@@ -325,6 +325,25 @@ def run_gpu_arm(args) -> None:
     peak, peak_src = measured_peak_gbs()
     traffic, ncu_info = ncu_traffic(dominant, n_win / max(dom_launches, 1))
 
+    # optional float32 mode of the linear FIR families (same workload, resident timing; reported next to the float64 headline)
+    f32_info = None
+    if world == 1:
+        dp32 = nm.DataProcessor(sfreq=SFREQ, settings=settings, channels=local_channels, line_noise=LINE_NOISE, verbose=False,
+                                device=local_rank, precision="f32")
+        pipe32 = dp32.plan(W).pipe
+        pipe32.upload(x)
+        for _ in range(3):
+            pipe32.run(starts, download=False)
+        pipe32.synchronize()
+        pipe32.timer_start()
+        for _ in range(args.steps):
+            pipe32.prepare_resident()
+            pipe32.run(starts, download=False)
+        ms32 = pipe32.timer_stop()
+        f32_info = {"value": n_win * args.steps / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32 / args.steps,
+                    "note": "nm_set_precision(1): float32 inside the notch / band-pass FFT convolutions, moments and outputs float64; "
+                            "parity gate 1e-5 relative (tests/test_parity_pipeline.py::test_float32_linear_mode_within_north_star_tolerance)"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -349,6 +368,8 @@ def run_gpu_arm(args) -> None:
                                  "the notched rows travel as float64"},
             "clocks": clocks.summary(),
         }
+        if f32_info is not None:
+            line["f32_linear_mode"] = f32_info
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single()
         print(json.dumps(line))

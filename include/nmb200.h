@@ -58,6 +58,12 @@ int nm_set_reref(nm_pipeline* p, int n_groups, const int* group_of, const double
                  const int* sp_ptr, const int* sp_col, const double* sp_val);
 /* NotchFilter.process: zero-phase FIR with reflect-limited padding (filter/notch_filter.py:78-93) */
 int nm_set_notch(nm_pipeline* p, const double* taps, int n_taps);
+/* Arithmetic of the linear FIR families (notch, band-pass power): 0 = float64 (default: agrees with the float64 reference to
+ * ~1e-12), 1 = float32 inside the FFT convolution (faster; north-star tolerance 1e-5 relative; moments and outputs stay
+ * float64).  Pipelines with threshold / peak decisions downstream of the notch (bursts, sharp waves, raw normaliser) keep the
+ * notch in float64 regardless. */
+int nm_set_precision(nm_pipeline* p, int float32_linear);
+
 /* RawNormalizer (processing/normalization.py:30-111, type "raw"): window 0 passes through and seeds the per-channel
  * history; window g >= 1 appends its last add_samples = int(sfreq / rate) preprocessed samples, is normalised against the
  * whole history (method 0 mean, 2 zscore), clipped (clip == 0: off) and the history is trimmed to n_keep - 1 samples

@@ -117,6 +117,12 @@ class Pipeline:
         a = _f64(taps)
         _lib.check(self.lib.nm_set_notch(self._h, _ptr(a, C.c_double), int(a.size)))
 
+    def set_precision(self, precision: str) -> None:
+        """'f64' (default) or 'f32': float32 arithmetic inside the FFT convolution of the linear families (notch, band power)."""
+        if precision not in ("f64", "f32"):
+            raise ValueError("precision must be 'f64' or 'f32'")
+        _lib.check(self.lib.nm_set_precision(self._h, int(precision == "f32")))
+
     def set_raw_normalizer(self, method: str, clip: float, n_keep: int, add_samples: int) -> None:
         """RawNormalizer in front of the features (mean / median / zscore / zscore-median; scikit-learn methods are out of scope)."""
         if method not in NORM_METHODS:

@@ -33,6 +33,8 @@ struct NmConvArgs {
     NmConv fft;
     const double* hperm;  // [nF][P] real spectra in slot order, scaled by 1/P
     const double* hx;     // same values in nm_convx_kernel's per-thread order (nm_cx_load_h), or nullptr
+    const float* hx32;    // float32 copies of hx / the twiddle table for the float32 mode of nm_convx_kernel, or nullptr
+    const cx<float>* tw32;
     int nF, mode, E, n_items;
     int f0;               // index of the first filter of this launch inside its bank (banks too large for shared memory run filter by filter)
     int scratch_in_tail;  // epilogue scratch aliases the unused padding tail of `work` (linear output only uses [0, P))
@@ -40,15 +42,17 @@ struct NmConvArgs {
 
 #define NM_PHYS(e, pad) ((e) + ((e) >> (pad)))
 
-template <bool INV>
-NM_DEV cx<double> nm_mulw(cx<double> a, double wr, double wi) {  // a * (wr + i*wi), conjugated for the inverse
-    return INV ? cx<double>{a.re * wr + a.im * wi, a.im * wr - a.re * wi} : cx<double>{a.re * wr - a.im * wi, a.im * wr + a.re * wi};
+// The register butterflies are templates on the scalar type: float64 is the default arithmetic of the path, float32 serves
+// the optional fast mode of the linear families (nm_set_precision).
+template <bool INV, typename T>
+NM_DEV cx<T> nm_mulw(cx<T> a, T wr, T wi) {  // a * (wr + i*wi), conjugated for the inverse
+    return INV ? cx<T>{a.re * wr + a.im * wi, a.im * wr - a.re * wi} : cx<T>{a.re * wr - a.im * wi, a.im * wr + a.re * wi};
 }
 
-template <bool INV>
-NM_DEV void nm_r4(cx<double>& a0, cx<double>& a1, cx<double>& a2, cx<double>& a3) {
-    const cx<double> t0 = cx_add(a0, a2), t1 = cx_sub(a0, a2), t2 = cx_add(a1, a3);
-    const cx<double> t3 = cx_rot<double, INV>(cx_sub(a1, a3));
+template <bool INV, typename T>
+NM_DEV void nm_r4(cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
+    const cx<T> t0 = cx_add(a0, a2), t1 = cx_sub(a0, a2), t2 = cx_add(a1, a3);
+    const cx<T> t3 = cx_rot<T, INV>(cx_sub(a1, a3));
     a0 = cx_add(t0, t2);
     a2 = cx_sub(t0, t2);
     a1 = cx_add(t1, t3);
@@ -56,9 +60,9 @@ NM_DEV void nm_r4(cx<double>& a0, cx<double>& a1, cx<double>& a2, cx<double>& a3
 }
 
 // 16-point DFT in registers, natural order in and out (4 x 4 Cooley-Tukey)
-template <bool INV>
-NM_DEV void nm_bfly16(cx<double>* v) {
-    const double c = 0.92387953251128675613, s = 0.38268343236508977173, h = 0.70710678118654752440;
+template <bool INV, typename T>
+NM_DEV void nm_bfly16(cx<T>* v) {
+    const T c = T(0.92387953251128675613), s = T(0.38268343236508977173), h = T(0.70710678118654752440);
 #pragma unroll
     for (int b = 0; b < 4; ++b) nm_r4<INV>(v[b], v[4 + b], v[8 + b], v[12 + b]);  // v[4*k1 + b] = u_b[k1]
     // twiddles w16^(b*k1)
@@ -66,7 +70,7 @@ NM_DEV void nm_bfly16(cx<double>* v) {
     v[8 + 1] = nm_mulw<INV>(v[8 + 1], h, -h);
     v[12 + 1] = nm_mulw<INV>(v[12 + 1], s, -c);
     v[4 + 2] = nm_mulw<INV>(v[4 + 2], h, -h);
-    v[8 + 2] = cx_rot<double, INV>(v[8 + 2]);
+    v[8 + 2] = cx_rot<T, INV>(v[8 + 2]);
     v[12 + 2] = nm_mulw<INV>(v[12 + 2], -h, -h);
     v[4 + 3] = nm_mulw<INV>(v[4 + 3], s, -c);
     v[8 + 3] = nm_mulw<INV>(v[8 + 3], -h, -h);
@@ -78,22 +82,22 @@ NM_DEV void nm_bfly16(cx<double>* v) {
     for (int k1 = 0; k1 < 4; ++k1)
 #pragma unroll
         for (int k2 = k1 + 1; k2 < 4; ++k2) {
-            const cx<double> t = v[4 * k1 + k2];
+            const cx<T> t = v[4 * k1 + k2];
             v[4 * k1 + k2] = v[4 * k2 + k1];
             v[4 * k2 + k1] = t;
         }
 }
 
 // 8-point DFT in registers (4 x 2)
-template <bool INV>
-NM_DEV void nm_bfly8(cx<double>* v) {
-    const double h = 0.70710678118654752440;
+template <bool INV, typename T>
+NM_DEV void nm_bfly8(cx<T>* v) {
+    const T h = T(0.70710678118654752440);
     nm_r4<INV>(v[0], v[2], v[4], v[6]);  // u_0[k1] at v[2*k1]
     nm_r4<INV>(v[1], v[3], v[5], v[7]);  // u_1[k1] at v[2*k1 + 1]
     v[3] = nm_mulw<INV>(v[3], h, -h);
-    v[5] = cx_rot<double, INV>(v[5]);
+    v[5] = cx_rot<T, INV>(v[5]);
     v[7] = nm_mulw<INV>(v[7], -h, -h);
-    cx<double> x[8];
+    cx<T> x[8];
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) {
         x[k1] = cx_add(v[2 * k1], v[2 * k1 + 1]);
@@ -103,13 +107,13 @@ NM_DEV void nm_bfly8(cx<double>* v) {
     for (int k = 0; k < 8; ++k) v[k] = x[k];
 }
 
-template <int R, bool INV>
-NM_DEV void nm_bflyR(cx<double>* v) {
+template <int R, bool INV, typename T>
+NM_DEV void nm_bflyR(cx<T>* v) {
     if (R == 16) nm_bfly16<INV>(v);
     if (R == 8) nm_bfly8<INV>(v);
     if (R == 4) nm_r4<INV>(v[0], v[1], v[2], v[3]);
     if (R == 2) {
-        const cx<double> a = v[0], b = v[1];
+        const cx<T> a = v[0], b = v[1];
         v[0] = cx_add(a, b);
         v[1] = cx_sub(a, b);
     }

@@ -46,25 +46,25 @@ struct NmCxPlan {
 static inline bool nm_convx_supported(int P) { return P == 1024 || P == 2048 || P == 4096; }
 
 // multiply the R-1 upper values of a butterfly by the powers of w1 (conjugated for the inverse)
-template <int R, bool INV>
-NM_DEV void nm_twiddle_w1(cx<double>* v, cx<double> w1) {
+template <int R, bool INV, typename T>
+NM_DEV void nm_twiddle_w1(cx<T>* v, cx<T> w1) {
     if (INV) w1.im = -w1.im;
     v[1] = cx_mul(v[1], w1);
-    const cx<double> w2 = cx_mul(w1, w1), w3 = cx_mul(w2, w1);
+    const cx<T> w2 = cx_mul(w1, w1), w3 = cx_mul(w2, w1);
     v[2] = cx_mul(v[2], w2);
     v[3] = cx_mul(v[3], w3);
-    const cx<double> w4 = cx_mul(w2, w2);
+    const cx<T> w4 = cx_mul(w2, w2);
     v[4] = cx_mul(v[4], w4);
     v[5] = cx_mul(v[5], cx_mul(w4, w1));
     v[6] = cx_mul(v[6], cx_mul(w4, w2));
     v[7] = cx_mul(v[7], cx_mul(w4, w3));
     if (R > 8) {
-        const cx<double> w8 = cx_mul(w4, w4);
+        const cx<T> w8 = cx_mul(w4, w4);
         v[8] = cx_mul(v[8], w8);
         v[9] = cx_mul(v[9], cx_mul(w8, w1));
         v[10] = cx_mul(v[10], cx_mul(w8, w2));
         v[11] = cx_mul(v[11], cx_mul(w8, w3));
-        const cx<double> w12 = cx_mul(w8, w4);
+        const cx<T> w12 = cx_mul(w8, w4);
         v[12] = cx_mul(v[12], w12);
         v[13] = cx_mul(v[13], cx_mul(w12, w1));
         v[14] = cx_mul(v[14], cx_mul(w12, w2));
@@ -73,15 +73,15 @@ NM_DEV void nm_twiddle_w1(cx<double>* v, cx<double> w1) {
 }
 
 // interior pass (pass 1): 16/R1 butterflies per thread, all sharing the same twiddle set
-template <class PL, bool INV>
-NM_DEV void nm_cx_pass1(cx<double>* sm, const cx<double> w1, int tid) {
+template <class PL, bool INV, typename T>
+NM_DEV void nm_cx_pass1(cx<T>* sm, const cx<T> w1, int tid) {
     constexpr int R = PL::R1;
     const int j = tid & (PL::M1 - 1);
     const int base = (tid - j) * R + j;
-    cx<double>* p = sm + base + (base >> PL::PAD);
+    cx<T>* p = sm + base + (base >> PL::PAD);
 #pragma unroll
     for (int i = 0; i < 16 / R; ++i) {
-        cx<double> v[R];
+        cx<T> v[R];
 #pragma unroll
         for (int t = 0; t < R; ++t) v[t] = p[i * PL::B1 + t * PL::S1];
         if (INV) {
@@ -105,35 +105,31 @@ static NM_HD int nm_cx_hx_index(int tid, int i, int t) {  // position of slot (t
     return ((i * (PL::R2 / 2) + (t >> 1)) * PL::NT + tid) * 2 + (t & 1);
 }
 
-template <class PL>
-NM_DEV void nm_cx_load_h(double* hv, const double* NM_RESTRICT hx, int tid) {
+template <class PL, typename T>
+NM_DEV void nm_cx_load_h(T* hv, const T* NM_RESTRICT hx, int tid) {
     constexpr int R = PL::R2;
 #pragma unroll
     for (int i = 0; i < 16 / R; ++i) {
-#ifdef NM_EMULATE
-#pragma unroll
-        for (int t = 0; t < R; ++t) hv[i * R + t] = hx[nm_cx_hx_index<PL>(tid, i, t)];
-#else
-        const double2* p = reinterpret_cast<const double2*>(hx) + (i * (R / 2)) * PL::NT + tid;
 #pragma unroll
         for (int t = 0; t < R / 2; ++t) {
-            const double2 d = __ldg(p + t * PL::NT);
-            hv[i * R + 2 * t] = d.x;
-            hv[i * R + 2 * t + 1] = d.y;
+            // one (2 x T)-wide load per pair: consecutive lanes read consecutive pairs
+            const cx<T> d = nm_ldg(reinterpret_cast<const cx<T>*>(hx) + (i * (R / 2) + t) * PL::NT + tid);
+            hv[i * R + 2 * t] = d.re;
+            hv[i * R + 2 * t + 1] = d.im;
         }
-#endif
     }
 }
 
 // host side: slot-ordered spectrum block (P values) -> thread-interleaved block
-template <int P>
-static inline void nm_cx_interleave_h(const double* h, double* hx) {
+template <int P, typename T>
+static inline void nm_cx_interleave_h(const double* h, T* hx) {
     using PL = NmCxPlan<P>;
     for (int tid = 0; tid < PL::NT; ++tid)
         for (int i = 0; i < 16 / PL::R2; ++i)
-            for (int t = 0; t < PL::R2; ++t) hx[nm_cx_hx_index<PL>(tid, i, t)] = h[(tid + PL::NT * i) * PL::R2 + t];
+            for (int t = 0; t < PL::R2; ++t) hx[nm_cx_hx_index<PL>(tid, i, t)] = (T)h[(tid + PL::NT * i) * PL::R2 + t];
 }
-static inline void nm_cx_interleave_h(int P, const double* h, double* hx) {
+template <typename T>
+static inline void nm_cx_interleave_h(int P, const double* h, T* hx) {
     if (P == 1024) nm_cx_interleave_h<1024>(h, hx);
     else if (P == 2048) nm_cx_interleave_h<2048>(h, hx);
     else nm_cx_interleave_h<4096>(h, hx);
@@ -142,13 +138,13 @@ static inline void nm_cx_interleave_h(int P, const double* h, double* hx) {
 // last forward pass (unit stride).  MODE 0: forward butterfly only (bank: spectrum stays in `src`).
 // MODE 1: forward butterfly, * H, inverse butterfly in place (single filter).
 // MODE 2: load the spectrum from `src`, * H, inverse butterfly, store to `dst` (one filter of a bank).
-template <class PL, int MODE>
-NM_DEV void nm_cx_pass2(cx<double>* dst, const cx<double>* src, const double* hv, int tid) {
+template <class PL, int MODE, typename T>
+NM_DEV void nm_cx_pass2(cx<T>* dst, const cx<T>* src, const T* hv, int tid) {
     constexpr int R = PL::R2;
     const int off = tid * (R + 1);  // tid*R + ((tid*R) >> PAD)
 #pragma unroll
     for (int i = 0; i < 16 / R; ++i) {
-        cx<double> v[R];
+        cx<T> v[R];
 #pragma unroll
         for (int t = 0; t < R; ++t) v[t] = src[off + i * PL::B2 + t];
         if (MODE != 2) nm_bflyR<R, false>(v);
@@ -181,6 +177,9 @@ NM_DEV void nm_cx_block_sum(double* v, double* red, int tid) {
     }
 }
 
+template <typename T>
+NM_DEV cx<double> nm_cx_wide(cx<T> a) { return {(double)a.re, (double)a.im}; }
+
 // ---------------------------------------------------------------- epilogue: store rows (+ fused scan features)
 // The notch kernel's epilogue: writes the filtered window to the chunk buffer for the other families and, when the
 // scan family is enabled, computes Hjorth activity / mobility / complexity, line length and the last sample
@@ -192,7 +191,7 @@ struct NmEpiStoreScan {
     int want_hjorth, want_raw, want_ll, want_scan;
     NmOut out;  // per_ch = 5: activity, mobility, complexity, raw, linelength
     static constexpr bool kRegs = true;
-    static constexpr bool kRegsOnly = true, kReflectOk = true, kSameOk = false, kConvxOnly = true;
+    static constexpr bool kRegsOnly = true, kReflectOk = true, kSameOk = false, kConvxOnly = true, kF32Ok = true;
     static constexpr bool kSyncsInside = false;  // (not on every path) -> the kernel adds the trailing barrier
     static NM_HD size_t smem_bytes(int /*nt*/) { return 0; }  // reductions use the padding tail of `work`
     NM_DEV bool regs_ok() const { return true; }
@@ -203,8 +202,8 @@ struct NmEpiStoreScan {
     static NM_HD int phys(int u) { return u + (u >> 3); }
 
     // part 1: needs the registers -- store the rows, lay the window out in natural order
-    template <class PL>
-    NM_DEV void consume(const cx<double>* v, cx<double>* work, double* /*red*/, State& /*st*/, int o0, int W, int n_ch, int w, int c0,
+    template <class PL, typename T>
+    NM_DEV void consume(const cx<T>* v, cx<T>* work, double* /*red*/, State& /*st*/, int o0, int W, int n_ch, int w, int c0,
                         bool has2, int /*f*/, int tid) const {
         constexpr int NT = PL::NT;
         if (y) {
@@ -228,11 +227,11 @@ struct NmEpiStoreScan {
     }
 
     // part 2: two-pass moments (numpy.var semantics) over chunks of consecutive samples, each sample loaded once per pass
-    template <class PL>
-    NM_DEV void finish(cx<double>* work, double* /*red*/, State& /*st*/, int /*o0*/, int W, int /*n_ch*/, int w, int c0, bool has2, int /*f*/,
+    template <class PL, typename T>
+    NM_DEV void finish(cx<T>* work, double* /*red*/, State& /*st*/, int /*o0*/, int W, int /*n_ch*/, int w, int c0, bool has2, int /*f*/,
                        int tid) const {
         constexpr int NT = PL::NT, NW = (PL::NT + 31) / 32;
-        static_assert((size_t)16 * NW * sizeof(double) <= (size_t)(PL::NBUF - PL::P) * sizeof(cx<double>), "reduction scratch must fit the tail");
+        static_assert((size_t)16 * NW * sizeof(double) <= (size_t)(PL::NBUF - PL::P) * sizeof(cx<T>), "reduction scratch must fit the tail");
         if (!want_scan) return;
         double* red = reinterpret_cast<double*>(work + PL::P);  // W + W/8 <= P for every supported plan
         __syncthreads();
@@ -240,9 +239,9 @@ struct NmEpiStoreScan {
         const int u0 = tid * CH, u1 = min(W, u0 + CH);
         double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per row: sum x, sum d, sum dd, sum |d|
         if (u0 < W) {
-            cx<double> xa = work[phys(u0)], xb = (u0 + 1 < W) ? work[phys(u0 + 1)] : cx<double>{0.0, 0.0};
+            cx<double> xa = nm_cx_wide(work[phys(u0)]), xb = (u0 + 1 < W) ? nm_cx_wide(work[phys(u0 + 1)]) : cx<double>{0.0, 0.0};
             for (int u = u0; u < u1; ++u) {
-                const cx<double> xc = (u + 2 < W) ? work[phys(u + 2)] : cx<double>{0.0, 0.0};
+                const cx<double> xc = (u + 2 < W) ? nm_cx_wide(work[phys(u + 2)]) : cx<double>{0.0, 0.0};
                 s[0] += xa.re; s[4] += xa.im;
                 if (u + 1 < W) {
                     const double da = xb.re - xa.re, db = xb.im - xa.im;
@@ -263,9 +262,9 @@ struct NmEpiStoreScan {
             const double m0a = s[0] / n0, m1a = s[1] / n1, m2a = s[2] / n2;
             const double m0b = s[4] / n0, m1b = s[5] / n1, m2b = s[6] / n2;
             if (u0 < W) {
-                cx<double> xa = work[phys(u0)], xb = (u0 + 1 < W) ? work[phys(u0 + 1)] : cx<double>{0.0, 0.0};
+                cx<double> xa = nm_cx_wide(work[phys(u0)]), xb = (u0 + 1 < W) ? nm_cx_wide(work[phys(u0 + 1)]) : cx<double>{0.0, 0.0};
                 for (int u = u0; u < u1; ++u) {
-                    const cx<double> xc = (u + 2 < W) ? work[phys(u + 2)] : cx<double>{0.0, 0.0};
+                    const cx<double> xc = (u + 2 < W) ? nm_cx_wide(work[phys(u + 2)]) : cx<double>{0.0, 0.0};
                     double e = xa.re - m0a; q[0] += e * e;
                     e = xa.im - m0b; q[3] += e * e;
                     if (u + 1 < W) {
@@ -292,7 +291,7 @@ struct NmEpiStoreScan {
                 nm_store(out, w, c, 1, mob);
                 nm_store(out, w, c, 2, nm_nan_to_num(sqrt(v2 / v1) / mob));
             }
-            const cx<double> last = work[phys(W - 1)];
+            const cx<double> last = nm_cx_wide(work[phys(W - 1)]);
             if (want_raw) nm_store(out, w, c, 3, k ? last.im : last.re);
             // mean(|dx| / (W-1)) over W-1 samples: the reference divides by (W-1) twice
             if (want_ll) nm_store(out, w, c, 4, ((k ? s[7] : s[3]) / n1) / n1);
@@ -306,8 +305,8 @@ struct NmEpiStoreScan {
 // Register epilogues come in two parts: consume() reads the 16 outputs a thread holds, finish() does whatever is left
 // (reductions, final formulas).  Between the two the kernel already issues the global loads of the NEXT item into the
 // freed registers, so their latency overlaps the reductions / barriers instead of stalling the next pass 0.
-template <int P, bool REFLECT>
-NM_DEV void nm_cx_load_item(cx<double>* v, const NmConvArgs& a, int item, int npair, int tid, int& w, int& c0, bool& has2) {
+template <int P, bool REFLECT, typename T>
+NM_DEV void nm_cx_load_item(cx<T>* v, const NmConvArgs& a, int item, int npair, int tid, int& w, int& c0, bool& has2) {
     constexpr int NT = NmCxPlan<P>::NT;
     const int W = a.in.W, E = a.E;
     w = item / npair;
@@ -328,7 +327,7 @@ NM_DEV void nm_cx_load_item(cx<double>* v, const NmConvArgs& a, int item, int np
             const double sgn = mid ? 1.0 : ((left || right) ? -1.0 : 0.0);
             const double ca = left ? a0 : (right ? a1 : 0.0), cb = left ? b0 : (right ? b1 : 0.0);
             const double va = fma(sgn, r0[idx], ca), vb = fma(sgn, r1[idx], cb);
-            v[t] = {va, has2 ? vb : 0.0};
+            v[t] = {(T)va, (T)(has2 ? vb : 0.0)};
         }
     } else {
 #pragma unroll
@@ -336,18 +335,36 @@ NM_DEV void nm_cx_load_item(cx<double>* v, const NmConvArgs& a, int item, int np
             const int n = tid + NT * t;
             const int idx = n < W ? n : 0;
             const double va = r0[idx], vb = r1[idx];
-            v[t] = {n < W ? va : 0.0, (has2 && n < W) ? vb : 0.0};
+            v[t] = {(T)(n < W ? va : 0.0), (T)((has2 && n < W) ? vb : 0.0)};
         }
     }
 }
 
-template <int P, bool REFLECT, bool BANK, class Epi>
-NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, BANK ? NmCxPlan<P>::MINBK : NmCxPlan<P>::MINB1) nm_convx_kernel(NmConvArgs a, Epi epi) {
+// float64 / float32 views of the twiddle and filter-spectrum tables of a launch
+template <typename T> NM_DEV const cx<T>* nm_cx_tw(const NmConvArgs& a);
+template <> NM_DEV const cx<double>* nm_cx_tw<double>(const NmConvArgs& a) { return a.fft.tw; }
+template <> NM_DEV const cx<float>* nm_cx_tw<float>(const NmConvArgs& a) { return a.tw32; }
+template <typename T> NM_DEV const T* nm_cx_hx(const NmConvArgs& a);
+template <> NM_DEV const double* nm_cx_hx<double>(const NmConvArgs& a) { return a.hx; }
+template <> NM_DEV const float* nm_cx_hx<float>(const NmConvArgs& a) { return a.hx32; }
+
+#ifndef NM_CX_F32_MINB1
+#define NM_CX_F32_MINB1 5  // resident CTAs per SM (128-thread plans) the float32 instantiations are register-limited to
+#define NM_CX_F32_MINBK 6
+#endif
+template <typename T, int P, bool BANK>
+struct NmCxOcc {
+    static constexpr int f32 = (BANK ? NM_CX_F32_MINBK : NM_CX_F32_MINB1) * 128 / NmCxPlan<P>::NT;
+    static constexpr int value = sizeof(T) == 4 ? (f32 < 1 ? 1 : f32) : (BANK ? NmCxPlan<P>::MINBK : NmCxPlan<P>::MINB1);
+};
+template <typename T, int P, bool REFLECT, bool BANK, class Epi>
+NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, (NmCxOcc<T, P, BANK>::value))
+nm_convx_kernel(NmConvArgs a, Epi epi) {
     using PL = NmCxPlan<P>;
     constexpr int NT = PL::NT;
     NM_SHARED_BYTES(smem);
-    cx<double>* work = reinterpret_cast<cx<double>*>(smem);
-    cx<double>* spec = BANK ? work + PL::NBUF : work;
+    cx<T>* work = reinterpret_cast<cx<T>*>(smem);
+    cx<T>* spec = BANK ? work + PL::NBUF : work;
     double* red = reinterpret_cast<double*>(work + (BANK ? 2 : 1) * PL::NBUF);  // NM_CX_RED_BYTES of reduction scratch
     unsigned char* scratch = a.scratch_in_tail ? reinterpret_cast<unsigned char*>(work + P)
                                                : reinterpret_cast<unsigned char*>(red) + NM_CX_RED_BYTES;
@@ -356,20 +373,21 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, BANK ? NmCxPlan<P>::MINBK : NmC
     const int npair = (a.in.n_ch + 1) >> 1;
     const int o0 = REFLECT ? a.E : 0;
     const int nF = BANK ? a.nF : 1;
-    const cx<double>* NM_RESTRICT tw = a.fft.tw;
-    cx<double>* const p0w = work + tid + (tid >> PL::PAD);
-    cx<double>* const p0s = spec + tid + (tid >> PL::PAD);
+    const cx<T>* NM_RESTRICT tw = nm_cx_tw<T>(a);
+    const T* NM_RESTRICT hx = nm_cx_hx<T>(a);
+    cx<T>* const p0w = work + tid + (tid >> PL::PAD);
+    cx<T>* const p0s = spec + tid + (tid >> PL::PAD);
     // twiddle generators; tid == 0 / j == 0 multiply by exactly 1, so no thread needs a special case
-    const cx<double> wA = nm_ldg(tw + tid);                          // exp(-2*pi*i*tid/P): pass 0
-    const cx<double> wB = nm_ldg(tw + (tid & (PL::M1 - 1)) * 16);    // exp(-2*pi*i*j/NT): pass 1 (table stride P/NT)
+    const cx<T> wA = nm_ldg(tw + tid);                          // exp(-2*pi*i*tid/P): pass 0
+    const cx<T> wB = nm_ldg(tw + (tid & (PL::M1 - 1)) * 16);    // exp(-2*pi*i*j/NT): pass 1 (table stride P/NT)
 
-    cx<double> v[16];
-    double hv[16];
+    cx<T> v[16];
+    T hv[16];
     int item = blockIdx.x, w = 0, c0 = 0;
     bool has2 = false;
     if (item >= a.n_items) return;
-    nm_cx_load_item<P, REFLECT>(v, a, item, npair, tid, w, c0, has2);
-    if (BANK) nm_cx_load_h<PL>(hv, a.hx, tid);
+    nm_cx_load_item<P, REFLECT, T>(v, a, item, npair, tid, w, c0, has2);
+    if (BANK) nm_cx_load_h<PL, T>(hv, hx, tid);
 
     while (item < a.n_items) {
         const int next = item + gridDim.x;
@@ -381,11 +399,11 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, BANK ? NmCxPlan<P>::MINBK : NmC
 #pragma unroll
         for (int t = 0; t < 16; ++t) p0s[t * PL::S0] = v[t];
         __syncthreads();
-        if (!BANK) nm_cx_load_h<PL>(hv, a.hx, tid);  // (L1 resident) lands while pass 1 computes
+        if (!BANK) nm_cx_load_h<PL, T>(hv, hx, tid);  // (L1 resident) lands while pass 1 computes
         nm_cx_pass1<PL, false>(spec, wB, tid);
         __syncthreads();
         if (BANK) {
-            nm_cx_pass2<PL, 0>(spec, spec, nullptr, tid);
+            nm_cx_pass2<PL, 0, T>(spec, spec, nullptr, tid);
             __syncthreads();
         }
 
@@ -394,7 +412,7 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, BANK ? NmCxPlan<P>::MINBK : NmC
             if (BANK) {
                 nm_cx_pass2<PL, 2>(work, spec, hv, tid);
                 // prefetch the next filter's spectrum (wrapping to filter 0 for the next item) one phase ahead
-                nm_cx_load_h<PL>(hv, a.hx + (size_t)(last ? 0 : fi + 1) * P, tid);
+                nm_cx_load_h<PL, T>(hv, hx + (size_t)(last ? 0 : fi + 1) * P, tid);
             } else {
                 nm_cx_pass2<PL, 1>(work, work, hv, tid);
             }
@@ -413,13 +431,13 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, BANK ? NmCxPlan<P>::MINBK : NmC
             if (in_regs) {
                 if constexpr (Epi::kRegs) {
                     typename Epi::State st;
-                    epi.template consume<PL>(v, work, red, st, o0, W, a.in.n_ch, w, c0, has2, fi, tid);
-                    if (last && next < a.n_items) nm_cx_load_item<P, REFLECT>(v, a, next, npair, tid, nw, nc0, nhas2);
-                    epi.template finish<PL>(work, red, st, o0, W, a.in.n_ch, w, c0, has2, fi, tid);
+                    epi.template consume<PL, T>(v, work, red, st, o0, W, a.in.n_ch, w, c0, has2, fi, tid);
+                    if (last && next < a.n_items) nm_cx_load_item<P, REFLECT, T>(v, a, next, npair, tid, nw, nc0, nhas2);
+                    epi.template finish<PL, T>(work, red, st, o0, W, a.in.n_ch, w, c0, has2, fi, tid);
                     if constexpr (!Epi::kSyncsInside) __syncthreads();
                 }
             } else {
-                if constexpr (!Epi::kRegsOnly) {
+                if constexpr (!Epi::kRegsOnly && sizeof(T) == 8) {  // (the shared-memory epilogues take float64 rows)
                     __syncthreads();
 #pragma unroll
                     for (int t = 0; t < 16; ++t) work[tid + NT * t] = v[t];
@@ -427,7 +445,7 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, BANK ? NmCxPlan<P>::MINBK : NmC
                     epi.run(work, o0, W, a.in.n_ch, w, c0, has2, fi, scratch, tid, NT);
                     __syncthreads();
                     // (no early prefetch here: these epilogues are register hungry and long enough to hide nothing)
-                    if (last && next < a.n_items) nm_cx_load_item<P, REFLECT>(v, a, next, npair, tid, nw, nc0, nhas2);
+                    if (last && next < a.n_items) nm_cx_load_item<P, REFLECT, T>(v, a, next, npair, tid, nw, nc0, nhas2);
                 }
             }
         }

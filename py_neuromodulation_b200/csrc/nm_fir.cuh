@@ -38,18 +38,26 @@ struct NmEpiStore {
     long long Wp;
     int nF;
     static constexpr bool kRegs = true;   // nm_conv_kernel hands over the 16 outputs of each thread in registers
-    static constexpr bool kRegsOnly = true, kReflectOk = false, kSameOk = true, kConvxOnly = false;  // nm_convx_kernel instantiation traits
+    static constexpr bool kRegsOnly = true, kReflectOk = false, kSameOk = true, kConvxOnly = false, kF32Ok = false;  // nm_convx_kernel instantiation traits
     static NM_HD size_t smem_bytes(int /*nt*/) { return 0; }
     NM_DEV bool regs_ok() const { return true; }
     static constexpr bool kSyncsInside = false;
     struct State {};
-    template <class PL>
-    NM_DEV void consume(const cx<double>* v, cx<double>* /*work*/, double* /*red*/, State& /*st*/, int o0, int W, int n_ch, int w, int c0,
+    template <class PL, typename T>
+    NM_DEV void consume(const cx<T>* v, cx<T>* /*work*/, double* /*red*/, State& /*st*/, int o0, int W, int n_ch, int w, int c0,
                         bool has2, int f, int tid) const {
-        run_regs(v, o0, W, n_ch, w, c0, has2, f, nullptr, tid, PL::NT);
+        double* r0 = y + (((size_t)w * n_ch + c0) * nF + f) * Wp;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int t = tid + PL::NT * k - o0;
+            if (t >= 0 && t < W) {
+                r0[t] = (double)v[k].re;
+                if (has2) r0[(size_t)nF * Wp + t] = (double)v[k].im;
+            }
+        }
     }
-    template <class PL>
-    NM_DEV void finish(cx<double>* /*work*/, double* /*red*/, State& /*st*/, int /*o0*/, int /*W*/, int /*n_ch*/, int /*w*/, int /*c0*/,
+    template <class PL, typename T>
+    NM_DEV void finish(cx<T>* /*work*/, double* /*red*/, State& /*st*/, int /*o0*/, int /*W*/, int /*n_ch*/, int /*w*/, int /*c0*/,
                        bool /*has2*/, int /*f*/, int /*tid*/) const {}
     // v[k] = filtered sample n = tid + nt*k of the (padded) row; the window occupies n in [o0, o0 + W)
     NM_DEV void run_regs(const cx<double>* v, int o0, int W, int n_ch, int w, int c0, bool has2, int f,
@@ -83,14 +91,14 @@ struct NmEpiBandpower {
     int want_act, want_mob, want_comp, log_act;
     NmOut out;             // per_ch = nF * 3  (activity, mobility, complexity)
     static constexpr bool kRegs = true;
-    static constexpr bool kRegsOnly = false, kReflectOk = false, kSameOk = true, kConvxOnly = false;
+    static constexpr bool kRegsOnly = false, kReflectOk = false, kSameOk = true, kConvxOnly = false, kF32Ok = true;
     static NM_HD size_t smem_bytes(int /*nt*/) { return 12 * 32 * sizeof(double); }
     // nm_convx_kernel register epilogue: tail moments from the registers, one barrier, then ONE warp (rotating with the
     // filter index) finishes the two channels on two lanes while the other warps already run the next filter.
     static constexpr bool kSyncsInside = true;
     struct State { double s[4]; int seg; };
-    template <class PL>
-    NM_DEV void consume(const cx<double>* v, cx<double>* /*work*/, double* /*red*/, State& st, int o0, int W, int /*n_ch*/, int /*w*/, int /*c0*/,
+    template <class PL, typename T>
+    NM_DEV void consume(const cx<T>* v, cx<T>* /*work*/, double* /*red*/, State& st, int o0, int W, int /*n_ch*/, int /*w*/, int /*c0*/,
                         bool /*has2*/, int f, int tid) const {
         constexpr int NT = PL::NT;
         int seg = (f < NM_BP_MAX_INLINE) ? seglen_k[f] : nm_ldg(seglen + f);
@@ -103,13 +111,14 @@ struct NmEpiBandpower {
         for (int k = 0; k < 16; ++k) {
             const int n = tid + NT * k;
             if (n >= lo && n < hi) {
-                st.s[0] += v[k].re; st.s[1] += v[k].re * v[k].re;
-                st.s[2] += v[k].im; st.s[3] += v[k].im * v[k].im;
+                const double re = (double)v[k].re, im = (double)v[k].im;  // moments are accumulated in float64 in either mode
+                st.s[0] += re; st.s[1] += re * re;
+                st.s[2] += im; st.s[3] += im * im;
             }
         }
     }
-    template <class PL>
-    NM_DEV void finish(cx<double>* /*work*/, double* red, State& st, int /*o0*/, int /*W*/, int /*n_ch*/, int w, int c0, bool has2, int f,
+    template <class PL, typename T>
+    NM_DEV void finish(cx<T>* /*work*/, double* red, State& st, int /*o0*/, int /*W*/, int /*n_ch*/, int w, int c0, bool has2, int f,
                        int tid) const {
         constexpr int NW = (PL::NT + 31) / 32;
         const int lane = tid & 31, wid = tid >> 5;

@@ -12,7 +12,7 @@ struct nm_pipeline;
 struct FirBank {
     int nF = 0, L = 0, Lh = 0, P = 0, mode = NM_FIR_SAME, E = 0;
     FftPlanHost fft;
-    DevBuf d_hperm, d_hx;
+    DevBuf d_hperm, d_hx, d_hx32, d_tw32;  // *32: float32 copies for the optional float32 mode of nm_convx_kernel
     bool pow2 = false;  // register-blocked power-of-two kernel (nm_conv.cuh) vs generic mixed-radix kernel (nm_fir.cuh)
     int pad = 3;
     int build(const double* taps, int nF_, int L_, int W, int mode_, cudaStream_t s) {
@@ -53,8 +53,17 @@ struct FirBank {
         if (nm_build_hperm(taps, nF, L, fft, hperm)) return -1;
         if (pow2 && nm_convx_supported(P)) {
             std::vector<double> hx(hperm.size());
-            for (int f = 0; f < nF; ++f) nm_cx_interleave_h(P, hperm.data() + (size_t)f * P, hx.data() + (size_t)f * P);
-            if (d_hx.upload(hx, s)) return -1;
+            std::vector<float> hx32(hperm.size());
+            for (int f = 0; f < nF; ++f) {
+                nm_cx_interleave_h(P, hperm.data() + (size_t)f * P, hx.data() + (size_t)f * P);
+                nm_cx_interleave_h(P, hperm.data() + (size_t)f * P, hx32.data() + (size_t)f * P);
+            }
+            std::vector<cx<float>> tw32(P);
+            for (int k = 0; k < P; ++k) {
+                const double ang = -2.0 * M_PI * (double)k / (double)P;
+                tw32[k] = {(float)std::cos(ang), (float)std::sin(ang)};
+            }
+            if (d_hx.upload(hx, s) || d_hx32.upload(hx32, s) || d_tw32.upload(tw32, s)) return -1;
         }
         return d_hperm.upload(hperm, s);
     }
@@ -82,6 +91,8 @@ struct FirBank {
         a.fft.tw = fft.d_tw.as<cx<double>>();
         a.hperm = d_hperm.as<double>() + (size_t)f0 * P;
         a.hx = d_hx.as<double>();
+        a.hx32 = d_hx32.as<float>();
+        a.tw32 = d_tw32.as<cx<float>>();
         a.nF = n < 0 ? nF : n;
         a.f0 = f0;
         a.mode = mode;
@@ -93,8 +104,9 @@ struct FirBank {
     bool epi_fits_tail(size_t epi) const { return pow2 && epi > 0 && epi <= (nm_conv_buf_elems(P, pad) - (size_t)P) * sizeof(cx<double>); }
     int threads() const { return pow2 ? P / 16 : NM_FFT_THREADS; }
     // nm_convx_kernel: reflect mode is single-filter (one buffer), 'same' mode always runs the bank code (two buffers)
-    size_t smem_x(size_t epi) const {
-        return nm_conv_buf_elems(P, pad) * sizeof(cx<double>) * (mode == NM_FIR_REFLECT ? 1 : 2) + NM_CX_RED_BYTES + (epi_fits_tail(epi) ? 0 : epi);
+    size_t smem_x(size_t epi, bool f32 = false) const {
+        return nm_conv_buf_elems(P, pad) * (f32 ? sizeof(cx<float>) : sizeof(cx<double>)) * (mode == NM_FIR_REFLECT ? 1 : 2) + NM_CX_RED_BYTES +
+               (epi_fits_tail(epi) ? 0 : epi);
     }
     size_t smem(size_t epi, int n_filters = -1) const {
         const size_t buf = pow2 ? nm_conv_buf_elems(P, pad) : (size_t)P;

@@ -150,6 +150,10 @@ struct nm_pipeline {
     DevBuf d_starts, d_yoff, d_y, d_out, d_nanflags;
     long long out_rows = 0;
     int chunk = 1, Wp = 0;
+    // arithmetic of the LINEAR families (notch, band power): 0 float64 (default), 1 float32 inside the FFT convolution.  Rows that
+    // feed threshold / peak decisions (bursts, sharp waves, raw normaliser clip) always stay float64, and so does the notch then.
+    int precision = 0;
+    bool f32_linear() const { return precision == 1 && !bursts && !sharpwave && !rawnorm; }
     std::vector<long long> h_starts_one;
     DevBuf d_win_in;  // staging of a single streamed window
 
@@ -178,28 +182,37 @@ static int nm_allow_smem(K kernel, size_t bytes, const nm_pipeline* p) {
 template <class Epi>
 using NmConvKernel = void (*)(NmConvArgs, Epi);
 
-template <class Epi>
-static NmConvKernel<Epi> nm_convx_pick(const FirBank& b) {
-    if (!b.pow2 || !nm_convx_supported(b.P)) return nullptr;
+template <typename T, class Epi>
+static NmConvKernel<Epi> nm_convx_pick_t(const FirBank& b) {
     if (b.mode == NM_FIR_REFLECT) {
         if constexpr (Epi::kReflectOk) {
             if (b.nF != 1) return nullptr;
             switch (b.P) {
-                case 1024: return nm_convx_kernel<1024, true, false, Epi>;
-                case 2048: return nm_convx_kernel<2048, true, false, Epi>;
-                default: return nm_convx_kernel<4096, true, false, Epi>;
+                case 1024: return nm_convx_kernel<T, 1024, true, false, Epi>;
+                case 2048: return nm_convx_kernel<T, 2048, true, false, Epi>;
+                default: return nm_convx_kernel<T, 4096, true, false, Epi>;
             }
         }
     } else {
         if constexpr (Epi::kSameOk) {
             switch (b.P) {
-                case 1024: return nm_convx_kernel<1024, false, true, Epi>;
-                case 2048: return nm_convx_kernel<2048, false, true, Epi>;
-                default: return nm_convx_kernel<4096, false, true, Epi>;
+                case 1024: return nm_convx_kernel<T, 1024, false, true, Epi>;
+                case 2048: return nm_convx_kernel<T, 2048, false, true, Epi>;
+                default: return nm_convx_kernel<T, 4096, false, true, Epi>;
             }
         }
     }
     return nullptr;
+}
+
+// f32: float32 arithmetic inside the transform (optional fast mode; only epilogues that work from registers offer it)
+template <class Epi>
+static NmConvKernel<Epi> nm_convx_pick(const FirBank& b, bool f32 = false) {
+    if (!b.pow2 || !nm_convx_supported(b.P)) return nullptr;
+    if constexpr (Epi::kF32Ok) {
+        if (f32) return nm_convx_pick_t<float, Epi>(b);
+    }
+    return nm_convx_pick_t<double, Epi>(b);
 }
 
 // a bank whose spectrum + work buffers do not fit the shared memory of one CTA (long filters at high sampling rates: P = 8192
@@ -218,8 +231,8 @@ static size_t nm_fir_smem(const FirBank& bank, size_t epi_bytes) {
 }
 
 template <class Epi>
-static int nm_allow_fir_smem(const FirBank& bank, size_t epi_bytes, const nm_pipeline* p) {
-    if (auto k = nm_convx_pick<Epi>(bank)) return nm_allow_smem(k, bank.smem_x(epi_bytes), p);
+static int nm_allow_fir_smem(const FirBank& bank, size_t epi_bytes, const nm_pipeline* p, bool f32 = false) {
+    if (auto k = nm_convx_pick<Epi>(bank, f32)) return nm_allow_smem(k, bank.smem_x(epi_bytes, f32 && Epi::kF32Ok), p);
     if constexpr (!Epi::kConvxOnly) {
         const size_t sm = bank.smem(epi_bytes, nm_fir_split<Epi>(bank, epi_bytes, p) ? 1 : -1);
         if (bank.pow2) return nm_allow_smem(nm_conv_kernel<Epi>, sm, p);
@@ -237,12 +250,13 @@ static int nm_resident_grid(const nm_pipeline* p, K kernel, int threads, size_t 
 }
 
 template <class Epi>
-static void nm_launch_fir(nm_pipeline* p, const FirBank& bank, const NmRows& rows, const Epi& epi, cudaStream_t stream, size_t epi_bytes) {
+static void nm_launch_fir(nm_pipeline* p, const FirBank& bank, const NmRows& rows, const Epi& epi, cudaStream_t stream, size_t epi_bytes,
+                          bool f32 = false) {
     const int threads = bank.threads();
-    if (auto k = nm_convx_pick<Epi>(bank)) {
+    if (auto k = nm_convx_pick<Epi>(bank, f32)) {
         NmConvArgs a = bank.conv_args(rows);
         a.scratch_in_tail = bank.epi_fits_tail(epi_bytes) ? 1 : 0;
-        const size_t sm = bank.smem_x(epi_bytes);
+        const size_t sm = bank.smem_x(epi_bytes, f32 && Epi::kF32Ok);
         const int grid = nm_resident_grid(p, k, threads, sm, a.n_items);
         NM_LAUNCH(k, dim3(grid), dim3(threads), sm, stream, a, epi);
         return;
@@ -279,7 +293,7 @@ static bool nm_launch_notch(nm_pipeline* p, const NmRows& rows, double* y, const
         epi.want_hjorth = p->scan_h; epi.want_raw = p->scan_r; epi.want_ll = p->scan_l;
         if (scan_out) epi.out = *scan_out;
         else epi.out = NmOut{nullptr, 0, 0, nullptr, 0};
-        nm_launch_fir(p, bank, rows, epi, stream, 0);
+        nm_launch_fir(p, bank, rows, epi, stream, 0, p->f32_linear());
         return scan_out != nullptr;
     }
     NmEpiStore epi{y, (long long)p->Wp, 1};
@@ -774,6 +788,13 @@ extern "C" int nm_add_feature_normalizer(nm_pipeline* p, int method, double clip
     return 0;
 }
 
+extern "C" int nm_set_precision(nm_pipeline* p, int float32_linear) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    p->precision = float32_linear ? 1 : 0;
+    return 0;
+}
+
 extern "C" int nm_set_raw_normalizer(nm_pipeline* p, int method, double clip, int n_keep, int add_samples) {
     NM_P_CHECK(p);
     NM_CHECK(!p->finalized, "pipeline already finalized");
@@ -819,8 +840,12 @@ extern "C" int nm_finalize(nm_pipeline* p) {
     if (p->rawnorm && p->rawnorm->need_median() && nm_allow_smem(nm_burst_thr_kernel, BurstsFam::thr_smem(), p)) return -1;
 
     // opt in to large dynamic shared memory once
-    if (p->notch && (nm_allow_fir_smem<NmEpiStore>(*p->notch, 0, p) || nm_allow_fir_smem<NmEpiStoreScan>(*p->notch, 0, p))) return -1;
-    if (p->bandpower && nm_allow_fir_smem<NmEpiBandpower>(p->bandpower->bank, p->bandpower->epi_smem(), p)) return -1;
+    if (p->notch && (nm_allow_fir_smem<NmEpiStore>(*p->notch, 0, p) || nm_allow_fir_smem<NmEpiStoreScan>(*p->notch, 0, p) ||
+                     nm_allow_fir_smem<NmEpiStoreScan>(*p->notch, 0, p, true)))
+        return -1;
+    if (p->bandpower && (nm_allow_fir_smem<NmEpiBandpower>(p->bandpower->bank, p->bandpower->epi_smem(), p) ||
+                         nm_allow_fir_smem<NmEpiBandpower>(p->bandpower->bank, p->bandpower->epi_smem(), p, true)))
+        return -1;
     size_t spec_max = 0;
     for (auto& f : p->spectral)
         if (!f->fast) spec_max = std::max(spec_max, f->smem());
@@ -1112,7 +1137,7 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         epi.want_act = f.act; epi.want_mob = f.mob; epi.want_comp = f.comp; epi.log_act = f.logt;
         epi.out = out_for(f.d_colmap, f.bank.nF * 3);
         p->prof_begin();
-        nm_launch_fir(p, f.bank, rows, epi, p->stream, f.epi_smem());
+        nm_launch_fir(p, f.bank, rows, epi, p->stream, f.epi_smem(), p->precision == 1 && !(f.mob || f.comp));
         p->prof_end(NM_PROF_BANDPOWER);
         p->launches++;
     }

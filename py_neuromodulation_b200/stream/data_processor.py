@@ -79,6 +79,7 @@ class _Plan:
             self.pipe = None
             return
         pipe = Pipeline(dp.n_raw_rows, len(names), window_samples, columns, device=dp.device)
+        pipe.set_precision(dp.precision)
         pipe.set_pick(dp.feature_idx)
         if dp.reref_factored is not None:  # channel-sharded run: coefficients come from the GLOBAL channel table
             pipe.set_reref_factored(*dp.reref_factored)
@@ -116,6 +117,7 @@ class DataProcessor:
         verbose: bool = True,
         device: int = 0,
         reref_factored: tuple | None = None,
+        precision: str | None = None,
     ) -> None:
         from .. import user_features
         from ..filter.notch_filter import NotchFilter
@@ -123,6 +125,13 @@ class DataProcessor:
         from ..processing.normalization import GPU_NORM_METHODS
         from ..processing.rereference import build_reference_matrix
 
+        # arithmetic of the linear FIR families: "f64" (default; ~1e-12 from the float64 reference) or "f32" (float32 inside the
+        # FFT convolution, 1e-5 relative); env NMB200_PRECISION overrides the default for callers that cannot pass the argument
+        import os
+
+        self.precision = precision or os.environ.get("NMB200_PRECISION", "f64")
+        if self.precision not in ("f64", "f32"):
+            raise ValueError("precision must be 'f64' or 'f32'")
         self.settings = NMSettings.load(settings)
         self.channels = io.load_channels(channels)
         self.sfreq_features: float = self.settings.sampling_rate_features_hz

@@ -329,3 +329,24 @@ def test_raw_normalizer_streaming_and_standalone(backend):
     s2.raw_normalization_settings.normalization_method = "robust"  # scikit-learn transformer
     with pytest.raises(NotImplementedError):
         nm.DataProcessor(sfreq=1000, settings=s2, channels=ch, line_noise=50, verbose=False)
+
+
+@pytest.mark.parametrize("name", ["dataprocessor_c3_nan", "dataprocessor_fast", "dataprocessor_prefilter_default"])
+def test_float32_linear_mode_within_north_star_tolerance(backend, name):
+    """precision="f32": float32 arithmetic inside the notch / band-pass FFT convolutions (moments and outputs float64).
+    Tolerance = the task's 1e-5 relative (|ref| >= 1: relative, else absolute 1e-5), NaN pattern identical."""
+    g = load_golden(name)
+    x = g["x"].astype(np.float64)
+    s = nm.NMSettings(**g["settings"])
+    s.postprocessing.feature_normalization = False  # z-scores of a handful of windows amplify any input difference
+    dp = nm.DataProcessor(sfreq=g["sfreq"], settings=s, channels=get_default_channels_from_data(x), line_noise=50, verbose=False,
+                          precision="f32")
+    starts, lengths, _ = window_grid(x.shape[1], g["sfreq"], s.sampling_rate_features_hz, s.segment_length_features_ms)
+    cols, mat = dp.process_windows(x, starts, int(lengths[0]))
+    dp64 = nm.DataProcessor(sfreq=g["sfreq"], settings=s, channels=get_default_channels_from_data(x), line_noise=50, verbose=False)
+    _, ref = dp64.process_windows(x, starts, int(lengths[0]))
+    assert np.array_equal(np.isnan(mat), np.isnan(ref))
+    fin = np.isfinite(ref)
+    err = np.abs(mat[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0)
+    assert err.max() < 1e-5, float(err.max())
+    assert err.max() > 0.0  # the float32 kernels really ran
