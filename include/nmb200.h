@@ -146,6 +146,12 @@ int nm_upload_f64(nm_pipeline* p, const double* data, long long n_samples, long 
  * on the host. */
 int nm_run_windows(nm_pipeline* p, const long long* starts, int n_windows, double* out_host);
 int nm_download(nm_pipeline* p, double* out_host, int n_windows);
+/* Row pitch (in elements, >= n_features; 0 = dense) of the HOST matrix that nm_run_windows / nm_download write: lets every rank
+ * of a channel-sharded run copy its (n_windows x F_local) block straight into its column range of one shared host matrix. */
+int nm_set_output_pitch(nm_pipeline* p, long long pitch_elems);
+/* page-lock / unlock caller-owned host memory (e.g. a POSIX shared-memory segment mapped by all ranks of a node) */
+int nm_host_register(void* ptr, long long bytes);
+int nm_host_unregister(void* ptr);
 /* DataProcessor.process for one (n_raw_rows, W) float64 window; keeps cross-window state. */
 int nm_process_window(nm_pipeline* p, const double* window, double* out_features);
 

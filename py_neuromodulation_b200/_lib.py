@@ -69,6 +69,9 @@ _SIGNATURES = {
     "nm_upload_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong]),
     "nm_upload_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong]),
     "nm_run_windows": (C.c_int, [C.c_void_p, c_ll_p, C.c_int, C.c_void_p]),
+    "nm_set_output_pitch": (C.c_int, [C.c_void_p, C.c_longlong]),
+    "nm_host_register": (C.c_int, [C.c_void_p, C.c_longlong]),
+    "nm_host_unregister": (C.c_int, [C.c_void_p]),
     "nm_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "nm_process_window": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nm_preprocess_window": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

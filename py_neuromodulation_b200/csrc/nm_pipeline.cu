@@ -149,6 +149,7 @@ struct nm_pipeline {
     bool have_data = false, upload_pending = false, resident_uses_gsum = false;
     DevBuf d_starts, d_yoff, d_y, d_out, d_nanflags;
     long long out_rows = 0;
+    long long out_pitch = 0;  // row pitch (elements) of the HOST result matrix; 0 = n_features (dense)
     int chunk = 1, Wp = 0;
     // arithmetic of the LINEAR families (notch, band power): 0 float64 (default), 1 float32 inside the FFT convolution.  Rows that
     // feed threshold / peak decisions (bursts, sharp waves, raw normaliser clip) always stay float64, and so does the notch then.
@@ -1209,8 +1210,10 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
                 }
                 NM_CUDA_CHECK(cudaEventRecord(p->chunk_ev[n_ev], p->stream));
                 NM_CUDA_CHECK(cudaStreamWaitEvent(p->copy_stream, p->chunk_ev[n_ev], 0));
-                NM_CUDA_CHECK(cudaMemcpyAsync(out_host + (size_t)w0 * p->F, p->d_out.as<double>() + (size_t)w0 * p->F,
-                                              (size_t)n * p->F * sizeof(double), cudaMemcpyDeviceToHost, p->copy_stream));
+                const size_t hp = (size_t)(p->out_pitch ? p->out_pitch : p->F);
+                NM_CUDA_CHECK(cudaMemcpy2DAsync(out_host + (size_t)w0 * hp, hp * sizeof(double), p->d_out.as<double>() + (size_t)w0 * p->F,
+                                                (size_t)p->F * sizeof(double), (size_t)p->F * sizeof(double), (size_t)n, cudaMemcpyDeviceToHost,
+                                                p->copy_stream));
                 ++n_ev;
             }
         }
@@ -1233,8 +1236,27 @@ extern "C" int nm_download(nm_pipeline* p, double* out_host, int n_windows) {
     NM_P_CHECK(p);
     NM_CHECK(out_host && n_windows > 0 && n_windows <= p->out_rows, "nothing to download");
     cudaSetDevice(p->device);
-    NM_CUDA_CHECK(cudaMemcpyAsync(out_host, p->d_out.p, (size_t)n_windows * p->F * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    const size_t hp = (size_t)(p->out_pitch ? p->out_pitch : p->F);
+    NM_CUDA_CHECK(cudaMemcpy2DAsync(out_host, hp * sizeof(double), p->d_out.p, (size_t)p->F * sizeof(double), (size_t)p->F * sizeof(double),
+                                    (size_t)n_windows, cudaMemcpyDeviceToHost, p->stream));
     NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int nm_set_output_pitch(nm_pipeline* p, long long pitch_elems) {
+    NM_P_CHECK(p);
+    NM_CHECK(pitch_elems == 0 || pitch_elems >= p->F, "output pitch %lld is smaller than the %d features of a row", pitch_elems, p->F);
+    p->out_pitch = pitch_elems;
+    return 0;
+}
+
+extern "C" int nm_host_register(void* ptr, long long bytes) {
+    NM_CHECK(ptr && bytes > 0, "bad arguments");
+    NM_CUDA_CHECK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return 0;
+}
+extern "C" int nm_host_unregister(void* ptr) {
+    NM_CUDA_CHECK(cudaHostUnregister(ptr));
     return 0;
 }
 

@@ -5,7 +5,10 @@ halo: rank r of R owns channels [r*C/R, (r+1)*C/R) for ALL windows.  The data pa
 
 1. common-average reference: one all-reduce(sum) of the per-sample channel-group sums (G x T float64) --
    ``nm_upload_begin_f32`` / ``nm_group_sums_device_ptr`` / ``nm_upload_finish`` in the C ABI;
-2. one gather of the (n_windows x F_local) float64 result blocks to rank 0 at the end.
+2. the (n_windows x F_local) float64 result blocks meet on rank 0.  On one node (the default) every rank copies the rows of
+   each finished chunk over its OWN PCIe link straight into its column range of one page-locked POSIX shared-memory matrix
+   (``nm_set_output_pitch`` + ``nm_host_register``), overlapped with the next chunk's kernels -- no collective, no funnel
+   through rank 0's link.  ``shared_host=False`` (or ranks on different nodes) uses one NCCL gather to rank 0 instead.
 
 The collectives go through ``torch.distributed`` (NCCL over NVLink on GPUs; gloo in the CPU tests, where the
 "device" buffers of the thread-emulated library are host memory).  torch is plumbing only: no torch kernel touches
@@ -102,9 +105,79 @@ def wrap_buffer(ptr: int, n: int, on_gpu: bool):
 class ShardedRun:
     """One rank's part of a channel-sharded offline run around an already-built local :class:`Pipeline`."""
 
-    def __init__(self, pipe, on_gpu: bool = True) -> None:
+    def __init__(self, pipe, on_gpu: bool = True, shared_host: bool = True) -> None:
         self.pipe = pipe
         self.on_gpu = on_gpu
+        self.shared_host = shared_host
+        self._shm = None
+        self._shm_key = None
+
+    # ------------------------------------------------------------------ shared host matrix (single node)
+    def _ensure_shared(self, n_windows: int):
+        """(matrix view, first column of this rank) of the node-wide result matrix; created on first use."""
+        import torch
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+
+        key = (n_windows, self.pipe.F)
+        if self._shm_key == key:
+            return self._shm_view, self._shm_col0
+        self._release_shared()
+        world, rank = dist.get_world_size(), dist.get_rank()
+        widths = [None] * world
+        dist.all_gather_object(widths, int(self.pipe.F))
+        total = int(sum(widths))
+        n_bytes = n_windows * total * 8
+        name = [None]
+        if rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=max(n_bytes, 8))
+            name[0] = shm.name
+        dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=name[0])
+        view = np.ndarray((n_windows, total), dtype=np.float64, buffer=shm.buf)
+        addr = view.ctypes.data
+        _lib.check(self.pipe.lib.nm_host_register(C.c_void_p(addr), n_bytes))
+        _lib.check(self.pipe.lib.nm_set_output_pitch(self.pipe._h, total))
+        self._shm, self._shm_view, self._shm_addr = shm, view, addr
+        self._shm_col0 = int(sum(widths[:rank]))
+        self._shm_key = key
+        self._shm_owner = rank == 0
+        dist.barrier()
+        return view, self._shm_col0
+
+    def _release_shared(self) -> None:
+        if self._shm is None:
+            return
+        try:
+            self.pipe.synchronize()
+            self.pipe.lib.nm_host_unregister(C.c_void_p(self._shm_addr))
+            self.pipe.lib.nm_set_output_pitch(self.pipe._h, 0)
+        except Exception:
+            pass
+        self._shm_view = None
+        shm, self._shm = self._shm, None
+        self._shm_key = None
+        shm.close()
+        if self._shm_owner:
+            try:
+                shm.unlink()
+            except FileNotFoundError:
+                pass
+
+    def close(self) -> None:
+        self._release_shared()
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self._release_shared()
+        except Exception:
+            pass
+
+    def _use_shared(self) -> bool:
+        import torch.distributed as dist
+
+        return self.shared_host and dist.is_initialized() and dist.get_world_size() > 1
 
     def upload(self, data_f32: np.ndarray) -> None:
         """H2D of the local shard, all-reduce of the group sums, re-reference."""
@@ -126,8 +199,15 @@ class ShardedRun:
         p._keep_data = a
 
     def run(self, starts: np.ndarray) -> None:
-        self.pipe.run(starts, download=False)
-        self.pipe.synchronize()
+        p = self.pipe
+        if not self._use_shared():
+            p.run(starts, download=False)
+            p.synchronize()
+            return
+        s = np.ascontiguousarray(starts, dtype=np.int64)
+        view, col0 = self._ensure_shared(int(s.size))
+        dst = view.ctypes.data + col0 * 8
+        _lib.check(p.lib.nm_run_windows(p._h, s.ctypes.data_as(C.POINTER(C.c_longlong)), int(s.size), C.c_void_p(dst)))
 
     def gather(self, n_windows: int):
         """Gather the (n_windows, F_local) blocks to rank 0; returns a host array (n_windows, sum F_local) there, else None.
@@ -138,6 +218,9 @@ class ShardedRun:
         import torch
         import torch.distributed as dist
 
+        if self._use_shared() and self._shm_key == (n_windows, self.pipe.F):
+            dist.barrier()  # every rank has returned from run(): its block is in the shared matrix
+            return self._shm_view if dist.get_rank() == 0 else None
         ptr, rows, cols = self.pipe.result_device_ptr()
         local = wrap_buffer(ptr, rows * cols, self.on_gpu)[: n_windows * cols].view(n_windows, cols)
         if not (dist.is_initialized() and dist.get_world_size() > 1):

@@ -16,7 +16,7 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank: int, world: int, port: int, x: np.ndarray, settings_dict: dict, out_file: str) -> None:
+def _worker(rank: int, world: int, port: int, x: np.ndarray, settings_dict: dict, out_file: str, shared_host: bool) -> None:
     import torch.distributed as dist
 
     from tests.emu_support import load_emu
@@ -41,18 +41,22 @@ def _worker(rank: int, world: int, port: int, x: np.ndarray, settings_dict: dict
                               verbose=False, reref_factored=reref)
         starts, lengths, _ = window_grid(x.shape[1], 1000, settings.sampling_rate_features_hz, settings.segment_length_features_ms)
         plan = dp.plan(int(lengths[0]))
-        run = ShardedRun(plan.pipe, on_gpu=False)
-        run.upload(x[lo:hi].astype(np.float32))
-        run.run(starts)
-        gathered = run.gather(len(starts))
+        run = ShardedRun(plan.pipe, on_gpu=False, shared_host=shared_host)
+        for _ in range(2):  # second pass: buffers / shared matrix reused
+            run.upload(x[lo:hi].astype(np.float32))
+            run.run(starts)
+            gathered = run.gather(len(starts))
         if rank == 0:
             cols, perm = merge_permutation(settings, list(channels["new_name"]), 1000, int(lengths[0]), world)
             np.savez(out_file, cols=np.array(cols), mat=gathered[:, perm])
+        dist.barrier()
+        run.close()
     finally:
         dist.destroy_process_group()
 
 
-def test_two_rank_channel_shard_matches_oracle(tmp_path):
+@pytest.mark.parametrize("shared_host", [True, False], ids=["shared-host-matrix", "nccl-style-gather"])
+def test_two_rank_channel_shard_matches_oracle(tmp_path, shared_host):
     import torch.multiprocessing as mp
 
     import py_neuromodulation_b200 as nm
@@ -67,7 +71,7 @@ def test_two_rank_channel_shard_matches_oracle(tmp_path):
     s.features.bandpass_filter = True
     s.features.linelength = True
     out_file = str(tmp_path / "gathered.npz")
-    mp.spawn(_worker, args=(2, _free_port(), x, s.model_dump(), out_file), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), x, s.model_dump(), out_file, shared_host), nprocs=2, join=True)
     got = np.load(out_file)
     ref_cols, ref = orc.run_offline(x, 1000, s.model_dump())
     ref_cols, ref = ref_cols[:-1], ref[:, :-1]  # drop the time column
