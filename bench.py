@@ -375,6 +375,8 @@ def run_gpu_arm(args) -> None:
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
+        if sharded is not None:
+            sharded.close()
         dist.destroy_process_group()
 
 

@@ -135,6 +135,12 @@ class ShardedRun:
         dist.broadcast_object_list(name, src=0)
         if rank != 0:
             shm = shared_memory.SharedMemory(name=name[0])
+            try:  # attaching registers the segment with this process's resource tracker too (CPython < 3.13): only the owner unlinks
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
         view = np.ndarray((n_windows, total), dtype=np.float64, buffer=shm.buf)
         addr = view.ctypes.data
         _lib.check(self.pipe.lib.nm_host_register(C.c_void_p(addr), n_bytes))

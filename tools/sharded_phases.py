@@ -55,6 +55,8 @@ def main():
         if rank == 0:
             d = np.diff(t) * 1e3
             print(f"iter {it}: upload {d[0]:.1f} ms, run {d[1]:.1f} ms, gather {d[2]:.1f} ms, barrier {d[3]:.1f} ms", flush=True)
+    dist.barrier()
+    sh.close()
     dist.destroy_process_group()
 
 
