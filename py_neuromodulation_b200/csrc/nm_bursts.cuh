@@ -15,6 +15,7 @@
 #pragma once
 
 #include "nm_fir.cuh"
+#include "nm_specx.cuh"
 
 struct NmEpiBursts {
     static constexpr bool kRegs = false;
@@ -28,13 +29,64 @@ struct NmEpiBursts {
     long long cap;
     long long win0;         // global index (since reset) of the chunk's first window
     int S;                  // samples appended by every window but the first
-    static NM_HD size_t smem_bytes_for(int W, int need_scratch) { return (size_t)W * sizeof(cx<double>) * (need_scratch ? 2 : 1); }
+    int fast_n;             // 1000 / 2000 / 500: W-point transforms through the register-blocked plans of nm_specx.cuh, else 0
+    static NM_HD size_t smem_bytes_for(int W, int need_scratch, int fast_n = 0) {
+        if (fast_n == 1000) return (size_t)NmSx1000::NBUF * sizeof(cx<double>);
+        if (fast_n == 2000) return (size_t)NmSx2000::NBUF * sizeof(cx<double>);
+        if (fast_n == 500) return (size_t)NmSx500::NBUF * sizeof(cx<double>);
+        return (size_t)W * sizeof(cx<double>) * (need_scratch ? 2 : 1);
+    }
+
+    // envelope of one sample pair -> chunk rows + history ring
+    NM_DEV void emit(int t, double xa, double xb, double ha, double hb_, int W, int n_ch, int w, int c0, bool has2, int f) const {
+        const long long gw = win0 + w;
+        const int take = (gw == 0) ? W : S;
+        const long long e_prev = (gw == 0) ? 0 : (long long)W + (gw - 1) * S;
+        const int j = t - (W - take);
+        for (int k = 0; k < (has2 ? 2 : 1); ++k) {
+            const int c = c0 + k;
+            const double re = k ? xb : xa, im = k ? hb_ : ha;
+            const double e = sqrt(re * re + im * im);
+            env[(((size_t)w * n_ch + c) * nB + f) * Wp + t] = e;
+            if (j >= 0) ring[((size_t)c * nB + f) * cap + (e_prev + j) % cap] = e;
+        }
+    }
+
+    // W-point analytic signal with a compile-time plan: forward, one-sided multiplier in slot order, inverse into registers
+    template <class PL>
+    NM_DEV void run_fast(const cx<double>* x, int W, int n_ch, int w, int c0, bool has2, int f, cx<double>* hb, int tid, int nt) const {
+        nm_sx_forward_smem<PL>(x, hb, hfft.tw, tid);
+        const double inv = 1.0 / W;
+        for (int e = tid; e < W; e += nt) {
+            const int k = nm_sx_freq_of_slot<PL>(e);
+            const cx<double> v = hb[PL::phys(e)];
+            cx<double> r = {0.0, 0.0};
+            if (k != 0 && 2 * k != W) {
+                if (2 * k < W) r = {v.im * inv, -v.re * inv};   // * (-i)
+                else r = {-v.im * inv, v.re * inv};             // * (+i)
+            }
+            hb[PL::phys(e)] = r;
+        }
+        __syncthreads();
+        cx<double> v[PL::R0];
+        nm_sx_inverse_regs<PL>(hb, hfft.tw, tid, v);
+        if (tid < PL::NA) {
+#pragma unroll
+            for (int k = 0; k < PL::R0; ++k) {
+                const int t = tid + PL::NA * k;
+                emit(t, x[t].re, x[t].im, v[k].re, v[k].im, W, n_ch, w, c0, has2, f);
+            }
+        }
+    }
 
     NM_DEV void run(const cx<double>* buf, int o0, int W, int n_ch, int w, int c0, bool has2, int f,
                     unsigned char* scratch_raw, int tid, int nt) const {
         cx<double>* hb = reinterpret_cast<cx<double>*>(scratch_raw);
-        cx<double>* sc = need_scratch ? hb + W : nullptr;
         const cx<double>* x = buf + o0;
+        if (fast_n == 1000) { run_fast<NmSx1000>(x, W, n_ch, w, c0, has2, f, hb, tid, nt); return; }
+        if (fast_n == 2000) { run_fast<NmSx2000>(x, W, n_ch, w, c0, has2, f, hb, tid, nt); return; }
+        if (fast_n == 500) { run_fast<NmSx500>(x, W, n_ch, w, c0, has2, f, hb, tid, nt); return; }
+        cx<double>* sc = need_scratch ? hb + W : nullptr;
         for (int t = tid; t < W; t += nt) hb[t] = x[t];
         __syncthreads();
         nm_fft_forward<double>(hb, sc, hfft, tid, nt);
@@ -51,22 +103,7 @@ struct NmEpiBursts {
         }
         __syncthreads();
         nm_fft_inverse<double>(hb, sc, hfft, tid, nt);
-        const long long gw = win0 + w;
-        const int take = (gw == 0) ? W : S;
-        const long long e_prev = (gw == 0) ? 0 : (long long)W + (gw - 1) * S;
-        for (int k = 0; k < (has2 ? 2 : 1); ++k) {
-            const int c = c0 + k;
-            double* erow = env + (((size_t)w * n_ch + c) * nB + f) * Wp;
-            double* rrow = ring + ((size_t)c * nB + f) * cap;
-            for (int t = tid; t < W; t += nt) {
-                const double re = k ? x[t].im : x[t].re;
-                const double im = k ? hb[t].im : hb[t].re;
-                const double e = sqrt(re * re + im * im);
-                erow[t] = e;
-                const int j = t - (W - take);
-                if (j >= 0) rrow[(e_prev + j) % cap] = e;
-            }
-        }
+        for (int t = tid; t < W; t += nt) emit(t, x[t].re, x[t].im, hb[t].re, hb[t].im, W, n_ch, w, c0, has2, f);
     }
 };
 
@@ -780,7 +817,8 @@ struct BurstsFam {
         batch = 0;
         if (d_qrow.p) cudaMemset(d_qrow.p, 0, (size_t)C * nB * sizeof(NmBurstQRow));  // valid = 0 for every row
     }
-    size_t epi_smem() const { return NmEpiBursts::smem_bytes_for(W, hfft.generic); }
+    int fast_n() const { return (nm_specx_supported(W) && bank.threads() >= (W == 500 ? NmSx500::NA : NmSx1000::NA)) ? W : 0; }
+    size_t epi_smem() const { return NmEpiBursts::smem_bytes_for(W, hfft.generic, fast_n()); }
     static size_t thr_smem() { return nm_bq_smem_bytes(); }
     int allow_smem(const nm_pipeline* p);
     long long run_base = 0;  // `batch` at the time prepare() ran

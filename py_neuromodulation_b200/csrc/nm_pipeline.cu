@@ -353,6 +353,7 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     NmEpiBursts epi;
     epi.hfft = hfft.dev();
     epi.need_scratch = hfft.generic ? 1 : 0;
+    epi.fast_n = fast_n();
     epi.env = d_env.as<double>();
     epi.Wp = Wp;
     epi.nB = nB;

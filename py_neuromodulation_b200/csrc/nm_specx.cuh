@@ -78,6 +78,121 @@ struct NmSxPlan {
     static NM_HD int phys(int e) { return PADU ? e + e / PADU : e; }
 };
 
+// inverse DFT in registers through the conjugation identity  IDFT(v) = conj(DFT(conj(v)))  (unnormalised)
+template <int R>
+NM_DEV void nm_dft_reg_inv(cx<double>* v) {
+#pragma unroll
+    for (int k = 0; k < R; ++k) v[k].im = -v[k].im;
+    nm_dft_reg<R>(v);
+#pragma unroll
+    for (int k = 0; k < R; ++k) v[k].im = -v[k].im;
+}
+
+// v[k] *= conj(w1)^k, k = 1..R-1
+template <int R>
+NM_DEV void nm_twiddle_pow_conj(cx<double>* v, cx<double> w1) {
+    w1.im = -w1.im;
+    nm_twiddle_pow<R>(v, w1);
+}
+
+// Forward transform of a natural-order row that already sits in shared memory (`src`, N elements) into `buf` (padded slot
+// order, PL::NBUF elements); `src` and `buf` must not overlap.  All threads of the CTA call it; ends with a barrier.
+template <class PL>
+NM_DEV void nm_sx_forward_smem(const cx<double>* src, cx<double>* buf, const cx<double>* NM_RESTRICT tw, int tid) {
+    constexpr int R0 = PL::R0, R1 = PL::R1, R2 = PL::R2, NA = PL::NA;
+    const bool active = tid < NA;
+    if (active) {
+        cx<double> v[R0];
+#pragma unroll
+        for (int t = 0; t < R0; ++t) v[t] = src[tid + NA * t];
+        nm_dft_reg<R0>(v);
+        nm_twiddle_pow<R0>(v, nm_ldg(tw + tid));
+#pragma unroll
+        for (int k = 0; k < R0; ++k) buf[PL::phys(tid + NA * k)] = v[k];
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < R0 / R1; ++i) {
+            const int q = tid + NA * i;
+            const int blk = q / PL::M1, j = q - blk * PL::M1;
+            const int e0 = blk * PL::L1 + j;
+            cx<double> u[R1];
+#pragma unroll
+            for (int t = 0; t < R1; ++t) u[t] = buf[PL::phys(e0 + t * PL::M1)];
+            nm_dft_reg<R1>(u);
+            nm_twiddle_pow<R1>(u, nm_ldg(tw + j * R0));
+#pragma unroll
+            for (int t = 0; t < R1; ++t) buf[PL::phys(e0 + t * PL::M1)] = u[t];
+        }
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < R0 / R2; ++i) {
+            const int e0 = (tid + NA * i) * R2;
+            cx<double> u[R2];
+#pragma unroll
+            for (int t = 0; t < R2; ++t) u[t] = buf[PL::phys(e0 + t)];
+            nm_dft_reg<R2>(u);
+#pragma unroll
+            for (int t = 0; t < R2; ++t) buf[PL::phys(e0 + t)] = u[t];
+        }
+    }
+    __syncthreads();
+}
+
+// frequency index held by slot e of the padded buffer after nm_sx_forward_smem (digit-reversed order of radices R0, R1, R2)
+template <class PL>
+NM_DEV int nm_sx_freq_of_slot(int e) {
+    const int k0 = e / PL::L1, r = e - k0 * PL::L1;
+    const int k1 = r / PL::R2, k2 = r - k1 * PL::R2;
+    return k0 + PL::R0 * k1 + PL::R0 * PL::R1 * k2;
+}
+
+// Unnormalised inverse of nm_sx_forward_smem: slot-ordered spectrum in `buf` -> natural-order samples n = tid + NA * t left in
+// the registers v[t] of the active threads (tid < NA).  Starts after a barrier of the caller, contains two barriers.
+template <class PL>
+NM_DEV void nm_sx_inverse_regs(cx<double>* buf, const cx<double>* NM_RESTRICT tw, int tid, cx<double>* v) {
+    constexpr int R0 = PL::R0, R1 = PL::R1, R2 = PL::R2, NA = PL::NA;
+    const bool active = tid < NA;
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < R0 / R2; ++i) {
+            const int e0 = (tid + NA * i) * R2;
+            cx<double> u[R2];
+#pragma unroll
+            for (int t = 0; t < R2; ++t) u[t] = buf[PL::phys(e0 + t)];
+            nm_dft_reg_inv<R2>(u);
+#pragma unroll
+            for (int t = 0; t < R2; ++t) buf[PL::phys(e0 + t)] = u[t];
+        }
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < R0 / R1; ++i) {
+            const int q = tid + NA * i;
+            const int blk = q / PL::M1, j = q - blk * PL::M1;
+            const int e0 = blk * PL::L1 + j;
+            cx<double> u[R1];
+#pragma unroll
+            for (int t = 0; t < R1; ++t) u[t] = buf[PL::phys(e0 + t * PL::M1)];
+            nm_twiddle_pow_conj<R1>(u, nm_ldg(tw + j * R0));
+            nm_dft_reg_inv<R1>(u);
+#pragma unroll
+            for (int t = 0; t < R1; ++t) buf[PL::phys(e0 + t * PL::M1)] = u[t];
+        }
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < R0; ++k) v[k] = buf[PL::phys(tid + NA * k)];
+        nm_twiddle_pow_conj<R0>(v, nm_ldg(tw + tid));
+        nm_dft_reg_inv<R0>(v);
+    }
+}
+
 static NM_HD size_t nm_specx_smem_bytes(int nbuf, int nk, int nsegv) {
     return (size_t)nbuf * sizeof(cx<double>) + (size_t)2 * nk * nsegv * sizeof(double) + 2 * 32 * sizeof(double);
 }
