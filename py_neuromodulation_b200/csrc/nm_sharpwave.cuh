@@ -47,24 +47,35 @@ NM_DEV double nm_sw_v(const cx<double>* x, int comp, double sign, int t) { retur
 // local maxima of s*d (s = +1 peaks, -1 troughs) -> ascending midpoints in `list`; returns the count
 NM_DEV int nm_sw_local_maxima(const cx<double>* x, int comp, double sign, int W, unsigned short* list, int lane) {
     int n = 0;
-    for (int base = 1; base <= W - 2; base += 32) {
-        const int i = base + lane;
-        bool pred = false;
-        int mid = 0;
-        if (i <= W - 2) {
-            const double di = nm_sw_v(x, comp, sign, i);
-            if (nm_sw_v(x, comp, sign, i - 1) < di) {
-                int j = i + 1;
-                while (j < W - 1 && nm_sw_v(x, comp, sign, j) == di) ++j;
-                if (nm_sw_v(x, comp, sign, j) < di) {
-                    pred = true;
-                    mid = (i + j - 1) / 2;
+    // four 32-sample groups per step: their loads and comparisons are independent, only the list positions (ballot prefix
+    // counts) are sequential -- the scan is latency bound otherwise (one warp walks the whole row)
+    for (int base = 1; base <= W - 2; base += 128) {
+        bool pred[4];
+        int mid[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + 32 * u + lane;
+            pred[u] = false;
+            mid[u] = 0;
+            if (i <= W - 2) {
+                const double di = nm_sw_v(x, comp, sign, i);
+                if (nm_sw_v(x, comp, sign, i - 1) < di) {
+                    int j = i + 1;
+                    double dj = nm_sw_v(x, comp, sign, j);
+                    while (j < W - 1 && dj == di) dj = nm_sw_v(x, comp, sign, ++j);
+                    if (dj < di) {
+                        pred[u] = true;
+                        mid[u] = (i + j - 1) / 2;
+                    }
                 }
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, pred);
-        if (pred) list[n + __popc(m & ((lane == 0) ? 0u : (0xffffffffu >> (32 - lane))))] = (unsigned short)mid;
-        n += __popc(m);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned m = __ballot_sync(0xffffffffu, pred[u]);
+            if (pred[u]) list[n + __popc(m & ((lane == 0) ? 0u : (0xffffffffu >> (32 - lane))))] = (unsigned short)mid[u];
+            n += __popc(m);
+        }
     }
     __syncwarp();
     return n;
