@@ -117,12 +117,11 @@ struct NmEpiBursts {
 //
 //   bracket [lo_key, hi_key)   a key interval around the current quantile holding <= NM_BQ_CAP history samples
 //   cnt_below                  number of history samples with key < lo_key
-//   queue                      the history samples inside the bracket, SORTED BY KEY, each with its logical sample index
-//                              (for expiry): an order statistic is then plain indexing
+//   queue                      the history samples inside the bracket, in TIME order (FIFO: they enter and expire
+//                              in time order), with their logical sample index
 //
-// A window step classifies only the S entering and S expiring samples (cnt_below +-), drops the expired queue entries and
-// merges the few entering ones in place (one read + one write of <= 2048 shared-memory slots held in registers in between);
-// the threshold is queue[k_lo - cnt_below].  When the target rank leaves the
+// A window step classifies only the S entering and S expiring samples (cnt_below +-, queue append / pop) and selects
+// rank k_lo - cnt_below among the queue entries (<= 2048 keys in shared memory).  When the target rank leaves the
 // bracket, the queue overflows or there is no valid state (first window, reset), the bracket is rebuilt from the ring
 // with a two-level radix histogram (the former per-window algorithm, which also remains the fallback when a single
 // 2^-12-binade sub-bin holds more samples than the queue, e.g. an all-zero signal).
@@ -167,16 +166,10 @@ struct NmBqSmem {
     int* ctl;                   // 16
     unsigned long long* res;    // 4
     int* wcnt;                  // 32
-    unsigned long long* newk;   // NM_BQ_NEW entering keys inside the bracket (unordered), then their sorted copy
-    unsigned long long* snk;
-    unsigned* newi;
-    unsigned* sni;
-    int* scan;                  // NM_BQ_THREADS + 1
 };
 
 static NM_HD size_t nm_bq_smem_bytes() {
-    return NM_SEL_BINS * sizeof(int) + NM_BQ_CAP * 8 + NM_BQ_CAP * 4 + 16 * sizeof(int) + 4 * 8 + 32 * sizeof(int) + 64 +
-           2 * 256 * 8 + 2 * 256 * 4 + (256 + 8) * sizeof(int);
+    return NM_SEL_BINS * sizeof(int) + NM_BQ_CAP * 8 + NM_BQ_CAP * 4 + 16 * sizeof(int) + 4 * 8 + 32 * sizeof(int) + 64;
 }
 
 // order-preserving map double -> unsigned 64-bit key (all finite values, either sign) and back: the sliding order
@@ -442,131 +435,89 @@ NM_DEV bool nm_bq_rebuild(const double* rrow, long long cap, long long first, in
     return nm_bq_gather(rrow, cap, first, n, lo_key, hi_key, sm, cnt_below, head, count, tid, nt);
 }
 
-// Sort the queue entries [0, count) by key, in place (bitonic network over the whole NM_BQ_CAP array, padding = max key).
-// Used after a (re)build / re-centre; between those the queue is kept sorted by nm_bq_step_sorted.
-NM_DEV void nm_bq_sort(const NmBqSmem& sm, int count, int tid, int nt) {
-    for (int j = count + tid; j < NM_BQ_CAP; j += nt) { sm.qk[j] = ~0ull; sm.qi[j] = 0u; }
-    __syncthreads();
-    for (int k = 2; k <= NM_BQ_CAP; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < NM_BQ_CAP / 2; t += nt) {
-                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
-                const bool up = (lo & k) == 0;
-                const unsigned long long x = sm.qk[lo], y = sm.qk[hi];
-                if ((x > y) == up) {
-                    sm.qk[lo] = y; sm.qk[hi] = x;
-                    const unsigned u = sm.qi[lo];
-                    sm.qi[lo] = sm.qi[hi]; sm.qi[hi] = u;
-                }
+// rank-`r` key (0-based) among the queue entries, plus (when wanted) the next order statistic: res[0] = a, res[1] = b.
+// Requires 0 <= r and r + (want_next ? 1 : 0) < count.
+NM_DEV void nm_bq_select_queue(const NmBqSmem& sm, int head, int count, unsigned long long lo_key, unsigned long long hi_key, int r,
+                               bool want_next, int tid, int nt) {
+    const int lane = tid & 31;
+    unsigned long long lo = lo_key, range = hi_key - lo_key;
+    int rr = r;
+    unsigned long long a_key = 0ull;
+    while (true) {
+        int sh = 56 - __clzll((long long)((range - 1ull) | 1ull));  // smallest shift with (range - 1) >> sh <= 255
+        if (sh < 0) sh = 0;
+        for (int i = tid; i < 256; i += nt) sm.hist[i] = 0;
+        __syncthreads();
+        for (int j = tid; j < count; j += nt) {
+            const unsigned long long key = sm.qk[(head + j) & NM_BQ_MASK];
+            if (key >= lo && key - lo < range) atomicAdd(&sm.hist[(int)((key - lo) >> sh)], 1);
+        }
+        __syncthreads();
+        nm_bq_find_bin(sm.hist, 256, rr, sm.ctl, tid);
+        __syncthreads();
+        const int tb = sm.ctl[0], below = sm.ctl[1], cnt = sm.ctl[2];
+        __syncthreads();
+        lo += (unsigned long long)tb << sh;
+        range = 1ull << sh;
+        rr -= below;
+        if (sh == 0) { a_key = lo; break; }  // every key of the bin equals lo
+        if (cnt <= 256) {
+            // gather the bin's members (order irrelevant) and rank them by counting
+            if (tid == 0) sm.ctl[3] = 0;
+            __syncthreads();
+            unsigned long long* mem = reinterpret_cast<unsigned long long*>(sm.hist + 256);
+            for (int j = tid; j < count; j += nt) {
+                const unsigned long long key = sm.qk[(head + j) & NM_BQ_MASK];
+                if (key >= lo && key - lo < range) mem[atomicAdd(&sm.ctl[3], 1)] = key;
             }
             __syncthreads();
-        }
-    }
-}
-
-#define NM_BQ_NEW 256                       // entering samples that may land inside the bracket per window step
-#define NM_BQ_CHUNK (NM_BQ_CAP / NM_BQ_THREADS)  // consecutive queue slots owned by one thread
-
-// One window step on the key-SORTED queue: drop the expired entries (logical index < first), merge the entering samples
-// that fall inside the bracket (already collected, unordered, in newk / newi [0, m)), in place.  Every thread keeps its
-// NM_BQ_CHUNK consecutive slots in registers between the read and the write phase, so no second buffer is needed.
-// Returns the new count, or -1 (uniformly) if the queue would overflow.
-NM_DEV int nm_bq_step_sorted(const NmBqSmem& sm, unsigned long long* newk, unsigned* newi, unsigned long long* snk, unsigned* sni, int* scan,
-                             int count, int m, long long first, int tid, int nt) {
-    const int lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
-    // (a) rank-sort the few new entries: snk / sni = sorted copies
-    for (int j = tid; j < m; j += nt) {
-        const unsigned long long x = newk[j];
-        int r = 0;
-        for (int i = 0; i < m; ++i) {
-            const unsigned long long y = newk[i];
-            r += (y < x || (y == x && i < j)) ? 1 : 0;
-        }
-        snk[r] = x;
-        sni[r] = newi[j];
-    }
-    // (b) my chunk of the old queue into registers + dead flags
-    unsigned long long k[NM_BQ_CHUNK];
-    unsigned ix[NM_BQ_CHUNK];
-    int dead_mask = 0, n_dead = 0;
-    const int p0 = tid * NM_BQ_CHUNK;
-#pragma unroll
-    for (int c = 0; c < NM_BQ_CHUNK; ++c) {
-        const int p = p0 + c;
-        k[c] = 0ull; ix[c] = 0u;
-        if (p < count) {
-            k[c] = sm.qk[p];
-            ix[c] = sm.qi[p];
-            if ((int)(ix[c] - (unsigned)first) < 0) { dead_mask |= 1 << c; ++n_dead; }
-        }
-    }
-    // exclusive scan of the per-thread dead counts over the CTA -> scan[tid], total in scan[nt]
-    int incl = n_dead;
-    for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += u;
-    }
-    if (lane == 31) sm.wcnt[wid] = incl;
-    __syncthreads();  // also publishes snk / sni
-    int woff = 0, total_dead = 0;
-    for (int q = 0; q < nwarp; ++q) {
-        const int c = sm.wcnt[q];
-        if (q < wid) woff += c;
-        total_dead += c;
-    }
-    const int dead_before_chunk = woff + incl - n_dead;
-    scan[tid] = dead_before_chunk;
-    const int new_count = count - total_dead + m;
-    if (new_count > NM_BQ_CAP) {
-        __syncthreads();
-        return -1;
-    }
-    __syncthreads();
-    // (c) new positions.  Old alive entry at p: p - dead_before(p) + #(new keys < key).  Equal keys: old entries first.
-    int pos[NM_BQ_CHUNK];
-    int db = dead_before_chunk;
-#pragma unroll
-    for (int c = 0; c < NM_BQ_CHUNK; ++c) {
-        const int p = p0 + c;
-        pos[c] = -1;
-        if (p < count) {
-            if (dead_mask & (1 << c)) {
-                ++db;
-            } else {
-                int lo = 0, hi = m;  // first new key >= k[c]
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (snk[mid] < k[c]) lo = mid + 1; else hi = mid;
+            for (int i = tid; i < cnt; i += nt) {
+                const unsigned long long x = mem[i];
+                int q = 0;
+                for (int j = 0; j < cnt; ++j) {
+                    const unsigned long long y = mem[j];
+                    q += (y < x || (y == x && j < i)) ? 1 : 0;
                 }
-                pos[c] = p - db + lo;
+                if (q == rr) sm.res[0] = x;
             }
+            __syncthreads();
+            a_key = sm.res[0];
+            break;
         }
     }
-    // new entry j (sorted rank j): j + #(alive old entries with key <= its key)
-    int npos = -1;
-    unsigned long long nk = 0ull;
-    unsigned ni = 0u;
-    if (tid < m) {
-        nk = snk[tid];
-        ni = sni[tid];
-        int lo = 0, hi = count;  // first old slot with key > nk
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (sm.qk[mid] <= nk) lo = mid + 1; else hi = mid;
-        }
-        // dead entries among the first `lo` slots: whole chunks from the scan + the partial chunk by inspection
-        const int ch = lo / NM_BQ_CHUNK;
-        int d = (ch < nt) ? scan[ch] : total_dead;
-        for (int q = ch * NM_BQ_CHUNK; q < lo; ++q) d += ((int)(sm.qi[q] - (unsigned)first) < 0) ? 1 : 0;
-        npos = tid + lo - d;
-    }
-    __syncthreads();  // every read of the old queue is done
-#pragma unroll
-    for (int c = 0; c < NM_BQ_CHUNK; ++c)
-        if (pos[c] >= 0) { sm.qk[pos[c]] = k[c]; sm.qi[pos[c]] = ix[c]; }
-    if (npos >= 0) { sm.qk[npos] = nk; sm.qi[npos] = ni; }
+    if (tid == 0) { sm.res[0] = a_key; sm.ctl[4] = 0; sm.ctl[5] = 0; }
     __syncthreads();
-    return new_count;
+    if (want_next) {
+        int less = 0, eq = 0;
+        unsigned long long mg = ~0ull;
+        for (int j = tid; j < count; j += nt) {
+            const unsigned long long key = sm.qk[(head + j) & NM_BQ_MASK];
+            less += key < a_key;
+            eq += key == a_key;
+            if (key > a_key && key < mg) mg = key;
+        }
+        less = nm_warp_sum_i(less);
+        eq = nm_warp_sum_i(eq);
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long u = __shfl_xor_sync(0xffffffffu, mg, o);
+            mg = u < mg ? u : mg;
+        }
+        if (lane == 0) {
+            atomicAdd(&sm.ctl[4], less);
+            atomicAdd(&sm.ctl[5], eq);
+            reinterpret_cast<unsigned long long*>(sm.hist)[tid >> 5] = mg;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long best = ~0ull;
+            for (int q = 0; q < ((nt + 31) >> 5); ++q) {
+                const unsigned long long u = reinterpret_cast<unsigned long long*>(sm.hist)[q];
+                best = u < best ? u : best;
+            }
+            sm.res[1] = (r + 1 < sm.ctl[4] + sm.ctl[5]) ? a_key : best;
+        }
+        __syncthreads();
+    }
 }
 
 NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
@@ -578,12 +529,7 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
     sm.ctl = reinterpret_cast<int*>(sm.qi + NM_BQ_CAP);
     sm.res = reinterpret_cast<unsigned long long*>(sm.ctl + 16);
     sm.wcnt = reinterpret_cast<int*>(sm.res + 4);
-    sm.newk = reinterpret_cast<unsigned long long*>(sm.wcnt + 32);
-    sm.snk = sm.newk + NM_BQ_NEW;
-    sm.newi = reinterpret_cast<unsigned*>(sm.snk + NM_BQ_NEW);
-    sm.sni = sm.newi + NM_BQ_NEW;
-    sm.scan = reinterpret_cast<int*>(sm.sni + NM_BQ_NEW);
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
     const int n_rows = a.n_ch * a.nB;
 
     for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
@@ -616,26 +562,51 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
                 int delta = 0;
                 nm_bq_for_each(rrow, a.cap, first_prev % a.cap, 0, (int)(first - first_prev), tid, nt,
                                [&](int, unsigned long long key) { delta -= (key < lo_key) ? 1 : 0; });
+                int nexp = 0;
+                for (int j = tid; j < count; j += nt) nexp += ((int)(sm.qi[(head + j) & NM_BQ_MASK] - (unsigned)first) < 0) ? 1 : 0;
+                nexp = nm_warp_sum_i(nexp);
+                if (lane == 0 && nexp) atomicAdd(&sm.ctl[11], nexp);
+                __syncthreads();
+                nexp = sm.ctl[11];
+                head = (head + nexp) & NM_BQ_MASK;
+                count -= nexp;
                 const int n_enter = (int)(e - e_prev);
-                nm_bq_for_each(rrow, a.cap, e_prev % a.cap, 0, n_enter, tid, nt, [&](int i, unsigned long long key) {
-                    if (key < lo_key) {
-                        delta += 1;
-                    } else if (key < hi_key) {
-                        const int slot = atomicAdd(&sm.ctl[11], 1);
-                        if (slot < NM_BQ_NEW) { sm.newk[slot] = key; sm.newi[slot] = (unsigned)(e_prev + i); }
+                const long long enter_mod = e_prev % a.cap;
+                for (int base = 0; base < n_enter && valid; base += nt) {
+                    const int i = base + tid;
+                    unsigned long long key = 0ull;
+                    bool in = false;
+                    if (i < n_enter) {
+                        long long p = enter_mod + i;
+                        if (p >= a.cap) p -= a.cap;
+                        key = nm_key_of(rrow[p]);
+                        if (key < lo_key) delta += 1;
+                        else in = key < hi_key;
                     }
-                });
+                    const unsigned bm = __ballot_sync(0xffffffffu, in);
+                    if (lane == 0) sm.wcnt[wid] = __popc(bm);
+                    __syncthreads();
+                    int off = 0, tot = 0;
+                    for (int q = 0; q < nwarp; ++q) {
+                        const int c = sm.wcnt[q];
+                        if (q < wid) off += c;
+                        tot += c;
+                    }
+                    if (count + tot > NM_BQ_CAP) {
+                        valid = false;  // uniform: queue overflow -> rebuild below
+                    } else {
+                        if (in) {
+                            const int pos = (head + count + off + __popc(bm & ((1u << lane) - 1u))) & NM_BQ_MASK;
+                            sm.qk[pos] = key;
+                            sm.qi[pos] = (unsigned)(e_prev + i);
+                        }
+                        count += tot;
+                    }
+                    __syncthreads();
+                }
                 delta = nm_warp_sum_i(delta);
                 if (lane == 0 && delta) atomicAdd(&sm.ctl[10], delta);
                 __syncthreads();
-                const int m = sm.ctl[11];
-                if (m > NM_BQ_NEW) {
-                    valid = false;  // uniform: more entering samples inside the bracket than the merge list holds -> rebuild below
-                } else {
-                    const int nc = nm_bq_step_sorted(sm, sm.newk, sm.newi, sm.snk, sm.sni, sm.scan, count, m, first, tid, nt);
-                    if (nc < 0) valid = false;
-                    else count = nc;
-                }
                 cnt_below += sm.ctl[10];
                 const int r = k_lo - cnt_below;
                 __syncthreads();
@@ -648,7 +619,6 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
                     ++n_recentre;
                     valid = nhi > nlo && nm_bq_gather(rrow, a.cap, first, n, nlo, nhi, sm, cnt_below, head, count, tid, nt);
                     if (valid) {
-                        nm_bq_sort(sm, count, tid, nt);
                         lo_key = nlo;
                         hi_key = nhi;
                         const int r2 = k_lo - cnt_below;
@@ -661,18 +631,17 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
             if (!valid && a.incremental) {
                 ++n_rebuild;
                 valid = nm_bq_rebuild(rrow, a.cap, first, n, k_lo, sm, lo_key, hi_key, cnt_below, head, count, tid, nt);
-                if (valid) nm_bq_sort(sm, count, tid, nt);
                 if (valid) {
                     const int r = k_lo - cnt_below;
                     if (r < 0 || r + (want_next ? 1 : 0) >= count) valid = false;  // bracket clipped at a binade edge
                 }
             }
             if (valid) {
-                const int r = k_lo - cnt_below;  // the queue is sorted by key: order statistics are plain indexing
-                const double av = nm_val_of(sm.qk[r]);
+                nm_bq_select_queue(sm, head, count, lo_key, hi_key, k_lo - cnt_below, want_next, tid, nt);
+                const double av = nm_val_of(sm.res[0]);
                 thr = av;
                 if (want_next) {
-                    const double bv = nm_val_of(sm.qk[r + 1]);
+                    const double bv = nm_val_of(sm.res[1]);
                     const double g = a.gamma[w];
                     const double diff = bv - av;
                     double lerp = av + diff * g;
@@ -693,8 +662,8 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
         if (a.incremental) {
             if (valid) {
                 for (int j = tid; j < count; j += nt) {
-                    a.qkey[(size_t)row * NM_BQ_CAP + j] = sm.qk[j];
-                    a.qidx[(size_t)row * NM_BQ_CAP + j] = sm.qi[j];
+                    a.qkey[(size_t)row * NM_BQ_CAP + j] = sm.qk[(head + j) & NM_BQ_MASK];
+                    a.qidx[(size_t)row * NM_BQ_CAP + j] = sm.qi[(head + j) & NM_BQ_MASK];
                 }
             }
             if (tid == 0) {
