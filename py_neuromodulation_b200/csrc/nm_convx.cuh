@@ -41,7 +41,7 @@ struct NmCxPlan {
     static_assert(R1 * R2 * 16 == P, "three-pass plan");
 };
 
-#define NM_CX_RED_BYTES 256  // 4 values x 8 warps of doubles, owned by the register epilogues
+#define NM_CX_RED_BYTES 512  // 8 values x 8 warps of doubles, owned by the register epilogues
 
 static inline bool nm_convx_supported(int P) { return P == 1024 || P == 2048 || P == 4096; }
 
@@ -226,60 +226,62 @@ struct NmEpiStoreScan {
         }
     }
 
-    // part 2: two-pass moments (numpy.var semantics) over chunks of consecutive samples, each sample loaded once per pass
+    // one chunk sample of the two moment passes: PASS 1 sums x, d, dd, |d|; PASS 2 the centred squares (m = the six means)
+    template <int PASS>
+    NM_DEV static void acc(double* s, const double* m, cx<double> xa, cx<double> xb, cx<double> xc, bool has1, bool has2nd) {
+        const double da = xb.re - xa.re, db = xb.im - xa.im;
+        const double dda = (xc.re - xb.re) - da, ddb = (xc.im - xb.im) - db;
+        if (PASS == 1) {
+            s[0] += xa.re; s[4] += xa.im;
+            if (has1) { s[1] += da; s[5] += db; s[3] += fabs(da); s[7] += fabs(db); }
+            if (has2nd) { s[2] += dda; s[6] += ddb; }
+        } else {
+            double e = xa.re - m[0]; s[0] += e * e;
+            e = xa.im - m[3]; s[3] += e * e;
+            if (has1) { e = da - m[1]; s[1] += e * e; e = db - m[4]; s[4] += e * e; }
+            if (has2nd) { e = dda - m[2]; s[2] += e * e; e = ddb - m[5]; s[5] += e * e; }
+        }
+    }
+
+    // one moment pass over this thread's chunk of CH consecutive window samples with a sliding three-sample window (a fully
+    // unrolled CH == 8 variant with all ten loads up front was slower: 40 more live registers at the 128-register cap)
+    template <int PASS, typename T>
+    NM_DEV void chunk_pass(const cx<T>* work, int W, int CH, int tid, double* s, const double* m) const {
+        const int u0 = tid * CH;
+        if (u0 >= W) return;
+        const int u1 = min(W, u0 + CH);
+        const cx<double> zero = {0.0, 0.0};
+        cx<double> xa = nm_cx_wide(work[phys(u0)]), xb = (u0 + 1 < W) ? nm_cx_wide(work[phys(u0 + 1)]) : zero;
+        for (int u = u0; u < u1; ++u) {
+            const cx<double> xc = (u + 2 < W) ? nm_cx_wide(work[phys(u + 2)]) : zero;
+            acc<PASS>(s, m, xa, xb, xc, u + 1 < W, u + 2 < W);
+            xa = xb; xb = xc;
+        }
+    }
+
+    // part 2: two-pass moments (numpy.var semantics) over chunks of consecutive samples, each sample loaded once per pass.
+    // Ends with every thread past its last read of `work` and of the reduction scratch, so the kernel needs no trailing barrier:
+    // the two threads that finish the formulas and store the results overlap with the next window's first pass.
     template <class PL, typename T>
-    NM_DEV void finish(cx<T>* work, double* /*red*/, State& /*st*/, int /*o0*/, int W, int /*n_ch*/, int w, int c0, bool has2, int /*f*/,
+    NM_DEV void finish(cx<T>* work, double* red, State& /*st*/, int /*o0*/, int W, int /*n_ch*/, int w, int c0, bool has2, int /*f*/,
                        int tid) const {
         constexpr int NT = PL::NT, NW = (PL::NT + 31) / 32;
-        static_assert((size_t)16 * NW * sizeof(double) <= (size_t)(PL::NBUF - PL::P) * sizeof(cx<T>), "reduction scratch must fit the tail");
+        static_assert((size_t)8 * NW * sizeof(double) <= NM_CX_RED_BYTES, "reduction scratch");
         if (!want_scan) return;
-        double* red = reinterpret_cast<double*>(work + PL::P);  // W + W/8 <= P for every supported plan
-        __syncthreads();
+        __syncthreads();  // natural-order copy complete
         const int CH = (W + NT - 1) / NT;
-        const int u0 = tid * CH, u1 = min(W, u0 + CH);
+        const cx<double> last = nm_cx_wide(work[phys(W - 1)]);
         double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per row: sum x, sum d, sum dd, sum |d|
-        if (u0 < W) {
-            cx<double> xa = nm_cx_wide(work[phys(u0)]), xb = (u0 + 1 < W) ? nm_cx_wide(work[phys(u0 + 1)]) : cx<double>{0.0, 0.0};
-            for (int u = u0; u < u1; ++u) {
-                const cx<double> xc = (u + 2 < W) ? nm_cx_wide(work[phys(u + 2)]) : cx<double>{0.0, 0.0};
-                s[0] += xa.re; s[4] += xa.im;
-                if (u + 1 < W) {
-                    const double da = xb.re - xa.re, db = xb.im - xa.im;
-                    s[1] += da; s[5] += db;
-                    s[3] += fabs(da); s[7] += fabs(db);
-                    if (u + 2 < W) {
-                        s[2] += (xc.re - xb.re) - da;
-                        s[6] += (xc.im - xb.im) - db;
-                    }
-                }
-                xa = xb; xb = xc;
-            }
-        }
+        chunk_pass<1, T>(work, W, CH, tid, s, nullptr);
         nm_cx_block_sum<8, NW>(s, red, tid);
         const double n0 = W, n1 = W - 1, n2 = W - 2;
         double q[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // 6 used; 8 for the power-of-two exchange reduction
         if (want_hjorth) {
-            const double m0a = s[0] / n0, m1a = s[1] / n1, m2a = s[2] / n2;
-            const double m0b = s[4] / n0, m1b = s[5] / n1, m2b = s[6] / n2;
-            if (u0 < W) {
-                cx<double> xa = nm_cx_wide(work[phys(u0)]), xb = (u0 + 1 < W) ? nm_cx_wide(work[phys(u0 + 1)]) : cx<double>{0.0, 0.0};
-                for (int u = u0; u < u1; ++u) {
-                    const cx<double> xc = (u + 2 < W) ? nm_cx_wide(work[phys(u + 2)]) : cx<double>{0.0, 0.0};
-                    double e = xa.re - m0a; q[0] += e * e;
-                    e = xa.im - m0b; q[3] += e * e;
-                    if (u + 1 < W) {
-                        const double da = xb.re - xa.re, db = xb.im - xa.im;
-                        e = da - m1a; q[1] += e * e;
-                        e = db - m1b; q[4] += e * e;
-                        if (u + 2 < W) {
-                            e = ((xc.re - xb.re) - da) - m2a; q[2] += e * e;
-                            e = ((xc.im - xb.im) - db) - m2b; q[5] += e * e;
-                        }
-                    }
-                    xa = xb; xb = xc;
-                }
-            }
-            nm_cx_block_sum<8, NW>(q, red + 8 * NW, tid);
+            const double m[6] = {s[0] / n0, s[1] / n1, s[2] / n2, s[4] / n0, s[5] / n1, s[6] / n2};
+            chunk_pass<2, T>(work, W, CH, tid, q, m);
+            nm_cx_block_sum<8, NW>(q, red, tid);  // (its leading barrier orders it after every read of the first reduction)
+        } else {
+            __syncthreads();  // every thread is past its reads of `work`
         }
         if (tid < (has2 ? 2 : 1)) {
             const bool k = tid != 0;  // selects by predicate: no dynamically indexed local arrays
@@ -291,12 +293,14 @@ struct NmEpiStoreScan {
                 nm_store(out, w, c, 1, mob);
                 nm_store(out, w, c, 2, nm_nan_to_num(sqrt(v2 / v1) / mob));
             }
-            const cx<double> last = nm_cx_wide(work[phys(W - 1)]);
             if (want_raw) nm_store(out, w, c, 3, k ? last.im : last.re);
             // mean(|dx| / (W-1)) over W-1 samples: the reference divides by (W-1) twice
             if (want_ll) nm_store(out, w, c, 4, ((k ? s[7] : s[3]) / n1) / n1);
         }
     }
+    // without the scan part there is no barrier inside the epilogue: the kernel must separate the register reads of `work`
+    // from the next pass
+    NM_DEV bool needs_trailing_barrier() const { return !want_scan; }
 };
 
 // ---------------------------------------------------------------- the kernel
@@ -434,7 +438,9 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
                     epi.template consume<PL, T>(v, work, red, st, o0, W, a.in.n_ch, w, c0, has2, fi, tid);
                     if (last && next < a.n_items) nm_cx_load_item<P, REFLECT, T>(v, a, next, npair, tid, nw, nc0, nhas2);
                     epi.template finish<PL, T>(work, red, st, o0, W, a.in.n_ch, w, c0, has2, fi, tid);
-                    if constexpr (!Epi::kSyncsInside) __syncthreads();
+                    if constexpr (!Epi::kSyncsInside) {
+                        if (epi.needs_trailing_barrier()) __syncthreads();
+                    }
                 }
             } else {
                 if constexpr (!Epi::kRegsOnly && sizeof(T) == 8) {  // (the shared-memory epilogues take float64 rows)

@@ -59,6 +59,7 @@ struct NmEpiStore {
     template <class PL, typename T>
     NM_DEV void finish(cx<T>* /*work*/, double* /*red*/, State& /*st*/, int /*o0*/, int /*W*/, int /*n_ch*/, int /*w*/, int /*c0*/,
                        bool /*has2*/, int /*f*/, int /*tid*/) const {}
+    NM_DEV bool needs_trailing_barrier() const { return true; }
     // v[k] = filtered sample n = tid + nt*k of the (padded) row; the window occupies n in [o0, o0 + W)
     NM_DEV void run_regs(const cx<double>* v, int o0, int W, int n_ch, int w, int c0, bool has2, int f,
                          unsigned char* /*scratch*/, int tid, int nt) const {
