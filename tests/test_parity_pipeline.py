@@ -350,3 +350,39 @@ def test_float32_linear_mode_within_north_star_tolerance(backend, name):
     err = np.abs(mat[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0)
     assert err.max() < 1e-5, float(err.max())
     assert err.max() > 0.0  # the float32 kernels really ran
+
+
+def test_c_abi_error_paths_are_loud_and_recoverable(backend):
+    """Errors come back as RuntimeError with the library's message (rc != 0 + nm_last_error) and leave the pipeline usable."""
+    from py_neuromodulation_b200 import _lib
+    from py_neuromodulation_b200._pipeline import Pipeline, ScanSpec
+
+    names = ["a", "b"]
+    spec = ScanSpec(names, hjorth=True, raw=True, linelength=True)
+    cols = spec.keys_hjorth() + spec.keys_raw() + spec.keys_linelength()
+    pipe = Pipeline(2, 2, 200, cols)
+    with pytest.raises(RuntimeError, match="finalize"):
+        pipe.upload(np.zeros((2, 1000)))
+    spec.attach(pipe)
+    pipe.finalize()
+    with pytest.raises(RuntimeError, match="already finalized"):
+        pipe.finalize()
+    with pytest.raises(RuntimeError, match="upload a recording"):
+        pipe.run([0])
+    x = np.random.default_rng(0).random((2, 1000))
+    pipe.upload(x)
+    with pytest.raises(RuntimeError, match="outside the recording"):
+        pipe.run([0, 900])
+    with pytest.raises(RuntimeError, match="bad recording geometry"):
+        pipe.upload(np.zeros((2, 100)))  # shorter than one window
+    with pytest.raises(ValueError):
+        pipe.upload(np.zeros((3, 1000)))  # wrong number of rows: refused by the host wrapper
+    lib = _lib.load()
+    assert lib.nm_set_output_pitch(pipe._h, 1) != 0 and b"pitch" in lib.nm_last_error()
+    out = pipe.run([0, 400, 800])  # still works after the failures
+    ref = orc.hjorth(x[:, 800:1000], names)
+    assert abs(out[2, cols.index("a_RawHjorth_Activity")] - ref["a_RawHjorth_Activity"]) < 1e-12
+    with pytest.raises(RuntimeError, match="out of range"):
+        Pipeline(2, 2, 200, cols).set_pick([0, 5])
+    with pytest.raises(RuntimeError):
+        Pipeline(2, 3, 200, cols)  # more feature channels than raw rows
