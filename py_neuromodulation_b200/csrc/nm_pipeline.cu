@@ -94,9 +94,9 @@ struct nm_pipeline {
     // fork after the notch and a join before the next chunk: their kernels are latency / occupancy limited in different ways
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
-    std::vector<cudaEvent_t> slice_ev, chunk_ev;
+    std::vector<cudaEvent_t> slice_ev, chunk_ev, red_ev;  // red_ev[k]: group sums of slice k are all-reduced (sharded runs)
     long long slice_len = 0;
-    int n_slices = 0, slices_prepped = 0;
+    int n_slices = 0, slices_prepped = 0, slices_reduced = 0;
     int n_sm = 1, smem_max = 48 * 1024;
     long long launches = 0;
     // optional per-family kernel timing (nm_set_profiling): events around every launch, host-synchronised
@@ -578,6 +578,7 @@ extern "C" void nm_pipeline_destroy(nm_pipeline* p) {
         if (p->ev_join[b]) cudaEventDestroy(p->ev_join[b]);
     }
     for (auto e : p->slice_ev) cudaEventDestroy(e);
+    for (auto e : p->red_ev) cudaEventDestroy(e);
     for (auto e : p->chunk_ev) cudaEventDestroy(e);
     cudaStream_t s = p->stream, cs = p->copy_stream;
     delete p;
@@ -905,8 +906,15 @@ static NmPrepArgs nm_prep_args(nm_pipeline* p) {
 static int nm_ensure_prepped(nm_pipeline* p, long long upto) {
     while (p->slices_prepped < p->n_slices && (long long)p->slices_prepped * p->slice_len < upto) {
         const int k = p->slices_prepped;
-        NM_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->slice_ev[k], 0));
         NmPrepArgs a = nm_prep_args(p);
+        if (p->resident_uses_gsum) {  // channel-sharded upload: the slice's group sums must have been all-reduced
+            NM_CHECK(k < p->slices_reduced, "slice %d of the sharded upload has not been reduced yet (nm_upload_slice_reduced)", k);
+            NM_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->red_ev[k], 0));
+            a.gsum_ext = p->d_gsum.as<double>();
+            a.gsum_pitch = p->gsum_pitch;
+        } else {
+            NM_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->slice_ev[k], 0));
+        }
         a.t0 = (long long)k * p->slice_len;
         a.t1 = std::min<long long>(p->T, a.t0 + p->slice_len);
         const int threads = NM_ROW_THREADS;
@@ -944,6 +952,40 @@ static int nm_stage_raw(nm_pipeline* p, const void* data, bool f64, long long n_
     return 0;
 }
 
+// geometry + asynchronous H2D of the recording in `n_slices` time slices on the copy stream (slice_ev[k] = slice k has landed)
+static int nm_stage_slices(nm_pipeline* p, const void* data, bool f64, long long n_samples, long long pitch, int n_slices) {
+    const size_t esz = f64 ? 8 : 4;
+    p->raw_f64 = f64;
+    p->T = n_samples;
+    p->raw_pitch = (n_samples + 3) & ~3LL;
+    p->xr_pitch = (n_samples + 1) & ~1LL;
+    p->nanblk_pitch = (n_samples + 31) / 32;
+    if (p->d_raw.ensure((size_t)p->C_all * p->raw_pitch * esz)) return -1;
+    if (p->d_xr.ensure((size_t)p->C * p->xr_pitch * sizeof(double))) return -1;
+    if (p->d_nanblk.ensure((size_t)p->C_all * p->nanblk_pitch)) return -1;
+    p->slice_len = ((n_samples + n_slices - 1) / n_slices + 255) & ~255LL;
+    p->n_slices = (int)((n_samples + p->slice_len - 1) / p->slice_len);
+    p->slices_prepped = 0;
+    p->slices_reduced = 0;
+    while ((int)p->slice_ev.size() < p->n_slices) {
+        cudaEvent_t e;
+        NM_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        p->slice_ev.push_back(e);
+        NM_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        p->red_ev.push_back(e);
+    }
+    // kernels of the previous run may still read the buffers that are about to be overwritten
+    NM_CUDA_CHECK(cudaEventRecord(p->ev_sync, p->stream));
+    NM_CUDA_CHECK(cudaStreamWaitEvent(p->copy_stream, p->ev_sync, 0));
+    for (int k = 0; k < p->n_slices; ++k) {
+        const long long t0 = (long long)k * p->slice_len, len = std::min<long long>(p->slice_len, n_samples - t0);
+        NM_CUDA_CHECK(cudaMemcpy2DAsync((char*)p->d_raw.p + (size_t)t0 * esz, (size_t)p->raw_pitch * esz, (const char*)data + (size_t)t0 * esz,
+                                        (size_t)pitch * esz, (size_t)len * esz, (size_t)p->C_all, cudaMemcpyHostToDevice, p->copy_stream));
+        NM_CUDA_CHECK(cudaEventRecord(p->slice_ev[k], p->copy_stream));
+    }
+    return 0;
+}
+
 static int nm_upload_impl(nm_pipeline* p, const void* data, bool f64, long long n_samples, long long pitch) {
     NM_P_CHECK(p);
     NM_CHECK(p->finalized, "call nm_finalize first");
@@ -955,31 +997,7 @@ static int nm_upload_impl(nm_pipeline* p, const void* data, bool f64, long long 
     if (n_samples >= NM_UPLOAD_MIN_PIPELINED) {
         // pipelined upload: time slices on the copy stream, each followed by an event; nm_ensure_prepped() makes the compute
         // stream wait for (and re-reference) a slice only when a chunk of windows first needs it
-        const size_t esz = f64 ? 8 : 4;
-        p->raw_f64 = f64;
-        p->T = n_samples;
-        p->raw_pitch = (n_samples + 3) & ~3LL;
-        p->xr_pitch = (n_samples + 1) & ~1LL;
-        p->nanblk_pitch = (n_samples + 31) / 32;
-        if (p->d_raw.ensure((size_t)p->C_all * p->raw_pitch * esz)) return -1;
-        if (p->d_xr.ensure((size_t)p->C * p->xr_pitch * sizeof(double))) return -1;
-        if (p->d_nanblk.ensure((size_t)p->C_all * p->nanblk_pitch)) return -1;
-        p->slice_len = ((n_samples + NM_UPLOAD_SLICES - 1) / NM_UPLOAD_SLICES + 255) & ~255LL;
-        p->n_slices = (int)((n_samples + p->slice_len - 1) / p->slice_len);
-        while ((int)p->slice_ev.size() < p->n_slices) {
-            cudaEvent_t e;
-            NM_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            p->slice_ev.push_back(e);
-        }
-        // kernels of the previous run may still read the buffers that are about to be overwritten
-        NM_CUDA_CHECK(cudaEventRecord(p->ev_sync, p->stream));
-        NM_CUDA_CHECK(cudaStreamWaitEvent(p->copy_stream, p->ev_sync, 0));
-        for (int k = 0; k < p->n_slices; ++k) {
-            const long long t0 = (long long)k * p->slice_len, len = std::min<long long>(p->slice_len, n_samples - t0);
-            NM_CUDA_CHECK(cudaMemcpy2DAsync((char*)p->d_raw.p + (size_t)t0 * esz, (size_t)p->raw_pitch * esz, (const char*)data + (size_t)t0 * esz,
-                                            (size_t)pitch * esz, (size_t)len * esz, (size_t)p->C_all, cudaMemcpyHostToDevice, p->copy_stream));
-            NM_CUDA_CHECK(cudaEventRecord(p->slice_ev[k], p->copy_stream));
-        }
+        if (nm_stage_slices(p, data, f64, n_samples, pitch, NM_UPLOAD_SLICES)) return -1;
     } else {
         if (nm_stage_raw(p, data, f64, n_samples, pitch)) return -1;
         const int threads = NM_ROW_THREADS;

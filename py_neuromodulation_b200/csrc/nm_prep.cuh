@@ -91,8 +91,8 @@ NM_GLOBAL void nm_prep_kernel(NmPrepArgs a) {
 
 // local per-sample group sums of this rank's shard -> gsum (G, gsum_pitch)
 NM_GLOBAL void nm_gsum_kernel(NmPrepArgs a, double* gsum) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.T) return;
+    const long long t = a.t0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.t1) return;
     double S[NM_MAX_GROUPS];
 #pragma unroll
     for (int g = 0; g < NM_MAX_GROUPS; ++g) S[g] = 0.0;

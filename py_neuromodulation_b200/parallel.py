@@ -186,23 +186,42 @@ class ShardedRun:
         return self.shared_host and dist.is_initialized() and dist.get_world_size() > 1
 
     def upload(self, data_f32: np.ndarray) -> None:
-        """H2D of the local shard, all-reduce of the group sums, re-reference."""
+        """Asynchronous, sliced: H2D of the local shard, per-slice group sums, per-slice all-reduce on the library's side stream.
+
+        Nothing here blocks the host: the re-reference of a slice happens inside ``run`` right before the first chunk of
+        windows that needs it, so transfers, reductions and window kernels of different slices overlap."""
+        import contextlib
+
         import torch.distributed as dist
 
         p = self.pipe
         a = np.ascontiguousarray(data_f32, dtype=np.float32)
         _lib.check(p.lib.nm_upload_begin_f32(p._h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[1]))
+        p._keep_data = a
+        n_slices, slice_len, n_groups, pitch = C.c_int(), C.c_longlong(), C.c_int(), C.c_longlong()
+        _lib.check(p.lib.nm_upload_slices(p._h, C.byref(n_slices), C.byref(slice_len), C.byref(n_groups), C.byref(pitch)))
         ptr, n = C.c_void_p(), C.c_longlong()
         _lib.check(p.lib.nm_group_sums_device_ptr(p._h, C.byref(ptr), C.byref(n)))
-        sums = wrap_buffer(ptr.value, n.value, self.on_gpu)
-        if dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        multi = dist.is_initialized() and dist.get_world_size() > 1
+        ctx = contextlib.nullcontext()
+        sums = None
+        if multi:
+            sums = wrap_buffer(ptr.value, n.value, self.on_gpu).view(n_groups.value, pitch.value)
             if self.on_gpu:
                 import torch
 
-                torch.cuda.current_stream().synchronize()
+                h = C.c_void_p()
+                _lib.check(p.lib.nm_side_stream_handle(p._h, C.byref(h)))
+                ctx = torch.cuda.stream(torch.cuda.ExternalStream(h.value))  # the collective is ordered on the library's stream
+        T = a.shape[1]
+        for k in range(n_slices.value):
+            if multi:
+                t0, t1 = k * slice_len.value, min(T, (k + 1) * slice_len.value)
+                with ctx:
+                    for g in range(n_groups.value):
+                        dist.all_reduce(sums[g, t0:t1], op=dist.ReduceOp.SUM)
+            _lib.check(p.lib.nm_upload_slice_reduced(p._h, k))
         _lib.check(p.lib.nm_upload_finish(p._h))
-        p._keep_data = a
 
     def run(self, starts: np.ndarray) -> None:
         p = self.pipe

@@ -55,8 +55,9 @@ def _worker(rank: int, world: int, port: int, x: np.ndarray, settings_dict: dict
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("shared_host", [True, False], ids=["shared-host-matrix", "nccl-style-gather"])
-def test_two_rank_channel_shard_matches_oracle(tmp_path, shared_host):
+@pytest.mark.parametrize("shared_host,n_samples,rate", [(True, 1800, 10), (False, 1800, 10), (True, 66_000, 2)],
+                         ids=["shared-host-matrix", "nccl-style-gather", "sliced-upload"])
+def test_two_rank_channel_shard_matches_oracle(tmp_path, shared_host, n_samples, rate):
     import torch.multiprocessing as mp
 
     import py_neuromodulation_b200 as nm
@@ -64,8 +65,9 @@ def test_two_rank_channel_shard_matches_oracle(tmp_path, shared_host):
     from tests.emu_support import build_emu
 
     build_emu()
-    x = neural_like(31, 5, 1800)  # odd channel count: shards of 3 and 2
+    x = neural_like(31, 5, n_samples)  # odd channel count: shards of 3 and 2; >= 65 536 samples: upload in 8 reduced slices
     s = nm.NMSettings.get_default().reset()
+    s.sampling_rate_features_hz = rate
     s.features.fft = True
     s.features.raw_hjorth = True
     s.features.bandpass_filter = True
