@@ -197,15 +197,17 @@ long long nm_kernel_launches(nm_pipeline* p);
 int nm_result_device_ptr(nm_pipeline* p, void** ptr, long long* n_rows, int* n_cols);
 int nm_stream_handle(nm_pipeline* p, void** cuda_stream);
 /* Channel-sharded multi-GPU runs (asynchronous, sliced in time like nm_upload_f32).  nm_upload_begin_f32 enqueues the H2D
- * slices of the local shard and, per slice, the local per-sample group sums S (n_groups x group_pitch float64 at
- * nm_group_sums_device_ptr) on the stream returned by nm_side_stream_handle.  The host all-reduces S[:, k*slice_len : ...]
- * across ranks ON THAT STREAM (slice geometry: nm_upload_slices), reports every slice with nm_upload_slice_reduced (in order)
+ * slices of the local shard.  Per slice k (in order): nm_upload_slice_sums enqueues the local per-sample group sums S
+ * (n_groups x group_pitch float64 at nm_group_sums_device_ptr) on the stream returned by nm_side_stream_handle, the host
+ * all-reduces S[:, k*slice_len : ...] across ranks ON THAT STREAM (slice geometry: nm_upload_slices) and reports
+ * nm_upload_slice_reduced;
  * and closes with nm_upload_finish; nm_run_windows then re-references each slice with the global sums right before the first
  * chunk of windows that needs it.  `data` must stay valid until the next nm_run_windows / nm_synchronize has returned. */
 int nm_upload_begin_f32(nm_pipeline* p, const float* data, long long n_samples, long long pitch);
 int nm_group_sums_device_ptr(nm_pipeline* p, void** ptr, long long* n_values);
 int nm_upload_slices(nm_pipeline* p, int* n_slices, long long* slice_len, int* n_groups, long long* group_pitch);
 int nm_side_stream_handle(nm_pipeline* p, void** cuda_stream);
+int nm_upload_slice_sums(nm_pipeline* p, int slice);
 int nm_upload_slice_reduced(nm_pipeline* p, int slice);
 int nm_upload_finish(nm_pipeline* p);
 

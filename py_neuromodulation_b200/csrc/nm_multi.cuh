@@ -3,8 +3,8 @@
 // Every rank owns a contiguous block of channels of the recording.  After re-referencing all hot-path features are
 // per-channel, so the only exchange on the data path is the common-average reference.  The upload is asynchronous and sliced
 // in time like the single-GPU one:
-//   nm_upload_begin_f32       H2D of the local shard in time slices (copy stream); per slice, on side stream 0, the local
-//                             per-sample group sums S_g[t]
+//   nm_upload_begin_f32       H2D of the local shard in time slices (copy stream)
+//   nm_upload_slice_sums(k)   local per-sample group sums S_g[t] of slice k on side stream 0 (after the slice has landed)
 //   (host, per slice k)       all-reduce(sum) of S[:, slice k] over the ranks, enqueued on side stream 0 (the host hands
 //                             the stream to its collective library: torch.cuda.ExternalStream + NCCL), then
 //   nm_upload_slice_reduced   records "slice k reduced" on that stream
@@ -26,20 +26,28 @@ extern "C" int nm_upload_begin_f32(nm_pipeline* p, const float* data, long long 
     if (p->d_gsum.ensure((size_t)p->G * p->gsum_pitch * sizeof(double))) return -1;
     // side stream 0 must not run ahead of the previous run's readers of d_gsum (compute stream)
     NM_CUDA_CHECK(cudaStreamWaitEvent(p->side[0], p->ev_sync, 0));
-    for (int k = 0; k < p->n_slices; ++k) {
-        NmPrepArgs a = nm_prep_args(p);
-        a.gsum_pitch = p->gsum_pitch;
-        a.t0 = (long long)k * p->slice_len;
-        a.t1 = std::min<long long>(p->T, a.t0 + p->slice_len);
-        const int threads = NM_ROW_THREADS;
-        const unsigned grid = (unsigned)((a.t1 - a.t0 + threads - 1) / threads);
-        NM_CUDA_CHECK(cudaStreamWaitEvent(p->side[0], p->slice_ev[k], 0));
-        NM_LAUNCH(nm_gsum_kernel, dim3(grid), dim3(threads), 0, p->side[0], a, p->d_gsum.as<double>());
-        p->launches++;
-    }
     NM_CUDA_CHECK(cudaGetLastError());
     p->upload_pending = true;
     p->have_data = false;
+    return 0;
+}
+
+// local group sums of slice k on side stream 0 (enqueued per slice, right before the host's all-reduce of that slice, so that
+// the stream order is  sums(0), reduce(0), sums(1), reduce(1), ...  and slice 0 does not wait for the last transfer)
+extern "C" int nm_upload_slice_sums(nm_pipeline* p, int k) {
+    NM_P_CHECK(p);
+    NM_CHECK(p->upload_pending && k >= 0 && k < p->n_slices, "no such slice");
+    cudaSetDevice(p->device);
+    NmPrepArgs a = nm_prep_args(p);
+    a.gsum_pitch = p->gsum_pitch;
+    a.t0 = (long long)k * p->slice_len;
+    a.t1 = std::min<long long>(p->T, a.t0 + p->slice_len);
+    const int threads = NM_ROW_THREADS;
+    const unsigned grid = (unsigned)((a.t1 - a.t0 + threads - 1) / threads);
+    NM_CUDA_CHECK(cudaStreamWaitEvent(p->side[0], p->slice_ev[k], 0));
+    NM_LAUNCH(nm_gsum_kernel, dim3(grid), dim3(threads), 0, p->side[0], a, p->d_gsum.as<double>());
+    p->launches++;
+    NM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 

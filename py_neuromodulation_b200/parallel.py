@@ -3,8 +3,9 @@
 After re-referencing every hot-path feature is computed per channel, so the recording shards by channel with no
 halo: rank r of R owns channels [r*C/R, (r+1)*C/R) for ALL windows.  The data path has exactly two exchanges:
 
-1. common-average reference: one all-reduce(sum) of the per-sample channel-group sums (G x T float64) --
-   ``nm_upload_begin_f32`` / ``nm_group_sums_device_ptr`` / ``nm_upload_finish`` in the C ABI;
+1. common-average reference: all-reduce(sum) of the per-sample channel-group sums (G x T float64), slice by slice on the
+   library's side stream so that transfers, reductions and window kernels overlap -- ``nm_upload_begin_f32`` /
+   ``nm_upload_slice_sums`` / ``nm_upload_slice_reduced`` / ``nm_upload_finish`` in the C ABI;
 2. the (n_windows x F_local) float64 result blocks meet on rank 0.  On one node (the default) every rank copies the rows of
    each finished chunk over its OWN PCIe link straight into its column range of one page-locked POSIX shared-memory matrix
    (``nm_set_output_pitch`` + ``nm_host_register``), overlapped with the next chunk's kernels -- no collective, no funnel
@@ -215,6 +216,7 @@ class ShardedRun:
                 ctx = torch.cuda.stream(torch.cuda.ExternalStream(h.value))  # the collective is ordered on the library's stream
         T = a.shape[1]
         for k in range(n_slices.value):
+            _lib.check(p.lib.nm_upload_slice_sums(p._h, k))
             if multi:
                 t0, t1 = k * slice_len.value, min(T, (k + 1) * slice_len.value)
                 with ctx:

@@ -38,7 +38,7 @@ def main():
                           verbose=False, device=local, reref_factored=reref)
     starts, lengths, _ = window_grid(n_samples, bench.SFREQ, settings.sampling_rate_features_hz, settings.segment_length_features_ms)
     pipe = dp.plan(int(lengths[0])).pipe
-    sh = ShardedRun(pipe, on_gpu=True)
+    sh = ShardedRun(pipe, on_gpu=True, shared_host=os.environ.get("SHARED_HOST", "1") == "1")
     n_win = int(starts.size)
 
     def sync():
@@ -48,13 +48,14 @@ def main():
     for it in range(4):
         dist.barrier(); sync()
         t = [time.perf_counter()]
-        sh.upload(x); sync(); t.append(time.perf_counter())
+        sh.upload(x); t_host = time.perf_counter() - t[0]; sync() if os.environ.get("SYNC_AFTER_UPLOAD", "0") == "1" else None
+        t.append(time.perf_counter())
         sh.run(starts); sync(); t.append(time.perf_counter())
         sh.gather(n_win); sync(); t.append(time.perf_counter())
         dist.barrier(); t.append(time.perf_counter())
         if rank == 0:
             d = np.diff(t) * 1e3
-            print(f"iter {it}: upload {d[0]:.1f} ms, run {d[1]:.1f} ms, gather {d[2]:.1f} ms, barrier {d[3]:.1f} ms", flush=True)
+            print(f"iter {it}: upload call returned after {t_host * 1e3:.2f} ms; upload {d[0]:.1f} ms, run {d[1]:.1f} ms, gather {d[2]:.1f} ms, barrier {d[3]:.1f} ms", flush=True)
     dist.barrier()
     sh.close()
     dist.destroy_process_group()
