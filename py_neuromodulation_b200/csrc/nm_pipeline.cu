@@ -1200,7 +1200,6 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
         na.flags = p->d_nanflags.as<unsigned char>() + (size_t)w0 * p->C_all;
         const long long tot = (long long)n * p->C_all;
         const unsigned grid = (unsigned)((tot + NM_ROW_THREADS - 1) / NM_ROW_THREADS);
-        NM_LAUNCH(nm_nanflag_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, na);
         NmNanFillArgs nf;
         nf.flags = na.flags;
         nf.n_windows = n;
@@ -1210,8 +1209,8 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
         nf.out = p->d_out.as<double>();
         nf.row0 = w0;
         nf.F = p->F;
-        NM_LAUNCH(nm_nanfill_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, nf);
-        p->launches += 2;
+        NM_LAUNCH(nm_nanfix_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, na, nf);
+        p->launches += 1;
     };
     if (p->bursts && p->bursts->prepare(p, n_windows)) return -1;
     int n_ev = 0;

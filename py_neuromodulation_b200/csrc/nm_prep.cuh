@@ -119,7 +119,21 @@ struct NmNanArgs {
     unsigned char* flags;
 };
 
-NM_GLOBAL void nm_nanflag_kernel(NmNanArgs a) {
+// out[(row0 + w) * F + col] = NaN for every column listed for a flagged raw row
+struct NmNanFillArgs {
+    const unsigned char* flags;
+    int n_windows;
+    int C_all;
+    const int* col_ptr;  // [C_all + 1]
+    const int* cols;
+    double* out;
+    long long row0;
+    int F;
+};
+
+// flag of every (window, raw row) from the 32-sample NaN block map (exact check at the window edges) and, if set, the NaN
+// fill of the columns listed for that raw row -- one thread per (window, raw row)
+NM_GLOBAL void nm_nanfix_kernel(NmNanArgs a, NmNanFillArgs f) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)a.n_windows * a.p.C_all) return;
     const int w = (int)(idx / a.p.C_all), r = (int)(idx - (long long)w * a.p.C_all);
@@ -139,25 +153,7 @@ NM_GLOBAL void nm_nanflag_kernel(NmNanArgs a) {
         }
     }
     a.flags[idx] = (unsigned char)flag;
-}
-
-// out[(row0 + w) * F + col] = NaN for every column listed for a flagged raw row
-struct NmNanFillArgs {
-    const unsigned char* flags;
-    int n_windows;
-    int C_all;
-    const int* col_ptr;  // [C_all + 1]
-    const int* cols;
-    double* out;
-    long long row0;
-    int F;
-};
-
-NM_GLOBAL void nm_nanfill_kernel(NmNanFillArgs a) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)a.n_windows * a.C_all) return;
-    if (!a.flags[idx]) return;
-    const int w = (int)(idx / a.C_all), r = (int)(idx - (long long)w * a.C_all);
+    if (!flag) return;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    for (int k = a.col_ptr[r]; k < a.col_ptr[r + 1]; ++k) a.out[(size_t)(a.row0 + w) * a.F + a.cols[k]] = qnan;
+    for (int k = f.col_ptr[r]; k < f.col_ptr[r + 1]; ++k) f.out[(size_t)(f.row0 + w) * f.F + f.cols[k]] = qnan;
 }
