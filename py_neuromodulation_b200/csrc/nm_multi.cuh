@@ -4,8 +4,8 @@
 // per-channel, so the only exchange on the data path is the common-average reference.  The upload is asynchronous and sliced
 // in time like the single-GPU one:
 //   nm_upload_begin_f32       H2D of the local shard in time slices (copy stream)
-//   nm_upload_slice_sums(k)   local per-sample group sums S_g[t] of slice k on side stream 0 (after the slice has landed)
-//   (host, per slice k)       all-reduce(sum) of S[:, slice k] over the ranks, enqueued on side stream 0 (the host hands
+//   nm_upload_slice_sums(k)   local per-sample group sums S_g[t] of slice k on the reduction stream (after the slice has landed)
+//   (host, per slice k)       all-reduce(sum) of S[:, slice k] over the ranks, enqueued on the reduction stream (the host hands
 //                             the stream to its collective library: torch.cuda.ExternalStream + NCCL), then
 //   nm_upload_slice_reduced   records "slice k reduced" on that stream
 //   nm_upload_finish          switches the pipeline to the sharded re-reference: nm_run_windows re-references slice k on the
@@ -24,15 +24,15 @@ extern "C" int nm_upload_begin_f32(nm_pipeline* p, const float* data, long long 
     if (nm_stage_slices(p, data, false, n_samples, pitch, n_slices)) return -1;
     p->gsum_pitch = (n_samples + 1) & ~1LL;
     if (p->d_gsum.ensure((size_t)p->G * p->gsum_pitch * sizeof(double))) return -1;
-    // side stream 0 must not run ahead of the previous run's readers of d_gsum (compute stream)
-    NM_CUDA_CHECK(cudaStreamWaitEvent(p->side[0], p->ev_sync, 0));
+    // the reduction stream must not run ahead of the previous run's readers of d_gsum (compute stream)
+    NM_CUDA_CHECK(cudaStreamWaitEvent(p->red_stream, p->ev_sync, 0));
     NM_CUDA_CHECK(cudaGetLastError());
     p->upload_pending = true;
     p->have_data = false;
     return 0;
 }
 
-// local group sums of slice k on side stream 0 (enqueued per slice, right before the host's all-reduce of that slice, so that
+// local group sums of slice k on the reduction stream (enqueued per slice, right before the host's all-reduce of that slice, so that
 // the stream order is  sums(0), reduce(0), sums(1), reduce(1), ...  and slice 0 does not wait for the last transfer)
 extern "C" int nm_upload_slice_sums(nm_pipeline* p, int k) {
     NM_P_CHECK(p);
@@ -44,8 +44,8 @@ extern "C" int nm_upload_slice_sums(nm_pipeline* p, int k) {
     a.t1 = std::min<long long>(p->T, a.t0 + p->slice_len);
     const int threads = NM_ROW_THREADS;
     const unsigned grid = (unsigned)((a.t1 - a.t0 + threads - 1) / threads);
-    NM_CUDA_CHECK(cudaStreamWaitEvent(p->side[0], p->slice_ev[k], 0));
-    NM_LAUNCH(nm_gsum_kernel, dim3(grid), dim3(threads), 0, p->side[0], a, p->d_gsum.as<double>());
+    NM_CUDA_CHECK(cudaStreamWaitEvent(p->red_stream, p->slice_ev[k], 0));
+    NM_LAUNCH(nm_gsum_kernel, dim3(grid), dim3(threads), 0, p->red_stream, a, p->d_gsum.as<double>());
     p->launches++;
     NM_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -70,7 +70,7 @@ extern "C" int nm_upload_slices(nm_pipeline* p, int* n_slices, long long* slice_
 
 extern "C" int nm_side_stream_handle(nm_pipeline* p, void** cuda_stream) {
     NM_P_CHECK(p);
-    if (cuda_stream) *cuda_stream = (void*)p->side[0];
+    if (cuda_stream) *cuda_stream = (void*)p->red_stream;
     return 0;
 }
 
@@ -79,7 +79,7 @@ extern "C" int nm_upload_slice_reduced(nm_pipeline* p, int k) {
     NM_CHECK(p->upload_pending && k == p->slices_reduced && k < p->n_slices, "slices must be reported in order (got %d, expected %d)", k,
              p->slices_reduced);
     cudaSetDevice(p->device);
-    NM_CUDA_CHECK(cudaEventRecord(p->red_ev[k], p->side[0]));
+    NM_CUDA_CHECK(cudaEventRecord(p->red_ev[k], p->red_stream));
     p->slices_reduced = k + 1;
     return 0;
 }

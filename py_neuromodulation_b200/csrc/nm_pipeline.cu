@@ -93,6 +93,7 @@ struct nm_pipeline {
     // independent feature families of a chunk (spectral + band power | sharp waves | bursts) run on side streams between a
     // fork after the notch and a join before the next chunk: their kernels are latency / occupancy limited in different ways
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t red_stream = nullptr;  // channel-sharded uploads: per-slice group sums + the host's all-reduce (nm_multi.cuh)
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> slice_ev, chunk_ev, red_ev;  // red_ev[k]: group sums of slice k are all-reduced (sharded runs)
     long long slice_len = 0;
@@ -546,6 +547,7 @@ extern "C" int nm_pipeline_create(int device, int n_raw_rows, int n_ch, int wind
     NM_CUDA_CHECK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
     NM_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_sync, cudaEventDisableTiming));
     NM_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    NM_CUDA_CHECK(cudaStreamCreateWithFlags(&p->red_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 3; ++b) {
         NM_CUDA_CHECK(cudaStreamCreateWithFlags(&p->side[b], cudaStreamNonBlocking));
         NM_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_join[b], cudaEventDisableTiming));
@@ -573,6 +575,7 @@ extern "C" void nm_pipeline_destroy(nm_pipeline* p) {
     if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
     if (p->ev_sync) cudaEventDestroy(p->ev_sync);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->red_stream) { cudaStreamSynchronize(p->red_stream); cudaStreamDestroy(p->red_stream); }
     for (int b = 0; b < 3; ++b) {
         if (p->side[b]) { cudaStreamSynchronize(p->side[b]); cudaStreamDestroy(p->side[b]); }
         if (p->ev_join[b]) cudaEventDestroy(p->ev_join[b]);
