@@ -9,6 +9,13 @@ FFT + band-pass power + Hjorth + line length, 10 Hz feature rate -> 2 991 window
 With N GPUs every rank owns its own 256-channel shard of a 256*N-channel recording (common average over ALL channels).
 A step = one pass of the hot path over the whole recording; metric = feature-windows/s where one unit is one
 256 ch x 1000 samp window with all its features (BASELINE.json `metric`).
+
+`value`  = resident step (recording already in HBM: re-reference + every window kernel), float64 arithmetic.
+`e2e`    = the public call with HOST buffers: pinned recording in, feature matrix out (sliced asynchronous upload, rows of
+           finished chunks copied back while the next chunk computes; N > 1: per-slice all-reduce of the common-average sums,
+           every rank writes its block into one shared page-locked host matrix).
+`roofline`, `cpu_baseline`, `clocks`, `gpu_launches`: see DESIGN.md section 5-6.  `f32_linear_mode` (N = 1 only) reports the
+optional float32 mode of the FIR families beside the float64 headline.
 """
 
 from __future__ import annotations
