@@ -42,10 +42,9 @@ extern "C" int nm_upload_slice_sums(nm_pipeline* p, int k) {
     a.gsum_pitch = p->gsum_pitch;
     a.t0 = (long long)k * p->slice_len;
     a.t1 = std::min<long long>(p->T, a.t0 + p->slice_len);
-    const int threads = NM_ROW_THREADS;
-    const unsigned grid = (unsigned)((a.t1 - a.t0 + threads - 1) / threads);
+    const unsigned grid = (unsigned)((a.t1 - a.t0 + 31) / 32);
     NM_CUDA_CHECK(cudaStreamWaitEvent(p->red_stream, p->slice_ev[k], 0));
-    NM_LAUNCH(nm_gsum_kernel, dim3(grid), dim3(threads), 0, p->red_stream, a, p->d_gsum.as<double>());
+    NM_LAUNCH(nm_gsum_kernel, dim3(grid), dim3(NM_PREP_THREADS), nm_prep_smem_bytes(), p->red_stream, a, p->d_gsum.as<double>());
     p->launches++;
     NM_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -920,10 +920,9 @@ static int nm_ensure_prepped(nm_pipeline* p, long long upto) {
         }
         a.t0 = (long long)k * p->slice_len;
         a.t1 = std::min<long long>(p->T, a.t0 + p->slice_len);
-        const int threads = NM_ROW_THREADS;
-        const unsigned grid = (unsigned)((a.t1 - a.t0 + threads - 1) / threads);
+        const unsigned grid = (unsigned)((a.t1 - a.t0 + 31) / 32);
         p->prof_begin();
-        NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(threads), 0, p->stream, a);
+        NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(NM_PREP_THREADS), nm_prep_smem_bytes(), p->stream, a);
         p->prof_end(NM_PROF_PREP);
         p->launches++;
         p->slices_prepped++;
@@ -1003,10 +1002,9 @@ static int nm_upload_impl(nm_pipeline* p, const void* data, bool f64, long long 
         if (nm_stage_slices(p, data, f64, n_samples, pitch, NM_UPLOAD_SLICES)) return -1;
     } else {
         if (nm_stage_raw(p, data, f64, n_samples, pitch)) return -1;
-        const int threads = NM_ROW_THREADS;
-        const unsigned grid = (unsigned)((n_samples + threads - 1) / threads);
+        const unsigned grid = (unsigned)((n_samples + 31) / 32);
         p->prof_begin();
-        NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(threads), 0, p->stream, nm_prep_args(p));
+        NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(NM_PREP_THREADS), nm_prep_smem_bytes(), p->stream, nm_prep_args(p));
         p->prof_end(NM_PROF_PREP);
         p->launches++;
         NM_CUDA_CHECK(cudaGetLastError());
@@ -1023,15 +1021,14 @@ extern "C" int nm_prepare_resident(nm_pipeline* p) {
     NM_CHECK(p->have_data && !p->upload_pending, "no resident recording");
     cudaSetDevice(p->device);
     if (nm_ensure_prepped(p, p->T)) return -1;  // (a pipelined upload may still be in flight)
-    const int threads = NM_ROW_THREADS;
-    const unsigned grid = (unsigned)((p->T + threads - 1) / threads);
+    const unsigned grid = (unsigned)((p->T + 31) / 32);
     NmPrepArgs a = nm_prep_args(p);
     if (p->resident_uses_gsum) {  // channel-sharded recording: keep using the all-reduced group sums
         a.gsum_ext = p->d_gsum.as<double>();
         a.gsum_pitch = p->gsum_pitch;
     }
     p->prof_begin();
-    NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(threads), 0, p->stream, a);
+    NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(NM_PREP_THREADS), nm_prep_smem_bytes(), p->stream, a);
     p->prof_end(NM_PROF_PREP);
     p->launches++;
     NM_CUDA_CHECK(cudaGetLastError());

@@ -47,41 +47,72 @@ NM_DEV double nm_raw_at(const NmPrepArgs& a, int row, long long t) {
                         : (double)nm_ldg(reinterpret_cast<const float*>(a.raw) + (size_t)row * a.raw_pitch + t);
 }
 
-NM_GLOBAL void nm_prep_kernel(NmPrepArgs a) {
-    const long long t = a.t0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // t0 is a multiple of 32 (NaN block map)
-    const bool active = t < a.t1;
-    const int lane = threadIdx.x & 31;
+// CTA = 32 consecutive samples (lanes) x NM_PREP_WARPS channel groups (warps): warp g serves the channels / raw rows
+// congruent to g, so a time slice of a few ten thousand samples already fills the GPU and every global access is a coalesced
+// row segment.  The per-sample group sums are combined across the warps through shared memory (fixed order: deterministic).
+#define NM_PREP_WARPS 8
+#define NM_PREP_THREADS (32 * NM_PREP_WARPS)
+static NM_HD size_t nm_prep_smem_bytes() { return (size_t)NM_PREP_WARPS * NM_MAX_GROUPS * 32 * sizeof(double); }
 
-    for (int r = 0; r < a.C_all; ++r) {
-        double v = active ? nm_raw_at(a, r, t) : 0.0;
-        unsigned bits = __ballot_sync(0xffffffffu, v != v);
-        if (lane == 0 && active) a.nanblk[(size_t)r * a.nanblk_pitch + (t >> 5)] = bits ? 1 : 0;
-    }
-    if (!active) return;
-
-    double S[NM_MAX_GROUPS];
+// group sums of this CTA's 32 samples over the local channels -> S[NM_MAX_GROUPS] in every thread (contains two barriers)
+NM_DEV void nm_prep_group_sums(const NmPrepArgs& a, long long t, bool active, int lane, int g, double* part, double* S) {
+    double P[NM_MAX_GROUPS];
 #pragma unroll
-    for (int g = 0; g < NM_MAX_GROUPS; ++g) S[g] = 0.0;
-    if (a.G > 0 && a.gsum_ext) {
-#pragma unroll
-        for (int g = 0; g < NM_MAX_GROUPS; ++g)
-            if (g < a.G) S[g] = a.gsum_ext[(size_t)g * a.gsum_pitch + t];
-    } else if (a.G > 0) {
-        for (int j = 0; j < a.C; ++j) {
-            const int g = nm_ldg(a.group_of + j);
-            if (g >= 0) {
+    for (int q = 0; q < NM_MAX_GROUPS; ++q) P[q] = 0.0;
+    if (active) {
+        for (int j = g; j < a.C; j += NM_PREP_WARPS) {
+            const int grp = nm_ldg(a.group_of + j);
+            if (grp >= 0) {
                 const double v = nm_nan_to_num(nm_raw_at(a, nm_ldg(a.pick + j), t));
 #pragma unroll
-                for (int gg = 0; gg < NM_MAX_GROUPS; ++gg)
-                    if (gg == g) S[gg] += v;
+                for (int q = 0; q < NM_MAX_GROUPS; ++q)
+                    if (q == grp) P[q] += v;
             }
         }
     }
-    for (int i = 0; i < a.C; ++i) {
+#pragma unroll
+    for (int q = 0; q < NM_MAX_GROUPS; ++q)
+        if (q < a.G) part[(g * NM_MAX_GROUPS + q) * 32 + lane] = P[q];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NM_MAX_GROUPS; ++q) {
+        double s = 0.0;
+        if (q < a.G)
+            for (int w = 0; w < NM_PREP_WARPS; ++w) s += part[(w * NM_MAX_GROUPS + q) * 32 + lane];
+        S[q] = s;
+    }
+    __syncthreads();
+}
+
+NM_GLOBAL void nm_prep_kernel(NmPrepArgs a) {
+    NM_SHARED_BYTES(smem);
+    double* part = reinterpret_cast<double*>(smem);
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const long long t = a.t0 + (long long)blockIdx.x * 32 + lane;  // t0 is a multiple of 32 (NaN block map)
+    const bool active = t < a.t1;
+
+    for (int r = g; r < a.C_all; r += NM_PREP_WARPS) {
+        const double v = active ? nm_raw_at(a, r, t) : 0.0;
+        const unsigned bits = __ballot_sync(0xffffffffu, v != v);
+        if (lane == 0 && active) a.nanblk[(size_t)r * a.nanblk_pitch + (t >> 5)] = bits ? 1 : 0;
+    }
+
+    double S[NM_MAX_GROUPS];
+#pragma unroll
+    for (int q = 0; q < NM_MAX_GROUPS; ++q) S[q] = 0.0;
+    if (a.G > 0 && a.gsum_ext) {
+#pragma unroll
+        for (int q = 0; q < NM_MAX_GROUPS; ++q)
+            if (q < a.G && active) S[q] = a.gsum_ext[(size_t)q * a.gsum_pitch + t];
+    } else if (a.G > 0) {
+        nm_prep_group_sums(a, t, active, lane, g, part, S);
+    }
+    if (!active) return;
+    for (int i = g; i < a.C; i += NM_PREP_WARPS) {
         double acc = 0.0;
 #pragma unroll
-        for (int g = 0; g < NM_MAX_GROUPS; ++g)
-            if (g < a.G) acc += nm_ldg(a.gcoef + (size_t)i * a.G + g) * S[g];
+        for (int q = 0; q < NM_MAX_GROUPS; ++q)
+            if (q < a.G) acc += nm_ldg(a.gcoef + (size_t)i * a.G + q) * S[q];
         const int k1 = nm_ldg(a.sp_ptr + i + 1);
         for (int k = nm_ldg(a.sp_ptr + i); k < k1; ++k)
             acc += nm_ldg(a.sp_val + k) * nm_nan_to_num(nm_raw_at(a, nm_ldg(a.pick + nm_ldg(a.sp_col + k)), t));
@@ -89,25 +120,17 @@ NM_GLOBAL void nm_prep_kernel(NmPrepArgs a) {
     }
 }
 
-// local per-sample group sums of this rank's shard -> gsum (G, gsum_pitch)
+// local per-sample group sums of this rank's shard -> gsum (G, gsum_pitch); same CTA geometry as nm_prep_kernel
 NM_GLOBAL void nm_gsum_kernel(NmPrepArgs a, double* gsum) {
-    const long long t = a.t0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.t1) return;
+    NM_SHARED_BYTES(smem);
+    double* part = reinterpret_cast<double*>(smem);
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const long long t = a.t0 + (long long)blockIdx.x * 32 + lane;
+    const bool active = t < a.t1;
     double S[NM_MAX_GROUPS];
-#pragma unroll
-    for (int g = 0; g < NM_MAX_GROUPS; ++g) S[g] = 0.0;
-    for (int j = 0; j < a.C; ++j) {
-        const int g = nm_ldg(a.group_of + j);
-        if (g >= 0) {
-            const double v = nm_nan_to_num(nm_raw_at(a, nm_ldg(a.pick + j), t));
-#pragma unroll
-            for (int gg = 0; gg < NM_MAX_GROUPS; ++gg)
-                if (gg == g) S[gg] += v;
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < NM_MAX_GROUPS; ++g)
-        if (g < a.G) gsum[(size_t)g * a.gsum_pitch + t] = S[g];
+    nm_prep_group_sums(a, t, active, lane, g, part, S);
+    if (!active) return;
+    for (int q = g; q < a.G; q += NM_PREP_WARPS) gsum[(size_t)q * a.gsum_pitch + t] = S[q];
 }
 
 // flags[w * C_all + r] = 1 iff raw row r has a NaN inside window [start[w], start[w] + W)
