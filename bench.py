@@ -122,7 +122,7 @@ def ncu_traffic(kernel: str, windows_per_launch: float) -> tuple[float | None, d
     try:
         d = json.loads(f.read_text())
         k = d["kernels"][kernel]
-        scale = windows_per_launch / d["windows_per_launch"]
+        scale = windows_per_launch / k["windows_per_launch"]
         return (k["dram_bytes_read"] + k["dram_bytes_write"]) * scale, {"fp64_pipe_pct": k["fp64_pipe_pct"], "l1tex_pct": k["l1tex_pct"],
                                                                            "source": d["source"]}
     except Exception:
