@@ -386,3 +386,20 @@ def test_c_abi_error_paths_are_loud_and_recoverable(backend):
         Pipeline(2, 2, 200, cols).set_pick([0, 5])
     with pytest.raises(RuntimeError):
         Pipeline(2, 3, 200, cols)  # more feature channels than raw rows
+
+
+def test_default_configurations_are_served_by_the_specialised_kernels(backend):
+    """nm_describe_plan: at the default 1 kHz / 2 kHz geometries every FIR family runs nm_convx_kernel and every segment
+    DFT nm_specx_kernel (the runtime-plan / generic kernels are for unusual sizes only)."""
+    for sfreq in (1000.0, 2000.0):
+        x = np.zeros((4, int(sfreq) * 2))
+        s = nm.NMSettings.get_default()
+        s.features.bandpass_filter = True
+        s.features.stft = True
+        s.raw_resampling_settings.resample_freq_hz = sfreq
+        dp = nm.DataProcessor(sfreq=sfreq, settings=s, channels=get_default_channels_from_data(x), line_noise=50, verbose=False)
+        plan = dp.plan(int(sfreq)).pipe.describe_plan()
+        lines = plan.splitlines()[1:]
+        assert len(lines) == 7, plan  # notch+scan, fft, welch, stft, bandpower, sharpwave, bursts
+        assert all(("nm_convx_kernel" in ln) or ("nm_specx_kernel" in ln) for ln in lines), plan
+        assert lines[0].startswith("notch+scan"), plan
