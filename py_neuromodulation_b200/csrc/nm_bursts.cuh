@@ -485,6 +485,7 @@ NM_DEV void nm_bq_select_queue(const NmBqSmem& sm, int head, int count, unsigned
             break;
         }
     }
+    __syncthreads();  // every thread has read res[0] (the counting path publishes the rank-r key there)
     if (tid == 0) { sm.res[0] = a_key; sm.ctl[4] = 0; sm.ctl[5] = 0; }
     __syncthreads();
     if (want_next) {
