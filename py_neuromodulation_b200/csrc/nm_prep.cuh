@@ -60,7 +60,6 @@ NM_DEV void nm_prep_group_sums(const NmPrepArgs& a, long long t, bool active, in
 #pragma unroll
     for (int q = 0; q < NM_MAX_GROUPS; ++q) P[q] = 0.0;
     if (active) {
-#pragma unroll 4
         for (int j = g; j < a.C; j += NM_PREP_WARPS) {
             const int grp = nm_ldg(a.group_of + j);
             if (grp >= 0) {
@@ -92,7 +91,6 @@ NM_GLOBAL void nm_prep_kernel(NmPrepArgs a) {
     const long long t = a.t0 + (long long)blockIdx.x * 32 + lane;  // t0 is a multiple of 32 (NaN block map)
     const bool active = t < a.t1;
 
-#pragma unroll 4
     for (int r = g; r < a.C_all; r += NM_PREP_WARPS) {
         const double v = active ? nm_raw_at(a, r, t) : 0.0;
         const unsigned bits = __ballot_sync(0xffffffffu, v != v);
@@ -110,7 +108,6 @@ NM_GLOBAL void nm_prep_kernel(NmPrepArgs a) {
         nm_prep_group_sums(a, t, active, lane, g, part, S);
     }
     if (!active) return;
-#pragma unroll 4
     for (int i = g; i < a.C; i += NM_PREP_WARPS) {
         double acc = 0.0;
 #pragma unroll
