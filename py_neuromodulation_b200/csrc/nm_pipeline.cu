@@ -176,6 +176,21 @@ static int nm_allow_smem(K kernel, size_t bytes, const nm_pipeline* p) {
     return 0;
 }
 
+// nm_prep_kernel over samples [a.t0, a.t1), specialised when there is at most one reference group
+static void nm_launch_prep(nm_pipeline* p, const NmPrepArgs& a) {
+    const unsigned grid = (unsigned)((a.t1 - a.t0 + 31) / 32);
+    p->prof_begin();
+    if (a.G <= 1 && a.raw_is_f64) {
+        NM_LAUNCH((nm_prep_kernel<1, 1>), dim3(grid), dim3(NM_PREP_THREADS), nm_prep_smem_bytes(), p->stream, a);
+    } else if (a.G <= 1) {
+        NM_LAUNCH((nm_prep_kernel<1, 0>), dim3(grid), dim3(NM_PREP_THREADS), nm_prep_smem_bytes(), p->stream, a);
+    } else {
+        NM_LAUNCH((nm_prep_kernel<NM_MAX_GROUPS, -1>), dim3(grid), dim3(NM_PREP_THREADS), nm_prep_smem_bytes(), p->stream, a);
+    }
+    p->prof_end(NM_PROF_PREP);
+    p->launches++;
+}
+
 // ------------------------------------------------------------------------------- FIR launches
 // Three kernels implement the same contract; the most specialised one that covers the bank is used:
 //   nm_convx_kernel  P in {1024, 2048, 4096}, compile-time plan (nm_convx.cuh)   <- every default configuration
@@ -920,11 +935,7 @@ static int nm_ensure_prepped(nm_pipeline* p, long long upto) {
         }
         a.t0 = (long long)k * p->slice_len;
         a.t1 = std::min<long long>(p->T, a.t0 + p->slice_len);
-        const unsigned grid = (unsigned)((a.t1 - a.t0 + 31) / 32);
-        p->prof_begin();
-        NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(NM_PREP_THREADS), nm_prep_smem_bytes(), p->stream, a);
-        p->prof_end(NM_PROF_PREP);
-        p->launches++;
+        nm_launch_prep(p, a);
         p->slices_prepped++;
     }
     NM_CUDA_CHECK(cudaGetLastError());
@@ -1002,11 +1013,7 @@ static int nm_upload_impl(nm_pipeline* p, const void* data, bool f64, long long 
         if (nm_stage_slices(p, data, f64, n_samples, pitch, NM_UPLOAD_SLICES)) return -1;
     } else {
         if (nm_stage_raw(p, data, f64, n_samples, pitch)) return -1;
-        const unsigned grid = (unsigned)((n_samples + 31) / 32);
-        p->prof_begin();
-        NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(NM_PREP_THREADS), nm_prep_smem_bytes(), p->stream, nm_prep_args(p));
-        p->prof_end(NM_PROF_PREP);
-        p->launches++;
+        nm_launch_prep(p, nm_prep_args(p));
         NM_CUDA_CHECK(cudaGetLastError());
     }
     p->have_data = true;
@@ -1021,16 +1028,12 @@ extern "C" int nm_prepare_resident(nm_pipeline* p) {
     NM_CHECK(p->have_data && !p->upload_pending, "no resident recording");
     cudaSetDevice(p->device);
     if (nm_ensure_prepped(p, p->T)) return -1;  // (a pipelined upload may still be in flight)
-    const unsigned grid = (unsigned)((p->T + 31) / 32);
     NmPrepArgs a = nm_prep_args(p);
     if (p->resident_uses_gsum) {  // channel-sharded recording: keep using the all-reduced group sums
         a.gsum_ext = p->d_gsum.as<double>();
         a.gsum_pitch = p->gsum_pitch;
     }
-    p->prof_begin();
-    NM_LAUNCH(nm_prep_kernel, dim3(grid), dim3(NM_PREP_THREADS), nm_prep_smem_bytes(), p->stream, a);
-    p->prof_end(NM_PROF_PREP);
-    p->launches++;
+    nm_launch_prep(p, a);
     NM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -42,6 +42,13 @@ struct NmPrepArgs {
     long long t0, t1;      // samples [t0, t1) are processed by this launch (time slices of a pipelined upload)
 };
 
+template <int RT>
+NM_DEV double nm_raw_at_t(const NmPrepArgs& a, int row, long long t) {
+    const bool f64 = RT < 0 ? a.raw_is_f64 != 0 : RT != 0;
+    return f64 ? nm_ldg(reinterpret_cast<const double*>(a.raw) + (size_t)row * a.raw_pitch + t)
+               : (double)nm_ldg(reinterpret_cast<const float*>(a.raw) + (size_t)row * a.raw_pitch + t);
+}
+
 NM_DEV double nm_raw_at(const NmPrepArgs& a, int row, long long t) {
     return a.raw_is_f64 ? nm_ldg(reinterpret_cast<const double*>(a.raw) + (size_t)row * a.raw_pitch + t)
                         : (double)nm_ldg(reinterpret_cast<const float*>(a.raw) + (size_t)row * a.raw_pitch + t);
@@ -55,27 +62,29 @@ NM_DEV double nm_raw_at(const NmPrepArgs& a, int row, long long t) {
 static NM_HD size_t nm_prep_smem_bytes() { return (size_t)NM_PREP_WARPS * NM_MAX_GROUPS * 32 * sizeof(double); }
 
 // group sums of this CTA's 32 samples over the local channels -> S[NM_MAX_GROUPS] in every thread (contains two barriers)
+// NG = compile-time bound of the group count (a.G <= NG), RT = raw type (0 float32, 1 float64, -1 read a.raw_is_f64)
+template <int NG, int RT>
 NM_DEV void nm_prep_group_sums(const NmPrepArgs& a, long long t, bool active, int lane, int g, double* part, double* S) {
-    double P[NM_MAX_GROUPS];
+    double P[NG];
 #pragma unroll
-    for (int q = 0; q < NM_MAX_GROUPS; ++q) P[q] = 0.0;
+    for (int q = 0; q < NG; ++q) P[q] = 0.0;
     if (active) {
         for (int j = g; j < a.C; j += NM_PREP_WARPS) {
             const int grp = nm_ldg(a.group_of + j);
             if (grp >= 0) {
-                const double v = nm_nan_to_num(nm_raw_at(a, nm_ldg(a.pick + j), t));
+                const double v = nm_nan_to_num(nm_raw_at_t<RT>(a, nm_ldg(a.pick + j), t));
 #pragma unroll
-                for (int q = 0; q < NM_MAX_GROUPS; ++q)
+                for (int q = 0; q < NG; ++q)
                     if (q == grp) P[q] += v;
             }
         }
     }
 #pragma unroll
-    for (int q = 0; q < NM_MAX_GROUPS; ++q)
+    for (int q = 0; q < NG; ++q)
         if (q < a.G) part[(g * NM_MAX_GROUPS + q) * 32 + lane] = P[q];
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < NM_MAX_GROUPS; ++q) {
+    for (int q = 0; q < NG; ++q) {
         double s = 0.0;
         if (q < a.G)
             for (int w = 0; w < NM_PREP_WARPS; ++w) s += part[(w * NM_MAX_GROUPS + q) * 32 + lane];
@@ -84,6 +93,9 @@ NM_DEV void nm_prep_group_sums(const NmPrepArgs& a, long long t, bool active, in
     __syncthreads();
 }
 
+// specialisations: <1, 0> / <1, 1> = at most one reference group (common average) on float32 / float64 input; <NM_MAX_GROUPS, -1> =
+// everything else.  Same arithmetic in the same order in all of them.
+template <int NG, int RT>
 NM_GLOBAL void nm_prep_kernel(NmPrepArgs a) {
     NM_SHARED_BYTES(smem);
     double* part = reinterpret_cast<double*>(smem);
@@ -92,30 +104,30 @@ NM_GLOBAL void nm_prep_kernel(NmPrepArgs a) {
     const bool active = t < a.t1;
 
     for (int r = g; r < a.C_all; r += NM_PREP_WARPS) {
-        const double v = active ? nm_raw_at(a, r, t) : 0.0;
+        const double v = active ? nm_raw_at_t<RT>(a, r, t) : 0.0;
         const unsigned bits = __ballot_sync(0xffffffffu, v != v);
         if (lane == 0 && active) a.nanblk[(size_t)r * a.nanblk_pitch + (t >> 5)] = bits ? 1 : 0;
     }
 
-    double S[NM_MAX_GROUPS];
+    double S[NG];
 #pragma unroll
-    for (int q = 0; q < NM_MAX_GROUPS; ++q) S[q] = 0.0;
+    for (int q = 0; q < NG; ++q) S[q] = 0.0;
     if (a.G > 0 && a.gsum_ext) {
 #pragma unroll
-        for (int q = 0; q < NM_MAX_GROUPS; ++q)
+        for (int q = 0; q < NG; ++q)
             if (q < a.G && active) S[q] = a.gsum_ext[(size_t)q * a.gsum_pitch + t];
     } else if (a.G > 0) {
-        nm_prep_group_sums(a, t, active, lane, g, part, S);
+        nm_prep_group_sums<NG, RT>(a, t, active, lane, g, part, S);
     }
     if (!active) return;
     for (int i = g; i < a.C; i += NM_PREP_WARPS) {
         double acc = 0.0;
 #pragma unroll
-        for (int q = 0; q < NM_MAX_GROUPS; ++q)
+        for (int q = 0; q < NG; ++q)
             if (q < a.G) acc += nm_ldg(a.gcoef + (size_t)i * a.G + q) * S[q];
         const int k1 = nm_ldg(a.sp_ptr + i + 1);
         for (int k = nm_ldg(a.sp_ptr + i); k < k1; ++k)
-            acc += nm_ldg(a.sp_val + k) * nm_nan_to_num(nm_raw_at(a, nm_ldg(a.pick + nm_ldg(a.sp_col + k)), t));
+            acc += nm_ldg(a.sp_val + k) * nm_nan_to_num(nm_raw_at_t<RT>(a, nm_ldg(a.pick + nm_ldg(a.sp_col + k)), t));
         a.xr[(size_t)i * a.xr_pitch + t] = acc;
     }
 }
@@ -128,7 +140,7 @@ NM_GLOBAL void nm_gsum_kernel(NmPrepArgs a, double* gsum) {
     const long long t = a.t0 + (long long)blockIdx.x * 32 + lane;
     const bool active = t < a.t1;
     double S[NM_MAX_GROUPS];
-    nm_prep_group_sums(a, t, active, lane, g, part, S);
+    nm_prep_group_sums<NM_MAX_GROUPS, -1>(a, t, active, lane, g, part, S);
     if (!active) return;
     for (int q = g; q < a.G; q += NM_PREP_WARPS) gsum[(size_t)q * a.gsum_pitch + t] = S[q];
 }
