@@ -144,13 +144,43 @@ def _oracle_settings() -> dict:
     return c3_settings().model_dump()
 
 
-def cpu_baseline_single(budget_s: float = 12.0) -> dict:
-    """Oracle port of the reference (one process, like the reference runs) on a bounded sample of the same workload."""
+# The CPU legs time the UNMODIFIED reference (`DataProcessor.process`, stream/data_processor.py:238-311) whenever its files are
+# present -- /root/reference in the authoring container, the byte-identical copy under the git-ignored baseline/_ref on the GPU box
+# (oracle/build_ref.py) -- through oracle/ref_shim.py (bare package objects + the restated mne.filter entry points: MNE itself is
+# not installed).  Only when neither exists they fall back to the NumPy port (oracle/np_oracle.py, kind "port").
+_REF_DP = None
+_REF_X = None
+
+
+def _reference_processor(n_ch: int):
+    """Reference DataProcessor for the C3 settings on `n_ch` default channels, or None when the reference files are absent."""
+    import logging
+
+    from oracle import ref_shim
+
+    if not ref_shim.reference_available():
+        return None
+    ref = ref_shim.load_reference()
+    ref.logger.setLevel(logging.ERROR)
+    settings = ref.NMSettings(**_oracle_settings())
+    channels = ref.utils.channels.get_default_channels_from_data(np.empty((n_ch, 1)))
+    return ref.DataProcessor(sfreq=SFREQ, settings=settings, channels=channels, line_noise=LINE_NOISE, verbose=False)
+
+
+def _port_processor(n_ch: int):
     from oracle import np_oracle as orc
 
+    return orc.WindowOracle(SFREQ, _oracle_settings(), n_channels=n_ch, line_noise=LINE_NOISE)
+
+
+def cpu_baseline_single(budget_s: float = 12.0) -> dict:
+    """The reference (else its port) in one process -- the way the reference runs -- on a bounded sample of the same workload."""
     n_win_max = 400
     x = synth(CH_PER_GPU, int(1000 + 100 * n_win_max), seed=0).astype(np.float64)
-    proc = orc.WindowOracle(SFREQ, _oracle_settings(), n_channels=CH_PER_GPU, line_noise=LINE_NOISE)
+    proc = _reference_processor(CH_PER_GPU)
+    kind = "reference" if proc is not None else "port"
+    if proc is None:
+        proc = _port_processor(CH_PER_GPU)
     proc.process(x[:, :1000])  # warm-up: FIR design, FFT plans
     done, t0 = 0, time.perf_counter()
     while done < n_win_max:
@@ -159,67 +189,73 @@ def cpu_baseline_single(budget_s: float = 12.0) -> dict:
         if time.perf_counter() - t0 > budget_s and done >= 8:
             break
     dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{done} consecutive windows of the C3 workload (256 ch x 1000 samp, float64), {dt:.1f} s, single process"}
+    what = "unmodified reference DataProcessor.process via oracle/ref_shim.py" if kind == "reference" else "NumPy port (oracle/np_oracle.py)"
+    return {"value": done / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"{done} consecutive windows of the C3 workload (256 ch x 1000 samp, float64), {dt:.1f} s, single process, {what}"}
 
 
-def _ref_worker(args):
-    """One worker of the multi-process reference arm: notch + features on a channel subset (re-reference done before)."""
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    from oracle import np_oracle as orc
+def _ref_init(n_ch: int, n_samples: int) -> None:
+    """Pool initialiser: one processor per worker process, BLAS / OpenMP threads pinned to 1 (the pool supplies the parallelism)."""
+    global _REF_DP, _REF_X
+    try:
+        from threadpoolctl import threadpool_limits
 
-    xr, names, n_win = args
-    sd = _oracle_settings()
-    taps = orc.design_notch(SFREQ, LINE_NOISE)
-    fft = orc.OscOracle("fft", sd, names, SFREQ)
-    bp = orc.BandPowerOracle(sd, names, SFREQ)
-    for k in range(n_win):
-        y = orc.apply_notch(xr[:, 100 * k : 100 * k + 1000].copy(), taps)
-        orc.hjorth(y, names)
-        fft.calc(y)
-        bp.calc(y)
-        orc.linelength(y, names)
-    return n_win
+        threadpool_limits(1)
+    except Exception:
+        pass
+    _REF_DP = _reference_processor(n_ch) or _port_processor(n_ch)
+    _REF_X = synth(n_ch, n_samples, seed=0).astype(np.float64)
+    _REF_DP.process(_REF_X[:, :1000])  # warm-up
+
+
+def _ref_windows(ks) -> int:
+    for k in ks:
+        _REF_DP.process(_REF_X[:, 100 * k : 100 * k + 1000])
+    return len(ks)
 
 
 def run_reference_arm(args) -> None:
-    """--impl reference: the reference algorithm on the host cores, all cores, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores.
+
+    Every worker process runs the unmodified `DataProcessor.process` on whole 256-channel windows; the windows of a step are dealt
+    round-robin to the workers (C3 has no state across windows, so this is the reference's best embarrassingly-parallel case and
+    needs no change to its code).  A step is a bounded sample (4 windows per core, at least 64); `value` uses the MEDIAN step time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
 
-    from oracle import np_oracle as orc
+    from oracle import ref_shim
 
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = "1"
+    kind = "reference" if ref_shim.reference_available() else "port"
     cores = os.cpu_count() or 1
-    n_win = 16
-    x = synth(CH_PER_GPU, 1000 + 100 * (n_win - 1), seed=0).astype(np.float64)
-    ref = orc.reref_matrix(orc.default_channels(CH_PER_GPU))
-    names = orc.default_channels(CH_PER_GPU)["new_name"]
-    bounds = np.linspace(0, CH_PER_GPU, cores + 1).astype(int)
-
-    def one_step(pool) -> None:
-        xr = ref @ x  # re-reference before the channel split (the only cross-channel step)
-        jobs = [(xr[a:b], names[a:b], n_win) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
-        pool.map(_ref_worker, jobs)
-
-    with mp.get_context("fork").Pool(cores) as pool:
+    n_win = max(64, 4 * cores)
+    n_samples = 1000 + 100 * (n_win - 1)
+    jobs = [list(range(w, n_win, cores)) for w in range(cores)]
+    steps = max(args.steps, 5)
+    times = []
+    with mp.get_context("fork").Pool(cores, initializer=_ref_init, initargs=(CH_PER_GPU, n_samples)) as pool:
         for _ in range(max(1, args.warmup)):
-            one_step(pool)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            one_step(pool)
-        dt = time.perf_counter() - t0
-    value = n_win * args.steps / dt
-    sample = (f"{n_win} windows of the C3 workload per step (256 ch x 1000 samp, float64), {cores} processes over disjoint "
-              "channel subsets after re-referencing, OMP threads = 1")
+            pool.map(_ref_windows, jobs, chunksize=1)
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            pool.map(_ref_windows, jobs, chunksize=1)
+            times.append(time.perf_counter() - t0)
+    dt = float(np.median(times))
+    value = n_win / dt
+    what = ("unmodified reference DataProcessor.process (baseline/_ref or /root/reference through oracle/ref_shim.py; mne.filter restated)"
+            if kind == "reference" else "NumPy port of the reference (oracle/np_oracle.py)")
+    sample = (f"{n_win} windows of the C3 workload per step (256 ch x 1000 samp, float64), dealt to {cores} worker processes, "
+              f"BLAS/OMP threads = 1, median of {steps} steps (min {min(times):.2f} s, max {max(times):.2f} s); {what}")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C3: 256ch x 1000samp windows, notch+CAR, FFT+bandpass+Hjorth+linelength (bounded sample: "
                                f"{n_win} windows/step)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -325,7 +361,8 @@ def run_gpu_arm(args) -> None:
     pipe.set_profiling(False)
     dominant = max(prof, key=lambda k: prof[k][0])
     dom_ms, dom_launches = prof[dominant]
-    feats_of = {"notch": 0, "scan": 4 * CH_PER_GPU, "spectral": 4 * CH_PER_GPU, "bandpower": 4 * CH_PER_GPU, "prep": 0}
+    feats_of = {"notch": 0, "scan": 4 * CH_PER_GPU, "spectral": 4 * CH_PER_GPU, "bandpower": 4 * CH_PER_GPU, "prep": 0,
+                "fused": F}  # the fused window kernel writes every feature column of C3
     unit_bytes = CH_PER_GPU * W * 4 + feats_of.get(dominant, 0) * 4  # fp32 tile in + fp32 features out
     bytes_per_launch = unit_bytes * n_win / max(dom_launches, 1)
     achieved = bytes_per_launch / (dom_ms / max(dom_launches, 1) * 1e-3) / 1e9

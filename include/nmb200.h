@@ -63,6 +63,13 @@ int nm_set_notch(nm_pipeline* p, const double* taps, int n_taps);
  * float64).  Pipelines with threshold / peak decisions downstream of the notch (bursts, sharp waves, raw normaliser) keep the
  * notch in float64 regardless. */
 int nm_set_precision(nm_pipeline* p, int float32_linear);
+/* Kernel organisation of the window chain.  0 (default): one kernel per stage -- re-reference (once per recording), notch (+ Hjorth /
+ * line length / raw), segment DFTs, band-pass bank -- the notched rows travel through HBM / L2.  1: ONE persistent kernel per
+ * (window, channel pair) (csrc/nm_fused.cuh): raw rows staged by cp.async.bulk + mbarrier, re-reference folded into the load, notch
+ * -> scan -> DFT band features -> band-pass bank without the re-referenced recording or the notched rows ever existing in HBM.
+ * Same results (tests run both); measured 15 % slower on B200 at float64 because the merged kernel runs every phase at the bank's
+ * occupancy, hence opt-in.  -1: take the choice from the environment (NMB200_FUSED, default 0). */
+int nm_set_fused(nm_pipeline* p, int mode);
 
 /* RawNormalizer (processing/normalization.py:30-111, type "raw"): window 0 passes through and seeds the per-channel
  * history; window g >= 1 appends its last add_samples = int(sfreq / rate) preprocessed samples, is normalised against the

@@ -1,10 +1,10 @@
 """TEST INFRASTRUCTURE (oracle) -- import the UNMODIFIED reference hot-path modules.
 
-Works only where ``/root/reference`` exists (the authoring container); the GPU box
-does not have it, so nothing under ``-m gpu``, ``smoke()`` or ``bench.py`` may call
-this.  It is used by ``tests/golden/make_golden.py`` to generate the committed
-fixtures and by CPU tests (skipped when the reference is absent) that pin
-``oracle/np_oracle.py`` against the live reference.
+Needs the reference files: ``/root/reference`` (authoring container only) or the unmodified copy that
+``oracle/build_ref.py`` places under the git-ignored ``baseline/_ref`` so that it travels to the GPU box.
+It is used by ``tests/golden/make_golden.py`` to generate the committed fixtures, by CPU tests (skipped
+when the reference is absent) that pin ``oracle/np_oracle.py`` against the live reference, and by the
+CPU legs of ``bench.py`` (``cpu_baseline`` / ``--impl reference``); never by ``-m gpu`` tests or ``smoke()``.
 
 Why a shim: ``import py_neuromodulation`` fails here (``__init__.py:12`` needs
 package metadata; ``stream/__init__.py:2`` imports ``mne``; ``__init__.py:77,88``
@@ -26,8 +26,20 @@ import sys
 import types
 from pathlib import Path, PurePath
 
-REFERENCE_ROOT = Path("/root/reference")
 _PKG = "py_neuromodulation"
+# the authoring container has the reference checkout; elsewhere (GPU box) the same unmodified files may have been placed under the
+# git-ignored baseline/_ref by oracle/build_ref.py -- only bench.py's CPU legs use that copy
+_CANDIDATES = (Path("/root/reference"), Path(__file__).resolve().parents[1] / "baseline" / "_ref")
+
+
+def _find_root() -> Path:
+    for r in _CANDIDATES:
+        if (r / _PKG / "stream" / "data_processor.py").is_file():
+            return r
+    return _CANDIDATES[0]
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
@@ -61,7 +73,7 @@ def _install_mne_stub() -> None:
 def load_reference() -> types.ModuleType:
     """Return the shimmed ``py_neuromodulation`` package object (idempotent)."""
     if not reference_available():
-        raise RuntimeError("reference tree not present at /root/reference")
+        raise RuntimeError("reference tree not present (neither /root/reference nor baseline/_ref)")
     if _PKG in sys.modules and getattr(sys.modules[_PKG], "__nm_oracle_shim__", False):
         return sys.modules[_PKG]
     try:

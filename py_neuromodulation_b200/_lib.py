@@ -56,6 +56,7 @@ _SIGNATURES = {
     "nm_set_reref": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_double_p, c_int_p, c_int_p, c_double_p]),
     "nm_set_notch": (C.c_int, [C.c_void_p, c_double_p, C.c_int]),
     "nm_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "nm_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
     "nm_set_raw_normalizer": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int]),
     "nm_add_prefilter": (C.c_int, [C.c_void_p, c_double_p, C.c_int]),
     "nm_set_nan_columns": (C.c_int, [C.c_void_p, c_int_p, c_int_p]),

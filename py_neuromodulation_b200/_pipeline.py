@@ -123,6 +123,10 @@ class Pipeline:
             raise ValueError("precision must be 'f64' or 'f32'")
         _lib.check(self.lib.nm_set_precision(self._h, int(precision == "f32")))
 
+    def set_fused(self, mode: int) -> None:
+        """Window chain as ONE persistent kernel (1), as one kernel per stage (0, default) or as the environment says (-1)."""
+        _lib.check(self.lib.nm_set_fused(self._h, int(mode)))
+
     def set_raw_normalizer(self, method: str, clip: float, n_keep: int, add_samples: int) -> None:
         """RawNormalizer in front of the features (mean / median / zscore / zscore-median; scikit-learn methods are out of scope)."""
         if method not in NORM_METHODS:
@@ -212,7 +216,7 @@ class Pipeline:
         return ms.value
 
     PROFILE_FAMILIES = ("prep", "notch", "scan", "spectral", "bandpower", "sharpwave", "burst_envelope", "burst_threshold",
-                        "burst_features", "normalizer", "nan")
+                        "burst_features", "normalizer", "nan", "fused")
 
     def prepare_resident(self) -> None:
         _lib.check(self.lib.nm_prepare_resident(self._h))
@@ -644,10 +648,10 @@ class IdentityNormPipeline:
     """Feature normaliser for a bare vector: every entry travels as a 3-sample constant 'channel' whose last
     sample is the feature (scan kernel, ``raw``), followed by the rolling-normalisation kernel."""
 
-    def __init__(self, n: int, method_index: int, clip: float, n_keep: int) -> None:
+    def __init__(self, n: int, method_index: int, clip: float, n_keep: int, device: int = 0) -> None:
         names = [f"f{i}" for i in range(n)]
         cols = [f"{c}_raw" for c in names]
-        self.pipe = Pipeline(n, n, 3, cols)
+        self.pipe = Pipeline(n, n, 3, cols, device=device)
         ScanSpec(names, raw=True).attach(self.pipe)
         self.pipe.add_feature_normalizer(NORM_METHODS[method_index], clip, n_keep, cols)
         self.pipe.finalize()

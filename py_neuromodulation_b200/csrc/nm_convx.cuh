@@ -415,8 +415,10 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
             const bool last = fi + 1 == nF;
             if (BANK) {
                 nm_cx_pass2<PL, 2>(work, spec, hv, tid);
+#ifdef NM_CX_HV_EARLY
                 // prefetch the next filter's spectrum (wrapping to filter 0 for the next item) one phase ahead
                 nm_cx_load_h<PL, T>(hv, hx + (size_t)(last ? 0 : fi + 1) * P, tid);
+#endif
             } else {
                 nm_cx_pass2<PL, 1>(work, work, hv, tid);
             }
@@ -428,6 +430,12 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
             for (int t = 0; t < 16; ++t) v[t] = p0w[t * PL::S0];
             nm_twiddle_w1<16, true>(v, wA);
             nm_bfly16<true>(v);
+#ifndef NM_CX_HV_EARLY
+            // next filter's spectrum (wrapping to filter 0 for the next item): issued where the register pressure is lowest -- a
+            // load that the compiler has to spill right away stalls on its own L2 latency (ncu: STL of the loaded pair right
+            // behind the LDG, round 2) -- and it lands during the epilogue's reduction and barrier
+            if (BANK) nm_cx_load_h<PL, T>(hv, hx + (size_t)(last ? 0 : fi + 1) * P, tid);
+#endif
             // `work` may still be read by slower threads: an epilogue (or the next filter's pass) must not write it
             // before a barrier.  Register epilogues either synchronise inside (kSyncsInside) or get a trailing barrier.
             bool in_regs = Epi::kRegsOnly;

@@ -23,7 +23,7 @@ extern "C" int nm_upload_begin_f32(nm_pipeline* p, const float* data, long long 
     const int n_slices = n_samples >= NM_UPLOAD_MIN_PIPELINED ? NM_UPLOAD_SLICES : 1;
     if (nm_stage_slices(p, data, false, n_samples, pitch, n_slices)) return -1;
     p->gsum_pitch = (n_samples + 1) & ~1LL;
-    if (p->d_gsum.ensure((size_t)p->G * p->gsum_pitch * sizeof(double))) return -1;
+    if (p->d_gsum.ensure((size_t)p->G * p->gsum_pitch * sizeof(double) + 16)) return -1;
     // the reduction stream must not run ahead of the previous run's readers of d_gsum (compute stream)
     NM_CUDA_CHECK(cudaStreamWaitEvent(p->red_stream, p->ev_sync, 0));
     NM_CUDA_CHECK(cudaGetLastError());

@@ -20,6 +20,7 @@
 #include "nm_firbank.h"
 #include "nm_scan.cuh"
 #include "nm_specx.cuh"
+#include "nm_fused.cuh"
 #include "nm_bursts.cuh"
 #include "nm_sharpwave.cuh"
 #include "nm_norm.cuh"
@@ -79,7 +80,7 @@ struct BandpowerFam {
 };
 
 enum { NM_PROF_PREP = 0, NM_PROF_NOTCH, NM_PROF_SCAN, NM_PROF_SPEC, NM_PROF_BANDPOWER, NM_PROF_SHARPWAVE, NM_PROF_BURST_ENV,
-       NM_PROF_BURST_THR, NM_PROF_BURST_FEAT, NM_PROF_NORM, NM_PROF_NAN, NM_PROF_N };
+       NM_PROF_BURST_THR, NM_PROF_BURST_FEAT, NM_PROF_NORM, NM_PROF_NAN, NM_PROF_FUSED, NM_PROF_N };
 
 struct nm_pipeline {
     int device = 0, C_all = 0, C = 0, W = 0, F = 0;
@@ -123,6 +124,16 @@ struct nm_pipeline {
     DevBuf d_pick, d_group_of, d_gcoef, d_sp_ptr, d_sp_col, d_sp_val;
     int G = 0;
     bool has_reref = false;
+    // fused window kernel (nm_fused.cuh): the re-reference must fold into the load as  x_i = d_i * raw_i + g_i * S  (at most one
+    // group sum, no off-diagonal remainder); decided at nm_finalize, switchable with NMB200_FUSED=0 for A/B measurements
+    bool reref_foldable = true, fused = false, force_xr = false, fused_bp = false;
+    int fused_mode = -1;  // nm_set_fused: 0 off, 1 on, -1 environment (NMB200_FUSED, default off)
+    std::vector<double> h_dfold, h_gfold;
+    DevBuf d_dfold, d_gfold;
+    int fused_sx = 0;                       // segment length of the in-kernel DFT families (0: none)
+    std::vector<int> fused_spec;            // indices into `spectral` of the families computed inside the fused kernel
+    std::vector<NmSpecArgs> h_fused_spec;
+    DevBuf d_fused_spec;                    // their NmSpecArgs blocks (out.row0 == 0; the launch passes the batch's first row)
     std::unique_ptr<FirBank> notch;
     std::vector<double> notch_taps;
     // PreprocessingFilter (processing/filter_preprocessing.py): single-filter 'same' FIR stages applied one after the
@@ -541,6 +552,95 @@ int NormFam::run(nm_pipeline* p, int n_windows) {
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------- fused window kernel (nm_fused.cuh)
+typedef void (*NmFusedKernel)(NmFusedArgs);
+static NmFusedKernel nm_fused_pick(int P, int sx, bool raw64) {
+    if (P == 1024) return raw64 ? nm_fused_kernel<1024, NmSxNone, true> : nm_fused_kernel<1024, NmSxNone, false>;
+    if (P == 2048) {
+        if (sx == 1000) return raw64 ? nm_fused_kernel<2048, NmSx1000, true> : nm_fused_kernel<2048, NmSx1000, false>;
+        return raw64 ? nm_fused_kernel<2048, NmSxNone, true> : nm_fused_kernel<2048, NmSxNone, false>;
+    }
+    if (P == 4096) {
+        if (sx == 2000) return raw64 ? nm_fused_kernel<4096, NmSx2000, true> : nm_fused_kernel<4096, NmSx2000, false>;
+        return raw64 ? nm_fused_kernel<4096, NmSxNone, true> : nm_fused_kernel<4096, NmSxNone, false>;
+    }
+    return nullptr;
+}
+static size_t nm_fused_smem(int P) {
+    return P == 1024 ? nm_fused_smem_bytes<1024>() : (P == 2048 ? nm_fused_smem_bytes<2048>() : nm_fused_smem_bytes<4096>());
+}
+static size_t nm_fused_nbuf(int P) { return P == 1024 ? NmCxPlan<1024>::NBUF : (P == 2048 ? NmCxPlan<2048>::NBUF : NmCxPlan<4096>::NBUF); }
+
+// decide at nm_finalize whether the window chain runs in the fused kernel and which families it serves
+static int nm_fused_plan(nm_pipeline* p) {
+    p->fused = false;
+    p->fused_bp = false;
+    p->fused_sx = 0;
+    p->fused_spec.clear();
+    int want = p->fused_mode;
+    if (want < 0) {
+        const char* env = getenv("NMB200_FUSED");
+        want = env ? atoi(env) : 0;
+    }
+    if (want == 0) return 0;
+    if (!p->notch || !p->reref_foldable || !p->prefilters.empty() || p->rawnorm || p->f32_linear() || p->precision == 1) return 0;
+    const FirBank& nb = *p->notch;
+    if (!nb.pow2 || !nm_convx_supported(nb.P) || nb.nF != 1 || nb.mode != NM_FIR_REFLECT) return 0;
+    const size_t buf_bytes = nm_fused_nbuf(nb.P) * sizeof(cx<double>);
+    if (NmFzStage<true>::bytes(p->W) > buf_bytes) return 0;  // the stage of one item must fit a transform buffer
+    const int nat_elems = (NmEpiStoreScan::phys(p->W - 1) + 2) & ~1;
+    if ((size_t)nat_elems * sizeof(cx<double>) > buf_bytes) return 0;
+    if (nm_fused_smem(nb.P) > (size_t)p->smem_max) return 0;
+    p->fused = true;
+    const int sx_ok = nb.P == 2048 ? 1000 : (nb.P == 4096 ? 2000 : 0);
+    for (size_t i = 0; i < p->spectral.size() && sx_ok; ++i) {
+        const SpectralFam& f = *p->spectral[i];
+        const nm_spectral_cfg& c = f.cfg;
+        const size_t vals = (size_t)2 * f.nk * sizeof(double);
+        if (f.fast && c.nper == sx_ok && c.nseg == 1 && !c.keep_segments && c.start >= 0 && c.start + c.nper <= p->W &&
+            (size_t)nat_elems * sizeof(cx<double>) + vals <= buf_bytes && (int)p->fused_spec.size() < NM_FZ_MAX_SPEC) {
+            p->fused_spec.push_back((int)i);
+            p->fused_sx = sx_ok;
+        }
+    }
+    if (p->bandpower) {
+        const BandpowerFam& f = *p->bandpower;
+        p->fused_bp = f.bank.pow2 && f.bank.P == nb.P && f.bank.mode == NM_FIR_SAME && !(f.mob || f.comp) && f.bank.d_hx.p != nullptr;
+    }
+    if (p->d_dfold.upload(p->h_dfold, p->stream) || p->d_gfold.upload(p->h_gfold, p->stream)) return -1;
+    for (int raw64 = 0; raw64 < 2; ++raw64)
+        if (nm_allow_smem(nm_fused_pick(nb.P, p->fused_sx, raw64 != 0), nm_fused_smem(nb.P), p)) return -1;
+    return 0;
+}
+static bool nm_spec_in_fused(const nm_pipeline* p, size_t i) {
+    for (int k : p->fused_spec)
+        if ((size_t)k == i) return true;
+    return false;
+}
+
+static NmSpecArgs nm_spec_args(const nm_pipeline* p, const SpectralFam& f, const NmRows& rows, const NmOut& out, int n) {
+    NmSpecArgs a;
+    const nm_spectral_cfg& c = f.cfg;
+    a.in = rows;
+    a.fft = f.fft.dev();
+    a.need_scratch = f.fft.generic ? 1 : 0;
+    a.nseg = c.nseg; a.hop = c.hop; a.start = c.start;
+    a.ext_even = c.ext_even; a.ext_len = c.ext_len;
+    a.detrend = c.detrend;
+    a.win = c.win;
+    a.power = c.power; a.scale = c.scale; a.log = c.log;
+    a.keep_segments = c.keep_segments;
+    a.k0 = f.k0; a.nk = f.nk;
+    a.n_bands = c.n_bands;
+    a.band_lo = f.d_lo.as<int>(); a.band_hi = f.d_hi.as<int>();
+    a.est_mask = c.est_mask;
+    a.want_spectrum = c.want_spectrum;
+    a.out = out;
+    a.n_items = n * ((p->C + 1) / 2);
+    return a;
+}
+
 // ------------------------------------------------------------------------------- life cycle
 extern "C" int nm_pipeline_create(int device, int n_raw_rows, int n_ch, int window_samples, int n_features, nm_pipeline** out) {
     NM_CHECK(out, "out is NULL");
@@ -639,6 +739,17 @@ extern "C" int nm_set_reref(nm_pipeline* p, int n_groups, const int* group_of, c
     if (p->d_sp_val.upload(sp_val, (size_t)nnz, p->stream)) return -1;
     NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
     p->has_reref = true;
+    // can the matrix be folded into the fused kernel's load?  row i = d_i on its own channel + g_i on the (single) group sum
+    p->reref_foldable = n_groups <= 1;
+    p->h_dfold.assign(p->C, 0.0);
+    p->h_gfold.assign(p->C, 0.0);
+    for (int i = 0; i < p->C && p->reref_foldable; ++i) {
+        if (n_groups == 1) p->h_gfold[i] = gcoef[i];
+        for (int k = sp_ptr[i]; k < sp_ptr[i + 1]; ++k) {
+            if (sp_col[k] != i || k != sp_ptr[i]) { p->reref_foldable = false; break; }
+            p->h_dfold[i] = sp_val[k];
+        }
+    }
     return 0;
 }
 
@@ -816,6 +927,14 @@ extern "C" int nm_set_precision(nm_pipeline* p, int float32_linear) {
     return 0;
 }
 
+extern "C" int nm_set_fused(nm_pipeline* p, int mode) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    NM_CHECK(mode >= -1 && mode <= 1, "fused mode must be -1 (environment), 0 (off) or 1 (on)");
+    p->fused_mode = mode;
+    return 0;
+}
+
 extern "C" int nm_set_raw_normalizer(nm_pipeline* p, int method, double clip, int n_keep, int add_samples) {
     NM_P_CHECK(p);
     NM_CHECK(!p->finalized, "pipeline already finalized");
@@ -842,6 +961,12 @@ extern "C" int nm_finalize(nm_pipeline* p) {
             p->d_sp_col.upload(col, p->stream) || p->d_sp_val.upload(val, p->stream))
             return -1;
     }
+    if (!p->has_reref) {
+        p->reref_foldable = true;
+        p->h_dfold.assign(p->C, 1.0);
+        p->h_gfold.assign(p->C, 0.0);
+    }
+    if (nm_fused_plan(p)) return -1;
     p->Wp = (p->W + 1) & ~1;
     // chunk of windows per launch: as many as possible up to 64 windows / 384 MB of notched rows (+ burst envelopes).  L2 residency
     // of the chunk turned out not to matter (the consumers are compute / latency bound: a 24..128 MB sweep moved the C3 step by
@@ -912,6 +1037,11 @@ static NmPrepArgs nm_prep_args(nm_pipeline* p) {
     a.nanblk_pitch = p->nanblk_pitch;
     a.gsum_ext = nullptr;
     a.gsum_pitch = 0;
+    // fused pipelines keep only the group sums (the re-reference is folded into the window kernel's load)
+    const bool fused = p->fused && !p->force_xr;
+    a.write_xr = fused ? 0 : 1;
+    a.gsum_out = (fused && p->G > 0) ? p->d_gsum.as<double>() : nullptr;
+    if (a.gsum_out) a.gsum_pitch = p->gsum_pitch;
     a.t0 = 0;
     a.t1 = p->T;
     return a;
@@ -930,6 +1060,7 @@ static int nm_ensure_prepped(nm_pipeline* p, long long upto) {
             NM_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->red_ev[k], 0));
             a.gsum_ext = p->d_gsum.as<double>();
             a.gsum_pitch = p->gsum_pitch;
+            a.gsum_out = nullptr;
         } else {
             NM_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->slice_ev[k], 0));
         }
@@ -939,6 +1070,20 @@ static int nm_ensure_prepped(nm_pipeline* p, long long upto) {
         p->slices_prepped++;
     }
     NM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// device buffers of a recording whose geometry (T, pitches) has just been set; a fused pipeline keeps the group sums instead of
+// the re-referenced float64 copy.  The raw rows get 16 spare bytes: the fused kernel's bulk copies round sizes up to 16 bytes.
+static int nm_stage_buffers(nm_pipeline* p, size_t esz) {
+    if (p->d_raw.ensure((size_t)p->C_all * p->raw_pitch * esz + 16)) return -1;
+    const bool fused = p->fused && !p->force_xr;
+    if (!fused && p->d_xr.ensure((size_t)p->C * p->xr_pitch * sizeof(double))) return -1;
+    if (p->d_nanblk.ensure((size_t)p->C_all * p->nanblk_pitch)) return -1;
+    if (fused && p->G > 0) {
+        p->gsum_pitch = (p->T + 1) & ~1LL;
+        if (p->d_gsum.ensure((size_t)p->G * p->gsum_pitch * sizeof(double) + 16)) return -1;
+    }
     return 0;
 }
 
@@ -952,9 +1097,7 @@ static int nm_stage_raw(nm_pipeline* p, const void* data, bool f64, long long n_
     p->raw_pitch = (n_samples + 3) & ~3LL;
     p->xr_pitch = (n_samples + 1) & ~1LL;
     p->nanblk_pitch = (n_samples + 31) / 32;
-    if (p->d_raw.ensure((size_t)p->C_all * p->raw_pitch * esz)) return -1;
-    if (p->d_xr.ensure((size_t)p->C * p->xr_pitch * sizeof(double))) return -1;
-    if (p->d_nanblk.ensure((size_t)p->C_all * p->nanblk_pitch)) return -1;
+    if (nm_stage_buffers(p, esz)) return -1;
     if (pitch == p->raw_pitch) {
         NM_CUDA_CHECK(cudaMemcpyAsync(p->d_raw.p, data, (size_t)p->C_all * pitch * esz, cudaMemcpyHostToDevice, p->stream));
     } else {
@@ -973,9 +1116,7 @@ static int nm_stage_slices(nm_pipeline* p, const void* data, bool f64, long long
     p->raw_pitch = (n_samples + 3) & ~3LL;
     p->xr_pitch = (n_samples + 1) & ~1LL;
     p->nanblk_pitch = (n_samples + 31) / 32;
-    if (p->d_raw.ensure((size_t)p->C_all * p->raw_pitch * esz)) return -1;
-    if (p->d_xr.ensure((size_t)p->C * p->xr_pitch * sizeof(double))) return -1;
-    if (p->d_nanblk.ensure((size_t)p->C_all * p->nanblk_pitch)) return -1;
+    if (nm_stage_buffers(p, esz)) return -1;
     p->slice_len = ((n_samples + n_slices - 1) / n_slices + 255) & ~255LL;
     p->n_slices = (int)((n_samples + p->slice_len - 1) / p->slice_len);
     p->slices_prepped = 0;
@@ -1032,6 +1173,7 @@ extern "C" int nm_prepare_resident(nm_pipeline* p) {
     if (p->resident_uses_gsum) {  // channel-sharded recording: keep using the all-reduced group sums
         a.gsum_ext = p->d_gsum.as<double>();
         a.gsum_pitch = p->gsum_pitch;
+        a.gsum_out = nullptr;
     }
     nm_launch_prep(p, a);
     NM_CUDA_CHECK(cudaGetLastError());
@@ -1080,7 +1222,58 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
     };
     nm_run_prefilters(p, rows);
     bool scan_done = false;
-    if (p->notch) {
+    if (p->fused) {
+        // ---- one kernel: folded re-reference, notch, scan, in-kernel DFT families, band-pass bank (nm_fused.cuh)
+        bool y_needed = p->sharpwave || p->bursts || (p->bandpower && !p->fused_bp) || !(p->has_scan || !p->fused_spec.empty() || p->fused_bp);
+        for (size_t i = 0; i < p->spectral.size(); ++i) y_needed = y_needed || !nm_spec_in_fused(p, i);
+        const FirBank& nb = *p->notch;
+        NmFusedArgs a;
+        a.raw = p->d_raw.p;
+        a.raw_pitch = p->raw_pitch;
+        a.pick = p->d_pick.as<int>();
+        a.dcoef = p->d_dfold.as<double>();
+        a.gcoef = p->d_gfold.as<double>();
+        a.gsum = p->G > 0 ? p->d_gsum.as<double>() : nullptr;
+        a.start = p->d_starts.as<long long>() + w0;
+        a.n_windows = n; a.n_ch = p->C; a.W = p->W; a.E = nb.E;
+        a.n_items = n * ((p->C + 1) / 2);
+        a.tw = nb.fft.d_tw.as<cx<double>>();
+        a.hx_notch = nb.d_hx.as<double>();
+        a.hx_bank = nullptr;
+        a.nF = 0;
+        a.scan.y = y_needed ? p->d_y.as<double>() : nullptr;
+        a.scan.Wp = p->Wp;
+        a.scan.want_scan = p->has_scan ? 1 : 0;
+        a.scan.want_hjorth = p->scan_h; a.scan.want_raw = p->scan_r; a.scan.want_ll = p->scan_l;
+        a.scan.out = p->has_scan ? out_for(p->d_scan_colmap, 5) : NmOut{nullptr, 0, 0, nullptr, 0};
+        a.bp.seglen = nullptr;
+        a.bp.want_act = a.bp.want_mob = a.bp.want_comp = a.bp.log_act = 0;
+        a.bp.out = NmOut{nullptr, 0, 0, nullptr, 0};
+        for (int b = 0; b < NM_BP_MAX_INLINE; ++b) a.bp.seglen_k[b] = 1;
+        if (p->fused_bp) {
+            BandpowerFam& f = *p->bandpower;
+            a.hx_bank = f.bank.d_hx.as<double>();
+            a.nF = f.bank.nF;
+            a.bp.seglen = f.d_seglen.as<int>();
+            for (int b = 0; b < NM_BP_MAX_INLINE; ++b) a.bp.seglen_k[b] = b < (int)f.h_seglen.size() ? f.h_seglen[b] : 1;
+            a.bp.want_act = f.act; a.bp.want_mob = f.mob; a.bp.want_comp = f.comp; a.bp.log_act = f.logt;
+            a.bp.out = out_for(f.d_colmap, f.bank.nF * 3);
+        }
+        a.n_spec = (int)p->fused_spec.size();
+        a.spec = p->d_fused_spec.as<NmSpecArgs>();
+        a.row0 = w0;
+        auto kern = nm_fused_pick(nb.P, p->fused_sx, p->raw_f64);
+        const size_t sm = nm_fused_smem(nb.P);
+        const int threads = nb.P / 16;
+        p->prof_begin();
+        NM_LAUNCH(kern, dim3(nm_resident_grid(p, kern, threads, sm, a.n_items)), dim3(threads), sm, p->stream, a);
+        p->prof_end(NM_PROF_FUSED);
+        p->launches++;
+        scan_done = true;
+        rows.base = p->d_y.as<double>();
+        rows.ch_stride = p->Wp;
+        rows.off = p->d_yoff.as<long long>();
+    } else if (p->notch) {
         const bool y_needed = !p->spectral.empty() || p->bandpower || p->sharpwave || p->bursts || p->rawnorm;
         const bool fuse_scan = p->has_scan && !p->rawnorm;  // the scan features are taken from the NORMALISED rows otherwise
         NmOut so;
@@ -1124,25 +1317,10 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         cudaStreamWaitEvent(main_stream, p->ev_join[b], 0);
     };
     branch_begin(0);
-    for (auto& f : p->spectral) {
-        NmSpecArgs a;
-        const nm_spectral_cfg& c = f->cfg;
-        a.in = rows;
-        a.fft = f->fft.dev();
-        a.need_scratch = f->fft.generic ? 1 : 0;
-        a.nseg = c.nseg; a.hop = c.hop; a.start = c.start;
-        a.ext_even = c.ext_even; a.ext_len = c.ext_len;
-        a.detrend = c.detrend;
-        a.win = c.win;
-        a.power = c.power; a.scale = c.scale; a.log = c.log;
-        a.keep_segments = c.keep_segments;
-        a.k0 = f->k0; a.nk = f->nk;
-        a.n_bands = c.n_bands;
-        a.band_lo = f->d_lo.as<int>(); a.band_hi = f->d_hi.as<int>();
-        a.est_mask = c.est_mask;
-        a.want_spectrum = c.want_spectrum;
-        a.out = out_for(f->d_colmap, f->per_ch);
-        a.n_items = n * ((p->C + 1) / 2);
+    for (size_t fi = 0; fi < p->spectral.size(); ++fi) {
+        auto& f = p->spectral[fi];
+        if (p->fused && nm_spec_in_fused(p, fi)) continue;
+        NmSpecArgs a = nm_spec_args(p, *f, rows, out_for(f->d_colmap, f->per_ch), n);
         const size_t sm = f->smem();
         p->prof_begin();
         if (f->fast) {
@@ -1154,7 +1332,7 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         p->prof_end(NM_PROF_SPEC);
         p->launches++;
     }
-    if (p->bandpower) {
+    if (p->bandpower && !(p->fused && p->fused_bp)) {
         BandpowerFam& f = *p->bandpower;
         NmEpiBandpower epi;
         epi.seglen = f.d_seglen.as<int>();
@@ -1189,6 +1367,21 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
     cudaSetDevice(p->device);
     if (p->d_starts.upload(starts, (size_t)n_windows, p->stream)) return -1;
     if (p->d_out.ensure((size_t)n_windows * p->F * sizeof(double))) return -1;
+    if (p->fused && !p->fused_spec.empty()) {  // argument blocks of the in-kernel DFT families (they hold the d_out pointer)
+        p->h_fused_spec.clear();
+        NmRows none{};
+        for (int k : p->fused_spec) {
+            const SpectralFam& f = *p->spectral[k];
+            NmOut o;
+            o.out = p->d_out.as<double>();
+            o.row0 = 0;
+            o.F = p->F;
+            o.colmap = f.d_colmap.as<int>();
+            o.per_ch = f.per_ch;
+            p->h_fused_spec.push_back(nm_spec_args(p, f, none, o, 0));
+        }
+        if (p->d_fused_spec.upload(p->h_fused_spec, p->stream)) return -1;
+    }
     p->out_rows = n_windows;
     NM_CUDA_CHECK(cudaMemsetAsync(p->d_out.p, 0, (size_t)n_windows * p->F * sizeof(double), p->stream));
     // without the (sequential) normaliser a chunk's rows are final when its kernels end: ship them chunk by chunk
@@ -1297,7 +1490,10 @@ extern "C" int nm_process_window(nm_pipeline* p, const double* window, double* o
 extern "C" int nm_preprocess_window(nm_pipeline* p, const double* window, double* out_rows) {
     NM_P_CHECK(p);
     NM_CHECK(window && out_rows, "NULL argument");
-    if (nm_upload_impl(p, window, true, p->W, p->W)) return -1;
+    p->force_xr = true;  // this entry hands out the re-referenced / notched ROWS: materialise them (un-fused kernels)
+    const int rc_up = nm_upload_impl(p, window, true, p->W, p->W);
+    p->force_xr = false;
+    if (rc_up) return -1;
     const long long zero = 0;
     if (p->d_starts.upload(&zero, 1, p->stream)) return -1;
     NmRows rows;
@@ -1400,17 +1596,24 @@ extern "C" int nm_describe_plan(nm_pipeline* p, char* buf, int n) {
     snprintf(line, sizeof(line), "window=%d channels=%d features=%d chunk=%d\n", p->W, p->C, p->F, p->chunk);
     s += line;
     for (auto& b : p->prefilters) nm_describe_fir<NmEpiStore>(s, "prefilter", *b, 0);
-    if (p->notch) {
+    if (p->fused) {
+        snprintf(line, sizeof(line), "fused: nm_fused_kernel P=%d threads=%d smem=%zu [re-reference + notch%s%s%s] dft_families=%d\n", p->notch->P,
+                 p->notch->P / 16, nm_fused_smem(p->notch->P), p->has_scan ? " + scan" : "", p->fused_sx ? " + segment DFT" : "",
+                 p->fused_bp ? " + band-pass bank" : "", (int)p->fused_spec.size());
+        s += line;
+    } else if (p->notch) {
         if (nm_convx_pick<NmEpiStoreScan>(*p->notch)) nm_describe_fir<NmEpiStoreScan>(s, p->has_scan ? "notch+scan" : "notch", *p->notch, 0);
         else nm_describe_fir<NmEpiStore>(s, "notch", *p->notch, 0);
     }
-    if (p->has_scan && !(p->notch && nm_convx_pick<NmEpiStoreScan>(*p->notch))) s += "scan: nm_scan_kernel\n";
-    for (auto& f : p->spectral) {
+    if (p->has_scan && !p->fused && !(p->notch && nm_convx_pick<NmEpiStoreScan>(*p->notch))) s += "scan: nm_scan_kernel\n";
+    for (size_t fi = 0; fi < p->spectral.size(); ++fi) {
+        auto& f = p->spectral[fi];
+        if (p->fused && nm_spec_in_fused(p, fi)) continue;
         snprintf(line, sizeof(line), "spectral: %s nper=%d nseg=%d bins=%d threads=%d smem=%zu\n", f->fast ? "nm_specx_kernel" : "nm_spec_kernel",
                  f->cfg.nper, f->cfg.nseg, f->nk, f->threads(), f->smem());
         s += line;
     }
-    if (p->bandpower) nm_describe_fir<NmEpiBandpower>(s, "bandpower", p->bandpower->bank, p->bandpower->epi_smem());
+    if (p->bandpower && !(p->fused && p->fused_bp)) nm_describe_fir<NmEpiBandpower>(s, "bandpower", p->bandpower->bank, p->bandpower->epi_smem());
     if (p->sharpwave) nm_describe_fir<NmEpiSharpwave>(s, "sharpwave", p->sharpwave->bank, p->sharpwave->epi_smem());
     if (p->bursts) nm_describe_fir<NmEpiBursts>(s, "bursts", p->bursts->bank, p->bursts->epi_smem());
     if (buf && n > 0) {

@@ -40,6 +40,10 @@ struct NmPrepArgs {
     const double* gsum_ext;
     long long gsum_pitch;
     long long t0, t1;      // samples [t0, t1) are processed by this launch (time slices of a pipelined upload)
+    // fused window kernel (nm_fused.cuh): the re-referenced copy is not materialised (write_xr == 0); the launch only leaves
+    // the NaN block map and the local group sums (gsum_out, (G, gsum_pitch), nullptr when gsum_ext already holds them)
+    double* gsum_out;
+    int write_xr;
 };
 
 template <int RT>
@@ -120,6 +124,12 @@ NM_GLOBAL void nm_prep_kernel(NmPrepArgs a) {
         nm_prep_group_sums<NG, RT>(a, t, active, lane, g, part, S);
     }
     if (!active) return;
+    if (a.gsum_out) {
+#pragma unroll
+        for (int q = 0; q < NG; ++q)
+            if (q < a.G && (q % NM_PREP_WARPS) == g) a.gsum_out[(size_t)q * a.gsum_pitch + t] = S[q];
+    }
+    if (!a.write_xr) return;
     for (int i = g; i < a.C; i += NM_PREP_WARPS) {
         double acc = 0.0;
 #pragma unroll

@@ -66,7 +66,7 @@ def build_specs(settings, names, sfreq, window_samples: int, user_feature_names=
 class _Plan:
     """Everything that depends on the window length."""
 
-    def __init__(self, dp: "DataProcessor", window_samples: int, with_normalizer: bool) -> None:
+    def __init__(self, dp: "DataProcessor", window_samples: int, with_normalizer: bool, nan_reinsert: bool = True) -> None:
         from .._pipeline import Pipeline
 
         s, names = dp.settings, dp.ch_names_used_features
@@ -80,6 +80,7 @@ class _Plan:
             return
         pipe = Pipeline(dp.n_raw_rows, len(names), window_samples, columns, device=dp.device)
         pipe.set_precision(dp.precision)
+        pipe.set_fused(-1 if dp.fused is None else int(bool(dp.fused)))
         pipe.set_pick(dp.feature_idx)
         if dp.reref_factored is not None:  # channel-sharded run: coefficients come from the GLOBAL channel table
             pipe.set_reref_factored(*dp.reref_factored)
@@ -99,7 +100,8 @@ class _Plan:
             cols = columns if ns.normalize_psd else [k for k in columns if "psd" not in k]
             pipe.add_feature_normalizer(ns.normalization_method, ns.clip, dp.norm_keep, cols)
             self.normalized = True
-        pipe.set_nan_columns(dp.nan_names_by_raw_row)
+        if nan_reinsert:
+            pipe.set_nan_columns(dp.nan_names_by_raw_row)
         pipe.finalize()
         self.pipe = pipe
 
@@ -118,6 +120,7 @@ class DataProcessor:
         device: int = 0,
         reref_factored: tuple | None = None,
         precision: str | None = None,
+        fused: bool | None = None,
     ) -> None:
         from .. import user_features
         from ..filter.notch_filter import NotchFilter
@@ -129,6 +132,9 @@ class DataProcessor:
         # FFT convolution, 1e-5 relative); env NMB200_PRECISION overrides the default for callers that cannot pass the argument
         import os
 
+        # kernel organisation: None = library default / NMB200_FUSED, True = one persistent kernel per (window, channel pair)
+        # (csrc/nm_fused.cuh), False = one kernel per stage
+        self.fused = fused
         self.precision = precision or os.environ.get("NMB200_PRECISION", "f64")
         if self.precision not in ("f64", "f32"):
             raise ValueError("precision must be 'f64' or 'f32'")
@@ -157,8 +163,11 @@ class DataProcessor:
         self.ch_names_used_features = [ch.loc[i, "new_name"] for i in self.feature_idx]
         if len(self.ch_names_used) == len(self.ch_names_used_features):
             self.ch_names_used_features = list(self.ch_names_used)
-        # NaN re-insertion indexes ch_names_used with a mask over ALL raw rows (reference quirk: lengths must agree)
-        self.nan_names_by_raw_row = [self.ch_names_used[r] if r < len(self.ch_names_used) else None for r in range(self.n_raw_rows)]
+        # NaN re-insertion (stream/data_processor.py:297-306): a NaN in raw row r turns every feature whose key contains that
+        # row's channel name into NaN.  The reference indexes ch_names_used with a mask over ALL raw rows, which is only
+        # defined when every row is used and good (it raises IndexError otherwise); here every used, good row maps to its OWN
+        # channel name and unused / bad rows to nothing -- identical whenever the reference is defined.
+        self.nan_names_by_raw_row = [ch.loc[r, "new_name"] if bool(good_used.iloc[r]) else None for r in range(self.n_raw_rows)]
 
         self.preproc_plan = preprocessing_plan(self.settings, self.sfreq_raw)
         self.notch_taps = None
@@ -194,28 +203,43 @@ class DataProcessor:
         self.user_feature_names = list(user_features.keys())
         self._user_plugins = {name: cls(self.settings, self.ch_names_used_features, self.sfreq_raw) for name, cls in user_features.items()}
         self._user_norm = None
-        self._plans: dict[tuple[int, bool], _Plan] = {}
+        self._plans: dict[tuple, _Plan] = {}
+        self._stream_window: int | None = None
         self.cnt_samples = 0
         # validate the plug-in settings now (bands, filters, estimators) like the reference constructor does
         self._probe = _ProbeOnly(self)
 
     # ------------------------------------------------------------------ plans
-    def plan(self, window_samples: int, with_normalizer: bool = True) -> _Plan:
-        key = (int(window_samples), bool(with_normalizer))
+    def plan(self, window_samples: int, with_normalizer: bool = True, nan_reinsert: bool = True) -> _Plan:
+        key = (int(window_samples), bool(with_normalizer), bool(nan_reinsert))
         if key not in self._plans:
-            self._plans[key] = _Plan(self, int(window_samples), with_normalizer)
+            self._plans[key] = _Plan(self, int(window_samples), with_normalizer, nan_reinsert)
         return self._plans[key]
+
+    @property
+    def stateful(self) -> bool:
+        """Stages that carry state from window to window (one history per window length would be wrong)."""
+        return bool(self.normalize or self.rawnorm_cfg is not None or "bursts" in self.settings.features.get_enabled())
 
     def reset_state(self) -> None:
         for p in self._plans.values():
             if p.pipe is not None:
                 p.pipe.reset_state()
         self._user_norm = None
+        self._stream_window = None
 
     # ------------------------------------------------------------------ one window (reference interface)
     def process(self, data: np.ndarray) -> dict[str, float]:
         start_time = time()
         data = np.asarray(data)
+        if self._stream_window is None:
+            self._stream_window = int(data.shape[1])
+        elif self._stream_window != int(data.shape[1]) and self.stateful:
+            # the reference keeps ONE normaliser / burst history across window lengths; a pipeline here is built per length
+            raise NotImplementedError(
+                f"window length changed from {self._stream_window} to {data.shape[1]} samples while a stateful stage (feature / raw "
+                "normalisation, bursts) is enabled: use an integer segment length / stride or the batched Stream.run path"
+            )
         plan = self.plan(data.shape[1])
         feats: dict = {}
         if plan.pipe is not None:
@@ -237,7 +261,9 @@ class DataProcessor:
         from .._pipeline import IdentityNormPipeline
         from ..processing.normalization import GPU_NORM_METHODS
 
-        pre_pipe = plan.pipe if plan.pipe is not None else self._preprocess_only(data.shape[1])
+        # a pipeline of its own: the feature pipeline has already advanced its (stateful) raw normaliser for this window, and
+        # preprocessing the window a second time on it would advance it twice
+        pre_pipe = self._preprocess_only(data.shape[1])
         pre = pre_pipe.preprocess_window(data.astype(np.float64, copy=False))
         out: dict = {}
         for plugin in self._user_plugins.values():
@@ -248,7 +274,7 @@ class DataProcessor:
             if keys:
                 if self._user_norm is None:
                     self._user_norm = IdentityNormPipeline(len(keys), GPU_NORM_METHODS.index(ns.normalization_method),
-                                                           float(ns.clip or 0.0), self.norm_keep)
+                                                           float(ns.clip or 0.0), self.norm_keep, device=self.device)
                 normed = self._user_norm.step(np.array([float(out[k]) for k in keys]))
                 out.update(zip(keys, normed))
         nan_rows = np.isnan(data).any(axis=1)
@@ -285,9 +311,9 @@ class DataProcessor:
 
     # ------------------------------------------------------------------ batched offline entry
     def process_windows(self, data: np.ndarray, starts: np.ndarray, window_samples: int, with_normalizer: bool = True,
-                        upload: bool = True, out: np.ndarray | None = None):
+                        upload: bool = True, out: np.ndarray | None = None, nan_reinsert: bool = True):
         """All windows ``[starts[k], starts[k] + W)`` of a resident recording -> ``(columns, (n, F) float64)``."""
-        plan = self.plan(window_samples, with_normalizer)
+        plan = self.plan(window_samples, with_normalizer, nan_reinsert)
         if plan.pipe is None:
             return [], np.empty((len(starts), 0))
         if upload:

@@ -173,12 +173,14 @@ class Stream:
             # non-integer segment length / stride: two window lengths alternate.  Features are computed per length
             # without the normaliser, merged back in window order, and normalised in a second GPU pass.
             columns, matrix = None, None
+            if dp.rawnorm_cfg is not None:
+                raise NotImplementedError("raw normalisation needs a constant window length (stateful sample history)")
             for w in distinct:
                 sel = np.flatnonzero(lengths == w)
-                plan = dp.plan(int(w), with_normalizer=False)
+                plan = dp.plan(int(w), with_normalizer=False, nan_reinsert=False)
                 if plan.has_bursts:
                     raise NotImplementedError("burst features need a constant window length (stateful envelope history)")
-                cols, part = dp.process_windows(data, starts[sel], int(w), with_normalizer=False)
+                cols, part = dp.process_windows(data, starts[sel], int(w), with_normalizer=False, nan_reinsert=False)
                 if matrix is None:
                     columns, matrix = cols, np.empty((starts.size, len(cols)))
                 elif cols != columns:
@@ -186,6 +188,9 @@ class Stream:
                 matrix[sel] = part
             if dp.normalize and matrix.shape[1]:
                 matrix = self._normalize_matrix(columns, matrix)
+            # NaN re-insertion comes AFTER the normaliser (stream/data_processor.py:263-306): the history keeps the values
+            # computed from the nan_to_num'ed samples
+            self._reinsert_nan(data, starts, lengths, columns, matrix)
         self.batch_count = int(starts.size)
 
         t_idx, t_names = self._targets()
@@ -200,6 +205,17 @@ class Stream:
         if self.save_csv:
             writer.save_csv(frame)
         return frame if self.return_df else {}
+
+    def _reinsert_nan(self, data: np.ndarray, starts: np.ndarray, lengths: np.ndarray, columns: list[str], matrix: np.ndarray) -> None:
+        """NaN for every feature of a channel that has a NaN inside the window (bookkeeping on the NaN mask only)."""
+        names = self.data_processor.nan_names_by_raw_row
+        rows = [r for r in range(data.shape[0]) if names[r] is not None and np.isnan(data[r]).any()]
+        for r in rows:
+            cs = np.concatenate(([0], np.cumsum(np.isnan(data[r]))))
+            hit = (cs[starts + lengths] - cs[starts]) > 0
+            if hit.any():
+                cols = [i for i, k in enumerate(columns) if names[r] in k]
+                matrix[np.ix_(np.flatnonzero(hit), cols)] = np.nan
 
     def _normalize_matrix(self, columns: list[str], matrix: np.ndarray) -> np.ndarray:
         """Rolling normalisation of a finished (n_windows, F) matrix: columns travel as 'channels', windows as time."""

@@ -75,3 +75,33 @@ def rel_err(got, ref):
     ref = np.asarray(ref, dtype=np.float64)
     fin = np.isfinite(ref)
     return float(np.max(np.abs(got[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1e-300))) if fin.any() else 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------- tolerance rule
+# err = |got - ref| / max(|ref|, floor(column)):
+#   * log10 outputs (FFT / Welch / STFT band features, band-pass `activity` with the log transform) and rolling z-scores are
+#     differences of O(1) quantities: the ABSOLUTE error is the meaningful figure there -> floor 1;
+#   * every other feature (Hjorth, line length, raw, burst amplitudes / durations, sharp-wave features, linear band power) is
+#     judged PURELY RELATIVE, with a floor of 1e-12 that only matters for exact zeros.
+LOG_LIKE = ("_fft_", "_welch_", "_stft_", "_bandpass_activity_")
+# differences of samples / times whose operands are O(signal): cancellation makes the absolute error (relative to the operand
+# scale) the figure the arithmetic can guarantee
+DIFF_LIKE = ("_slope_ratio_", "_sharpness_", "_prominence_", "_raw")
+REL_FLOOR = 1e-12
+
+
+def column_floors(cols, normalized: bool = False, log_like=LOG_LIKE) -> np.ndarray:
+    if normalized:
+        return np.ones(len(cols))
+    return np.array([1.0 if any(t in k for t in log_like) else (1e-3 if (k.endswith("_raw") or any(t in k for t in DIFF_LIKE[:3])) else REL_FLOOR)
+                     for k in cols])
+
+
+def parity_err(cols, got, ref, normalized: bool = False) -> np.ndarray:
+    """Per-entry error of a (n, F) or (F,) result against the reference under the rule above (NaN / inf entries -> 0)."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    floors = column_floors(list(cols), normalized)
+    fin = np.isfinite(ref)
+    err = np.abs(np.where(fin, got - ref, 0.0)) / np.maximum(np.abs(np.where(fin, ref, 1.0)), floors)
+    return np.where(fin, err, 0.0)

@@ -7,20 +7,18 @@ import py_neuromodulation_b200 as nm
 from oracle import np_oracle as orc
 from py_neuromodulation_b200.stream.generator import window_grid
 from py_neuromodulation_b200.utils.channels import get_default_channels_from_data
-from tests.helpers import load_golden, uniform, neural_like
+from tests.helpers import load_golden, uniform, neural_like, parity_err
 
-TOL = 1e-8  # relative to max(1, |ref|); z-scored features amplify the 1e-16 rounding differences of their inputs
+TOL = 1e-8  # tests/helpers.py::parity_err: pure relative for linear features, absolute for log10 outputs and z-scores
 
 
-def check_matrix(cols, mat, keys_ref, ref, what, tol=TOL):
+def check_matrix(cols, mat, keys_ref, ref, what, tol=TOL, normalized=True):
     assert list(cols) == list(keys_ref), f"{what}: column order differs"
     assert mat.shape == ref.shape, f"{what}: {mat.shape} vs {ref.shape}"
     assert np.array_equal(np.isnan(mat), np.isnan(ref)), f"{what}: NaN pattern differs"
     inf = np.isinf(ref)
     assert np.array_equal(mat[inf], ref[inf]), f"{what}: inf pattern differs"
-    fin = np.isfinite(ref)
-    err = np.abs(mat - ref) / np.maximum(np.abs(ref), 1.0)
-    err[~fin] = 0
+    err = parity_err(cols, mat, ref, normalized)
     w, c = np.unravel_index(np.argmax(err), err.shape)
     assert err.max() <= tol, f"{what}: window {w} {cols[c]}: got {mat[w, c]!r} ref {ref[w, c]!r}"
     for j, k in enumerate(cols):
@@ -28,11 +26,11 @@ def check_matrix(cols, mat, keys_ref, ref, what, tol=TOL):
             pass  # checked exactly in the non-normalised cases below
 
 
-def run_dp(g, n_windows=None, with_norm=True):
+def run_dp(g, n_windows=None, with_norm=True, fused=None):
     x = g["x"].astype(np.float64)
     s = nm.NMSettings(**g["settings"])
     dp = nm.DataProcessor(sfreq=g["sfreq"], settings=s, channels=get_default_channels_from_data(x),
-                          line_noise=g.get("line_noise", 50), verbose=False)
+                          line_noise=g.get("line_noise", 50), verbose=False, fused=fused)
     starts, lengths, _ = window_grid(x.shape[1], g["sfreq"], s.sampling_rate_features_hz, s.segment_length_features_ms)
     if n_windows:
         starts = starts[:n_windows]
@@ -49,11 +47,53 @@ def test_window_processor_matches_reference_golden(backend, name, n_emu):
     g = load_golden(name)
     n = n_emu if backend == "emu" else None  # the thread emulator is slow: fewer windows on CPU, all on the GPU
     _, cols, mat, starts = run_dp(g, n)
-    check_matrix(cols, mat, g["keys"], g["vals"][: len(starts)], name)
+    normalized = bool(g["settings"]["postprocessing"]["feature_normalization"]) or "raw_normalization" in g["settings"]["preprocessing"]
+    check_matrix(cols, mat, g["keys"], g["vals"][: len(starts)], name, normalized=normalized)
     if name == "dataprocessor_realdata":  # not normalised: integer-valued burst outputs must be bit-exact
         for j, k in enumerate(cols):
             if k.endswith("_in_burst") or k.endswith("_duration_max"):
                 assert np.array_equal(mat[:, j], g["vals"][: len(starts), j]), k
+
+
+@pytest.mark.parametrize("name,n_emu", [("dataprocessor_c3_nan", None), ("dataprocessor_fast", None), ("dataprocessor_default", 12),
+                                        ("dataprocessor_realdata", 8)])
+def test_fused_window_kernel_matches_reference_golden(backend, name, n_emu):
+    """The same fixtures through the single persistent kernel (csrc/nm_fused.cuh: bulk-copy staged raw rows, re-reference folded
+    into the load, notch -> scan -> DFT band features -> band-pass bank on chip) -- and bit-identical to the staged kernels."""
+    g = load_golden(name)
+    n = n_emu if backend == "emu" else None
+    dp, cols, mat, starts = run_dp(g, n, fused=True)
+    # common average over < 5 channels is handed over as a sparse matrix (no group sum): not foldable into the load, so the
+    # staged kernels serve that pipeline whatever was asked for
+    assert ("nm_fused_kernel" in dp.plan(1000).pipe.describe_plan()) == (g["x"].shape[0] >= 5)
+    normalized = bool(g["settings"]["postprocessing"]["feature_normalization"])
+    check_matrix(cols, mat, g["keys"], g["vals"][: len(starts)], name + " (fused)", normalized=normalized)
+    _, _, mat0, _ = run_dp(g, n, fused=False)
+    assert np.array_equal(np.isnan(mat), np.isnan(mat0))
+    assert parity_err(cols, mat, mat0, normalized).max() < 1e-12
+
+
+def test_fused_window_kernel_float64_recording_and_odd_channels(backend):
+    """float64 uploads (what reference users pass), an odd channel count and window starts that are not multiples of 4 samples
+    (the bulk copies start at the 16-byte aligned sample below the window)."""
+    x = neural_like(21, 5, 2600)
+    s = nm.NMSettings.get_fast_compute()
+    s.features.raw_hjorth = True
+    s.features.linelength = True
+    s.features.return_raw = True
+    s.features.bandpass_filter = True
+    s.features.welch = True
+    s.postprocessing.feature_normalization = False
+    s.sampling_rate_features_hz = 7  # stride 142.86 samples: starts 0, 142, 285, 428, ...
+    for dtype in (np.float64, np.float32):
+        xs = x.astype(dtype)
+        dp = nm.DataProcessor(sfreq=1000, settings=s, channels=get_default_channels_from_data(x), line_noise=50, verbose=False, fused=True)
+        starts, lengths, _ = window_grid(x.shape[1], 1000, 7, 1000)
+        cols, mat = dp.process_windows(xs, starts, 1000)
+        assert "nm_fused_kernel" in dp.plan(1000).pipe.describe_plan()
+        ref_cols, ref = orc.run_offline(xs.astype(np.float64), 1000, s.model_dump())
+        assert ref_cols[: len(cols)] == cols
+        assert parity_err(cols, mat, ref[:, : len(cols)]).max() < 1e-9
 
 
 def test_streaming_process_equals_batch(backend):

@@ -10,7 +10,7 @@ import pytest
 
 import py_neuromodulation_b200 as nm
 from oracle import np_oracle as orc
-from tests.helpers import load_golden, uniform, neural_like
+from tests.helpers import load_golden, uniform, neural_like, parity_err
 
 TOL = 1e-9
 
@@ -32,10 +32,9 @@ def compare(keys_ref, vals_ref, got: dict, what: str, tol: float = TOL):
     assert np.array_equal(np.isnan(g), np.isnan(r)), f"{what}: NaN pattern"
     inf = np.isinf(r)
     assert np.array_equal(g[inf], r[inf]), f"{what}: inf pattern"
-    fin = np.isfinite(r)
-    err = np.abs(g[fin] - r[fin]) / np.maximum(np.abs(r[fin]), 1.0)
+    err = parity_err(keys_ref, g, r)  # pure relative for the linear features, absolute for log10 outputs (tests/helpers.py)
     worst = int(np.argmax(err)) if err.size else 0
-    assert err.max(initial=0) <= tol, f"{what}: {np.array(keys_ref)[fin][worst]} got {g[fin][worst]!r} ref {r[fin][worst]!r}"
+    assert err.max(initial=0) <= tol, f"{what}: {keys_ref[worst]} got {g[worst]!r} ref {r[worst]!r}"
     for i, k in enumerate(keys_ref):
         if k.endswith(EXACT_SUFFIX) or any(s in k for s in EXACT_SUBSTR):
             assert g[i] == r[i] or (np.isnan(g[i]) and np.isnan(r[i])), f"{what}: integer feature {k}: {g[i]} != {r[i]}"

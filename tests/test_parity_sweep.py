@@ -10,7 +10,7 @@ import py_neuromodulation_b200 as nm
 from oracle import np_oracle as orc
 from py_neuromodulation_b200.stream.generator import window_grid
 from py_neuromodulation_b200.utils.channels import get_default_channels_from_data
-from tests.helpers import neural_like
+from tests.helpers import neural_like, parity_err
 
 FEATURES = ["raw_hjorth", "return_raw", "bandpass_filter", "stft", "fft", "welch", "sharpwave_analysis", "bursts", "linelength"]
 
@@ -70,9 +70,11 @@ def test_random_configuration_matches_oracle(backend, seed):
     assert np.array_equal(np.isnan(mat), np.isnan(ref)), dp.plan(int(lengths[0])).pipe.describe_plan()
     fin = np.isfinite(ref)
     assert np.array_equal(mat[~fin & ~np.isnan(ref)], ref[~fin & ~np.isnan(ref)])
-    err = np.abs(mat[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0)
-    # z-scored features divide by a rolling std that can be tiny: 1e-7 there, 1e-9 otherwise (gate of the task: 1e-5)
-    tol = 1e-7 if (s.postprocessing.feature_normalization or "raw_normalization" in s.preprocessing) else 1e-9
+    # z-scored features divide by a rolling std that can be tiny: 1e-7 (absolute) there, 1e-9 PURELY RELATIVE for the linear
+    # features otherwise (tests/helpers.py::parity_err; gate of the task: 1e-5)
+    normalized = bool(s.postprocessing.feature_normalization or "raw_normalization" in s.preprocessing)
+    err = parity_err(cols, mat, ref, normalized)
+    tol = 1e-7 if normalized else 1e-9
     assert err.max() < tol, (float(err.max()), s.features.get_enabled(), s.preprocessing, dp.plan(int(lengths[0])).pipe.describe_plan())
 
 
@@ -153,6 +155,6 @@ def test_random_feature_options_match_oracle(backend, seed):
     assert np.array_equal(np.isnan(mat), np.isnan(ref))
     fin = np.isfinite(ref)
     assert np.array_equal(mat[~fin & ~np.isnan(ref)], ref[~fin & ~np.isnan(ref)])
-    err = np.abs(mat[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0)
+    err = parity_err(cols, mat, ref, bool(s.postprocessing.feature_normalization))
     tol = 1e-7 if s.postprocessing.feature_normalization else 1e-9
     assert err.max() < tol, (float(err.max()), cols[int(np.argmax(np.abs(np.where(fin, mat - ref, 0)).max(axis=0)))])

@@ -1,0 +1,115 @@
+"""Regression tests for the round-2 review findings on the host side of the window processor
+(stream/data_processor.py, stream/stream.py): stateful stages must advance once per window, NaN re-insertion maps a raw row
+to its OWN channel and follows the normaliser, and window-length changes are rejected where a per-length history would be wrong."""
+import numpy as np
+import pytest
+
+import py_neuromodulation_b200 as nm
+from oracle import np_oracle as orc
+from py_neuromodulation_b200.utils.channels import get_default_channels_from_data
+from tests.helpers import neural_like, parity_err, uniform
+
+
+class _ChannelMean:
+    def __init__(self, settings, ch_names, sfreq):
+        self.ch_names = ch_names
+
+    def calc_feature(self, data):
+        return {f"{ch}_chmean": float(np.mean(data[i])) for i, ch in enumerate(self.ch_names)}
+
+
+def _rawnorm_settings():
+    s = nm.NMSettings.get_fast_compute()
+    s.features.raw_hjorth = True
+    s.postprocessing.feature_normalization = False
+    s.preprocessing = ["notch_filter", "re_referencing", "raw_normalization"]
+    s.raw_normalization_settings.normalization_time_s = 2
+    return s
+
+
+def test_user_feature_does_not_advance_the_raw_normalizer_twice(backend):
+    """A custom Python feature next to the GPU features (reference features/feature_processor.py:52-53) must not change the
+    built-in features: both see a RawNormalizer (processing/normalization.py:44-51) that advanced ONCE per window."""
+    x = neural_like(3, 3, 2200)
+    wins = [x[:, 100 * k : 100 * k + 1000] for k in range(6)]
+
+    def run():
+        dp = nm.DataProcessor(sfreq=1000, settings=_rawnorm_settings(), channels=get_default_channels_from_data(x), line_noise=50, verbose=False)
+        return [dp.process(w) for w in wins]
+
+    plain = run()
+    nm.add_custom_feature("channel_mean", _ChannelMean)
+    try:
+        both = run()
+    finally:
+        nm.remove_custom_feature("channel_mean")
+    wo = orc.WindowOracle(1000, _rawnorm_settings().model_dump(), n_channels=3, line_noise=50)
+    for k, (a, b) in enumerate(zip(plain, both)):
+        assert [key for key in b if not key.endswith("_chmean")] == list(a)
+        for key, v in a.items():
+            assert b[key] == v, (k, key)  # identical pipeline state -> identical bits
+        pre = wo.preprocess(wins[k])  # the oracle's normaliser advances once per window as well
+        for i in range(3):
+            got = b[f"ch{i}_avgref_chmean"]
+            assert abs(got - pre[i].mean()) < 1e-9 * max(1.0, abs(pre[i].mean())), (k, i)
+
+
+def test_nan_reinsertion_maps_each_raw_row_to_its_own_channel(backend):
+    """stream/data_processor.py:253,297-306 with an unused / bad channel in front of used ones: a NaN in the unused row touches
+    nothing, a NaN in a used row turns exactly that channel's features into NaN."""
+    x = uniform(5, 3, 1000)
+    ch = get_default_channels_from_data(x)
+    ch.loc[1, "status"] = "bad"
+    ch.loc[1, "used"] = 0
+    s = nm.NMSettings.get_fast_compute()
+    s.postprocessing.feature_normalization = False
+    dp = nm.DataProcessor(sfreq=1000, settings=s, channels=ch, line_noise=50, verbose=False)
+    clean = dp.process(x)
+    assert not any(np.isnan(v) for v in clean.values())
+    names = list(ch["new_name"])
+    x1 = x.copy()
+    x1[1, 10:20] = np.nan  # unused row
+    f1 = dp.process(x1)
+    assert f1 == clean
+    x2 = x.copy()
+    x2[2, 500] = np.nan
+    f2 = dp.process(x2)
+    for k, v in f2.items():
+        assert np.isnan(v) == (names[2] in k), k
+
+
+def test_window_length_change_with_stateful_stage_is_rejected(backend, tmp_path):
+    x = uniform(6, 2, 2400)
+    s = nm.NMSettings.get_fast_compute()  # feature normalisation on
+    dp = nm.DataProcessor(sfreq=1000, settings=s, channels=get_default_channels_from_data(x), line_noise=50, verbose=False)
+    dp.process(x[:, :1000])
+    with pytest.raises(NotImplementedError):
+        dp.process(x[:, :1001])
+    # batched path: alternating window lengths (float sfreq) + RawNormalizer has no single sample history
+    s2 = _rawnorm_settings()
+    s2.segment_length_features_ms = 333
+    s2.fft_settings.windowlength_ms = 333
+    stream = nm.Stream(sfreq=1111.111, data=uniform(7, 2, 3000), sampling_rate_features_hz=3, settings=s2)
+    with pytest.raises(NotImplementedError):
+        stream.run(out_dir=tmp_path, experiment_name="x")
+
+
+def test_variable_window_length_normaliser_keeps_values_of_nan_windows(backend, tmp_path):
+    """Alternating window lengths (reference tests/test_timing.py:43-73) + rolling normalisation + a NaN span: the normaliser's
+    history holds the values computed from the nan_to_num'ed samples and NaN is re-inserted afterwards
+    (stream/data_processor.py:255-306), so the windows FOLLOWING the span match the reference as well."""
+    x = uniform(8, 3, 4000)
+    x[1, 1500:1510] = np.nan
+    s = nm.NMSettings.get_fast_compute()
+    s.segment_length_features_ms = 333
+    s.fft_settings.windowlength_ms = 333
+    s.preprocessing = ["notch_filter", "re_referencing"]
+    s.sampling_rate_features_hz = 3
+    stream = nm.Stream(sfreq=1111.111, data=x, sampling_rate_features_hz=3, settings=s)
+    df = stream.run(out_dir=tmp_path, experiment_name="floatfs_nan")
+    cols, ref = orc.run_offline(x, 1111.111, s.model_dump())
+    assert list(df.columns) == cols
+    mat = df.to_numpy()
+    assert np.array_equal(np.isnan(mat), np.isnan(ref))
+    assert np.isnan(ref).any() and not np.isnan(ref[-1]).any()
+    assert parity_err(cols, mat, ref, normalized=True).max() < 1e-7
