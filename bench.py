@@ -2,7 +2,8 @@
 
     python bench.py --gpus 1 --steps 10 --warmup 3            # this implementation on 1 B200
     torchrun ... bench.py --gpus N ...                        # channel-sharded over N B200s (weak scaling)
-    python bench.py --impl reference ...                      # the reference algorithm (oracle port) on the host cores
+    python bench.py --impl reference ...                      # the UNMODIFIED reference (baseline/_ref through the shim) on the host cores
+    python bench.py --config c4|c5|default [--gpus N]         # BASELINE.json configs[3..4] / the reference's default settings
 
 Workload = BASELINE.json configs[2] ("C3"): 256 ch x 300 s @ 1 kHz, default preprocessing (notch + common average),
 FFT + band-pass power + Hjorth + line length, 10 Hz feature rate -> 2 991 windows of 256 x 1000 samples per step.
@@ -262,166 +263,285 @@ def run_reference_arm(args) -> None:
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def c4_settings():
+    import py_neuromodulation_b200 as nm
+
+    s = nm.NMSettings.get_default().reset()
+    for f in ("fft", "welch", "stft", "bursts", "sharpwave_analysis"):
+        s.features[f] = True
+    return s
+
+
+def default_settings(sfreq: float = 1000.0):
+    import py_neuromodulation_b200 as nm
+
+    return nm.NMSettings.get_default()  # untouched: raw_resampling -> 1000 Hz, notch, common average, 7 plug-ins, z-score
+
+
+# name -> (channels, weak scaling?, sfreq, seconds, settings factory, description).  weak: `channels` per GPU (the recording grows
+# with N, common average over ALL channels); strong: `channels` in total, split N ways (BASELINE.json configs[3..4]).
+CONFIGS = {
+    "c3": (256, True, 1000.0, 300, c3_settings, "C3 (BASELINE.json configs[2]): notch+CAR, FFT+bandpass+Hjorth+linelength"),
+    "c4": (256, False, 1000.0, 300, c4_settings, "C4 (configs[3]): 256 ch split over the GPUs, notch+CAR, oscillatory (FFT+Welch+STFT) + bursts + sharp waves"),
+    "c5": (1024, False, 2000.0, 600, default_settings, "C5 (configs[4]): 1024 ch x 600 s @ 2 kHz split over the GPUs, untouched default settings (resample to 1 kHz, notch, CAR, "
+                                                       "raw Hjorth, raw, FFT, Welch, sharp waves, bursts, line length, z-score)"),
+    "default": (256, True, 1000.0, 300, default_settings, "reference default settings (all seven default plug-ins + feature normaliser)"),
+}
+
+
+def synth_rows(row0: int, n_rows: int, n_samples: int, seed: int, out: np.ndarray | None = None) -> np.ndarray:
+    """Rows [row0, row0 + n_rows) of the GLOBAL synthetic recording (uniform [0, 1) float32, README.rst:83).  Every global channel
+    has its own generator, so any rank -- and the parity check on rank 0 -- can reproduce any channel's first samples."""
+    if out is None:
+        out = np.empty((n_rows, n_samples), dtype=np.float32)
+    for r in range(n_rows):
+        np.random.default_rng([seed, row0 + r]).random(out=out[r], dtype=np.float32)
+    return out
+
+
 def run_gpu_arm(args) -> None:
     import py_neuromodulation_b200 as nm
     from py_neuromodulation_b200 import _lib
-    from py_neuromodulation_b200.parallel import ShardedRun, car_shard_factorization, shard_bounds
+    from py_neuromodulation_b200.parallel import NativeComm, ShardedRun, car_shard_factorization, merge_permutation, shard_bounds
     from py_neuromodulation_b200.stream.generator import window_grid
     from py_neuromodulation_b200.utils.channels import get_default_channels_from_data
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE {world}"
-
     lib = _lib.load()
-    n_samples = int(DURATION_S * SFREQ)
-    settings = c3_settings()
-    c_total = CH_PER_GPU * world
+    # collectives live in libnmb200 (nm_comm_*: NCCL, dlopen'ed); torch only supplies the TCP store of the rendezvous
+    comm = NativeComm.from_env(device=local_rank) if world > 1 else None
+
+    ch_cfg, weak, sfreq, dur, make_settings, label = CONFIGS[args.config]
+    settings = make_settings()
+    n_samples = int(dur * sfreq)
+    c_total = ch_cfg * world if weak else ch_cfg
     lo, hi = shard_bounds(c_total, world, rank)
-    x = pinned_array(lib, (CH_PER_GPU, n_samples), np.float32)
-    synth(CH_PER_GPU, n_samples, seed=rank, out=x)
+    n_loc = hi - lo
+    x = pinned_array(lib, (n_loc, n_samples), np.float32)
+    synth_rows(lo, n_loc, n_samples, seed=args.seed, out=x)
 
     channels = get_default_channels_from_data(np.empty((c_total, 1)))
     local_channels = channels.iloc[lo:hi].reset_index(drop=True)
     reref = None
     if world > 1:
         reref = car_shard_factorization(list(channels["type"]), list(channels["status"]), list(channels["rereference"]), lo, hi)
-    dp = nm.DataProcessor(sfreq=SFREQ, settings=settings, channels=local_channels, line_noise=LINE_NOISE, verbose=False,
+    dp = nm.DataProcessor(sfreq=sfreq, settings=settings, channels=local_channels, line_noise=LINE_NOISE, verbose=False,
                           device=local_rank, reref_factored=reref)
-    starts, lengths, _ = window_grid(n_samples, SFREQ, settings.sampling_rate_features_hz, settings.segment_length_features_ms)
+    starts, lengths, _ = window_grid(n_samples, sfreq, settings.sampling_rate_features_hz, settings.segment_length_features_ms)
     W = int(lengths[0])
     plan = dp.plan(W)
     pipe = plan.pipe
     n_win, F = int(starts.size), pipe.F
     out = pinned_array(lib, (n_win, F), np.float64)
-    sharded = ShardedRun(pipe, on_gpu=True) if world > 1 else None
+    sharded = ShardedRun(pipe, on_gpu=True, comm=comm) if world > 1 else None
+    stateful = dp.stateful
 
     def barrier() -> None:
-        if dist is not None:
-            dist.barrier()
         pipe.synchronize()
+        if comm is not None:
+            comm.barrier()
 
     def step_e2e() -> None:
         """Public call with HOST buffers: H2D of the recording, all kernels, D2H of the feature matrix."""
+        if stateful:
+            pipe.reset_state()
         if sharded is None:
             pipe.upload(x)
             pipe.run(starts, out=out)
         else:
-            sharded.upload(x)
+            sharded.upload(x)   # nm_upload_sharded_f32: sliced H2D, per-slice sums + ncclAllReduce inside the library
             sharded.run(starts)
             sharded.gather(n_win)
 
     def step_resident() -> None:
-        """Recording already in HBM: preprocessing + all window kernels, results stay on the device."""
-        pipe.prepare_resident()  # sharded recordings keep using their all-reduced group sums
+        """Recording already in HBM: window-independent preprocessing (N > 1: group sums + ncclAllReduce of the common average)
+        + all window kernels; results stay on the device."""
+        if stateful:
+            pipe.reset_state()
+        if sharded is None:
+            pipe.prepare_resident()
+        else:
+            _lib.check(lib.nm_prepare_resident_sharded(pipe._h, comm._h))
         pipe.run(starts, download=False)
 
     def timed(fn, n: int) -> float:
+        """CUDA events on the pipeline's stream around n steps (both sides behind a barrier + device sync); max over ranks."""
         barrier()
         t0 = time.perf_counter()
         pipe.timer_start()
         for _ in range(n):
             fn()
         ms = pipe.timer_stop()
-        barrier()
+        pipe.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
-        local = max(ms, 0.0) if sharded is None else wall  # sharded steps also spend time on torch's NCCL stream
-        if dist is not None:
-            import torch
-
-            t = torch.tensor([local], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            local = float(t.item())
-        return local
+        # e2e steps also spend time on the copy stream / in host-side waits after the last kernel: take the larger figure
+        local = max(ms, wall) if fn is step_e2e else ms
+        return comm.max(local) if comm is not None else local
 
     for _ in range(max(args.warmup, 3)):
         step_e2e()
     with ClockSampler(local_rank) as clocks:
         launches0 = pipe.kernel_launches
+        coll0 = comm.collectives if comm is not None else 0
         ms_res = timed(step_resident, args.steps)
         launches = pipe.kernel_launches - launches0
+        collectives = (comm.collectives - coll0) if comm is not None else 0
         ms_e2e = timed(step_e2e, args.steps)
-    units = n_win * world * args.steps
+    units = n_win * (world if weak else 1) * args.steps
     value = units / (ms_res * 1e-3)
     e2e_value = units / (ms_e2e * 1e-3)
 
-    # per-kernel profile of one more (untimed) step -> roofline of the dominant kernel
-    pipe.set_profiling(True)
-    step_resident()
-    pipe.synchronize()
-    prof = pipe.profile()
-    pipe.set_profiling(False)
-    dominant = max(prof, key=lambda k: prof[k][0])
-    dom_ms, dom_launches = prof[dominant]
-    feats_of = {"notch": 0, "scan": 4 * CH_PER_GPU, "spectral": 4 * CH_PER_GPU, "bandpower": 4 * CH_PER_GPU, "prep": 0,
-                "fused": F}  # the fused window kernel writes every feature column of C3
-    unit_bytes = CH_PER_GPU * W * 4 + feats_of.get(dominant, 0) * 4  # SURVEY.md 8(d): fp32 tile in + fp32 features out
-    bytes_per_launch = unit_bytes * n_win / max(dom_launches, 1)
-    achieved = bytes_per_launch / (dom_ms / max(dom_launches, 1) * 1e-3) / 1e9
-    peak, peak_src = measured_peak_gbs()
-    traffic, ncu_info = ncu_traffic(dominant, n_win / max(dom_launches, 1))
+    # ---- parity of the gathered matrix against the oracle on the first windows (after the timed region)
+    parity = None
+    n_chk = 4 if args.config != "c5" else 2
+    gathered = sharded.gather(n_win) if sharded is not None else out
+    if rank == 0 and not args.no_parity:
+        from oracle import np_oracle as orc
 
-    # optional float32 mode of the linear FIR families (same workload, resident timing; reported next to the float64 headline)
-    f32_info = None
+        t_chk = int(starts[n_chk - 1] + W)
+        xg = synth_rows(0, c_total, t_chk, seed=args.seed).astype(np.float64)
+        ref_cols, ref = orc.run_offline(xg, sfreq, settings.model_dump(), line_noise=LINE_NOISE, max_windows=n_chk)
+        if world > 1:
+            cols, perm = merge_permutation(settings, list(channels["new_name"]), dp.sfreq_raw, W, world)
+            got = np.asarray(gathered)[:n_chk][:, perm]
+        else:
+            cols, got = plan.columns, np.asarray(gathered)[:n_chk]
+        assert ref_cols[: len(cols)] == list(cols), "column order differs from the oracle"
+        ref = ref[:n_chk, : len(cols)]
+        fin = np.isfinite(ref)
+        err = float(np.max(np.abs(np.where(fin, got - ref, 0.0)) / np.maximum(np.abs(np.where(fin, ref, 1.0)), 1.0)))
+        same_special = bool(np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~fin & ~np.isnan(ref)], ref[~fin & ~np.isnan(ref)]))
+        parity = {"parity_checked": bool(err < 1e-5 and same_special), "windows": n_chk, "columns": len(cols), "max_err": err,
+                  "rule": "|got - oracle| <= 1e-5 * max(|oracle|, 1), NaN / inf patterns equal; oracle = oracle/np_oracle.py on the un-sharded recording"}
+
+    # ---- N = 1 extras: per-kernel profile -> roofline of the dominant kernel, float32 mode, zero-overlap run, Stream.run e2e
+    roof, f32_info, overlap_info, stream_info = None, None, None, None
     if world == 1:
-        dp32 = nm.DataProcessor(sfreq=SFREQ, settings=settings, channels=local_channels, line_noise=LINE_NOISE, verbose=False,
-                                device=local_rank, precision="f32")
-        pipe32 = dp32.plan(W).pipe
-        pipe32.upload(x)
-        for _ in range(3):
-            pipe32.run(starts, download=False)
-        pipe32.synchronize()
-        pipe32.timer_start()
-        for _ in range(args.steps):
-            pipe32.prepare_resident()
-            pipe32.run(starts, download=False)
-        ms32 = pipe32.timer_stop()
-        f32_info = {"value": n_win * args.steps / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32 / args.steps,
-                    "note": "nm_set_precision(1): float32 inside the notch / band-pass FFT convolutions, moments and outputs float64; "
-                            "parity gate 1e-5 relative (tests/test_parity_pipeline.py::test_float32_linear_mode_within_north_star_tolerance)"}
+        pipe.set_profiling(True)
+        step_resident()
+        pipe.synchronize()
+        prof = pipe.profile()
+        pipe.set_profiling(False)
+        dominant = max(prof, key=lambda k: prof[k][0])
+        dom_ms, dom_launches = prof[dominant]
+        per_ch = F // max(n_loc, 1)
+        feats_of = {"notch": 0, "scan": 4 * n_loc, "spectral": 4 * n_loc, "bandpower": 4 * n_loc, "prep": 0, "fused": F}
+        unit_bytes = n_loc * W * 4 + feats_of.get(dominant, per_ch * n_loc) * 4  # SURVEY.md 8(d): fp32 tile in + fp32 features out
+        bytes_per_launch = unit_bytes * n_win / max(dom_launches, 1)
+        achieved = bytes_per_launch / (dom_ms / max(dom_launches, 1) * 1e-3) / 1e9
+        peak, peak_src = measured_peak_gbs()
+        traffic, ncu_info = ncu_traffic(dominant, n_win / max(dom_launches, 1))
+        step_bytes_windowed = n_win * (n_loc * W * 4 + F * 4)
+        step_bytes_unique = n_loc * n_samples * 4 + n_win * F * 4
+        roof = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch, "ncu": ncu_info, "peak_source": peak_src,
+                "launches_per_step": int(dom_launches), "ms_per_launch": dom_ms / max(dom_launches, 1),
+                "profile_ms_per_step": {k: round(v[0], 3) for k, v in prof.items()},
+                "whole_step": {"windowed_bytes": step_bytes_windowed, "unique_bytes": step_bytes_unique,
+                               "windowed_gbs": step_bytes_windowed / (ms_res / args.steps * 1e-3) / 1e9,
+                               "unique_gbs": step_bytes_unique / (ms_res / args.steps * 1e-3) / 1e9,
+                               "frac_of_measured_peak": step_bytes_windowed / (ms_res / args.steps * 1e-3) / 1e9 / peak,
+                               "frac_of_nominal_8000": step_bytes_windowed / (ms_res / args.steps * 1e-3) / 1e9 / 8000.0},
+                "note": "FFT-convolution kernels are FP64-pipe / shared-memory bound, not HBM bound (DESIGN.md section 5): "
+                        "the honest utilisation figure is ncu.fp64_pipe_pct; windows overlap 90 %, so windowed bytes exceed unique bytes 10x"}
+        if args.config == "c3":
+            # zero-overlap variant (BASELINE.md section 3): feature rate 1 Hz -> stride = W, windowed bytes == unique bytes
+            s1 = make_settings()
+            s1.sampling_rate_features_hz = 1
+            dp1 = nm.DataProcessor(sfreq=sfreq, settings=s1, channels=local_channels, line_noise=LINE_NOISE, verbose=False, device=local_rank)
+            st1, _, _ = window_grid(n_samples, sfreq, 1, s1.segment_length_features_ms)
+            pipe1 = dp1.plan(W).pipe
+            pipe1.upload(x)
+            for _ in range(3):
+                pipe1.run(st1, download=False)
+            pipe1.synchronize()
+            pipe1.timer_start()
+            for _ in range(args.steps):
+                pipe1.prepare_resident()
+                pipe1.run(st1, download=False)
+            ms1 = pipe1.timer_stop() / args.steps
+            b1 = int(st1.size) * (n_loc * W * 4 + F * 4)
+            overlap_info = {"windows": int(st1.size), "ms_per_step": ms1, "value": st1.size / (ms1 * 1e-3), "unit": UNIT,
+                            "gbs": b1 / (ms1 * 1e-3) / 1e9, "note": "feature rate 1 Hz: stride == window, no sample is read twice"}
+            pipe1.close()
+            # optional float32 mode of the linear FIR families (same workload, resident timing; reported next to the float64 headline)
+            dp32 = nm.DataProcessor(sfreq=sfreq, settings=settings, channels=local_channels, line_noise=LINE_NOISE, verbose=False,
+                                    device=local_rank, precision="f32")
+            pipe32 = dp32.plan(W).pipe
+            pipe32.upload(x)
+            for _ in range(3):
+                pipe32.run(starts, download=False)
+            pipe32.synchronize()
+            pipe32.timer_start()
+            for _ in range(args.steps):
+                pipe32.prepare_resident()
+                pipe32.run(starts, download=False)
+            ms32 = pipe32.timer_stop()
+            f32_info = {"value": n_win * args.steps / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32 / args.steps,
+                        "note": "nm_set_precision(1): float32 inside the notch / band-pass FFT convolutions, moments and outputs float64; "
+                                "parity gate 1e-5 relative (tests/test_parity_pipeline.py::test_float32_linear_mode_within_north_star_tolerance)"}
+            pipe32.close()
+        # the call a reference user makes: nm.Stream(...).run(data) -> DataFrame (window grid, upload, kernels, download, frame)
+        import tempfile
+
+        reps = 3
+        stream = nm.Stream(sfreq=sfreq, data=x, settings=settings, line_noise=LINE_NOISE, verbose=False)
+        with tempfile.TemporaryDirectory() as td:
+            stream.run(out_dir=td, experiment_name="bench", save_csv=False)  # builds the processor / pipeline once more (warm-up)
+            ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                df = stream.run(out_dir=td, experiment_name="bench", save_csv=False)
+                ts.append(time.perf_counter() - t0)
+        t_med = float(np.median(ts))
+        stream_info = {"value": n_win / t_med, "unit": UNIT, "ms_per_step": 1e3 * t_med, "frame_shape": list(df.shape),
+                       "note": "nm.Stream.run(data, save_csv=False) wall clock, median of 3: new DataProcessor + pipeline per call (like the "
+                               "reference), H2D, kernels, D2H, pandas DataFrame; CSV writing excluded"}
 
     if rank == 0:
+        tile = f"{n_loc}x{W}"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"C3 (BASELINE.json configs[2]): {CH_PER_GPU}ch/GPU x {DURATION_S}s @ {int(SFREQ)}Hz, notch+CAR, "
-                            f"FFT+bandpass+Hjorth+linelength, {n_win} windows of {CH_PER_GPU}x{W} per GPU per step, F={F}/GPU",
+                "workload": f"{label}; {c_total} ch x {dur} s @ {int(sfreq)} Hz -> {n_win} windows per step, {n_loc} ch per GPU "
+                            f"(tile {tile} per GPU), F = {F} per GPU",
+                "name": args.config,
+                "unit_definition": f"one window of all {c_total} channels with all its features" if not weak else
+                                   "one 256 ch x 1000 samp window with all its features (per GPU; the recording grows with N)",
                 "sharding": "channels" if world > 1 else "none",
-                "l2": "inputs larger than L2 (raw 307 MB f32 + re-referenced 614 MB f64 per GPU)",
-                "timing": "CUDA events on the pipeline stream (N=1); barrier + device sync wall clock, max over ranks (N>1)",
+                "collectives": "libnmb200 nm_comm (NCCL): per-step ncclAllReduce of the common-average sums inside `value`; e2e adds the per-slice "
+                               "all-reduce of the pipelined upload; results meet in one page-locked shared host matrix (no collective)" if world > 1 else "none",
+                "l2": f"inputs larger than L2 (raw {x.nbytes / 1e6:.0f} MB f32 per GPU)",
+                "timing": "CUDA events on the pipeline stream, barrier + device sync on both sides, max over ranks (nm_comm_allreduce_max)",
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes * world + starts.nbytes * world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((x.nbytes + starts.nbytes) * world),
                     "d2h_bytes_per_step": int(out.nbytes * world), "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch, "ncu": ncu_info, "peak_source": peak_src, "launches_per_step": int(dom_launches),
-                         "ms_per_launch": dom_ms / max(dom_launches, 1),
-                         "profile_ms_per_step": {k: round(v[0], 3) for k, v in prof.items()},
-                         "note": "FFT-convolution kernels are FP64-pipe / shared-memory bound, not HBM bound (DESIGN.md section 5): "
-                                 "the honest utilisation figure is ncu.fp64_pipe_pct; traffic exceeds the fp32 algorithmic bytes because "
-                                 "the notched rows travel as float64"},
+            "gpu_launches": int(launches), "nccl_collectives_in_value": int(collectives),
             "clocks": clocks.summary(),
         }
+        if parity is not None:
+            line["parity"] = parity
+            line["parity_checked"] = parity["parity_checked"]
+        if roof is not None:
+            line["roofline"] = roof
         if f32_info is not None:
             line["f32_linear_mode"] = f32_info
-        if world == 1 and not args.no_cpu_baseline:
+        if overlap_info is not None:
+            line["zero_overlap"] = overlap_info
+        if stream_info is not None:
+            line["e2e_stream"] = stream_info
+        if world == 1 and not args.no_cpu_baseline and args.config == "c3":
             line["cpu_baseline"] = cpu_baseline_single()
         print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        if sharded is not None:
-            sharded.close()
-        dist.destroy_process_group()
+    if comm is not None:
+        comm.barrier()
+        sharded.close()
+        comm.close()
 
 
 def main() -> None:
@@ -430,7 +550,10 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

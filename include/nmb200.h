@@ -218,6 +218,29 @@ int nm_upload_slice_sums(nm_pipeline* p, int slice);
 int nm_upload_slice_reduced(nm_pipeline* p, int slice);
 int nm_upload_finish(nm_pipeline* p);
 
+/* ---- collectives inside the library (csrc/nm_comm.cuh): NCCL over NVLink / NVSwitch, one process per GPU, no torch.
+ * The reference has no multi-GPU path; these entry points are what a binding adds for SURVEY.md section 8e (channel shards,
+ * one all-reduce of the common-average sums, one gather of the result blocks).  NCCL is dlopen'ed ("libnccl.so.2"). */
+typedef struct nm_comm nm_comm;
+/* rank 0 creates the 128-byte NCCL unique id; the application hands it to every rank (MPI, file, TCP store, ...) */
+int nm_comm_unique_id(unsigned char* id128);
+int nm_comm_create(const unsigned char* id128, int rank, int world, int device, nm_comm** out);
+void nm_comm_destroy(nm_comm* c);
+int nm_comm_rank(const nm_comm* c);
+int nm_comm_size(const nm_comm* c);
+long long nm_comm_collectives(const nm_comm* c);        /* collective launches issued so far (grouped calls count once) */
+int nm_comm_barrier(nm_comm* c);
+int nm_comm_allreduce_max(nm_comm* c, double* value);   /* in place, host value: "time on the device, max over ranks" */
+/* nm_upload_begin_f32 + per slice {local group sums, ncclAllReduce(sum) of that slice on the reduction stream} + nm_upload_finish:
+ * returns without blocking the host; nm_run_windows waits per slice on an event.  The pipeline's re-reference must have been set
+ * from the GLOBAL channel table (nm_set_reref with group coefficients -1/(n_global - 1)). */
+int nm_upload_sharded_f32(nm_pipeline* p, nm_comm* c, const float* data, long long n_samples, long long pitch);
+/* result blocks of all ranks -> rank 0: out_host (n_windows x sum(widths)), rank-major column blocks; widths[r] = feature columns
+ * of rank r (uneven shards allowed).  Other ranks pass out_host = NULL.  Blocking on rank 0 (returns after the D2H). */
+int nm_gather_results(nm_pipeline* p, nm_comm* c, int n_windows, const int* widths, double* out_host);
+/* sharded counterpart of nm_prepare_resident: local group sums of the resident shard, ncclAllReduce, window-independent preprocessing */
+int nm_prepare_resident_sharded(nm_pipeline* p, nm_comm* c);
+
 #ifdef __cplusplus
 }
 #endif

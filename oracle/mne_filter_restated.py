@@ -282,3 +282,64 @@ def _overlap_add_filter(x, h, n_fft=None, phase="zero", picks=None, n_jobs=1, co
             acc[lo:hi] += prod[p0 : p0 + hi - lo]
         out[r] = acc[:w]
     return out[0] if one_d else out
+
+
+# ----------------------------------------------------------------------------- resample (processing/resample.py:58-60)
+def _smart_pad2(x: np.ndarray, npads, pad: str = "reflect_limited") -> np.ndarray:
+    """MNE ``_smart_pad`` with separate left / right pad counts (odd reflection about the end points, zero fill beyond)."""
+    n0, n1 = int(npads[0]), int(npads[1])
+    if n0 == 0 and n1 == 0:
+        return x
+    if pad != "reflect_limited":
+        raise NotImplementedError(pad)
+    lz = np.zeros(max(n0 - len(x) + 1, 0), dtype=x.dtype)
+    rz = np.zeros(max(n1 - len(x) + 1, 0), dtype=x.dtype)
+    return np.concatenate([lz, 2 * x[0] - x[n0:0:-1], x, 2 * x[-1] - x[-2 : -n1 - 2 : -1], rz])
+
+
+def resample(x, up=1.0, down=1.0, *, axis=-1, window="auto", n_jobs=None, pad="auto", npad="auto", method="fft", verbose=None):
+    """Restated ``mne.filter.resample`` for the one call pattern of the reference -- ``resample(x.astype(float64), up=ratio,
+    down=1.0)`` with every other argument at its default (method="fft", npad="auto", pad="auto" -> "reflect_limited",
+    window="auto" -> boxcar).  Written from MNE's documented behaviour (``_resamp_ratio_len`` / ``_resample_fft`` /
+    ``_fft_resample``); MNE itself is not installed here, so this part is parity-unpinned like the FIR design above.
+
+      ratio = up / down;  final_len = max(round(ratio * n), 1)
+      npad "auto": min_add = min(n // 8, 100) * 2; pad to the next power of two >= n + min_add, split (floor, ceil)
+      new_len = max(round(ratio * orig_len), 1); to_remove = [round(ratio * npad0), new_len - final_len - that]
+      X = rfft(padded); if min(new_len, orig_len) is even: X[nyq] *= 2 (shorter) or 0.5 (longer)
+      y = irfft(X * (new_len / orig_len), new_len)[to_remove0 : new_len - to_remove1]
+    """
+    from scipy.fft import irfft, rfft
+
+    if method != "fft" or axis != -1 or not (isinstance(npad, str) and npad == "auto"):
+        raise NotImplementedError("only the reference's call pattern is restated")
+    x = np.asarray(x)
+    if x.dtype != np.float64:
+        raise TypeError("Arrays passed for resampling must have a dtype of np.float64")
+    ratio = float(up) / down
+    n = x.shape[-1]
+    final_len = max(int(round(ratio * n)), 1)
+    flat = x.reshape(-1, n)
+    min_add = min(n // 8, 100) * 2
+    npad_tot = 2 ** int(np.ceil(np.log2(n + min_add))) - n
+    n0, extra = divmod(npad_tot, 2)
+    npads = np.array([n0, n0 + extra], int)
+    orig_len = n + int(npads.sum())
+    new_len = max(int(round(ratio * orig_len)), 1)
+    rem0 = int(round(ratio * npads[0]))
+    rem1 = new_len - final_len - rem0
+    shorter = new_len < orig_len
+    use_len = new_len if shorter else orig_len
+    # boxcar window, folded onto the rfft bins and scaled (MNE: W = ifftshift(boxcar) * new_len / orig_len)
+    scale = float(new_len) / float(orig_len)
+    out = np.zeros((flat.shape[0], new_len - rem0 - rem1), dtype=np.float64)
+    for i, row in enumerate(flat):
+        xp = _smart_pad2(row, npads)
+        xf = rfft(xp)
+        if use_len % 2 == 0:
+            nyq = use_len // 2
+            xf[nyq : nyq + 1] *= 2 if shorter else 0.5
+        xf *= scale
+        y = irfft(xf, new_len)
+        out[i] = y[rem0 : y.shape[0] - rem1] if (rem0 > 0 or rem1 > 0) else y
+    return out.reshape(x.shape[:-1] + (out.shape[-1],))

@@ -729,6 +729,7 @@ class WindowOracle:
         self.ref = None
         self.prefilters = None
         self.rawnorm = None
+        self.resample_up = None
         self.pre = []
         for p in pre:
             if p == "preprocessing_filter":
@@ -744,8 +745,12 @@ class WindowOracle:
                 self.ref = reref_matrix(self.ch)
                 self.pre.append(p)
             elif p == "raw_resampling":
-                if settings["raw_resampling_settings"]["resample_freq_hz"] != self.sfreq:
-                    raise NotImplementedError("resampling with ratio != 1 is a 'next' row (SURVEY.md section 8f-2)")
+                # processing/resample.py:28-60: ratio 1 is the identity; everything downstream keeps the ORIGINAL sfreq
+                # (stream/data_processor.py:55,77-81 never update sfreq_raw) -- reproduced, not repaired
+                ratio = float(settings["raw_resampling_settings"]["resample_freq_hz"] / self.sfreq)
+                if ratio != 1.0:
+                    self.resample_up = ratio
+                    self.pre.append(p)
             else:
                 raise NotImplementedError(f"unknown preprocessor {p}")
         self.plugins = []
@@ -781,6 +786,10 @@ class WindowOracle:
                 d = apply_notch(d, self.notch)
             elif p == "raw_normalization":
                 d = self.rawnorm.process(d)
+            elif p == "raw_resampling":
+                from oracle.mne_filter_restated import resample
+
+                d = resample(d.astype(np.float64), up=self.resample_up, down=1.0)
             elif self.ref is not None:
                 d = self.ref @ d
         return d

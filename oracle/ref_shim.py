@@ -65,6 +65,7 @@ def _install_mne_stub() -> None:
     filt = types.ModuleType("mne.filter")
     filt.create_filter = restated.create_filter  # type: ignore[attr-defined]
     filt._overlap_add_filter = restated._overlap_add_filter  # type: ignore[attr-defined]
+    filt.resample = restated.resample  # type: ignore[attr-defined]
     mne.filter = filt  # type: ignore[attr-defined]
     sys.modules["mne"] = mne
     sys.modules["mne.filter"] = filt

@@ -97,6 +97,17 @@ _SIGNATURES = {
     "nm_upload_slice_sums": (C.c_int, [C.c_void_p, C.c_int]),
     "nm_upload_slice_reduced": (C.c_int, [C.c_void_p, C.c_int]),
     "nm_upload_finish": (C.c_int, [C.c_void_p]),
+    "nm_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "nm_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "nm_comm_destroy": (None, [C.c_void_p]),
+    "nm_comm_rank": (C.c_int, [C.c_void_p]),
+    "nm_comm_size": (C.c_int, [C.c_void_p]),
+    "nm_comm_collectives": (C.c_longlong, [C.c_void_p]),
+    "nm_comm_barrier": (C.c_int, [C.c_void_p]),
+    "nm_comm_allreduce_max": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "nm_upload_sharded_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong]),
+    "nm_gather_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
+    "nm_prepare_resident_sharded": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

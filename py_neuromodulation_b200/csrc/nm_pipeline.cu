@@ -1698,3 +1698,4 @@ extern "C" int nm_fir_apply(int device, const double* taps, int n_filters, int n
 // ------------------------------------------------------------------------------- sharded upload
 // (implemented with the multi-GPU path; see nm_multi.cuh)
 #include "nm_multi.cuh"
+#include "nm_comm.cuh"

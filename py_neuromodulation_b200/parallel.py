@@ -103,13 +103,94 @@ def wrap_buffer(ptr: int, n: int, on_gpu: bool):
     return torch.from_numpy(arr)
 
 
-class ShardedRun:
-    """One rank's part of a channel-sharded offline run around an already-built local :class:`Pipeline`."""
+class NativeComm:
+    """NCCL communicator owned by libnmb200 (``nm_comm_*``, csrc/nm_comm.cuh): the collectives of the sharded path run inside the
+    library, on its own streams -- no torch on the data path.
 
-    def __init__(self, pipe, on_gpu: bool = True, shared_host: bool = True) -> None:
+    ``NativeComm.from_env()`` is the rendezvous for ``torchrun``-style launches (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR /
+    MASTER_PORT): rank 0 creates the 128-byte unique id and publishes it through a ``torch.distributed.TCPStore`` -- plumbing
+    only.  Any other channel (MPI, a file) works with ``NativeComm(id_bytes, rank, world, device)``."""
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int) -> None:
+        self.lib = _lib.load()
+        self.rank, self.world, self.device = int(rank), int(world), int(device)
+        h = C.c_void_p()
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        _lib.check(self.lib.nm_comm_create(buf, self.rank, self.world, self.device, C.byref(h)))
+        self._h = h
+        self.store = None
+
+    @staticmethod
+    def new_unique_id() -> bytes:
+        lib = _lib.load()
+        buf = (C.c_ubyte * 128)()
+        _lib.check(lib.nm_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_env(cls, device: int | None = None, port_offset: int = 17) -> "NativeComm":
+        import os
+        from datetime import timedelta
+
+        from torch.distributed import TCPStore
+
+        rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        device = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
+        host = os.environ.get("MASTER_ADDR", "127.0.0.1")
+        port = int(os.environ.get("MASTER_PORT", "29500")) + port_offset  # next to (not on) torchrun's own store
+        store = TCPStore(host, port, world, is_master=(rank == 0), timeout=timedelta(seconds=120), wait_for_workers=False)
+        if rank == 0:
+            store.set("nmb200_nccl_id", cls.new_unique_id())
+        uid = bytes(store.get("nmb200_nccl_id"))
+        comm = cls(uid, rank, world, device)
+        comm.store = store  # keeps the rendezvous alive; also carries small host-side objects (column widths, shm names)
+        return comm
+
+    def barrier(self) -> None:
+        _lib.check(self.lib.nm_comm_barrier(self._h))
+
+    def max(self, value: float) -> float:
+        v = C.c_double(float(value))
+        _lib.check(self.lib.nm_comm_allreduce_max(self._h, C.byref(v)))
+        return float(v.value)
+
+    @property
+    def collectives(self) -> int:
+        return int(self.lib.nm_comm_collectives(self._h))
+
+    def exchange(self, key: str, value) -> list:
+        """All-gather of a small picklable host object through the rendezvous store (set-up time only)."""
+        import pickle
+
+        assert self.store is not None, "NativeComm.exchange needs the rendezvous store (from_env)"
+        self._xchg = getattr(self, "_xchg", 0) + 1
+        tag = f"{key}/{self._xchg}"
+        self.store.set(f"{tag}/{self.rank}", pickle.dumps(value))
+        return [pickle.loads(self.store.get(f"{tag}/{r}")) for r in range(self.world)]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.nm_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ShardedRun:
+    """One rank's part of a channel-sharded offline run around an already-built local :class:`Pipeline`.
+
+    ``comm=None``: collectives through ``torch.distributed`` (gloo in the CPU tests, NCCL on GPUs), driven slice by slice from the
+    host.  ``comm=NativeComm``: the library issues them itself (``nm_upload_sharded_f32`` / ``nm_gather_results``)."""
+
+    def __init__(self, pipe, on_gpu: bool = True, shared_host: bool = True, comm: "NativeComm | None" = None) -> None:
         self.pipe = pipe
         self.on_gpu = on_gpu
         self.shared_host = shared_host
+        self.comm = comm
         self._shm = None
         self._shm_key = None
 
@@ -124,16 +205,22 @@ class ShardedRun:
         if self._shm_key == key:
             return self._shm_view, self._shm_col0
         self._release_shared()
-        world, rank = dist.get_world_size(), dist.get_rank()
-        widths = [None] * world
-        dist.all_gather_object(widths, int(self.pipe.F))
+        world, rank = self._world_rank()
+        if self.comm is not None:
+            widths = self.comm.exchange("widths", int(self.pipe.F))
+        else:
+            widths = [None] * world
+            dist.all_gather_object(widths, int(self.pipe.F))
         total = int(sum(widths))
         n_bytes = n_windows * total * 8
         name = [None]
         if rank == 0:
             shm = shared_memory.SharedMemory(create=True, size=max(n_bytes, 8))
             name[0] = shm.name
-        dist.broadcast_object_list(name, src=0)
+        if self.comm is not None:
+            name[0] = self.comm.exchange("shm", name[0])[0]
+        else:
+            dist.broadcast_object_list(name, src=0)
         if rank != 0:
             shm = shared_memory.SharedMemory(name=name[0])
             try:  # attaching registers the segment with this process's resource tracker too (CPython < 3.13): only the owner unlinks
@@ -150,7 +237,8 @@ class ShardedRun:
         self._shm_col0 = int(sum(widths[:rank]))
         self._shm_key = key
         self._shm_owner = rank == 0
-        dist.barrier()
+        self._widths_all = [int(w) for w in widths]
+        self._barrier()
         return view, self._shm_col0
 
     def _release_shared(self) -> None:
@@ -181,10 +269,23 @@ class ShardedRun:
         except Exception:
             pass
 
-    def _use_shared(self) -> bool:
+    def _world_rank(self) -> tuple[int, int]:
+        if self.comm is not None:
+            return self.comm.world, self.comm.rank
         import torch.distributed as dist
 
-        return self.shared_host and dist.is_initialized() and dist.get_world_size() > 1
+        return (dist.get_world_size(), dist.get_rank()) if dist.is_initialized() else (1, 0)
+
+    def _barrier(self) -> None:
+        if self.comm is not None:
+            self.comm.barrier()
+        else:
+            import torch.distributed as dist
+
+            dist.barrier()
+
+    def _use_shared(self) -> bool:
+        return self.shared_host and self._world_rank()[0] > 1
 
     def upload(self, data_f32: np.ndarray) -> None:
         """Asynchronous, sliced: H2D of the local shard, per-slice group sums, per-slice all-reduce on the library's side stream.
@@ -197,6 +298,10 @@ class ShardedRun:
 
         p = self.pipe
         a = np.ascontiguousarray(data_f32, dtype=np.float32)
+        if self.comm is not None:  # sums + ncclAllReduce per slice are enqueued by the library itself
+            _lib.check(p.lib.nm_upload_sharded_f32(p._h, self.comm._h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[1]))
+            p._keep_data = a
+            return
         _lib.check(p.lib.nm_upload_begin_f32(p._h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[1]))
         p._keep_data = a
         n_slices, slice_len, n_groups, pitch = C.c_int(), C.c_longlong(), C.c_int(), C.c_longlong()
@@ -246,8 +351,25 @@ class ShardedRun:
         import torch.distributed as dist
 
         if self._use_shared() and self._shm_key == (n_windows, self.pipe.F):
-            dist.barrier()  # every rank has returned from run(): its block is in the shared matrix
-            return self._shm_view if dist.get_rank() == 0 else None
+            self._barrier()  # every rank has returned from run(): its block is in the shared matrix
+            return self._shm_view if self._world_rank()[1] == 0 else None
+        if self.comm is not None:  # one grouped ncclSend / ncclRecv gather inside the library
+            if getattr(self, "_native_key", None) != (n_windows, self.pipe.F):
+                self._widths_native = [int(w) for w in self.comm.exchange("gw", int(self.pipe.F))]
+                self._native_host = None
+                if self.comm.rank == 0:
+                    from . import _lib as L
+
+                    n_bytes = n_windows * sum(self._widths_native) * 8
+                    ptr = C.c_void_p()
+                    L.check(self.pipe.lib.nm_host_alloc(C.byref(ptr), n_bytes))
+                    buf = (C.c_char * n_bytes).from_address(ptr.value)
+                    self._native_host = np.frombuffer(buf, dtype=np.float64).reshape(n_windows, sum(self._widths_native))
+                self._native_key = (n_windows, self.pipe.F)
+            w = (C.c_int * self.comm.world)(*self._widths_native)
+            dst = self._native_host.ctypes.data_as(C.c_void_p) if self.comm.rank == 0 else None
+            _lib.check(self.pipe.lib.nm_gather_results(self.pipe._h, self.comm._h, int(n_windows), w, dst))
+            return self._native_host
         ptr, rows, cols = self.pipe.result_device_ptr()
         local = wrap_buffer(ptr, rows * cols, self.on_gpu)[: n_windows * cols].view(n_windows, cols)
         if not (dist.is_initialized() and dist.get_world_size() > 1):
