@@ -405,7 +405,7 @@ def run_gpu_arm(args) -> None:
         xg = synth_rows(0, c_total, t_chk, seed=args.seed).astype(np.float64)
         ref_cols, ref = orc.run_offline(xg, sfreq, settings.model_dump(), line_noise=LINE_NOISE, max_windows=n_chk)
         if world > 1:
-            cols, perm = merge_permutation(settings, list(channels["new_name"]), dp.sfreq_raw, W, world)
+            cols, perm = merge_permutation(settings, list(channels["new_name"]), dp.sfreq_raw, dp.feature_window(W), world)
             got = np.asarray(gathered)[:n_chk][:, perm]
         else:
             cols, got = plan.columns, np.asarray(gathered)[:n_chk]

@@ -82,6 +82,14 @@ int nm_set_raw_normalizer(nm_pipeline* p, int method, double clip, int n_keep, i
  * the notch. */
 int nm_add_prefilter(nm_pipeline* p, const double* taps, int n_taps);
 
+/* Resampler (processing/resample.py:28-60, mne.filter.resample(x, up = resample_freq_hz / sfreq, down = 1)): FFT resampling of
+ * a window row is a linear map; `op` is that map as a dense row-major (window_samples x n_in) float64 matrix designed by the
+ * host (processing/resample.py::resample_operator here).  Windows are then cut from the recording, pre-filtered and notched at
+ * n_in samples and every row is mapped to the pipeline's `window_samples` before re-referenced rows reach the raw normaliser and
+ * the feature families (the reference's fixed preprocessor order).  Call before nm_add_prefilter / nm_set_notch.  Everything
+ * downstream keeps the ORIGINAL sampling rate, like the reference (stream/data_processor.py:55,77-81). */
+int nm_set_resampler(nm_pipeline* p, int n_in, const double* op);
+
 /* NaN re-insertion (stream/data_processor.py:297-306): columns [col_ptr[r], col_ptr[r+1]) of `cols`
  * become NaN in every window where raw row r contains a NaN */
 int nm_set_nan_columns(nm_pipeline* p, const int* col_ptr, const int* cols);

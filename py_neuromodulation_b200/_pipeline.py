@@ -49,6 +49,7 @@ class Pipeline:
         if len(self.col_of) != len(self.columns):
             raise ValueError("duplicate feature names in the column list")
         self.n_raw_rows, self.n_ch, self.W, self.F = int(n_raw_rows), int(n_ch), int(window_samples), len(self.columns)
+        self.W_in = self.W  # raw samples per window (differs from W behind a resampler)
         handle = C.c_void_p()
         _lib.check(self.lib.nm_pipeline_create(int(device), self.n_raw_rows, self.n_ch, self.W, self.F, C.byref(handle)))
         self._h = handle
@@ -110,6 +111,15 @@ class Pipeline:
         a_ptr, a_col, a_val = _i32(sp_ptr), _i32(sp_col), _f64(sp_val)
         _lib.check(self.lib.nm_set_reref(self._h, int(n_groups), _ptr(a_go, C.c_int), _ptr(a_gc, C.c_double),
                                          _ptr(a_ptr, C.c_int), _ptr(a_col, C.c_int), _ptr(a_val, C.c_double)))
+
+    def set_resampler(self, operator: np.ndarray) -> None:
+        """``raw_resampling``: dense ``(window_samples, n_in)`` operator of ``mne.filter.resample`` (processing/resample.py).  The
+        pipeline then takes windows of ``n_in`` raw samples; must precede ``set_prefilters`` / ``set_notch``."""
+        a = _f64(operator)
+        if a.ndim != 2 or a.shape[0] != self.W:
+            raise ValueError(f"resampling operator must be ({self.W}, n_in), got {a.shape}")
+        _lib.check(self.lib.nm_set_resampler(self._h, int(a.shape[1]), _ptr(a, C.c_double)))
+        self.W_in = int(a.shape[1])
 
     def set_notch(self, taps: np.ndarray | None) -> None:
         if taps is None:
@@ -187,16 +197,16 @@ class Pipeline:
 
     def process_window(self, window: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(window, dtype=np.float64)
-        if a.shape != (self.n_raw_rows, self.W):
-            raise ValueError(f"expected a window of shape ({self.n_raw_rows}, {self.W}), got {a.shape}")
+        if a.shape != (self.n_raw_rows, self.W_in):
+            raise ValueError(f"expected a window of shape ({self.n_raw_rows}, {self.W_in}), got {a.shape}")
         out = np.empty(self.F, dtype=np.float64)
         _lib.check(self.lib.nm_process_window(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
         return out
 
     def preprocess_window(self, window: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(window, dtype=np.float64)
-        if a.shape != (self.n_raw_rows, self.W):
-            raise ValueError(f"expected a window of shape ({self.n_raw_rows}, {self.W}), got {a.shape}")
+        if a.shape != (self.n_raw_rows, self.W_in):
+            raise ValueError(f"expected a window of shape ({self.n_raw_rows}, {self.W_in}), got {a.shape}")
         out = np.empty((self.n_ch, self.W), dtype=np.float64)
         _lib.check(self.lib.nm_preprocess_window(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
         return out
@@ -216,7 +226,7 @@ class Pipeline:
         return ms.value
 
     PROFILE_FAMILIES = ("prep", "notch", "scan", "spectral", "bandpower", "sharpwave", "burst_envelope", "burst_threshold",
-                        "burst_features", "normalizer", "nan", "fused")
+                        "burst_features", "normalizer", "nan", "fused", "resample")
 
     def prepare_resident(self) -> None:
         _lib.check(self.lib.nm_prepare_resident(self._h))

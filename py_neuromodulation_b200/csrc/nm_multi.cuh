@@ -17,7 +17,7 @@
 extern "C" int nm_upload_begin_f32(nm_pipeline* p, const float* data, long long n_samples, long long pitch) {
     NM_P_CHECK(p);
     NM_CHECK(p->finalized, "call nm_finalize first");
-    NM_CHECK(data && n_samples >= p->W && pitch >= n_samples, "bad recording geometry");
+    NM_CHECK(data && n_samples >= p->Win && pitch >= n_samples, "bad recording geometry");
     NM_CHECK(p->G > 0, "nm_upload_begin_f32 needs a re-reference with at least one channel group");
     cudaSetDevice(p->device);
     const int n_slices = n_samples >= NM_UPLOAD_MIN_PIPELINED ? NM_UPLOAD_SLICES : 1;

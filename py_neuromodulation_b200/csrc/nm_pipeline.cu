@@ -25,6 +25,7 @@
 #include "nm_sharpwave.cuh"
 #include "nm_norm.cuh"
 #include "nm_rawnorm.cuh"
+#include "nm_resample.cuh"
 
 // ------------------------------------------------------------------------------- errors
 static thread_local char g_err[1024] = "";
@@ -80,10 +81,16 @@ struct BandpowerFam {
 };
 
 enum { NM_PROF_PREP = 0, NM_PROF_NOTCH, NM_PROF_SCAN, NM_PROF_SPEC, NM_PROF_BANDPOWER, NM_PROF_SHARPWAVE, NM_PROF_BURST_ENV,
-       NM_PROF_BURST_THR, NM_PROF_BURST_FEAT, NM_PROF_NORM, NM_PROF_NAN, NM_PROF_FUSED, NM_PROF_N };
+       NM_PROF_BURST_THR, NM_PROF_BURST_FEAT, NM_PROF_NORM, NM_PROF_NAN, NM_PROF_FUSED, NM_PROF_RESAMPLE, NM_PROF_N };
 
 struct nm_pipeline {
     int device = 0, C_all = 0, C = 0, W = 0, F = 0;
+    // raw_resampling (nm_resample.cuh): windows are cut, pre-filtered and notched at Win samples, every row is then mapped to W
+    // samples by the host-designed operator; without a resampler Win == W
+    int Win = 0, Wpi = 0;
+    bool has_resampler = false;
+    int rs_pitch = 0;                 // row pitch of the transposed operator
+    DevBuf d_rt, d_rs, d_roff;        // operator (Win x rs_pitch), resampled chunk rows (chunk x C x Wp), their window offsets
     bool finalized = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -316,7 +323,7 @@ static bool nm_launch_notch(nm_pipeline* p, const NmRows& rows, double* y, const
     if (nm_convx_pick<NmEpiStoreScan>(bank)) {
         NmEpiStoreScan epi;
         epi.y = y;
-        epi.Wp = p->Wp;
+        epi.Wp = p->Wpi;
         epi.want_scan = scan_out ? 1 : 0;
         epi.want_hjorth = p->scan_h; epi.want_raw = p->scan_r; epi.want_ll = p->scan_l;
         if (scan_out) epi.out = *scan_out;
@@ -324,7 +331,7 @@ static bool nm_launch_notch(nm_pipeline* p, const NmRows& rows, double* y, const
         nm_launch_fir(p, bank, rows, epi, stream, 0, p->f32_linear());
         return scan_out != nullptr;
     }
-    NmEpiStore epi{y, (long long)p->Wp, 1};
+    NmEpiStore epi{y, (long long)p->Wpi, 1};
     nm_launch_fir(p, bank, rows, epi, stream, 0);
     return false;
 }
@@ -511,7 +518,7 @@ int RawNormFam::run(nm_pipeline* p, NmRows& rows) {
     batch += n;
     rows.base = d_out.as<double>();
     rows.ch_stride = Wp;
-    rows.off = p->d_yoff.as<long long>();
+    rows.off = (p->has_resampler ? p->d_roff : p->d_yoff).as<long long>();
     return 0;
 }
 
@@ -584,7 +591,7 @@ static int nm_fused_plan(nm_pipeline* p) {
         want = env ? atoi(env) : 0;
     }
     if (want == 0) return 0;
-    if (!p->notch || !p->reref_foldable || !p->prefilters.empty() || p->rawnorm || p->f32_linear() || p->precision == 1) return 0;
+    if (!p->notch || !p->reref_foldable || !p->prefilters.empty() || p->rawnorm || p->has_resampler || p->f32_linear() || p->precision == 1) return 0;
     const FirBank& nb = *p->notch;
     if (!nb.pow2 || !nm_convx_supported(nb.P) || nb.nF != 1 || nb.mode != NM_FIR_REFLECT) return 0;
     const size_t buf_bytes = nm_fused_nbuf(nb.P) * sizeof(cx<double>);
@@ -657,6 +664,7 @@ extern "C" int nm_pipeline_create(int device, int n_raw_rows, int n_ch, int wind
     p->C_all = n_raw_rows;
     p->C = n_ch;
     p->W = window_samples;
+    p->Win = window_samples;
     p->F = n_features;
     NM_CUDA_CHECK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     NM_CUDA_CHECK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
@@ -763,8 +771,25 @@ extern "C" int nm_set_notch(nm_pipeline* p, const double* taps, int n_taps) {
     NM_CHECK(taps, "taps is NULL");
     cudaSetDevice(p->device);
     p->notch = std::make_unique<FirBank>();
-    if (p->notch->build(taps, 1, n_taps, p->W, NM_FIR_REFLECT, p->stream)) return -1;
+    if (p->notch->build(taps, 1, n_taps, p->Win, NM_FIR_REFLECT, p->stream)) return -1;
     NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int nm_set_resampler(nm_pipeline* p, int n_in, const double* op) {
+    NM_P_CHECK(p);
+    NM_CHECK(!p->finalized, "pipeline already finalized");
+    NM_CHECK(!p->notch && p->prefilters.empty(), "nm_set_resampler must be called before nm_add_prefilter / nm_set_notch (they filter the un-resampled window)");
+    NM_CHECK(op && n_in >= 3, "bad resampling operator");
+    cudaSetDevice(p->device);
+    p->Win = n_in;
+    p->rs_pitch = (p->W + 3) & ~3;
+    std::vector<double> rt((size_t)n_in * p->rs_pitch, 0.0);  // transposed: the GEMM reads it k-major
+    for (int j = 0; j < p->W; ++j)
+        for (int k = 0; k < n_in; ++k) rt[(size_t)k * p->rs_pitch + j] = op[(size_t)j * n_in + k];
+    if (p->d_rt.upload(rt, p->stream)) return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    p->has_resampler = true;
     return 0;
 }
 
@@ -774,7 +799,7 @@ extern "C" int nm_add_prefilter(nm_pipeline* p, const double* taps, int n_taps) 
     NM_CHECK(taps && n_taps > 0, "bad prefilter taps");
     cudaSetDevice(p->device);
     auto b = std::make_unique<FirBank>();
-    if (b->build(taps, 1, n_taps, p->W, NM_FIR_SAME, p->stream)) return -1;
+    if (b->build(taps, 1, n_taps, p->Win, NM_FIR_SAME, p->stream)) return -1;
     NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
     p->prefilters.push_back(std::move(b));
     return 0;
@@ -968,19 +993,25 @@ extern "C" int nm_finalize(nm_pipeline* p) {
     }
     if (nm_fused_plan(p)) return -1;
     p->Wp = (p->W + 1) & ~1;
+    p->Wpi = (p->Win + 1) & ~1;
     // chunk of windows per launch: as many as possible up to 64 windows / 384 MB of notched rows (+ burst envelopes).  L2 residency
     // of the chunk turned out not to matter (the consumers are compute / latency bound: a 24..128 MB sweep moved the C3 step by
     // < 3 %), while larger launches fill the persistent grids better: -11 % on the default feature set from 16 -> 64 windows
-    const size_t per_window = (size_t)p->C * p->Wp * sizeof(double) * (1 + (p->bursts ? p->bursts->nB : 0));
+    const size_t per_window = (size_t)p->C * std::max(p->Wp, p->Wpi) * sizeof(double) * (1 + (p->bursts ? p->bursts->nB : 0));
     size_t chunk_mb = 384;
     if (const char* e = getenv("NMB200_CHUNK_MB")) chunk_mb = (size_t)std::max(1, atoi(e));  // tuning knob (profiling only)
     p->chunk = (int)std::max<size_t>(1, std::min<size_t>(64, (chunk_mb << 20) / per_window));
     std::vector<long long> yoff(p->chunk);
-    for (int k = 0; k < p->chunk; ++k) yoff[k] = (long long)k * p->C * p->Wp;
+    for (int k = 0; k < p->chunk; ++k) yoff[k] = (long long)k * p->C * p->Wpi;
     if (p->d_yoff.upload(yoff, p->stream)) return -1;
-    if (p->notch && p->d_y.ensure((size_t)p->chunk * p->C * p->Wp * sizeof(double))) return -1;
+    if (p->notch && p->d_y.ensure((size_t)p->chunk * p->C * p->Wpi * sizeof(double))) return -1;
     for (size_t i = 0; i < std::min<size_t>(2, p->prefilters.size()); ++i)
-        if (p->d_pre[i].ensure((size_t)p->chunk * p->C * p->Wp * sizeof(double))) return -1;
+        if (p->d_pre[i].ensure((size_t)p->chunk * p->C * p->Wpi * sizeof(double))) return -1;
+    if (p->has_resampler) {
+        for (int k = 0; k < p->chunk; ++k) yoff[k] = (long long)k * p->C * p->Wp;
+        if (p->d_roff.upload(yoff, p->stream)) return -1;
+        if (p->d_rs.ensure((size_t)p->chunk * p->C * p->Wp * sizeof(double))) return -1;
+    }
     for (auto& b : p->prefilters)
         if (nm_allow_fir_smem<NmEpiStore>(*b, 0, p)) return -1;
     if (p->bursts && p->bursts->alloc_chunk(p->chunk, p->Wp)) return -1;
@@ -1143,8 +1174,8 @@ static int nm_stage_slices(nm_pipeline* p, const void* data, bool f64, long long
 static int nm_upload_impl(nm_pipeline* p, const void* data, bool f64, long long n_samples, long long pitch) {
     NM_P_CHECK(p);
     NM_CHECK(p->finalized, "call nm_finalize first");
-    NM_CHECK(data && n_samples >= p->W && pitch >= n_samples, "bad recording geometry (n_samples %lld, pitch %lld, W %d)", n_samples,
-             pitch, p->W);
+    NM_CHECK(data && n_samples >= p->Win && pitch >= n_samples, "bad recording geometry (n_samples %lld, pitch %lld, W %d)", n_samples,
+             pitch, p->Win);
     cudaSetDevice(p->device);
     p->n_slices = 0;
     p->slices_prepped = 0;
@@ -1191,15 +1222,36 @@ extern "C" int nm_upload_f64(nm_pipeline* p, const double* data, long long n_sam
 static void nm_run_prefilters(nm_pipeline* p, NmRows& rows) {
     for (size_t i = 0; i < p->prefilters.size(); ++i) {
         double* dst = p->d_pre[i & 1].as<double>();
-        NmEpiStore epi{dst, (long long)p->Wp, 1};
+        NmEpiStore epi{dst, (long long)p->Wpi, 1};
         p->prof_begin();
         nm_launch_fir(p, *p->prefilters[i], rows, epi, p->stream, 0);
         p->prof_end(NM_PROF_NOTCH);
         p->launches++;
         rows.base = dst;
-        rows.ch_stride = p->Wp;
+        rows.ch_stride = p->Wpi;
         rows.off = p->d_yoff.as<long long>();
     }
+}
+
+// raw_resampling of one batch of windows: rows of Win samples -> d_rs rows of W samples (nm_resample.cuh)
+static void nm_run_resampler(nm_pipeline* p, NmRows& rows) {
+    NmResampleArgs a;
+    a.in = rows;
+    a.rt = p->d_rt.as<double>();
+    a.n_out = p->W;
+    a.n_out_pitch = p->rs_pitch;
+    a.out = p->d_rs.as<double>();
+    a.out_pitch = p->Wp;
+    const long long n_rows = (long long)rows.n_windows * rows.n_ch;
+    const dim3 grid((unsigned)((n_rows + NM_RS_BM - 1) / NM_RS_BM), (unsigned)((p->W + NM_RS_BN - 1) / NM_RS_BN));
+    p->prof_begin();
+    NM_LAUNCH(nm_resample_kernel, grid, dim3(NM_RS_THREADS), nm_resample_smem_bytes(), p->stream, a);
+    p->prof_end(NM_PROF_RESAMPLE);
+    p->launches++;
+    rows.base = p->d_rs.as<double>();
+    rows.ch_stride = p->Wp;
+    rows.off = p->d_roff.as<long long>();
+    rows.W = p->W;
 }
 
 static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
@@ -1209,7 +1261,7 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
     rows.off = p->d_starts.as<long long>() + w0;
     rows.n_windows = n;
     rows.n_ch = p->C;
-    rows.W = p->W;
+    rows.W = p->Win;
 
     auto out_for = [&](const DevBuf& colmap, int per_ch) {
         NmOut o;
@@ -1274,8 +1326,9 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         rows.ch_stride = p->Wp;
         rows.off = p->d_yoff.as<long long>();
     } else if (p->notch) {
-        const bool y_needed = !p->spectral.empty() || p->bandpower || p->sharpwave || p->bursts || p->rawnorm;
-        const bool fuse_scan = p->has_scan && !p->rawnorm;  // the scan features are taken from the NORMALISED rows otherwise
+        const bool y_needed = !p->spectral.empty() || p->bandpower || p->sharpwave || p->bursts || p->rawnorm || p->has_resampler;
+        // the scan features are taken from the NORMALISED / RESAMPLED rows otherwise
+        const bool fuse_scan = p->has_scan && !p->rawnorm && !p->has_resampler;
         NmOut so;
         if (fuse_scan) so = out_for(p->d_scan_colmap, 5);
         p->prof_begin();
@@ -1283,9 +1336,10 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         p->prof_end(NM_PROF_NOTCH);
         p->launches++;
         rows.base = p->d_y.as<double>();
-        rows.ch_stride = p->Wp;
+        rows.ch_stride = p->Wpi;
         rows.off = p->d_yoff.as<long long>();
     }
+    if (p->has_resampler) nm_run_resampler(p, rows);
     if (p->rawnorm && p->rawnorm->run(p, rows)) return -1;
     if (p->has_scan && !scan_done) {
         NmScanArgs a;
@@ -1362,8 +1416,8 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
     NM_CHECK(p->finalized && p->have_data, "finalize the pipeline and upload a recording first");
     NM_CHECK(starts && n_windows > 0, "no windows given");
     for (int k = 0; k < n_windows; ++k)
-        NM_CHECK(starts[k] >= 0 && starts[k] + p->W <= p->T, "window %d [%lld, %lld) outside the recording (%lld samples)", k, starts[k],
-                 starts[k] + p->W, p->T);
+        NM_CHECK(starts[k] >= 0 && starts[k] + p->Win <= p->T, "window %d [%lld, %lld) outside the recording (%lld samples)", k, starts[k],
+                 starts[k] + p->Win, p->T);
     cudaSetDevice(p->device);
     if (p->d_starts.upload(starts, (size_t)n_windows, p->stream)) return -1;
     if (p->d_out.ensure((size_t)n_windows * p->F * sizeof(double))) return -1;
@@ -1392,7 +1446,7 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
         na.p = nm_prep_args(p);
         na.start = p->d_starts.as<long long>() + w0;
         na.n_windows = n;
-        na.W = p->W;
+        na.W = p->Win;
         na.flags = p->d_nanflags.as<unsigned char>() + (size_t)w0 * p->C_all;
         const long long tot = (long long)n * p->C_all;
         const unsigned grid = (unsigned)((tot + NM_ROW_THREADS - 1) / NM_ROW_THREADS);
@@ -1413,7 +1467,7 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
     for (int w0 = 0; w0 < n_windows; w0 += p->chunk) {
         const int n = std::min(p->chunk, n_windows - w0);
         long long upto = 0;
-        for (int k = 0; k < n; ++k) upto = std::max(upto, starts[w0 + k] + p->W);
+        for (int k = 0; k < n; ++k) upto = std::max(upto, starts[w0 + k] + p->Win);
         if (nm_ensure_prepped(p, upto)) return -1;
         if (nm_run_chunk(p, w0, n)) return -1;
         if (per_chunk) {
@@ -1479,7 +1533,7 @@ extern "C" int nm_host_unregister(void* ptr) {
 extern "C" int nm_process_window(nm_pipeline* p, const double* window, double* out_features) {
     NM_P_CHECK(p);
     NM_CHECK(window && out_features, "NULL argument");
-    if (nm_upload_impl(p, window, true, p->W, p->W)) return -1;
+    if (nm_upload_impl(p, window, true, p->Win, p->Win)) return -1;
     const long long zero = 0;
     return nm_run_windows(p, &zero, 1, out_features);
 }
@@ -1491,7 +1545,7 @@ extern "C" int nm_preprocess_window(nm_pipeline* p, const double* window, double
     NM_P_CHECK(p);
     NM_CHECK(window && out_rows, "NULL argument");
     p->force_xr = true;  // this entry hands out the re-referenced / notched ROWS: materialise them (un-fused kernels)
-    const int rc_up = nm_upload_impl(p, window, true, p->W, p->W);
+    const int rc_up = nm_upload_impl(p, window, true, p->Win, p->Win);
     p->force_xr = false;
     if (rc_up) return -1;
     const long long zero = 0;
@@ -1502,14 +1556,15 @@ extern "C" int nm_preprocess_window(nm_pipeline* p, const double* window, double
     rows.off = p->d_starts.as<long long>();
     rows.n_windows = 1;
     rows.n_ch = p->C;
-    rows.W = p->W;
+    rows.W = p->Win;
     nm_run_prefilters(p, rows);
     if (p->notch) {
         nm_launch_notch(p, rows, p->d_y.as<double>(), nullptr, p->stream);
         p->launches++;
         rows.base = p->d_y.as<double>();
-        rows.ch_stride = p->Wp;
+        rows.ch_stride = p->Wpi;
     }
+    if (p->has_resampler) nm_run_resampler(p, rows);
     if (p->rawnorm && p->rawnorm->run(p, rows)) return -1;
     NM_CUDA_CHECK(cudaGetLastError());
     const double* src = rows.base;
@@ -1595,6 +1650,10 @@ extern "C" int nm_describe_plan(nm_pipeline* p, char* buf, int n) {
     char line[256];
     snprintf(line, sizeof(line), "window=%d channels=%d features=%d chunk=%d\n", p->W, p->C, p->F, p->chunk);
     s += line;
+    if (p->has_resampler) {
+        snprintf(line, sizeof(line), "resampler: nm_resample_kernel %d -> %d samples per row (dense float64 operator)\n", p->Win, p->W);
+        s += line;
+    }
     for (auto& b : p->prefilters) nm_describe_fir<NmEpiStore>(s, "prefilter", *b, 0);
     if (p->fused) {
         snprintf(line, sizeof(line), "fused: nm_fused_kernel P=%d threads=%d smem=%zu [re-reference + notch%s%s%s] dft_families=%d\n", p->notch->P,

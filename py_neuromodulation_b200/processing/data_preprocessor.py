@@ -2,9 +2,9 @@
 
 The chain is executed in the fixed order of ``PREPROCESSOR_DICT`` -- NOT in the order of the
 ``settings.preprocessing`` list -- exactly like the reference (data_preprocessor.py:44-52).
-In scope on the GPU: ``preprocessing_filter``, ``notch_filter``, ``re_referencing`` and ``raw_resampling`` when it
-is the identity (resample_freq_hz == sfreq) and ``raw_normalization`` (mean / median / zscore / zscore-median).  Resampling
-with a ratio != 1 and the scikit-learn raw normalisers raise NotImplementedError.
+In scope on the GPU: ``preprocessing_filter``, ``notch_filter``, ``raw_resampling`` (any ratio; everything downstream keeps
+the ORIGINAL sampling rate like the reference, stream/data_processor.py:55,77-81), ``re_referencing`` and ``raw_normalization``
+(mean / median / zscore / zscore-median).  The scikit-learn raw normalisers raise NotImplementedError.
 """
 
 from __future__ import annotations
@@ -37,13 +37,9 @@ def preprocessing_plan(settings: "NMSettings", sfreq: float) -> list[str]:
         if name not in settings.preprocessing:
             continue
         if name == "raw_resampling":
-            if settings.raw_resampling_settings.resample_freq_hz != sfreq:
-                raise NotImplementedError(
-                    f"raw_resampling from {sfreq} Hz to {settings.raw_resampling_settings.resample_freq_hz} Hz is not on the "
-                    "B200 path yet (SURVEY.md section 8f-2); set raw_resampling_settings.resample_freq_hz = sfreq or drop "
-                    "'raw_resampling' from settings.preprocessing"
-                )
-            continue  # identity, like the reference (processing/resample.py:36-38)
+            # ratio 1 is the identity, like the reference (processing/resample.py:36-38)
+            if float(settings.raw_resampling_settings.resample_freq_hz / sfreq) == 1.0:
+                continue
         if name == "raw_normalization":
             method = settings.raw_normalization_settings.normalization_method
             if method not in ("mean", "median", "zscore", "zscore-median"):
@@ -60,6 +56,7 @@ class DataPreprocessor:
         from .filter_preprocessing import PreprocessingFilter
         from .normalization import RawNormalizer
         from .rereference import ReReferencer
+        from .resample import Resampler
 
         self.preprocessors: list[NMPreprocessor] = []
         for name in preprocessing_plan(settings, sfreq):
@@ -67,6 +64,8 @@ class DataPreprocessor:
                 self.preprocessors.append(PreprocessingFilter(settings=settings, sfreq=sfreq))
             elif name == "notch_filter":
                 self.preprocessors.append(NotchFilter(sfreq=sfreq, line_noise=line_noise))
+            elif name == "raw_resampling":
+                self.preprocessors.append(Resampler(sfreq=sfreq, resample_freq_hz=settings.raw_resampling_settings.resample_freq_hz))
             elif name == "re_referencing":
                 self.preprocessors.append(ReReferencer(sfreq=sfreq, channels=channels))
             elif name == "raw_normalization":

@@ -4,8 +4,8 @@ FFT resampling of one window is a LINEAR map of its samples: reflect-limited pad
 transform, spectrum truncated (down-sampling) or zero-extended (up-sampling) with the Nyquist-bin correction, inverse transform
 of the new length, padding cut off.  Like the FIR taps of the other preprocessors the map is *designed on the host* -- as the
 dense ``(n_out, n_in)`` operator ``R`` -- and handed to the library as data (``nm_set_resampler``); on the GPU every window row
-is ``y = R @ x`` (``csrc/nm_resample.cuh``, one float64 GEMM per chunk of windows, after the notch and before the re-reference
-like in the reference's fixed preprocessor order).  Any ratio works, including the non-integer ones of float sampling rates.
+is ``y = R @ x`` (``csrc/nm_resample.cuh``, one float64 GEMM per chunk of windows, after the notch like in the reference's fixed
+preprocessor order; the re-reference is hoisted in front of both -- it commutes with per-row linear maps).  Any ratio works, including the non-integer ones of float sampling rates.
 
 MNE is not installed in this image, so the construction below is written from MNE's documented algorithm
 (``_resample_fft`` / ``_fft_resample`` with the defaults npad="auto", pad="reflect_limited", window="boxcar") and is
@@ -16,6 +16,8 @@ Quirk kept on purpose: everything downstream of the resampler is still built wit
 """
 
 from __future__ import annotations
+
+from functools import lru_cache
 
 import numpy as np
 
@@ -36,6 +38,7 @@ def resample_geometry(n_in: int, ratio: float) -> dict:
     return {"final_len": final_len, "pads": pads, "orig_len": orig_len, "new_len": new_len, "remove": (rem0, new_len - final_len - rem0)}
 
 
+@lru_cache(maxsize=8)
 def resample_operator(n_in: int, ratio: float) -> np.ndarray:
     """Dense ``(n_out, n_in)`` float64 matrix ``R`` with ``mne.filter.resample(x, up=ratio) == R @ x`` for every row ``x``."""
     g = resample_geometry(n_in, ratio)
@@ -87,8 +90,9 @@ class Resampler(NMPreprocessor):
         key = data.shape
         if key not in self._pipes:
             names = [f"c{i}" for i in range(data.shape[0])]
-            pipe = Pipeline(data.shape[0], data.shape[0], data.shape[1], [f"{n}_raw" for n in names])
-            pipe.set_resampler(resample_operator(data.shape[1], self.up))
+            op = resample_operator(int(data.shape[1]), float(self.up))
+            pipe = Pipeline(data.shape[0], data.shape[0], op.shape[0], [f"{n}_raw" for n in names])
+            pipe.set_resampler(op)
             ScanSpec(names, raw=True).attach(pipe)
             pipe.finalize()
             self._pipes[key] = pipe

@@ -70,6 +70,10 @@ class _Plan:
         from .._pipeline import Pipeline
 
         s, names = dp.settings, dp.ch_names_used_features
+        # behind the resampler the families see round(W * ratio) samples per window -- designed with the ORIGINAL sampling rate
+        # (the reference never updates sfreq_raw: stream/data_processor.py:55,77-81)
+        raw_window = int(window_samples)
+        window_samples = dp.feature_window(raw_window)
         scan, specs, columns, enabled = build_specs(s, names, dp.sfreq_raw, window_samples, dp.user_feature_names)
         self.columns = columns
         self.has_bursts = "bursts" in enabled
@@ -86,6 +90,7 @@ class _Plan:
             pipe.set_reref_factored(*dp.reref_factored)
         elif "re_referencing" in dp.preproc_plan:
             pipe.set_reref(dp.ref_matrix)
+        dp.attach_resampler(pipe, raw_window)
         pipe.set_prefilters(dp.prefilter_taps)
         if "notch_filter" in dp.preproc_plan:
             pipe.set_notch(dp.notch_taps)
@@ -187,6 +192,9 @@ class DataProcessor:
             rs = self.settings.raw_normalization_settings.validate()
             self.rawnorm_cfg = (rs.normalization_method, rs.clip, int(rs.normalization_time_s * self.sfreq_raw),
                                 int(self.sfreq_raw / self.settings.sampling_rate_features_hz))
+        self.resample_ratio = None
+        if "raw_resampling" in self.preproc_plan:
+            self.resample_ratio = float(self.settings.raw_resampling_settings.resample_freq_hz / self.sfreq_raw)
         self.ref_matrix = None
         if "re_referencing" in self.preproc_plan:
             self.ref_matrix = build_reference_matrix(ch)
@@ -208,6 +216,21 @@ class DataProcessor:
         self.cnt_samples = 0
         # validate the plug-in settings now (bands, filters, estimators) like the reference constructor does
         self._probe = _ProbeOnly(self)
+
+    # ------------------------------------------------------------------ resampler
+    def feature_window(self, raw_window: int) -> int:
+        """Samples per window the feature families see (``mne.filter.resample``: ``round(ratio * n)``)."""
+        if self.resample_ratio is None:
+            return int(raw_window)
+        from ..processing.resample import resample_geometry
+
+        return int(resample_geometry(int(raw_window), self.resample_ratio)["final_len"])
+
+    def attach_resampler(self, pipe, raw_window: int) -> None:
+        if self.resample_ratio is not None:
+            from ..processing.resample import resample_operator
+
+            pipe.set_resampler(resample_operator(int(raw_window), self.resample_ratio))
 
     # ------------------------------------------------------------------ plans
     def plan(self, window_samples: int, with_normalizer: bool = True, nan_reinsert: bool = True) -> _Plan:
@@ -293,10 +316,11 @@ class DataProcessor:
         key = ("pre", window_samples)
         if key not in self._plans:
             names = self.ch_names_used_features
-            pipe = Pipeline(self.n_raw_rows, len(names), window_samples, ["_unused"], device=self.device)
+            pipe = Pipeline(self.n_raw_rows, len(names), self.feature_window(window_samples), ["_unused"], device=self.device)
             pipe.set_pick(self.feature_idx)
             if "re_referencing" in self.preproc_plan:
                 pipe.set_reref(self.ref_matrix)
+            self.attach_resampler(pipe, window_samples)
             pipe.set_prefilters(self.prefilter_taps)
             if "notch_filter" in self.preproc_plan:
                 pipe.set_notch(self.notch_taps)

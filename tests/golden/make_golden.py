@@ -198,10 +198,10 @@ def window_processor_cases(nm):
          vals=np.array(rows), sfreq=1000.0)
 
 
-def _run_windows(nm, st, x, line_noise=50):
+def _run_windows(nm, st, x, line_noise=50, sfreq=1000):
     ch = nm.utils.channels.get_default_channels_from_data(x)
-    dp = nm.DataProcessor(sfreq=1000, settings=st, channels=ch, line_noise=line_noise, verbose=False)
-    gen = nm.RawDataGenerator(x, 1000, st.sampling_rate_features_hz, st.segment_length_features_ms)
+    dp = nm.DataProcessor(sfreq=sfreq, settings=st, channels=ch, line_noise=line_noise, verbose=False)
+    gen = nm.RawDataGenerator(x, sfreq, st.sampling_rate_features_hz, st.segment_length_features_ms)
     rows, keys = [], None
     for _, batch in gen:
         d = dp.process(batch)
@@ -275,6 +275,36 @@ def stream_cases():
          vals=df.to_numpy(dtype=np.float64), sfreq=fs, rate=200.0)
 
 
+def resample_cases(nm):
+    """``raw_resampling`` with a ratio != 1 (processing/resample.py:28-60; the reference's DEFAULT preprocessing
+    list resamples to 1 kHz).  Unmodified reference through the shim; ``mne.filter.resample`` itself is the restatement in
+    ``oracle/mne_filter_restated.py`` (MNE is not installed), so the fixtures pin the reference's handling of the resampled rows --
+    every plug-in keeps the ORIGINAL sampling rate (stream/data_processor.py:55,77-81) -- not MNE's arithmetic."""
+    # untouched default settings at 2 kHz (C5's configuration): 2000 -> 1000 samples per window, z-scored features
+    st = nm.NMSettings.get_default()
+    x = neural_like(31, 4, 2000 + 200 * 34, sfreq=2000.0)
+    keys, vals = _run_windows(nm, st, x, sfreq=2000)
+    save("dataprocessor_resample_2k_default", x=x.astype(np.float32), settings=dump_settings(st), keys=json.dumps(keys), vals=vals, sfreq=2000.0)
+    # ratio 0.8 (1250 Hz: padded length 2048 -> 1638, not a power of two), un-normalised, plus band-pass power and STFT
+    st = nm.NMSettings.get_default()
+    st.postprocessing.feature_normalization = False
+    st.features.bandpass_filter = True
+    st.features.stft = True
+    x = neural_like(32, 3, 1250 + 125 * 30, sfreq=1250.0)
+    keys, vals = _run_windows(nm, st, x, sfreq=1250)
+    save("dataprocessor_resample_1250", x=x.astype(np.float32), settings=dump_settings(st), keys=json.dumps(keys), vals=vals, sfreq=1250.0)
+    # up-sampling (500 Hz -> 1 kHz) with the raw normaliser behind the resampler
+    st = nm.NMSettings.get_default().reset()
+    for f in ("fft", "raw_hjorth", "linelength", "return_raw", "sharpwave_analysis"):
+        st.features[f] = True
+    st.postprocessing.feature_normalization = False
+    st.preprocessing = ["raw_resampling", "notch_filter", "re_referencing", "raw_normalization"]
+    st.raw_normalization_settings.normalization_time_s = 2.0
+    x = neural_like(33, 3, 500 + 50 * 24, sfreq=500.0)
+    keys, vals = _run_windows(nm, st, x, sfreq=500)
+    save("dataprocessor_resample_up_rawnorm", x=x.astype(np.float32), settings=dump_settings(st), keys=json.dumps(keys), vals=vals, sfreq=500.0)
+
+
 def burst_history_case(nm):
     """Bursts across 320 windows (history overflows after window 290): faithful reference values."""
     st = nm.NMSettings.get_default()
@@ -321,8 +351,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "next":  # only the SURVEY 8f "next row" fixtures
         next_row_cases(nm)
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "resample":
+        resample_cases(nm)
+        raise SystemExit(0)
     plugin_cases(nm)
     preprocess_cases(nm)
+    resample_cases(nm)
     window_processor_cases(nm)
     burst_history_case(nm)
     real_data_case(nm)

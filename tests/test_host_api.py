@@ -167,11 +167,10 @@ def test_out_of_scope_requests_fail_loudly():
     s.raw_normalization_settings.normalization_method = "quantile"  # scikit-learn transformer: out of scope
     with pytest.raises(NotImplementedError):
         nm.Stream(sfreq=1000, data=x, settings=s)
-    s = nm.NMSettings.get_default()  # default resampling to 1 kHz of a 2 kHz recording: 'next' row 8f-2
-    with pytest.raises(NotImplementedError):
-        nm.Stream(sfreq=2000, data=x, settings=s)
-    s.raw_resampling_settings.resample_freq_hz = 2000  # identity -> accepted
-    nm.Stream(sfreq=2000, data=x, settings=s)
+    s = nm.NMSettings.get_default()  # default resampling to 1 kHz of a 2 kHz recording (row 8f-2) is served since round 2
+    assert nm.Stream(sfreq=2000, data=x, settings=s).data_processor.resample_ratio == 0.5
+    s.raw_resampling_settings.resample_freq_hz = 2000  # identity, like the reference
+    assert nm.Stream(sfreq=2000, data=x, settings=s).data_processor.resample_ratio is None
     s = nm.NMSettings.get_default()
     s.postprocessing.project_cortex = True
     with pytest.raises(NotImplementedError):

@@ -42,7 +42,10 @@ def run_dp(g, n_windows=None, with_norm=True, fused=None):
                                         ("dataprocessor_realdata", 12), ("dataprocessor_prefilter_default", None),
                                         ("dataprocessor_prefilter_lphp", None), ("dataprocessor_rawnorm_zscore", None),
                                         ("dataprocessor_rawnorm_mean", None), ("dataprocessor_rawnorm_median", None),
-                                        ("dataprocessor_rawnorm_zscore_median", None)])
+                                        ("dataprocessor_rawnorm_zscore_median", None),
+                                        # raw_resampling with a ratio != 1 (processing/resample.py:28-60; stale sampling rate downstream)
+                                        ("dataprocessor_resample_2k_default", 8), ("dataprocessor_resample_1250", 10),
+                                        ("dataprocessor_resample_up_rawnorm", None)])
 def test_window_processor_matches_reference_golden(backend, name, n_emu):
     g = load_golden(name)
     n = n_emu if backend == "emu" else None  # the thread emulator is slow: fewer windows on CPU, all on the GPU
@@ -129,6 +132,36 @@ def test_stream_readme_demo(backend, tmp_path):
 
     back = pd.read_csv(tmp_path / "demo" / "demo_FEATURES.csv")
     assert list(back.columns) == g["keys"] and back.shape == df.shape
+
+
+def test_stream_untouched_defaults_at_2khz(backend, tmp_path):
+    """The reference's default preprocessing list resamples to 1 kHz (default_settings.yaml:46-49): ``nm.Stream(sfreq=2000, data)``
+    with untouched settings runs the resampler (processing/resample.py:28-60) and designs every plug-in with the stale 2 kHz rate."""
+    g = load_golden("dataprocessor_resample_2k_default")
+    x = g["x"].astype(np.float64)
+    stream = nm.Stream(sfreq=2000, data=x)
+    df = stream.run(out_dir=tmp_path, experiment_name="rs2k", save_csv=False)
+    assert list(df.columns) == g["keys"] + ["time"]
+    assert df.shape[0] == g["vals"].shape[0]
+    plan = stream.data_processor.plan(2000)
+    assert "nm_resample_kernel 2000 -> 1000" in plan.pipe.describe_plan()
+    check_matrix(g["keys"], df[g["keys"]].to_numpy(dtype=np.float64), g["keys"], g["vals"], "2 kHz defaults")
+
+
+def test_standalone_resampler_matches_oracle(backend):
+    """``Resampler.process`` as a stand-alone preprocessor (same constructor as the reference class) against the restated
+    ``mne.filter.resample``: down-sampling by 2, ratio 0.9 and up-sampling by 2.5, odd lengths."""
+    from oracle.mne_filter_restated import resample
+    from py_neuromodulation_b200.processing.resample import Resampler
+
+    for sfreq, target, n in ((2000, 1000, 600), (1111.111, 1000, 371), (400, 1000, 233)):
+        x = neural_like(5, 3, n, sfreq=sfreq)
+        got = Resampler(sfreq=sfreq, resample_freq_hz=target).process(x)
+        ref = resample(x, up=float(target / sfreq), down=1.0)
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref)))
+    same = neural_like(6, 2, 100)
+    assert Resampler(sfreq=1000, resample_freq_hz=1000).process(same) is same  # ratio 1: identity, like the reference
 
 
 def test_stream_float_sampling_rate_variable_window_length(backend, tmp_path):
