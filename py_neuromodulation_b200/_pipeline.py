@@ -153,10 +153,22 @@ class Pipeline:
         """names_by_raw_row[r] = channel name whose features become NaN when raw row r holds a NaN (or None).
 
         The reference matches by SUBSTRING of the feature key (stream/data_processor.py:299-303)."""
+        # all occurrences of every name in ONE joined string (str.find runs at memory speed; a Python-level `name in key` over
+        # rows x columns costs 25 ms at 256 channels x 3072 columns)
+        sep = "\x00"
+        joined = sep.join(self.columns)
+        key_start = np.cumsum([0] + [len(k) + 1 for k in self.columns[:-1]]) if self.columns else np.zeros(0, dtype=np.int64)
         ptr = [0]
         cols: list[int] = []
         for name in names_by_raw_row:
-            if name is not None:
+            if name is not None and name != "" and sep not in name:
+                hits, at = [], joined.find(name)
+                while at >= 0:
+                    hits.append(at)
+                    at = joined.find(name, at + 1)
+                if hits:
+                    cols.extend(np.unique(np.searchsorted(key_start, hits, side="right") - 1).tolist())
+            elif name is not None:
                 cols.extend(i for i, key in enumerate(self.columns) if name in key)
             ptr.append(len(cols))
         a_ptr, a_cols = _i32(ptr), _i32(cols if cols else [0])
@@ -178,13 +190,24 @@ class Pipeline:
         self._keep_data = a
 
     def run(self, starts: Sequence[int], out: np.ndarray | None = None, download: bool = True) -> np.ndarray | None:
+        """``out`` may be a column block ``big[:, :F]`` of a wider C-contiguous float64 matrix: the rows are then written with the
+        wider matrix's row pitch (``nm_set_output_pitch``), so a caller that appends columns needs no second copy."""
         s = np.ascontiguousarray(starts, dtype=np.int64)
         n = int(s.size)
         if download:
             if out is None:
                 out = np.empty((n, self.F), dtype=np.float64)
-            assert out.shape == (n, self.F) and out.dtype == np.float64 and out.flags.c_contiguous
-            _lib.check(self.lib.nm_run_windows(self._h, _ptr(s, C.c_longlong), n, out.ctypes.data_as(C.c_void_p)))
+            assert out.shape == (n, self.F) and out.dtype == np.float64
+            pitch = self.F
+            if not out.flags.c_contiguous:
+                assert out.strides[1] == 8 and out.strides[0] % 8 == 0 and out.strides[0] >= 8 * self.F, "unsupported output layout"
+                pitch = out.strides[0] // 8
+            _lib.check(self.lib.nm_set_output_pitch(self._h, 0 if pitch == self.F else pitch))
+            try:
+                _lib.check(self.lib.nm_run_windows(self._h, _ptr(s, C.c_longlong), n, out.ctypes.data_as(C.c_void_p)))
+            finally:
+                if pitch != self.F:
+                    self.lib.nm_set_output_pitch(self._h, 0)
             return out
         _lib.check(self.lib.nm_run_windows(self._h, _ptr(s, C.c_longlong), n, None))
         return None
@@ -284,7 +307,7 @@ def factor_reference_matrix(m: np.ndarray, min_group: int = 4, max_groups: int =
     """
     c = m.shape[0]
     # candidate groups: distinct supports of "large" equal-valued runs in the rows
-    supports: list[frozenset[int]] = []
+    seen: dict[bytes, frozenset[int]] = {}
     for i in range(c):
         row = m[i]
         vals, counts = np.unique(row[row != 0], return_counts=True)
@@ -292,12 +315,13 @@ def factor_reference_matrix(m: np.ndarray, min_group: int = 4, max_groups: int =
             if cnt >= min_group:
                 # the row's own channel is excluded from its average; adding it back makes the supports of
                 # all rows of one channel type identical
-                supports.append(frozenset(int(j) for j in np.flatnonzero(row == v)) | {i})
-    # channel types produce identical supports once the row's own index is included
-    uniq: list[frozenset[int]] = []
-    for s in supports:
-        if s not in uniq:
-            uniq.append(s)
+                mask = row == v
+                mask[i] = True
+                key = mask.tobytes()
+                if key not in seen:
+                    seen[key] = frozenset(np.flatnonzero(mask).tolist())
+    # channel types produce identical supports once the row's own index is included (dict keeps first-seen order)
+    uniq: list[frozenset[int]] = list(seen.values())
     # keep disjoint groups only (a channel belongs to at most one group)
     groups: list[frozenset[int]] = []
     for s in sorted(uniq, key=len, reverse=True):
@@ -309,18 +333,18 @@ def factor_reference_matrix(m: np.ndarray, min_group: int = 4, max_groups: int =
             group_of[j] = g
     gcoef = np.zeros((c, len(groups)))
     rem = m.copy()
+    member_idx = [np.array(sorted(members), dtype=np.int64) for members in groups]
     for i in range(c):
-        for g, members in enumerate(groups):
-            idx = [j for j in members if j != i]
-            if len(idx) < min_group:
+        for g, members in enumerate(member_idx):
+            idx = members[members != i]
+            if idx.size < min_group:
                 continue
             vals, counts = np.unique(m[i, idx], return_counts=True)
             v = vals[np.argmax(counts)]
             if v == 0 or counts.max() < min_group:
                 continue
             gcoef[i, g] = v
-            for j in members:
-                rem[i, j] = m[i, j] - v
+            rem[i, members] = m[i, members] - v
     return len(groups), group_of, gcoef, rem
 
 

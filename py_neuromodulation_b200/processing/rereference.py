@@ -23,13 +23,21 @@ def build_reference_matrix(channels) -> np.ndarray | None:
     types = ch["type"].tolist()
     status = ch["status"].tolist()
     m = np.zeros((n, n))
+    refs = ch["rereference"].tolist()
+    good_mask = np.array([st == "good" for st in status])
+    type_arr = np.array([str(t) for t in types], dtype=object)
+    same_type_good: dict = {}  # type -> indices of the good channels of that type (computed once per type, not per row)
     for i in range(n):
         m[i, i] = 1
-        ref = ch["rereference"][i]
+        ref = refs[i]
         if pd.isnull(ref) or str(ref).lower() == "none" or status[i] != "good":
             continue
         if str(ref).lower() == "average":
-            idx = [j for j in range(n) if j != i and types[j] == types[i] and status[j] == "good"]
+            key = str(types[i])
+            if key not in same_type_good:
+                same_type_good[key] = np.flatnonzero(good_mask & (type_arr == key))
+            pool = same_type_good[key]
+            idx = pool[pool != i]
         else:
             idx = []
             for other in str(ref).split("&"):

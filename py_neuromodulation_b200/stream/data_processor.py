@@ -160,19 +160,21 @@ class DataProcessor:
         ch = self.channels
         good_used = (ch["used"] == 1) & (ch["status"] == "good")
         self.ch_names_used: list[str] = ch.loc[good_used, "new_name"].tolist()
+        status_l, new_names_l = ch["status"].tolist(), ch["new_name"].tolist()  # (plain lists: no per-row pandas look-ups)
         self.feature_idx: list[int] = [
-            int(i) for i in np.where(ch["used"].astype(bool) & ~ch["target"].astype(bool))[0] if ch.loc[i, "status"] == "good"
+            int(i) for i in np.where(ch["used"].astype(bool) & ~ch["target"].astype(bool))[0] if status_l[i] == "good"
         ]
         self.n_raw_rows = int(ch.shape[0])
         # names of the rows that are actually processed (identical to ch_names_used unless a used channel is a target)
-        self.ch_names_used_features = [ch.loc[i, "new_name"] for i in self.feature_idx]
+        self.ch_names_used_features = [new_names_l[i] for i in self.feature_idx]
         if len(self.ch_names_used) == len(self.ch_names_used_features):
             self.ch_names_used_features = list(self.ch_names_used)
         # NaN re-insertion (stream/data_processor.py:297-306): a NaN in raw row r turns every feature whose key contains that
         # row's channel name into NaN.  The reference indexes ch_names_used with a mask over ALL raw rows, which is only
         # defined when every row is used and good (it raises IndexError otherwise); here every used, good row maps to its OWN
         # channel name and unused / bad rows to nothing -- identical whenever the reference is defined.
-        self.nan_names_by_raw_row = [ch.loc[r, "new_name"] if bool(good_used.iloc[r]) else None for r in range(self.n_raw_rows)]
+        good_used_l = good_used.tolist()
+        self.nan_names_by_raw_row = [new_names_l[r] if good_used_l[r] else None for r in range(self.n_raw_rows)]
 
         self.preproc_plan = preprocessing_plan(self.settings, self.sfreq_raw)
         self.notch_taps = None

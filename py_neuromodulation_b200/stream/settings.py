@@ -235,7 +235,8 @@ class NMSettings(NMBaseModel):
             elif format == "yaml":
                 import yaml
 
-                yaml.dump(self.model_dump(), f, default_flow_style=None)
+                # same text as yaml.dump(...): the libyaml emitter when PyYAML was built with it (10x faster)
+                yaml.dump(self.model_dump(), f, default_flow_style=None, Dumper=getattr(yaml, "CDumper", yaml.Dumper))
             else:
                 raise ValueError("File format not supported.")
 

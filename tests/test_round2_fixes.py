@@ -113,3 +113,37 @@ def test_variable_window_length_normaliser_keeps_values_of_nan_windows(backend, 
     assert np.array_equal(np.isnan(mat), np.isnan(ref))
     assert np.isnan(ref).any() and not np.isnan(ref[-1]).any()
     assert parity_err(cols, mat, ref, normalized=True).max() < 1e-7
+
+
+def test_stream_keeps_the_processor_of_an_unchanged_configuration(backend, tmp_path):
+    """``Stream.run`` rebuilds its processor from the CURRENT settings like the reference (stream/stream.py:206-222) -- edits after
+    ``__init__`` count -- but an unchanged configuration keeps its filter design and GPU plans; stateful stages restart."""
+    x = neural_like(9, 3, 2600)
+    stream = nm.Stream(sfreq=1000, data=x)  # default settings: bursts + rolling z-score are stateful
+    dp0 = stream.data_processor
+    a = stream.run(out_dir=tmp_path, experiment_name="a", save_csv=False)
+    assert stream.data_processor is dp0
+    b = stream.run(out_dir=tmp_path, experiment_name="a", save_csv=False)
+    assert stream.data_processor is dp0
+    assert np.array_equal(a.to_numpy(), b.to_numpy(), equal_nan=True)  # history reset between runs
+    stream.settings.features.welch = False  # an edit after construction must be honoured
+    c = stream.run(out_dir=tmp_path, experiment_name="a", save_csv=False)
+    assert stream.data_processor is not dp0
+    assert not any("_welch_" in k for k in c.columns) and any("_welch_" in k for k in a.columns)
+    common = [k for k in c.columns if "_fft_" in k]
+    assert np.array_equal(c[common].to_numpy(), a[common].to_numpy(), equal_nan=True)
+
+
+def test_pipeline_writes_into_a_column_block_of_a_wider_table(backend):
+    """``Pipeline.run(out=big[:, :F])`` (nm_set_output_pitch): with and without the sequential normaliser."""
+    x = neural_like(4, 3, 2400)
+    for norm in (False, True):
+        s = nm.NMSettings.get_fast_compute()
+        s.postprocessing.feature_normalization = norm
+        dp = nm.DataProcessor(sfreq=1000, settings=s, channels=get_default_channels_from_data(x), line_noise=50, verbose=False)
+        starts = np.arange(0, 1400, 100)
+        cols, dense = dp.process_windows(x, starts, 1000)
+        dp.reset_state()
+        big = np.full((starts.size, len(cols) + 3), -7.0)
+        _, view = dp.process_windows(x, starts, 1000, out=big[:, : len(cols)])
+        assert np.array_equal(big[:, : len(cols)], dense, equal_nan=True) and np.all(big[:, len(cols):] == -7.0)
