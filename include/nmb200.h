@@ -88,7 +88,11 @@ int nm_add_prefilter(nm_pipeline* p, const double* taps, int n_taps);
  * n_in samples and every row is mapped to the pipeline's `window_samples` before re-referenced rows reach the raw normaliser and
  * the feature families (the reference's fixed preprocessor order).  Call before nm_add_prefilter / nm_set_notch.  Everything
  * downstream keeps the ORIGINAL sampling rate, like the reference (stream/data_processor.py:55,77-81). */
-int nm_set_resampler(nm_pipeline* p, int n_in, const double* op);
+int nm_set_resampler(nm_pipeline* p, int n_in, const double* op, int fft_decim);
+/* fft_decim: 0, or the integer factor D >= 2 when `op` is MNE's default FFT down-sampler by D (npad="auto", reflect-limited pad,
+ * boxcar window).  The library then checks entries of `op` against the closed form and, if the padded length is one of the
+ * specialised transform sizes, runs the resampler as an FFT convolution with an ideal low-pass whose epilogue stores every D-th
+ * sample (two transforms per channel pair) instead of the dense GEMM.  0 always selects the GEMM. */
 
 /* NaN re-insertion (stream/data_processor.py:297-306): columns [col_ptr[r], col_ptr[r+1]) of `cols`
  * become NaN in every window where raw row r contains a NaN */

@@ -94,7 +94,7 @@ _SIGNATURES = {
     "nm_group_sums_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), c_ll_p]),
     "nm_upload_slices": (C.c_int, [C.c_void_p, c_int_p, c_ll_p, c_int_p, c_ll_p]),
     "nm_side_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
-    "nm_set_resampler": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    "nm_set_resampler": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int]),
     "nm_upload_slice_sums": (C.c_int, [C.c_void_p, C.c_int]),
     "nm_upload_slice_reduced": (C.c_int, [C.c_void_p, C.c_int]),
     "nm_upload_finish": (C.c_int, [C.c_void_p]),

@@ -112,13 +112,15 @@ class Pipeline:
         _lib.check(self.lib.nm_set_reref(self._h, int(n_groups), _ptr(a_go, C.c_int), _ptr(a_gc, C.c_double),
                                          _ptr(a_ptr, C.c_int), _ptr(a_col, C.c_int), _ptr(a_val, C.c_double)))
 
-    def set_resampler(self, operator: np.ndarray) -> None:
+    def set_resampler(self, operator: np.ndarray, fft_decim: int = 0) -> None:
         """``raw_resampling``: dense ``(window_samples, n_in)`` operator of ``mne.filter.resample`` (processing/resample.py).  The
-        pipeline then takes windows of ``n_in`` raw samples; must precede ``set_prefilters`` / ``set_notch``."""
+        pipeline then takes windows of ``n_in`` raw samples; must precede ``set_prefilters`` / ``set_notch``.  ``fft_decim = D``
+        declares the operator as MNE's default FFT down-sampler by the integer factor D (the library verifies it and then runs it
+        as two transforms per channel pair instead of the dense GEMM)."""
         a = _f64(operator)
         if a.ndim != 2 or a.shape[0] != self.W:
             raise ValueError(f"resampling operator must be ({self.W}, n_in), got {a.shape}")
-        _lib.check(self.lib.nm_set_resampler(self._h, int(a.shape[1]), _ptr(a, C.c_double)))
+        _lib.check(self.lib.nm_set_resampler(self._h, int(a.shape[1]), _ptr(a, C.c_double), int(fft_decim)))
         self.W_in = int(a.shape[1])
 
     def set_notch(self, taps: np.ndarray | None) -> None:

@@ -67,6 +67,30 @@ struct FirBank {
         }
         return d_hperm.upload(hperm, s);
     }
+    // Ideal zero-phase low-pass of FFT down-sampling by D (nm_resample.cuh): the W-sample window is reflect-padded by `pad_each`
+    // samples per side to exactly P_ points and multiplied with H[k] = 1 for |k| <= P_/(2D), else 0 (circular: no taps).
+    int build_lowpass(int W, int P_, int pad_each, int D, cudaStream_t s) {
+        nF = 1; L = 1; Lh = 0; mode = NM_FIR_REFLECT; E = pad_each; P = P_; pow2 = true;
+        NM_CHECK(nm_convx_supported(P) && W + 2 * pad_each == P && P % (2 * D) == 0, "internal: bad down-sampling plan");
+        std::vector<int> radices{16};
+        int rem = P / 16;
+        if (rem == 64) { radices.push_back(8); radices.push_back(8); rem = 1; }
+        while (rem > 16) { radices.push_back(16); rem /= 16; }
+        if (rem > 1) radices.push_back(rem);
+        int last = radices.back(), lg = 0;
+        while ((1 << lg) < last) ++lg;
+        pad = std::max(3, lg);
+        if (fft.build_with(P, radices, s)) return -1;
+        const int nyq = P / (2 * D);
+        std::vector<double> hperm((size_t)P, 0.0), hx((size_t)P);
+        for (int k = 0; k < P; ++k) {
+            const int f = k <= P / 2 ? k : P - k;
+            hperm[fft.pos[k]] = f <= nyq ? 1.0 / (double)P : 0.0;  // (MNE's new_len / orig_len scale cancels irfft's 1 / new_len)
+        }
+        nm_cx_interleave_h(P, hperm.data(), hx.data());
+        if (d_hx.upload(hx, s)) return -1;
+        return d_hperm.upload(hperm, s);
+    }
     // args / conv_args(in, f0, n): the launch serves filters [f0, f0 + n) of the bank (n < 0: all of them)
     NmFirArgs args(const NmRows& in, int f0 = 0, int n = -1) const {
         NmFirArgs a;

@@ -91,6 +91,8 @@ struct nm_pipeline {
     bool has_resampler = false;
     int rs_pitch = 0;                 // row pitch of the transposed operator
     DevBuf d_rt, d_rs, d_roff;        // operator (Win x rs_pitch), resampled chunk rows (chunk x C x Wp), their window offsets
+    std::unique_ptr<FirBank> rs_bank; // integer down-sampling: ideal low-pass on the FFT-convolution kernel + decimating store
+    int rs_decim = 0;
     bool finalized = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -776,7 +778,20 @@ extern "C" int nm_set_notch(nm_pipeline* p, const double* taps, int n_taps) {
     return 0;
 }
 
-extern "C" int nm_set_resampler(nm_pipeline* p, int n_in, const double* op) {
+// MNE's padding for an n-sample row (npad="auto"): min(n // 8, 100) * 2 extra samples, then up to the next power of two
+static int nm_resample_fast_plan(int n_in, int n_out, int D, int* P_out, int* pad_out) {
+    if (D < 2 || n_in % 2 != 0 || n_in != n_out * D) return 0;
+    const int min_add = std::min(n_in / 8, 100) * 2;
+    int P = 1;
+    while (P < n_in + min_add) P <<= 1;
+    const int pad_each = (P - n_in) / 2;
+    if (!nm_convx_supported(P) || (P - n_in) % 2 != 0 || pad_each % D != 0 || pad_each > n_in - 1 || P % (2 * D) != 0) return 0;
+    *P_out = P;
+    *pad_out = pad_each;
+    return 1;
+}
+
+extern "C" int nm_set_resampler(nm_pipeline* p, int n_in, const double* op, int fft_decim) {
     NM_P_CHECK(p);
     NM_CHECK(!p->finalized, "pipeline already finalized");
     NM_CHECK(!p->notch && p->prefilters.empty(), "nm_set_resampler must be called before nm_add_prefilter / nm_set_notch (they filter the un-resampled window)");
@@ -784,10 +799,42 @@ extern "C" int nm_set_resampler(nm_pipeline* p, int n_in, const double* op) {
     cudaSetDevice(p->device);
     p->Win = n_in;
     p->rs_pitch = (p->W + 3) & ~3;
-    std::vector<double> rt((size_t)n_in * p->rs_pitch, 0.0);  // transposed: the GEMM reads it k-major
-    for (int j = 0; j < p->W; ++j)
-        for (int k = 0; k < n_in; ++k) rt[(size_t)k * p->rs_pitch + j] = op[(size_t)j * n_in + k];
-    if (p->d_rt.upload(rt, p->stream)) return -1;
+    p->rs_bank.reset();
+    p->rs_decim = 0;
+    int P = 0, pad_each = 0;
+    if (fft_decim >= 2 && nm_resample_fast_plan(n_in, p->W, fft_decim, &P, &pad_each)) {
+        // the caller says `op` is MNE's default FFT down-sampler by an integer factor: check a few interior entries of the operator
+        // against the closed form of the fast path before trusting the hint (g = circular impulse response of the ideal low-pass)
+        const int D = fft_decim, nyq = P / (2 * D);
+        auto g = [&](long long n) {
+            n = ((n % P) + P) % P;
+            double acc = 1.0;
+            for (int f = 1; f <= nyq; ++f) acc += 2.0 * std::cos(2.0 * M_PI * (double)((n * f) % P) / (double)P);
+            return acc / (double)P;
+        };
+        bool ok = true;
+        const int probes[4][2] = {{0, 1}, {p->W / 3, n_in / 2}, {p->W - 1, n_in - 2}, {p->W / 2, 3}};
+        for (const auto& pr : probes) {
+            const int j = pr[0], k = pr[1];
+            if (k <= 0 || k >= n_in - 1 || j < 0 || j >= p->W) continue;
+            const long long at = (long long)pad_each + (long long)D * j;  // padded position of output j
+            double r = g(at - (pad_each + k));
+            if (k <= pad_each) r -= g(at - (pad_each - k));                                  // left mirror: 2 x[0] - x[k]
+            if (n_in - 1 - k <= pad_each && n_in - 1 - k >= 1) r -= g(at - (pad_each + n_in - 1 + (n_in - 1 - k)));  // right mirror
+            if (std::fabs(r - op[(size_t)j * n_in + k]) > 1e-9) ok = false;
+        }
+        if (ok) {
+            p->rs_bank = std::make_unique<FirBank>();
+            if (p->rs_bank->build_lowpass(n_in, P, pad_each, D, p->stream)) return -1;
+            p->rs_decim = D;
+        }
+    }
+    if (!p->rs_bank) {
+        std::vector<double> rt((size_t)n_in * p->rs_pitch, 0.0);  // transposed: the GEMM reads it k-major
+        for (int j = 0; j < p->W; ++j)
+            for (int k = 0; k < n_in; ++k) rt[(size_t)k * p->rs_pitch + j] = op[(size_t)j * n_in + k];
+        if (p->d_rt.upload(rt, p->stream)) return -1;
+    }
     NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
     p->has_resampler = true;
     return 0;
@@ -1011,6 +1058,7 @@ extern "C" int nm_finalize(nm_pipeline* p) {
         for (int k = 0; k < p->chunk; ++k) yoff[k] = (long long)k * p->C * p->Wp;
         if (p->d_roff.upload(yoff, p->stream)) return -1;
         if (p->d_rs.ensure((size_t)p->chunk * p->C * p->Wp * sizeof(double))) return -1;
+        if (p->rs_bank && nm_allow_fir_smem<NmEpiStoreDecim>(*p->rs_bank, 0, p)) return -1;
     }
     for (auto& b : p->prefilters)
         if (nm_allow_fir_smem<NmEpiStore>(*b, 0, p)) return -1;
@@ -1245,7 +1293,12 @@ static void nm_run_resampler(nm_pipeline* p, NmRows& rows) {
     const long long n_rows = (long long)rows.n_windows * rows.n_ch;
     const dim3 grid((unsigned)((n_rows + NM_RS_BM - 1) / NM_RS_BM), (unsigned)((p->W + NM_RS_BN - 1) / NM_RS_BN));
     p->prof_begin();
-    NM_LAUNCH(nm_resample_kernel, grid, dim3(NM_RS_THREADS), nm_resample_smem_bytes(), p->stream, a);
+    if (p->rs_bank) {  // integer down-sampling: ideal low-pass by FFT convolution, every D-th sample stored
+        NmEpiStoreDecim epi{p->d_rs.as<double>(), (long long)p->Wp, p->rs_decim};
+        nm_launch_fir(p, *p->rs_bank, rows, epi, p->stream, 0);
+    } else {
+        NM_LAUNCH(nm_resample_kernel, grid, dim3(NM_RS_THREADS), nm_resample_smem_bytes(), p->stream, a);
+    }
     p->prof_end(NM_PROF_RESAMPLE);
     p->launches++;
     rows.base = p->d_rs.as<double>();
@@ -1651,7 +1704,11 @@ extern "C" int nm_describe_plan(nm_pipeline* p, char* buf, int n) {
     snprintf(line, sizeof(line), "window=%d channels=%d features=%d chunk=%d\n", p->W, p->C, p->F, p->chunk);
     s += line;
     if (p->has_resampler) {
-        snprintf(line, sizeof(line), "resampler: nm_resample_kernel %d -> %d samples per row (dense float64 operator)\n", p->Win, p->W);
+        if (p->rs_bank)
+            snprintf(line, sizeof(line), "resampler: nm_convx_kernel %d -> %d samples per row (P=%d ideal low-pass, every %d-th sample stored)\n",
+                     p->Win, p->W, p->rs_bank->P, p->rs_decim);
+        else
+            snprintf(line, sizeof(line), "resampler: nm_resample_kernel %d -> %d samples per row (dense float64 operator)\n", p->Win, p->W);
         s += line;
     }
     for (auto& b : p->prefilters) nm_describe_fir<NmEpiStore>(s, "prefilter", *b, 0);

@@ -11,12 +11,51 @@
 // per-sample combination of channels and commutes with a per-row linear map that is the same for all channels.  Works for any
 // ratio (2 kHz -> 1 kHz, 1111.111 Hz -> 1 kHz, up-sampling).
 //
-// Kernel: 128 x 64 output tile per CTA, 256 threads, 8 x 4 register tile per thread, K in steps of 16 through shared memory
+// Fast path (integer down-sampling, the default 2 kHz -> 1 kHz case): with ratio 1/D the new spectrum is the old one cut at the new
+// Nyquist bin, so  y[m] = x_lp[D m]  where x_lp is the padded window after an ideal zero-phase low-pass H[k] = 1 for
+// |k| <= P/(2D) (both +-Nyquist bins kept: their sum is MNE's doubled real Nyquist bin).  That is the notch kernel's own shape --
+// reflect-limited padding to P points, forward transform, * real symmetric spectrum, inverse -- with an epilogue that stores
+// every D-th sample of the window region (NmEpiStoreDecim on nm_convx_kernel<P, REFLECT>): two transforms per channel pair
+// instead of 2 * n_in * n_out multiply-adds per row.  Conditions (nm_resample_fast_ok): padded length P in {1024, 2048, 4096},
+// even window, pads divisible by D.  Everything else (up-sampling, ratio 0.8 / 0.9, odd windows) uses the GEMM below.
+//
+// GEMM kernel: 128 x 64 output tile per CTA, 256 threads, 8 x 4 register tile per thread, K in steps of 16 through shared memory
 // (A tile stored k-major so that both operands are read with 128-bit shared loads).  FP64-pipe bound by construction:
 // 32 DFMA per 6 LDS.128 per k.
 #pragma once
 
 #include "nm_common.cuh"
+#include "nm_convx.cuh"
+
+// ---------------------------------------------------------------- fast path: decimating store on the FFT-convolution kernel
+struct NmEpiStoreDecim {
+    double* y;        // (n_windows, n_ch, Wp) resampled rows
+    long long Wp;
+    int D;            // keep window samples t = 0, D, 2D, ...
+    static constexpr bool kRegs = true;
+    static constexpr bool kRegsOnly = true, kReflectOk = true, kSameOk = false, kConvxOnly = true, kF32Ok = false;
+    static constexpr bool kSyncsInside = false;
+    static NM_HD size_t smem_bytes(int /*nt*/) { return 0; }
+    NM_DEV bool regs_ok() const { return true; }
+    struct State {};
+    template <class PL, typename T>
+    NM_DEV void consume(const cx<T>* v, cx<T>* /*work*/, double* /*red*/, State& /*st*/, int o0, int W, int n_ch, int w, int c0,
+                        bool has2, int /*f*/, int tid) const {
+        double* r0 = y + ((size_t)w * n_ch + c0) * Wp;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int t = tid + PL::NT * k - o0;
+            if (t >= 0 && t < W && t % D == 0) {
+                r0[t / D] = (double)v[k].re;
+                if (has2) r0[Wp + t / D] = (double)v[k].im;
+            }
+        }
+    }
+    template <class PL, typename T>
+    NM_DEV void finish(cx<T>* /*work*/, double* /*red*/, State& /*st*/, int /*o0*/, int /*W*/, int /*n_ch*/, int /*w*/, int /*c0*/,
+                       bool /*has2*/, int /*f*/, int /*tid*/) const {}
+    NM_DEV bool needs_trailing_barrier() const { return true; }
+};
 
 #define NM_RS_BM 128
 #define NM_RS_BN 64

@@ -72,6 +72,14 @@ def resample_operator(n_in: int, ratio: float) -> np.ndarray:
     return np.ascontiguousarray(out)
 
 
+def integer_decimation(ratio: float) -> int:
+    """D >= 2 when ``ratio == 1 / D`` exactly (2 kHz -> 1 kHz, 4 kHz -> 1 kHz, ...), else 0."""
+    if not 0.0 < ratio < 1.0:
+        return 0
+    d = int(round(1.0 / ratio))
+    return d if d >= 2 and 1.0 / d == ratio else 0
+
+
 class Resampler(NMPreprocessor):
     """Same constructor / ``process`` contract as the reference class; the arithmetic runs on the GPU."""
 
@@ -92,7 +100,7 @@ class Resampler(NMPreprocessor):
             names = [f"c{i}" for i in range(data.shape[0])]
             op = resample_operator(int(data.shape[1]), float(self.up))
             pipe = Pipeline(data.shape[0], data.shape[0], op.shape[0], [f"{n}_raw" for n in names])
-            pipe.set_resampler(op)
+            pipe.set_resampler(op, integer_decimation(float(self.up)))
             ScanSpec(names, raw=True).attach(pipe)
             pipe.finalize()
             self._pipes[key] = pipe

@@ -230,9 +230,9 @@ class DataProcessor:
 
     def attach_resampler(self, pipe, raw_window: int) -> None:
         if self.resample_ratio is not None:
-            from ..processing.resample import resample_operator
+            from ..processing.resample import integer_decimation, resample_operator
 
-            pipe.set_resampler(resample_operator(int(raw_window), self.resample_ratio))
+            pipe.set_resampler(resample_operator(int(raw_window), self.resample_ratio), integer_decimation(self.resample_ratio))
 
     # ------------------------------------------------------------------ plans
     def plan(self, window_samples: int, with_normalizer: bool = True, nan_reinsert: bool = True) -> _Plan:

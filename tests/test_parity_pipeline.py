@@ -144,7 +144,8 @@ def test_stream_untouched_defaults_at_2khz(backend, tmp_path):
     assert list(df.columns) == g["keys"] + ["time"]
     assert df.shape[0] == g["vals"].shape[0]
     plan = stream.data_processor.plan(2000)
-    assert "nm_resample_kernel 2000 -> 1000" in plan.pipe.describe_plan()
+    # integer down-sampling runs as an FFT convolution with an ideal low-pass + decimating store, not as the dense GEMM
+    assert "resampler: nm_convx_kernel 2000 -> 1000" in plan.pipe.describe_plan()
     check_matrix(g["keys"], df[g["keys"]].to_numpy(dtype=np.float64), g["keys"], g["vals"], "2 kHz defaults")
 
 
