@@ -317,6 +317,8 @@ def run_gpu_arm(args) -> None:
     comm = NativeComm.from_env(device=local_rank) if world > 1 else None
 
     ch_cfg, weak, sfreq, dur, make_settings, label = CONFIGS[args.config]
+    if args.channels:  # (debugging / sweeps: not the BASELINE.json configuration any more)
+        ch_cfg, label = args.channels, label + f" [channels overridden: {args.channels}]"
     settings = make_settings()
     n_samples = int(dur * sfreq)
     c_total = ch_cfg * world if weak else ch_cfg
@@ -554,6 +556,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--channels", type=int, default=0, help="override the configuration's channel count (sweeps / debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()

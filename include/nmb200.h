@@ -230,6 +230,21 @@ int nm_upload_slice_sums(nm_pipeline* p, int slice);
 int nm_upload_slice_reduced(nm_pipeline* p, int slice);
 int nm_upload_finish(nm_pipeline* p);
 
+/* ---- streaming entry (csrc/nm_stream.cuh): one window at a time, the way the reference is driven by a live source
+ * (stream/stream.py:280-330 calls DataProcessor.process per batch; stream/mnelsl_stream.py feeds it).  A ring of page-locked slots:
+ * the producer writes the next (n_raw_rows x window) block into a slot's input, nm_stream_submit enqueues H2D + every kernel + D2H
+ * of the feature row WITHOUT blocking, nm_stream_wait blocks on that slot only.  The launch sequence of a window is captured into
+ * a CUDA graph per slot and replayed (window counters of the stateful stages are patched into the graph); stateful stages (bursts
+ * history, raw / feature normaliser) advance exactly as in nm_process_window, which is the synchronous wrapper of these calls.
+ * input_f32: slot samples are float32 instead of float64.  use_graph: 1 graph replay, 0 eager launches, -1 environment
+ * (NMB200_STREAM_GRAPH, default 1).  Batched entry points (nm_upload_*, nm_run_windows) close the stream. */
+int nm_stream_open(nm_pipeline* p, int n_slots, int input_f32, int use_graph);
+int nm_stream_input(nm_pipeline* p, int slot, void** ptr, long long* bytes);
+int nm_stream_submit(nm_pipeline* p, int slot);
+int nm_stream_wait(nm_pipeline* p, int slot, const double** features);
+int nm_stream_stats(nm_pipeline* p, long long* windows, long long* graph_launches, long long* graph_nodes, long long* patched);
+int nm_stream_close(nm_pipeline* p);
+
 /* ---- collectives inside the library (csrc/nm_comm.cuh): NCCL over NVLink / NVSwitch, one process per GPU, no torch.
  * The reference has no multi-GPU path; these entry points are what a binding adds for SURVEY.md section 8e (channel shards,
  * one all-reduce of the common-average sums, one gather of the result blocks).  NCCL is dlopen'ed ("libnccl.so.2"). */

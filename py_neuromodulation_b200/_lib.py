@@ -98,6 +98,12 @@ _SIGNATURES = {
     "nm_upload_slice_sums": (C.c_int, [C.c_void_p, C.c_int]),
     "nm_upload_slice_reduced": (C.c_int, [C.c_void_p, C.c_int]),
     "nm_upload_finish": (C.c_int, [C.c_void_p]),
+    "nm_stream_open": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "nm_stream_input": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]),
+    "nm_stream_submit": (C.c_int, [C.c_void_p, C.c_int]),
+    "nm_stream_wait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "nm_stream_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "nm_stream_close": (C.c_int, [C.c_void_p]),
     "nm_comm_unique_id": (C.c_int, [C.c_void_p]),
     "nm_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "nm_comm_destroy": (None, [C.c_void_p]),

@@ -236,6 +236,38 @@ class Pipeline:
         _lib.check(self.lib.nm_preprocess_window(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
         return out
 
+    # -- streaming entry (csrc/nm_stream.cuh): ring of page-locked slots, asynchronous submit / wait, CUDA-graph replay
+    def stream_open(self, slots: int = 2, f32: bool = False, graph: bool | None = None) -> None:
+        """``graph``: True = replay a captured CUDA graph per window, False = eager launches, None = NMB200_STREAM_GRAPH (default on)."""
+        _lib.check(self.lib.nm_stream_open(self._h, int(slots), int(f32), -1 if graph is None else int(bool(graph))))
+        self._stream_slots, self._stream_dtype = int(slots), (np.float32 if f32 else np.float64)
+
+    def stream_input(self, slot: int) -> np.ndarray:
+        """Writable ``(n_raw_rows, W_in)`` view of the slot's page-locked input block: produce the next window straight into it."""
+        ptr, n = C.c_void_p(), C.c_longlong()
+        _lib.check(self.lib.nm_stream_input(self._h, int(slot), C.byref(ptr), C.byref(n)))
+        buf = (C.c_char * n.value).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=self._stream_dtype).reshape(self.n_raw_rows, self.W_in)
+
+    def stream_submit(self, slot: int) -> None:
+        """Enqueue the slot's window (H2D, every kernel, D2H of the feature row); returns without waiting for the GPU."""
+        _lib.check(self.lib.nm_stream_submit(self._h, int(slot)))
+
+    def stream_wait(self, slot: int) -> np.ndarray:
+        """Block until the slot's feature row has landed; returns a view of the slot's page-locked output (valid until the slot
+        is submitted again)."""
+        ptr = C.c_void_p()
+        _lib.check(self.lib.nm_stream_wait(self._h, int(slot), C.byref(ptr)))
+        return np.ctypeslib.as_array((C.c_double * self.F).from_address(ptr.value))
+
+    def stream_stats(self) -> dict[str, int]:
+        w, g, n, pt = C.c_longlong(), C.c_longlong(), C.c_longlong(), C.c_longlong()
+        _lib.check(self.lib.nm_stream_stats(self._h, C.byref(w), C.byref(g), C.byref(n), C.byref(pt)))
+        return {"windows": w.value, "graph_launches": g.value, "graph_kernel_nodes": n.value, "patched_arguments": pt.value}
+
+    def stream_close(self) -> None:
+        _lib.check(self.lib.nm_stream_close(self._h))
+
     def add_feature_normalizer(self, method: str, clip: float, n_keep: int, columns: Sequence[str]) -> None:
         cols = _i32([self.col_of[k] for k in columns] or [0])
         _lib.check(self.lib.nm_add_feature_normalizer(self._h, NORM_METHODS.index(method), float(clip or 0.0), int(n_keep),

@@ -812,17 +812,24 @@ struct BurstsFam {
         const size_t rows = (size_t)C * nB;
         if (d_qrow.ensure(rows * sizeof(NmBurstQRow)) || d_qkey.ensure(rows * NM_BQ_CAP * 8) || d_qidx.ensure(rows * NM_BQ_CAP * 4)) return -1;
         NM_CUDA_CHECK(cudaMemset(d_qrow.p, 0, rows * sizeof(NmBurstQRow)));
+        NM_CUDA_CHECK(cudaDeviceSynchronize());  // (legacy-stream memset: finish before any non-blocking stream uses the rows)
         return 0;
     }
-    void reset() {
+    // stream-ordered: kernels of a run that has not been synchronised yet may still use the queue state (the pipeline's streams
+    // are non-blocking, so a cudaMemset on the legacy stream would NOT wait for them)
+    void reset(cudaStream_t s) {
         batch = 0;
-        if (d_qrow.p) cudaMemset(d_qrow.p, 0, (size_t)C * nB * sizeof(NmBurstQRow));  // valid = 0 for every row
+        if (d_qrow.p) cudaMemsetAsync(d_qrow.p, 0, (size_t)C * nB * sizeof(NmBurstQRow), s);  // valid = 0 for every row
     }
     int fast_n() const { return (nm_specx_supported(W) && bank.threads() >= (W == 500 ? NmSx500::NA : NmSx1000::NA)) ? W : 0; }
     size_t epi_smem() const { return NmEpiBursts::smem_bytes_for(W, hfft.generic, fast_n()); }
     static size_t thr_smem() { return nm_bq_smem_bytes(); }
     int allow_smem(const nm_pipeline* p);
     long long run_base = 0;  // `batch` at the time prepare() ran
+    // device arrays prepare() filled for the current run: the DevBufs above (batched runs) or the streaming parameter block
+    const long long* a_e_end = nullptr;
+    const int *a_n = nullptr, *a_lo = nullptr, *a_hi = nullptr;
+    const double* a_gamma = nullptr;
     int prepare(nm_pipeline* p, int n_windows);
     int run(nm_pipeline* p, const NmRows& rows, int w0);
 };

@@ -26,6 +26,7 @@
 #include "nm_norm.cuh"
 #include "nm_rawnorm.cuh"
 #include "nm_resample.cuh"
+#include "nm_stream.h"
 
 // ------------------------------------------------------------------------------- errors
 static thread_local char g_err[1024] = "";
@@ -178,6 +179,7 @@ struct nm_pipeline {
     bool f32_linear() const { return precision == 1 && !bursts && !sharpwave && !rawnorm; }
     std::vector<long long> h_starts_one;
     DevBuf d_win_in;  // staging of a single streamed window
+    std::unique_ptr<NmStream> strm;  // streaming entry (nm_stream.cuh): page-locked slot ring, parameter blocks, CUDA graphs
 
     int grid_for(size_t smem, int n_items, int threads) const {
         int occ = (int)std::max<size_t>(1, std::min<size_t>(2048 / threads, (size_t)(smem_max + 1024) / (smem + 1024)));
@@ -187,6 +189,37 @@ struct nm_pipeline {
 };
 
 #define NM_P_CHECK(p) NM_CHECK((p) != nullptr, "pipeline is NULL")
+
+// stream operations that a replayed CUDA graph already contains are skipped while the host pass only patches that graph
+#define NM_STREAM_OP(expr)                        \
+    do {                                          \
+        if (!nm_gs_updating()) NM_CUDA_CHECK(expr); \
+    } while (0)
+
+// Small per-launch host arrays (quantile positions, history ranges, ...) -> device.
+//   batched paths:   DevBuf upload from the (temporary) vector; *need_sync tells the caller to synchronise before the vector dies
+//   streaming pass:  the values are written into the slot's page-locked parameter block and copied by a small H2D on the SAME
+//                    stream ahead of the kernel that reads them -- fixed addresses (graph replay), no synchronisation
+template <typename T>
+static int nm_param_upload(nm_pipeline* p, DevBuf& buf, const std::vector<T>& v, const T** dev, bool* need_sync) {
+    NmStream* st = p->strm.get();
+    if (st && st->cur >= 0) {
+        const size_t bytes = v.size() * sizeof(T);
+        const size_t off = (st->par_used + 15) & ~(size_t)15;
+        NM_CHECK(off + bytes <= NM_STREAM_PAR_BYTES, "streaming parameter block too small");
+        unsigned char* h = st->slots[st->cur].par_host + off;
+        memcpy(h, v.data(), bytes);
+        unsigned char* d = st->d_par.as<unsigned char>() + off;
+        st->par_used = off + bytes;
+        if (bytes) NM_STREAM_OP(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, p->stream));
+        *dev = reinterpret_cast<const T*>(d);
+        return 0;
+    }
+    if (buf.upload(v, p->stream)) return -1;
+    *dev = buf.as<T>();
+    if (need_sync) *need_sync = true;
+    return 0;
+}
 
 template <class K>
 static int nm_allow_smem(K kernel, size_t bytes, const nm_pipeline* p) {
@@ -373,10 +406,12 @@ int BurstsFam::prepare(nm_pipeline* p, int n) {
         if (virt < 0) { lo = hi = 0; }
         klo[k] = (int)lo; khi[k] = (int)hi; gam[k] = g;
     }
-    if (d_e_end.upload(e_end, p->stream) || d_n.upload(nh, p->stream) || d_lo.upload(klo, p->stream) || d_hi.upload(khi, p->stream) ||
-        d_gamma.upload(gam, p->stream))
+    bool sync = false;
+    if (nm_param_upload(p, d_e_end, e_end, &a_e_end, &sync) || nm_param_upload(p, d_n, nh, &a_n, &sync) ||
+        nm_param_upload(p, d_lo, klo, &a_lo, &sync) || nm_param_upload(p, d_hi, khi, &a_hi, &sync) ||
+        nm_param_upload(p, d_gamma, gam, &a_gamma, &sync))
         return -1;
-    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));  // the staging vectors above are temporaries
+    if (sync) NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));  // the staging vectors above are temporaries
     run_base = batch;
     return 0;
 }
@@ -405,10 +440,10 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     ta.ring = d_ring.as<double>();
     ta.cap = cap;
     ta.n_ch = C; ta.nB = nB; ta.n_windows = n;
-    ta.e_end = d_e_end.as<long long>() + k0;
-    ta.n_hist = d_n.as<int>() + k0;
-    ta.k_lo = d_lo.as<int>() + k0; ta.k_hi = d_hi.as<int>() + k0;
-    ta.gamma = d_gamma.as<double>() + k0;
+    ta.e_end = a_e_end + k0;
+    ta.n_hist = a_n + k0;
+    ta.k_lo = a_lo + k0; ta.k_hi = a_hi + k0;
+    ta.gamma = a_gamma + k0;
     ta.thr = d_thr.as<double>();
     ta.qrow = d_qrow.as<NmBurstQRow>();
     ta.qkey = d_qkey.as<unsigned long long>();
@@ -472,8 +507,10 @@ int RawNormFam::run(nm_pipeline* p, NmRows& rows) {
         gam[k] = (hist % 2 == 0) ? 0.5 : 0.0;
     }
     NM_CHECK(n_keep > 1 || (long long)W + (batch + n) * add < cap, "raw normalisation history exceeds the ring (normalization_time_s * sfreq == 1)");
-    if (d_lo.upload(lo, p->stream)) return -1;
-    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));  // `lo` is a temporary
+    const long long* a_lo = nullptr;
+    bool sync = false;
+    if (nm_param_upload(p, d_lo, lo, &a_lo, &sync)) return -1;
+    if (sync) NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));  // `lo` is a temporary
     NmRawNormArgs a;
     a.in = rows;
     a.out = d_out.as<double>();
@@ -484,7 +521,7 @@ int RawNormFam::run(nm_pipeline* p, NmRows& rows) {
     a.blk_cap = blk_cap;
     a.g0 = batch;
     a.add = add;
-    a.lo = d_lo.as<long long>();
+    a.lo = a_lo;
     a.method = method;
     a.clip = clip;
     a.med = need_median() ? d_med.as<double>() : nullptr;
@@ -494,18 +531,23 @@ int RawNormFam::run(nm_pipeline* p, NmRows& rows) {
     p->prof_begin();
     NM_LAUNCH(nm_rawnorm_append_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
     if (need_median()) {
-        if (d_e_end.upload(e_end, p->stream) || d_n.upload(nh, p->stream) || d_klo.upload(klo, p->stream) || d_khi.upload(khi, p->stream) ||
-            d_gamma.upload(gam, p->stream))
+        const long long* m_e_end = nullptr;
+        const int *m_n = nullptr, *m_lo = nullptr, *m_hi = nullptr;
+        const double* m_gamma = nullptr;
+        bool msync = false;
+        if (nm_param_upload(p, d_e_end, e_end, &m_e_end, &msync) || nm_param_upload(p, d_n, nh, &m_n, &msync) ||
+            nm_param_upload(p, d_klo, klo, &m_lo, &msync) || nm_param_upload(p, d_khi, khi, &m_hi, &msync) ||
+            nm_param_upload(p, d_gamma, gam, &m_gamma, &msync))
             return -1;
-        NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+        if (msync) NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
         NmBurstThrArgs ta;
         ta.ring = d_ring.as<double>();
         ta.cap = cap;
         ta.n_ch = C; ta.nB = 1; ta.n_windows = n;
-        ta.e_end = d_e_end.as<long long>();
-        ta.n_hist = d_n.as<int>();
-        ta.k_lo = d_klo.as<int>(); ta.k_hi = d_khi.as<int>();
-        ta.gamma = d_gamma.as<double>();
+        ta.e_end = m_e_end;
+        ta.n_hist = m_n;
+        ta.k_lo = m_lo; ta.k_hi = m_hi;
+        ta.gamma = m_gamma;
         ta.thr = d_med.as<double>();
         ta.qrow = d_qrow.as<NmBurstQRow>();
         ta.qkey = d_qkey.as<unsigned long long>();
@@ -524,20 +566,28 @@ int RawNormFam::run(nm_pipeline* p, NmRows& rows) {
     return 0;
 }
 
+
 int NormFam::run(nm_pipeline* p, int n_windows) {
     if (n_cols == 0) return 0;
-    const size_t rows = (size_t)n_prev + n_windows;
-    if (d_ext.ensure(rows * n_cols * sizeof(double))) return -1;
+    // History of RAW rows: a fixed-capacity block of cap = n_keep - 1 rows, the valid ones RIGHT-aligned.  The streaming entry
+    // (one window per call) then always copies cap rows in and out -- constant sizes, so its CUDA graph never changes shape --
+    // and passes n_prev = cap: the kernel reads rows [row - (nh - 1), row] with nh <= g + 1, i.e. never an unwritten one.
+    const int cap = std::max(0, n_keep - 1);
+    const bool streaming = p->strm && p->strm->cur >= 0 && n_windows == 1;
+    const int prev = streaming ? cap : n_prev;
+    const size_t rows = (size_t)prev + n_windows;
+    if (d_ext.ensure(std::max(rows, (size_t)cap + 1) * n_cols * sizeof(double))) return -1;
     double* ext = d_ext.as<double>();
-    if (n_prev)
-        NM_CUDA_CHECK(cudaMemcpyAsync(ext, d_hist.p, (size_t)n_prev * n_cols * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    const double* hist_valid = d_hist.as<double>() + (size_t)(cap - prev) * n_cols;
+    if (prev)
+        NM_STREAM_OP(cudaMemcpyAsync(ext, hist_valid, (size_t)prev * n_cols * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
     const long long tot = (long long)n_windows * n_cols;
     const unsigned grid = (unsigned)((tot + NM_ROW_THREADS - 1) / NM_ROW_THREADS);
     NM_LAUNCH(nm_norm_gather_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, (const double*)p->d_out.as<double>(), p->F,
-              (const int*)d_cols.as<int>(), n_cols, n_windows, ext + (size_t)n_prev * n_cols);
+              (const int*)d_cols.as<int>(), n_cols, n_windows, ext + (size_t)prev * n_cols);
     NmNormArgs a;
     a.ext = ext;
-    a.n_prev = n_prev;
+    a.n_prev = prev;
     a.n_windows = n_windows;
     a.n_cols = n_cols;
     a.cols = d_cols.as<int>();
@@ -551,12 +601,12 @@ int NormFam::run(nm_pipeline* p, int n_windows) {
     NM_LAUNCH(nm_norm_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
     p->prof_end(NM_PROF_NORM);
     p->launches += 2;
-    // keep the last (n_keep - 1) raw rows for the next call
-    const int keep = (int)std::min<size_t>(rows, (size_t)std::max(0, n_keep - 1));
+    // keep the last cap raw rows for the next call (right-aligned)
+    const int keep = streaming ? cap : (int)std::min<size_t>(rows, (size_t)cap);
     if (keep)
-        NM_CUDA_CHECK(cudaMemcpyAsync(d_hist.p, ext + (rows - keep) * n_cols, (size_t)keep * n_cols * sizeof(double),
-                                      cudaMemcpyDeviceToDevice, p->stream));
-    n_prev = keep;
+        NM_STREAM_OP(cudaMemcpyAsync(d_hist.as<double>() + (size_t)(cap - keep) * n_cols, ext + (rows - keep) * n_cols,
+                                     (size_t)keep * n_cols * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    n_prev = (int)std::min<size_t>((size_t)n_prev + n_windows, (size_t)cap);
     batch += n_windows;
     return 0;
 }
@@ -689,6 +739,8 @@ extern "C" int nm_pipeline_create(int device, int n_raw_rows, int n_ch, int wind
     return 0;
 }
 
+static void nm_stream_release(nm_pipeline* p);
+
 extern "C" void nm_pipeline_destroy(nm_pipeline* p) {
     if (!p) return;
     cudaSetDevice(p->device);
@@ -708,6 +760,7 @@ extern "C" void nm_pipeline_destroy(nm_pipeline* p) {
     for (auto e : p->slice_ev) cudaEventDestroy(e);
     for (auto e : p->red_ev) cudaEventDestroy(e);
     for (auto e : p->chunk_ev) cudaEventDestroy(e);
+    nm_stream_release(p);
     cudaStream_t s = p->stream, cs = p->copy_stream;
     delete p;
     if (s) cudaStreamDestroy(s);
@@ -1088,9 +1141,10 @@ extern "C" int nm_finalize(nm_pipeline* p) {
 
 extern "C" int nm_reset_state(nm_pipeline* p) {
     NM_P_CHECK(p);
-    if (p->bursts) p->bursts->reset();
+    cudaSetDevice(p->device);
+    if (p->bursts) p->bursts->reset(p->stream);
     if (p->norm) p->norm->reset();
-    if (p->rawnorm) p->rawnorm->reset();
+    if (p->rawnorm) p->rawnorm->reset(p->stream);
     return 0;
 }
 
@@ -1225,6 +1279,7 @@ static int nm_upload_impl(nm_pipeline* p, const void* data, bool f64, long long 
     NM_CHECK(data && n_samples >= p->Win && pitch >= n_samples, "bad recording geometry (n_samples %lld, pitch %lld, W %d)", n_samples,
              pitch, p->Win);
     cudaSetDevice(p->device);
+    nm_stream_release(p);  // a streaming session (captured graphs, one-window geometry) does not survive a batched upload
     p->n_slices = 0;
     p->slices_prepped = 0;
     if (n_samples >= NM_UPLOAD_MIN_PIPELINED) {
@@ -1411,17 +1466,18 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
     cudaStream_t const main_stream = p->stream;
     const int n_branches = ((!p->spectral.empty() || p->bandpower) ? 1 : 0) + (p->sharpwave ? 1 : 0) + (p->bursts ? 1 : 0);
     const bool fork = !p->profiling && n_branches >= 2;
-    if (fork) NM_CUDA_CHECK(cudaEventRecord(p->ev_fork, main_stream));
+    const bool live = !nm_gs_updating();  // (a replayed graph already holds these dependencies)
+    if (fork && live) NM_CUDA_CHECK(cudaEventRecord(p->ev_fork, main_stream));
     auto branch_begin = [&](int b) {
         if (!fork) return;
-        cudaStreamWaitEvent(p->side[b], p->ev_fork, 0);
+        if (live) cudaStreamWaitEvent(p->side[b], p->ev_fork, 0);
         p->stream = p->side[b];
     };
     auto branch_end = [&](int b) {
         if (!fork) return;
-        cudaEventRecord(p->ev_join[b], p->side[b]);
+        if (live) cudaEventRecord(p->ev_join[b], p->side[b]);
         p->stream = main_stream;
-        cudaStreamWaitEvent(main_stream, p->ev_join[b], 0);
+        if (live) cudaStreamWaitEvent(main_stream, p->ev_join[b], 0);
     };
     branch_begin(0);
     for (size_t fi = 0; fi < p->spectral.size(); ++fi) {
@@ -1464,10 +1520,34 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
     return 0;
 }
 
+// per-window NaN-channel flags from the block map + NaN re-insertion by column list for windows [w0, w0 + n) of the current run
+static void nm_nan_fill(nm_pipeline* p, int w0, int n) {
+    NmNanArgs na;
+    na.p = nm_prep_args(p);
+    na.start = p->d_starts.as<long long>() + w0;
+    na.n_windows = n;
+    na.W = p->Win;
+    na.flags = p->d_nanflags.as<unsigned char>() + (size_t)w0 * p->C_all;
+    const long long tot = (long long)n * p->C_all;
+    const unsigned grid = (unsigned)((tot + NM_ROW_THREADS - 1) / NM_ROW_THREADS);
+    NmNanFillArgs nf;
+    nf.flags = na.flags;
+    nf.n_windows = n;
+    nf.C_all = p->C_all;
+    nf.col_ptr = p->d_nan_ptr.as<int>();
+    nf.cols = p->d_nan_cols.as<int>();
+    nf.out = p->d_out.as<double>();
+    nf.row0 = w0;
+    nf.F = p->F;
+    NM_LAUNCH(nm_nanfix_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, na, nf);
+    p->launches += 1;
+}
+
 extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_windows, double* out_host) {
     NM_P_CHECK(p);
     NM_CHECK(p->finalized && p->have_data, "finalize the pipeline and upload a recording first");
     NM_CHECK(starts && n_windows > 0, "no windows given");
+    nm_stream_release(p);
     for (int k = 0; k < n_windows; ++k)
         NM_CHECK(starts[k] >= 0 && starts[k] + p->Win <= p->T, "window %d [%lld, %lld) outside the recording (%lld samples)", k, starts[k],
                  starts[k] + p->Win, p->T);
@@ -1494,27 +1574,7 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
     // without the (sequential) normaliser a chunk's rows are final when its kernels end: ship them chunk by chunk
     const bool per_chunk = !p->norm && out_host != nullptr;
     if (p->has_nan_cols && p->d_nanflags.ensure((size_t)n_windows * p->C_all)) return -1;
-    auto nan_fill = [&](int w0, int n) {
-        NmNanArgs na;
-        na.p = nm_prep_args(p);
-        na.start = p->d_starts.as<long long>() + w0;
-        na.n_windows = n;
-        na.W = p->Win;
-        na.flags = p->d_nanflags.as<unsigned char>() + (size_t)w0 * p->C_all;
-        const long long tot = (long long)n * p->C_all;
-        const unsigned grid = (unsigned)((tot + NM_ROW_THREADS - 1) / NM_ROW_THREADS);
-        NmNanFillArgs nf;
-        nf.flags = na.flags;
-        nf.n_windows = n;
-        nf.C_all = p->C_all;
-        nf.col_ptr = p->d_nan_ptr.as<int>();
-        nf.cols = p->d_nan_cols.as<int>();
-        nf.out = p->d_out.as<double>();
-        nf.row0 = w0;
-        nf.F = p->F;
-        NM_LAUNCH(nm_nanfix_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, na, nf);
-        p->launches += 1;
-    };
+    auto nan_fill = [&](int w0, int n) { nm_nan_fill(p, w0, n); };
     if (p->bursts && p->bursts->prepare(p, n_windows)) return -1;
     int n_ev = 0;
     for (int w0 = 0; w0 < n_windows; w0 += p->chunk) {
@@ -1583,12 +1643,28 @@ extern "C" int nm_host_unregister(void* ptr) {
     return 0;
 }
 
+extern "C" int nm_stream_open(nm_pipeline* p, int n_slots, int input_f32, int use_graph);
+extern "C" int nm_stream_submit(nm_pipeline* p, int slot);
+extern "C" int nm_stream_wait(nm_pipeline* p, int slot, const double** features);
+
+// One window with caller-owned (pageable) buffers: the synchronous form of the streaming entry -- copy into a page-locked slot,
+// submit, wait, copy the feature row out.  Producers that can write into the slot themselves use nm_stream_* directly.
 extern "C" int nm_process_window(nm_pipeline* p, const double* window, double* out_features) {
     NM_P_CHECK(p);
     NM_CHECK(window && out_features, "NULL argument");
-    if (nm_upload_impl(p, window, true, p->Win, p->Win)) return -1;
-    const long long zero = 0;
-    return nm_run_windows(p, &zero, 1, out_features);
+    NM_CHECK(p->finalized, "call nm_finalize first");
+    if (!p->strm || p->strm->f32) {  // (batched entry points close the stream: its graphs hold their buffers' old addresses)
+        if (nm_stream_open(p, 2, 0, -1)) return -1;
+    }
+    NmStream& st = *p->strm;
+    const int slot = (int)(st.windows % st.n_slots);
+    if (st.slots[slot].busy && nm_stream_wait(p, slot, nullptr)) return -1;
+    memcpy(st.slots[slot].in_host, window, (size_t)p->C_all * p->Win * sizeof(double));
+    if (nm_stream_submit(p, slot)) return -1;
+    const double* f = nullptr;
+    if (nm_stream_wait(p, slot, &f)) return -1;
+    memcpy(out_features, f, (size_t)p->F * sizeof(double));
+    return 0;
 }
 
 // Preprocessed rows of one window (nan_to_num -> pick -> re-reference -> notch), float64 (n_ch, W).
@@ -1683,7 +1759,7 @@ extern "C" int nm_set_burst_threshold_mode(nm_pipeline* p, int incremental) {
         cudaSetDevice(p->device);
         NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
         p->bursts->incremental = incremental ? 1 : 0;
-        p->bursts->reset();
+        p->bursts->reset(p->stream);
     }
     return 0;
 }
@@ -1815,3 +1891,4 @@ extern "C" int nm_fir_apply(int device, const double* taps, int n_filters, int n
 // (implemented with the multi-GPU path; see nm_multi.cuh)
 #include "nm_multi.cuh"
 #include "nm_comm.cuh"
+#include "nm_stream.cuh"

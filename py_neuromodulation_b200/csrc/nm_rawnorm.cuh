@@ -173,13 +173,14 @@ struct RawNormFam {
             if (d_med.ensure((size_t)chunk * C * sizeof(double))) return -1;
             if (d_qrow.ensure((size_t)C * sizeof(NmBurstQRow)) || d_qkey.ensure((size_t)C * NM_BQ_CAP * 8) || d_qidx.ensure((size_t)C * NM_BQ_CAP * 4)) return -1;
             NM_CUDA_CHECK(cudaMemset(d_qrow.p, 0, (size_t)C * sizeof(NmBurstQRow)));
+            NM_CUDA_CHECK(cudaDeviceSynchronize());  // (legacy-stream memset: finish before any non-blocking stream uses the rows)
         }
         return 0;
     }
-    void reset() {
+    void reset(cudaStream_t s) {  // (stream-ordered, see BurstsFam::reset)
         batch = 0;
         len_prev = 0;
-        if (d_qrow.p) cudaMemset(d_qrow.p, 0, (size_t)C * sizeof(NmBurstQRow));
+        if (d_qrow.p) cudaMemsetAsync(d_qrow.p, 0, (size_t)C * sizeof(NmBurstQRow), s);
     }
     int run(nm_pipeline* p, NmRows& rows);
 };

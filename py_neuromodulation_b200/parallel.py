@@ -292,16 +292,16 @@ class ShardedRun:
 
         Nothing here blocks the host: the re-reference of a slice happens inside ``run`` right before the first chunk of
         windows that needs it, so transfers, reductions and window kernels of different slices overlap."""
+        p = self.pipe
+        a = np.ascontiguousarray(data_f32, dtype=np.float32)
+        if self.comm is not None:  # sums + ncclAllReduce per slice are enqueued by the library itself (no torch on this path)
+            _lib.check(p.lib.nm_upload_sharded_f32(p._h, self.comm._h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[1]))
+            p._keep_data = a
+            return
         import contextlib
 
         import torch.distributed as dist
 
-        p = self.pipe
-        a = np.ascontiguousarray(data_f32, dtype=np.float32)
-        if self.comm is not None:  # sums + ncclAllReduce per slice are enqueued by the library itself
-            _lib.check(p.lib.nm_upload_sharded_f32(p._h, self.comm._h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[1]))
-            p._keep_data = a
-            return
         _lib.check(p.lib.nm_upload_begin_f32(p._h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[1]))
         p._keep_data = a
         n_slices, slice_len, n_groups, pitch = C.c_int(), C.c_longlong(), C.c_int(), C.c_longlong()

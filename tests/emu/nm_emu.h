@@ -342,6 +342,7 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
 enum { cudaStreamNonBlocking = 1 };
 
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline bool nm_gs_updating() { return false; }  // (no CUDA graphs in the test build: the streaming entry always launches eagerly)
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }

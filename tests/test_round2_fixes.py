@@ -147,3 +147,45 @@ def test_pipeline_writes_into_a_column_block_of_a_wider_table(backend):
         big = np.full((starts.size, len(cols) + 3), -7.0)
         _, view = dp.process_windows(x, starts, 1000, out=big[:, : len(cols)])
         assert np.array_equal(big[:, : len(cols)], dense, equal_nan=True) and np.all(big[:, len(cols):] == -7.0)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_window_stream_slot_ring_equals_batched_run(backend, graph):
+    """Streaming entry: windows pushed through the page-locked slot ring -- two in flight, eager launches or CUDA-graph
+    replay with patched window counters -- give the rows of ONE batched run: burst history, raw-sample and feature normalisers
+    advance exactly once per window (reference: stream/data_processor.py:238-311 called per batch by stream/stream.py:280-330)."""
+    from py_neuromodulation_b200.stream.window_stream import WindowStream
+
+    x = neural_like(11, 5, 1000 + 100 * 23)
+    s = nm.NMSettings.get_default()  # bursts + sharp waves + FFT/Welch + Hjorth + rolling z-score
+    s.preprocessing = ["notch_filter", "re_referencing", "raw_normalization"]
+    s.raw_normalization_settings.normalization_time_s = 1.5
+    s.feature_normalization_settings.normalization_time_s = 1.2  # history shorter than the run: the fixed-capacity ring wraps
+    ch = get_default_channels_from_data(x)
+    starts = np.arange(0, 100 * 24, 100)
+    ref_cols, ref = nm.DataProcessor(sfreq=1000, settings=s, channels=ch, line_noise=50, verbose=False).process_windows(x, starts, 1000)
+
+    dp = nm.DataProcessor(sfreq=1000, settings=s, channels=ch, line_noise=50, verbose=False)
+    ws = WindowStream(dp, 1000, slots=2, graph=graph, capacity=8)  # (capacity 8: the table grows twice)
+    assert ws.columns == list(ref_cols)
+    for k, st in enumerate(starts):
+        ws.next_input()[...] = x[:, st : st + 1000]
+        ws.submit(time_ms=float(st + 1000))
+        if ws.in_flight == ws.slots:
+            ws.collect()
+    ws.drain()
+    stats = ws.pipe.stream_stats()
+    df = ws.to_frame()
+    ws.close()
+    got = df[ws.columns].to_numpy()
+    assert got.shape == ref.shape and list(df["time"]) == [float(t + 1000) for t in starts]
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert parity_err(ref_cols, got, ref, normalized=True).max() < 1e-11
+    for j, k in enumerate(ref_cols):
+        if k.endswith("_in_burst"):
+            assert np.array_equal(got[:, j], ref[:, j]), k
+    assert stats["windows"] == len(starts)
+    if backend == "gpu" and graph:  # captured once per slot, replayed for the rest, counters patched into the kernel nodes
+        assert stats["graph_launches"] == len(starts) - 2 and stats["graph_kernel_nodes"] > 5 and stats["patched_arguments"] > 0
+    else:
+        assert stats["graph_launches"] == 0 or backend == "gpu"
