@@ -35,8 +35,15 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
-# stdout carries exactly ONE JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line: everything native libraries print there (NCCL's version banner / NCCL_DEBUG output) is
+# sent to stderr at the file-descriptor level; emit() writes the line to the real stdout
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 CH_PER_GPU = 256
 SFREQ = 1000.0
@@ -252,7 +259,7 @@ def run_reference_arm(args) -> None:
             if kind == "reference" else "NumPy port of the reference (oracle/np_oracle.py)")
     sample = (f"{n_win} windows of the C3 workload per step (256 ch x 1000 samp, float64), dealt to {cores} worker processes, "
               f"BLAS/OMP threads = 1, median of {steps} steps (min {min(times):.2f} s, max {max(times):.2f} s); {what}")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -261,7 +268,7 @@ def run_reference_arm(args) -> None:
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -541,7 +548,7 @@ def run_gpu_arm(args) -> None:
             line["e2e_stream"] = stream_info
         if world == 1 and not args.no_cpu_baseline and args.config == "c3":
             line["cpu_baseline"] = cpu_baseline_single()
-        print(json.dumps(line))
+        emit(line)
     if comm is not None:
         comm.barrier()
         sharded.close()
