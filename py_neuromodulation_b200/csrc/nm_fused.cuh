@@ -405,3 +405,119 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, (NmFzOcc<P, true>::value)) nm_f
         item = next;
     }
 }
+
+// ================================================================ the "front" kernel: everything up to the notched window
+// Default organisation of the window chain since round 2.  nm_fused_kernel above keeps the whole chain in one CTA but pays for
+// it with two transform buffers and 168 registers (3 CTAs per SM, measured slower than the staged kernels).  This kernel takes
+// the part that profits from staying on chip and leaves the band-pass bank to nm_convx_kernel<.., BANK, NmEpiBandpower>:
+//
+//   raw rows (f32 / f64 as uploaded) + group sums --cp.async.bulk + mbarrier--> STAGE (its own small region, not a transform
+//   buffer) --nan_to_num, pick, folded re-reference, odd reflection--> forward, * H_notch, inverse --> registers
+//        --> notched rows to HBM only if a later family reads them (band power, bursts, sharp waves, STFT)
+//        --> Hjorth / line length / raw and the N-point segment DFT band features (FFT / Welch) from the on-chip window
+//
+// One transform buffer + stage: 53 KB per CTA at P = 2048 with float32 recordings -> 4 CTAs per SM at <= 128 registers.  The stage
+// is dead as soon as every thread has loaded its pass-0 inputs, so the NEXT item's bulk copies are issued behind the first
+// barrier of the current item and have the whole item to land (no register prefetch, no exposed global-load latency).
+// Replaces nm_prep_kernel's float64 copy of the recording, the notch kernel and the spectral kernels of the staged path.
+template <int P, bool RAW64>
+static NM_HD size_t nm_front_smem_bytes(int W) {
+    return (size_t)NmCxPlan<P>::NBUF * sizeof(cx<double>) + ((NmFzStage<RAW64>::bytes(W) + 15) & ~(size_t)15) + NM_CX_RED_BYTES + 16;
+}
+
+template <int P, bool RAW64>
+struct NmFrontOcc {
+    static constexpr int NT = NmCxPlan<P>::NT;
+    static constexpr int value = (NT >= 256) ? (RAW64 ? 1 : 2) : (NT == 128 ? (RAW64 ? 3 : 4) : 8);
+};
+
+template <int P, class SX, bool RAW64>
+NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, (NmFrontOcc<P, RAW64>::value)) nm_front_kernel(NmFusedArgs a) {
+    using PL = NmCxPlan<P>;
+    using T = double;
+    constexpr int NT = PL::NT;
+    NM_SHARED_BYTES(smem);
+    cx<T>* work = reinterpret_cast<cx<T>*>(smem);
+    unsigned char* stage = reinterpret_cast<unsigned char*>(work + PL::NBUF);
+    const int W = a.W, E = a.E;
+    double* red = reinterpret_cast<double*>(stage + ((NmFzStage<RAW64>::bytes(W) + 15) & ~(size_t)15));
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(red) + NM_CX_RED_BYTES);
+    const int tid = threadIdx.x;
+    const int npair = (a.n_ch + 1) >> 1;
+    const cx<T>* NM_RESTRICT tw = a.tw;
+    const cx<T> wA = nm_ldg(tw + tid);
+    const cx<T> wB = nm_ldg(tw + (tid & (PL::M1 - 1)) * 16);
+    cx<T>* const p0w = work + tid + (tid >> PL::PAD);
+    const int nat_elems = (NmEpiStoreScan::phys(W - 1) + 2) & ~1;
+
+    int item = blockIdx.x;
+    if (item >= a.n_items) return;
+    if (tid == 0) nm_mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) nm_fz_issue<RAW64>(a, item, npair, stage, bar);
+    unsigned parity = 0;
+
+    cx<T> v[16];
+    T hv[16];
+    while (item < a.n_items) {
+        const int next = item + gridDim.x;
+        const int w = item / npair, c0 = (item - w * npair) * 2;
+        const bool has2 = c0 + 1 < a.n_ch;
+        // ---- pass 0 straight from the stage
+        nm_mbar_wait(bar, parity);
+        parity ^= 1u;
+        nm_fz_load<P, RAW64>(v, a, stage, nm_ldg(a.start + w), c0, has2, tid);
+        nm_bfly16<false>(v);
+        nm_twiddle_w1<16, false>(v, wA);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) p0w[t * PL::S0] = v[t];
+        __syncthreads();  // every thread is done with the stage: the next item's rows may land from here on
+        if (tid == 0 && next < a.n_items) nm_fz_issue<RAW64>(a, next, npair, stage, bar);
+        nm_cx_load_h<PL, T>(hv, a.hx_notch, tid);  // (L1 resident) lands while pass 1 computes
+        nm_cx_pass1<PL, false>(work, wB, tid);
+        __syncthreads();
+        nm_cx_pass2<PL, 1, T>(work, work, hv, tid);
+        __syncthreads();
+        nm_cx_pass1<PL, true>(work, wB, tid);
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] = p0w[t * PL::S0];
+        nm_twiddle_w1<16, true>(v, wA);
+        nm_bfly16<true>(v);
+        // ---- notched window: registers -> HBM rows (only for families outside this kernel) + natural order on chip
+        if (a.scan.y) {
+            double* r0 = a.scan.y + ((size_t)w * a.n_ch + c0) * a.scan.Wp;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int t = tid + NT * k - E;
+                if (t >= 0 && t < W) {
+                    r0[t] = v[k].re;
+                    if (has2) r0[a.scan.Wp + t] = v[k].im;
+                }
+            }
+        }
+        const bool on_chip = a.scan.want_scan || (SX::N != 0 && a.n_spec > 0);
+        __syncthreads();  // every thread has read its final-pass inputs from `work`
+        if (on_chip) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int u = tid + NT * k - E;
+                if (u >= 0 && u < W) work[NmEpiStoreScan::phys(u)] = v[k];
+            }
+            if (a.scan.want_scan) {
+                NmEpiStoreScan::State st;
+                a.scan.template finish<PL, T>(work, red, st, E, W, a.n_ch, w, c0, has2, 0, tid);  // (begins with a barrier)
+            } else {
+                __syncthreads();
+            }
+            if constexpr (SX::N != 0) {
+#pragma unroll 1
+                for (int si = 0; si < a.n_spec; ++si)
+                    nm_fz_spectral<SX>(a.spec[si], work, work + nat_elems, reinterpret_cast<double*>(work + nat_elems + SX::NBUF), red,
+                                       w + (int)a.row0, c0, has2, tid, NT);  // (ends with a barrier)
+            }
+            // (no trailing barrier: the scan epilogue ends with every thread past its reads of `work`, the DFT ends with a barrier)
+        }
+        item = next;
+    }
+}

@@ -137,7 +137,8 @@ struct nm_pipeline {
     // fused window kernel (nm_fused.cuh): the re-reference must fold into the load as  x_i = d_i * raw_i + g_i * S  (at most one
     // group sum, no off-diagonal remainder); decided at nm_finalize, switchable with NMB200_FUSED=0 for A/B measurements
     bool reref_foldable = true, fused = false, force_xr = false, fused_bp = false;
-    int fused_mode = -1;  // nm_set_fused: 0 off, 1 on, -1 environment (NMB200_FUSED, default off)
+    bool front = false;   // `fused` through nm_front_kernel (notch + scan + segment DFT; the bank stays a kernel of its own)
+    int fused_mode = -1;  // nm_set_fused: 0 staged kernels, 1 whole chain in one kernel, 2 front kernel, -1 environment (NMB200_FUSED, default 2)
     std::vector<double> h_dfold, h_gfold;
     DevBuf d_dfold, d_gfold;
     int fused_sx = 0;                       // segment length of the in-kernel DFT families (0: none)
@@ -629,18 +630,36 @@ static NmFusedKernel nm_fused_pick(int P, int sx, bool raw64) {
 static size_t nm_fused_smem(int P) {
     return P == 1024 ? nm_fused_smem_bytes<1024>() : (P == 2048 ? nm_fused_smem_bytes<2048>() : nm_fused_smem_bytes<4096>());
 }
+static NmFusedKernel nm_front_pick(int P, int sx, bool raw64) {
+    if (P == 1024) return raw64 ? nm_front_kernel<1024, NmSxNone, true> : nm_front_kernel<1024, NmSxNone, false>;
+    if (P == 2048) {
+        if (sx == 1000) return raw64 ? nm_front_kernel<2048, NmSx1000, true> : nm_front_kernel<2048, NmSx1000, false>;
+        return raw64 ? nm_front_kernel<2048, NmSxNone, true> : nm_front_kernel<2048, NmSxNone, false>;
+    }
+    if (P == 4096) {
+        if (sx == 2000) return raw64 ? nm_front_kernel<4096, NmSx2000, true> : nm_front_kernel<4096, NmSx2000, false>;
+        return raw64 ? nm_front_kernel<4096, NmSxNone, true> : nm_front_kernel<4096, NmSxNone, false>;
+    }
+    return nullptr;
+}
+static size_t nm_front_smem(int P, int W, bool raw64) {
+    if (P == 1024) return raw64 ? nm_front_smem_bytes<1024, true>(W) : nm_front_smem_bytes<1024, false>(W);
+    if (P == 2048) return raw64 ? nm_front_smem_bytes<2048, true>(W) : nm_front_smem_bytes<2048, false>(W);
+    return raw64 ? nm_front_smem_bytes<4096, true>(W) : nm_front_smem_bytes<4096, false>(W);
+}
 static size_t nm_fused_nbuf(int P) { return P == 1024 ? NmCxPlan<1024>::NBUF : (P == 2048 ? NmCxPlan<2048>::NBUF : NmCxPlan<4096>::NBUF); }
 
 // decide at nm_finalize whether the window chain runs in the fused kernel and which families it serves
 static int nm_fused_plan(nm_pipeline* p) {
     p->fused = false;
+    p->front = false;
     p->fused_bp = false;
     p->fused_sx = 0;
     p->fused_spec.clear();
     int want = p->fused_mode;
     if (want < 0) {
         const char* env = getenv("NMB200_FUSED");
-        want = env ? atoi(env) : 0;
+        want = env ? atoi(env) : 2;
     }
     if (want == 0) return 0;
     if (!p->notch || !p->reref_foldable || !p->prefilters.empty() || p->rawnorm || p->has_resampler || p->f32_linear() || p->precision == 1) return 0;
@@ -650,26 +669,34 @@ static int nm_fused_plan(nm_pipeline* p) {
     if (NmFzStage<true>::bytes(p->W) > buf_bytes) return 0;  // the stage of one item must fit a transform buffer
     const int nat_elems = (NmEpiStoreScan::phys(p->W - 1) + 2) & ~1;
     if ((size_t)nat_elems * sizeof(cx<double>) > buf_bytes) return 0;
-    if (nm_fused_smem(nb.P) > (size_t)p->smem_max) return 0;
+    if (want == 2 ? nm_front_smem(nb.P, p->W, true) > (size_t)p->smem_max : nm_fused_smem(nb.P) > (size_t)p->smem_max) return 0;
     p->fused = true;
+    p->front = want == 2;
     const int sx_ok = nb.P == 2048 ? 1000 : (nb.P == 4096 ? 2000 : 0);
     for (size_t i = 0; i < p->spectral.size() && sx_ok; ++i) {
         const SpectralFam& f = *p->spectral[i];
         const nm_spectral_cfg& c = f.cfg;
         const size_t vals = (size_t)2 * f.nk * sizeof(double);
+        // front kernel: natural-order window, DFT buffer and bin values share ONE transform buffer
+        const size_t dft_buf = p->front ? (size_t)f.nbuf() * sizeof(cx<double>) : 0;
         if (f.fast && c.nper == sx_ok && c.nseg == 1 && !c.keep_segments && c.start >= 0 && c.start + c.nper <= p->W &&
-            (size_t)nat_elems * sizeof(cx<double>) + vals <= buf_bytes && (int)p->fused_spec.size() < NM_FZ_MAX_SPEC) {
+            (size_t)nat_elems * sizeof(cx<double>) + dft_buf + vals <= buf_bytes && (int)p->fused_spec.size() < NM_FZ_MAX_SPEC) {
             p->fused_spec.push_back((int)i);
             p->fused_sx = sx_ok;
         }
     }
-    if (p->bandpower) {
+    if (p->bandpower && !p->front) {
         const BandpowerFam& f = *p->bandpower;
         p->fused_bp = f.bank.pow2 && f.bank.P == nb.P && f.bank.mode == NM_FIR_SAME && !(f.mob || f.comp) && f.bank.d_hx.p != nullptr;
     }
     if (p->d_dfold.upload(p->h_dfold, p->stream) || p->d_gfold.upload(p->h_gfold, p->stream)) return -1;
-    for (int raw64 = 0; raw64 < 2; ++raw64)
-        if (nm_allow_smem(nm_fused_pick(nb.P, p->fused_sx, raw64 != 0), nm_fused_smem(nb.P), p)) return -1;
+    for (int raw64 = 0; raw64 < 2; ++raw64) {
+        if (p->front) {
+            if (nm_allow_smem(nm_front_pick(nb.P, p->fused_sx, raw64 != 0), nm_front_smem(nb.P, p->W, raw64 != 0), p)) return -1;
+        } else if (nm_allow_smem(nm_fused_pick(nb.P, p->fused_sx, raw64 != 0), nm_fused_smem(nb.P), p)) {
+            return -1;
+        }
+    }
     return 0;
 }
 static bool nm_spec_in_fused(const nm_pipeline* p, size_t i) {
@@ -1055,7 +1082,7 @@ extern "C" int nm_set_precision(nm_pipeline* p, int float32_linear) {
 extern "C" int nm_set_fused(nm_pipeline* p, int mode) {
     NM_P_CHECK(p);
     NM_CHECK(!p->finalized, "pipeline already finalized");
-    NM_CHECK(mode >= -1 && mode <= 1, "fused mode must be -1 (environment), 0 (off) or 1 (on)");
+    NM_CHECK(mode >= -1 && mode <= 2, "fused mode must be -1 (environment), 0 (staged kernels), 1 (one kernel) or 2 (front kernel)");
     p->fused_mode = mode;
     return 0;
 }
@@ -1422,8 +1449,8 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         a.n_spec = (int)p->fused_spec.size();
         a.spec = p->d_fused_spec.as<NmSpecArgs>();
         a.row0 = w0;
-        auto kern = nm_fused_pick(nb.P, p->fused_sx, p->raw_f64);
-        const size_t sm = nm_fused_smem(nb.P);
+        auto kern = p->front ? nm_front_pick(nb.P, p->fused_sx, p->raw_f64) : nm_fused_pick(nb.P, p->fused_sx, p->raw_f64);
+        const size_t sm = p->front ? nm_front_smem(nb.P, p->W, p->raw_f64) : nm_fused_smem(nb.P);
         const int threads = nb.P / 16;
         p->prof_begin();
         NM_LAUNCH(kern, dim3(nm_resident_grid(p, kern, threads, sm, a.n_items)), dim3(threads), sm, p->stream, a);
@@ -1789,9 +1816,10 @@ extern "C" int nm_describe_plan(nm_pipeline* p, char* buf, int n) {
     }
     for (auto& b : p->prefilters) nm_describe_fir<NmEpiStore>(s, "prefilter", *b, 0);
     if (p->fused) {
-        snprintf(line, sizeof(line), "fused: nm_fused_kernel P=%d threads=%d smem=%zu [re-reference + notch%s%s%s] dft_families=%d\n", p->notch->P,
-                 p->notch->P / 16, nm_fused_smem(p->notch->P), p->has_scan ? " + scan" : "", p->fused_sx ? " + segment DFT" : "",
-                 p->fused_bp ? " + band-pass bank" : "", (int)p->fused_spec.size());
+        snprintf(line, sizeof(line), "fused: %s P=%d threads=%d smem=%zu [re-reference + notch%s%s%s] dft_families=%d\n",
+                 p->front ? "nm_front_kernel" : "nm_fused_kernel", p->notch->P, p->notch->P / 16,
+                 p->front ? nm_front_smem(p->notch->P, p->W, p->raw_f64) : nm_fused_smem(p->notch->P), p->has_scan ? " + scan" : "",
+                 p->fused_sx ? " + segment DFT" : "", p->fused_bp ? " + band-pass bank" : "", (int)p->fused_spec.size());
         s += line;
     } else if (p->notch) {
         if (nm_convx_pick<NmEpiStoreScan>(*p->notch)) nm_describe_fir<NmEpiStoreScan>(s, p->has_scan ? "notch+scan" : "notch", *p->notch, 0);
