@@ -458,7 +458,7 @@ def run_gpu_arm(args) -> None:
                                "frac_of_nominal_8000": step_bytes_windowed / (ms_res / args.steps * 1e-3) / 1e9 / 8000.0},
                 "note": "FFT-convolution kernels are FP64-pipe / shared-memory bound, not HBM bound (DESIGN.md section 5): "
                         "the honest utilisation figure is ncu.fp64_pipe_pct; windows overlap 90 %, so windowed bytes exceed unique bytes 10x"}
-        if args.config == "c3":
+        if args.config == "c3" and not args.quick:
             # zero-overlap variant: feature rate 1 Hz -> stride = W, windowed bytes == unique bytes
             s1 = make_settings()
             s1.sampling_rate_features_hz = 1
@@ -498,19 +498,21 @@ def run_gpu_arm(args) -> None:
         # the call a reference user makes: nm.Stream(...).run(data) -> DataFrame (window grid, upload, kernels, download, frame)
         import tempfile
 
-        reps = 3
-        stream = nm.Stream(sfreq=sfreq, data=x, settings=settings, line_noise=LINE_NOISE, verbose=False)
-        with tempfile.TemporaryDirectory() as td:
-            stream.run(out_dir=td, experiment_name="bench", save_csv=False)  # builds the processor / pipeline once more (warm-up)
-            ts = []
-            for _ in range(reps):
-                t0 = time.perf_counter()
-                df = stream.run(out_dir=td, experiment_name="bench", save_csv=False)
-                ts.append(time.perf_counter() - t0)
-        t_med = float(np.median(ts))
-        stream_info = {"value": n_win / t_med, "unit": UNIT, "ms_per_step": 1e3 * t_med, "frame_shape": list(df.shape),
-                       "note": "nm.Stream.run(data, save_csv=False) wall clock, median of 3: new DataProcessor + pipeline per call (like the "
-                               "reference), H2D, kernels, D2H, pandas DataFrame; CSV writing excluded"}
+        if not args.quick:
+            reps = 3
+            stream = nm.Stream(sfreq=sfreq, data=x, settings=settings, line_noise=LINE_NOISE, verbose=False)
+            with tempfile.TemporaryDirectory() as td:
+                stream.run(out_dir=td, experiment_name="bench", save_csv=False)  # first call: builds the GPU plans (warm-up)
+                ts = []
+                for _ in range(reps):
+                    t0 = time.perf_counter()
+                    df = stream.run(out_dir=td, experiment_name="bench", save_csv=False)
+                    ts.append(time.perf_counter() - t0)
+            t_med = float(np.median(ts))
+            stream_info = {"value": n_win / t_med, "unit": UNIT, "ms_per_step": 1e3 * t_med, "frame_shape": list(df.shape),
+                           "note": "nm.Stream.run(data, save_csv=False) wall clock, median of 3 after one warm-up call: window grid, H2D from the "
+                                   "caller's (pageable) array, kernels, D2H straight into the final table, pandas DataFrame, side files; the "
+                                   "processor of an unchanged configuration is kept across calls; CSV writing excluded"}
 
     if rank == 0:
         tile = f"{n_loc}x{W}"
@@ -566,6 +568,7 @@ def main() -> None:
     ap.add_argument("--channels", type=int, default=0, help="override the configuration's channel count (sweeps / debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the N = 1 extras (zero-overlap run, float32 mode, Stream.run timing)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

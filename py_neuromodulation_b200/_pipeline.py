@@ -136,7 +136,9 @@ class Pipeline:
         _lib.check(self.lib.nm_set_precision(self._h, int(precision == "f32")))
 
     def set_fused(self, mode: int) -> None:
-        """Window chain as ONE persistent kernel (1), as one kernel per stage (0, default) or as the environment says (-1)."""
+        """Organisation of the window chain: 2 = front kernel (bulk-copy staged raw rows, folded re-reference, notch + scan + segment
+        DFT on chip; band-pass bank separate -- the default), 1 = the whole chain in ONE persistent kernel, 0 = one kernel per
+        stage, -1 = as the environment says (NMB200_FUSED, default 2)."""
         _lib.check(self.lib.nm_set_fused(self._h, int(mode)))
 
     def set_raw_normalizer(self, method: str, clip: float, n_keep: int, add_samples: int) -> None:

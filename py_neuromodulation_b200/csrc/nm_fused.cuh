@@ -425,10 +425,13 @@ static NM_HD size_t nm_front_smem_bytes(int W) {
     return (size_t)NmCxPlan<P>::NBUF * sizeof(cx<double>) + ((NmFzStage<RAW64>::bytes(W) + 15) & ~(size_t)15) + NM_CX_RED_BYTES + 16;
 }
 
+#ifndef NM_FRONT_MINB128
+#define NM_FRONT_MINB128 4  // resident CTAs per SM the 128-thread plan (P = 2048) with float32 recordings is register-limited to
+#endif
 template <int P, bool RAW64>
 struct NmFrontOcc {
     static constexpr int NT = NmCxPlan<P>::NT;
-    static constexpr int value = (NT >= 256) ? (RAW64 ? 1 : 2) : (NT == 128 ? (RAW64 ? 3 : 4) : 8);
+    static constexpr int value = (NT >= 256) ? (RAW64 ? 1 : 2) : (NT == 128 ? (RAW64 ? 3 : NM_FRONT_MINB128) : 8);
 };
 
 template <int P, class SX, bool RAW64>
@@ -518,6 +521,114 @@ NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, (NmFrontOcc<P, RAW64>::value)) 
             }
             // (no trailing barrier: the scan epilogue ends with every thread past its reads of `work`, the DFT ends with a barrier)
         }
+        item = next;
+    }
+}
+
+// ================================================================ notch kernel with bulk-copy staged rows
+// nm_convx_kernel<double, P, REFLECT, single filter, NmEpiStoreScan> with ONE change: the two float64 rows of the NEXT item are
+// brought into a shared-memory stage by the TMA engine (cp.async.bulk + mbarrier, issued by one elected thread behind the first
+// barrier of the current item) instead of being prefetched into registers during the epilogue.  Same arithmetic on the same
+// values; the rows are whatever the staged path feeds the notch (re-referenced recording, pre-filter chunk rows).  Frees the
+// prefetch registers (32 bytes of stack instead of 288 at the 128-register cap) and takes the global-load latency off the
+// critical path: 11.72 -> 11.08 ms per C3 step on one B200 (profiles/r2_ab_window_chain.txt).
+template <int P>
+static NM_HD size_t nm_notchx_stage_bytes(int W) { return (size_t)2 * ((W + 1 + 1) & ~1) * sizeof(double); }
+template <int P>
+static NM_HD size_t nm_notchx_smem_bytes(int W) {
+    return (size_t)NmCxPlan<P>::NBUF * sizeof(cx<double>) + nm_notchx_stage_bytes<P>(W) + NM_CX_RED_BYTES + 16;
+}
+
+// elected thread: rows (c0, c0 + 1) of window w -> stage; every copy starts at the 16-byte aligned sample at or below the window
+NM_DEV void nm_nx_issue(const NmConvArgs& a, int item, int npair, unsigned char* stage, unsigned long long* bar) {
+    const int W = a.in.W;
+    const int w = item / npair, c0 = (item - w * npair) * 2;
+    const bool has2 = c0 + 1 < a.in.n_ch;
+    const long long s = nm_ldg(a.in.off + w);
+    const int lead = (int)(s & 1);
+    const unsigned bx = (unsigned)(((lead + W + 1) & ~1) * 8);
+    const int rowe = (W + 1 + 1) & ~1;
+    const double* r0 = a.in.base + (size_t)c0 * a.in.ch_stride + (s - lead);
+    nm_fence_proxy_async();
+    nm_mbar_expect_tx(bar, bx * (has2 ? 2u : 1u));
+    nm_bulk_g2s(stage, r0, bx, bar);
+    if (has2) nm_bulk_g2s(stage + (size_t)rowe * 8, r0 + a.in.ch_stride, bx, bar);
+}
+
+template <int P>
+NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, (NmCxPlan<P>::MINB1)) nm_notchx_kernel(NmConvArgs a, NmEpiStoreScan epi) {
+    using PL = NmCxPlan<P>;
+    using T = double;
+    constexpr int NT = PL::NT;
+    NM_SHARED_BYTES(smem);
+    cx<T>* work = reinterpret_cast<cx<T>*>(smem);
+    unsigned char* stage = reinterpret_cast<unsigned char*>(work + PL::NBUF);
+    const int W = a.in.W, E = a.E;
+    double* red = reinterpret_cast<double*>(stage + nm_notchx_stage_bytes<P>(W));
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(red) + NM_CX_RED_BYTES);
+    const int tid = threadIdx.x;
+    const int npair = (a.in.n_ch + 1) >> 1;
+    const int rowe = (W + 1 + 1) & ~1;
+    const cx<T>* NM_RESTRICT tw = a.fft.tw;
+    const T* NM_RESTRICT hx = a.hx;
+    const cx<T> wA = nm_ldg(tw + tid);
+    const cx<T> wB = nm_ldg(tw + (tid & (PL::M1 - 1)) * 16);
+    cx<T>* const p0w = work + tid + (tid >> PL::PAD);
+
+    int item = blockIdx.x;
+    if (item >= a.n_items) return;
+    if (tid == 0) nm_mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) nm_nx_issue(a, item, npair, stage, bar);
+    unsigned parity = 0;
+
+    cx<T> v[16];
+    T hv[16];
+    while (item < a.n_items) {
+        const int next = item + gridDim.x;
+        const int w = item / npair, c0 = (item - w * npair) * 2;
+        const bool has2 = c0 + 1 < a.in.n_ch;
+        nm_mbar_wait(bar, parity);
+        parity ^= 1u;
+        {
+            // odd reflection about both end samples: the arithmetic of nm_cx_load_item<REFLECT>, rows read from the stage
+            const int lead = (int)(nm_ldg(a.in.off + w) & 1);
+            const double* r0 = reinterpret_cast<const double*>(stage) + lead;
+            const double* r1 = r0 + (has2 ? rowe : 0);
+            const double a0 = 2.0 * r0[0], b0 = 2.0 * r1[0], a1 = 2.0 * r0[W - 1], b1 = 2.0 * r1[W - 1];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int n = tid + NT * t;
+                const bool left = n < E, mid = !left && n < E + W, right = !left && !mid && n < W + 2 * E;
+                int idx = left ? E - n : (mid ? n - E : 2 * W + E - 2 - n);
+                idx = (left || mid || right) ? idx : 0;
+                const double sgn = mid ? 1.0 : ((left || right) ? -1.0 : 0.0);
+                const double ca = left ? a0 : (right ? a1 : 0.0), cb = left ? b0 : (right ? b1 : 0.0);
+                const double va = fma(sgn, r0[idx], ca), vb = fma(sgn, r1[idx], cb);
+                v[t] = {va, has2 ? vb : 0.0};
+            }
+        }
+        nm_bfly16<false>(v);
+        nm_twiddle_w1<16, false>(v, wA);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) p0w[t * PL::S0] = v[t];
+        __syncthreads();  // every thread is done with the stage: the next item's rows may land from here on
+        if (tid == 0 && next < a.n_items) nm_nx_issue(a, next, npair, stage, bar);
+        nm_cx_load_h<PL, T>(hv, hx, tid);
+        nm_cx_pass1<PL, false>(work, wB, tid);
+        __syncthreads();
+        nm_cx_pass2<PL, 1, T>(work, work, hv, tid);
+        __syncthreads();
+        nm_cx_pass1<PL, true>(work, wB, tid);
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] = p0w[t * PL::S0];
+        nm_twiddle_w1<16, true>(v, wA);
+        nm_bfly16<true>(v);
+        NmEpiStoreScan::State st;
+        epi.template consume<PL, T>(v, work, red, st, E, W, a.in.n_ch, w, c0, has2, 0, tid);
+        epi.template finish<PL, T>(work, red, st, E, W, a.in.n_ch, w, c0, has2, 0, tid);
+        if (epi.needs_trailing_barrier()) __syncthreads();
         item = next;
     }
 }

@@ -137,8 +137,9 @@ struct nm_pipeline {
     // fused window kernel (nm_fused.cuh): the re-reference must fold into the load as  x_i = d_i * raw_i + g_i * S  (at most one
     // group sum, no off-diagonal remainder); decided at nm_finalize, switchable with NMB200_FUSED=0 for A/B measurements
     bool reref_foldable = true, fused = false, force_xr = false, fused_bp = false;
+    bool notch_tma = false;  // staged path: the notch kernel gets its rows through cp.async.bulk + mbarrier (nm_notchx_kernel)
     bool front = false;   // `fused` through nm_front_kernel (notch + scan + segment DFT; the bank stays a kernel of its own)
-    int fused_mode = -1;  // nm_set_fused: 0 staged kernels, 1 whole chain in one kernel, 2 front kernel, -1 environment (NMB200_FUSED, default 2)
+    int fused_mode = -1;  // nm_set_fused: 0 staged kernels, 1 whole chain in one kernel, 2 front kernel, -1 environment (NMB200_FUSED, default 0)
     std::vector<double> h_dfold, h_gfold;
     DevBuf d_dfold, d_gfold;
     int fused_sx = 0;                       // segment length of the in-kernel DFT families (0: none)
@@ -354,6 +355,14 @@ static void nm_launch_fir(nm_pipeline* p, const FirBank& bank, const NmRows& row
 
 // Notch of one batch of windows: rows -> y (and, on the specialised kernel, the scan features of the notched rows).
 // Returns true when the scan family has been computed by the notch kernel's epilogue.
+typedef void (*NmNotchxKernel)(NmConvArgs, NmEpiStoreScan);
+static NmNotchxKernel nm_notchx_pick(int P) {
+    return P == 1024 ? nm_notchx_kernel<1024> : (P == 2048 ? nm_notchx_kernel<2048> : nm_notchx_kernel<4096>);
+}
+static size_t nm_notchx_smem(int P, int W) {
+    return P == 1024 ? nm_notchx_smem_bytes<1024>(W) : (P == 2048 ? nm_notchx_smem_bytes<2048>(W) : nm_notchx_smem_bytes<4096>(W));
+}
+
 static bool nm_launch_notch(nm_pipeline* p, const NmRows& rows, double* y, const NmOut* scan_out, cudaStream_t stream) {
     const FirBank& bank = *p->notch;
     if (nm_convx_pick<NmEpiStoreScan>(bank)) {
@@ -364,6 +373,16 @@ static bool nm_launch_notch(nm_pipeline* p, const NmRows& rows, double* y, const
         epi.want_hjorth = p->scan_h; epi.want_raw = p->scan_r; epi.want_ll = p->scan_l;
         if (scan_out) epi.out = *scan_out;
         else epi.out = NmOut{nullptr, 0, 0, nullptr, 0};
+        if (p->notch_tma && !p->f32_linear()) {
+            // float64 rows of the next item staged by the TMA engine (nm_notchx_kernel); row bases are 16-byte aligned: cudaMalloc'ed
+            // buffers with even row pitches (xr_pitch, Wpi)
+            NmConvArgs a = bank.conv_args(rows);
+            auto k = nm_notchx_pick(bank.P);
+            const size_t sm = nm_notchx_smem(bank.P, rows.W);
+            const int grid = nm_resident_grid(p, k, bank.threads(), sm, a.n_items);
+            NM_LAUNCH(k, dim3(grid), dim3(bank.threads()), sm, stream, a, epi);
+            return scan_out != nullptr;
+        }
         nm_launch_fir(p, bank, rows, epi, stream, 0, p->f32_linear());
         return scan_out != nullptr;
     }
@@ -659,7 +678,7 @@ static int nm_fused_plan(nm_pipeline* p) {
     int want = p->fused_mode;
     if (want < 0) {
         const char* env = getenv("NMB200_FUSED");
-        want = env ? atoi(env) : 2;
+        want = env ? atoi(env) : 0;  // staged kernels are the fastest organisation measured on B200
     }
     if (want == 0) return 0;
     if (!p->notch || !p->reref_foldable || !p->prefilters.empty() || p->rawnorm || p->has_resampler || p->f32_linear() || p->precision == 1) return 0;
@@ -672,7 +691,11 @@ static int nm_fused_plan(nm_pipeline* p) {
     if (want == 2 ? nm_front_smem(nb.P, p->W, true) > (size_t)p->smem_max : nm_fused_smem(nb.P) > (size_t)p->smem_max) return 0;
     p->fused = true;
     p->front = want == 2;
-    const int sx_ok = nb.P == 2048 ? 1000 : (nb.P == 4096 ? 2000 : 0);
+    int sx_ok = nb.P == 2048 ? 1000 : (nb.P == 4096 ? 2000 : 0);
+    if (p->front) {  // the segment DFTs run faster as a kernel of their own (11 CTAs per SM instead of 4): opt-in inside the front kernel
+        const char* env = getenv("NMB200_FRONT_DFT");
+        if (!env || atoi(env) == 0) sx_ok = 0;
+    }
     for (size_t i = 0; i < p->spectral.size() && sx_ok; ++i) {
         const SpectralFam& f = *p->spectral[i];
         const nm_spectral_cfg& c = f.cfg;
@@ -1133,7 +1156,7 @@ extern "C" int nm_finalize(nm_pipeline* p) {
     if (p->d_yoff.upload(yoff, p->stream)) return -1;
     if (p->notch && p->d_y.ensure((size_t)p->chunk * p->C * p->Wpi * sizeof(double))) return -1;
     for (size_t i = 0; i < std::min<size_t>(2, p->prefilters.size()); ++i)
-        if (p->d_pre[i].ensure((size_t)p->chunk * p->C * p->Wpi * sizeof(double))) return -1;
+        if (p->d_pre[i].ensure((size_t)p->chunk * p->C * p->Wpi * sizeof(double) + 16)) return -1;
     if (p->has_resampler) {
         for (int k = 0; k < p->chunk; ++k) yoff[k] = (long long)k * p->C * p->Wp;
         if (p->d_roff.upload(yoff, p->stream)) return -1;
@@ -1146,6 +1169,16 @@ extern "C" int nm_finalize(nm_pipeline* p) {
     if (p->rawnorm && p->rawnorm->alloc_chunk(p->chunk, p->Wp)) return -1;
     if (p->rawnorm && p->rawnorm->need_median() && nm_allow_smem(nm_burst_thr_kernel, BurstsFam::thr_smem(), p)) return -1;
 
+    // bulk-copy staged notch rows: needs the specialised single-filter reflect plan and room for the stage
+    p->notch_tma = false;
+    if (p->notch && nm_convx_pick<NmEpiStoreScan>(*p->notch)) {
+        const char* env = getenv("NMB200_NOTCH_TMA");
+        const bool want = env ? atoi(env) != 0 : true;
+        if (want && nm_notchx_smem(p->notch->P, p->Win) <= (size_t)p->smem_max) {
+            if (nm_allow_smem(nm_notchx_pick(p->notch->P), nm_notchx_smem(p->notch->P, p->Win), p)) return -1;
+            p->notch_tma = true;
+        }
+    }
     // opt in to large dynamic shared memory once
     if (p->notch && (nm_allow_fir_smem<NmEpiStore>(*p->notch, 0, p) || nm_allow_fir_smem<NmEpiStoreScan>(*p->notch, 0, p) ||
                      nm_allow_fir_smem<NmEpiStoreScan>(*p->notch, 0, p, true)))
@@ -1238,7 +1271,7 @@ static int nm_ensure_prepped(nm_pipeline* p, long long upto) {
 static int nm_stage_buffers(nm_pipeline* p, size_t esz) {
     if (p->d_raw.ensure((size_t)p->C_all * p->raw_pitch * esz + 16)) return -1;
     const bool fused = p->fused && !p->force_xr;
-    if (!fused && p->d_xr.ensure((size_t)p->C * p->xr_pitch * sizeof(double))) return -1;
+    if (!fused && p->d_xr.ensure((size_t)p->C * p->xr_pitch * sizeof(double) + 16)) return -1;
     if (p->d_nanblk.ensure((size_t)p->C_all * p->nanblk_pitch)) return -1;
     if (fused && p->G > 0) {
         p->gsum_pitch = (p->T + 1) & ~1LL;
@@ -1547,6 +1580,27 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
     return 0;
 }
 
+// argument blocks of the in-kernel DFT families of the fused / front kernel (they hold the d_out pointer: refreshed whenever d_out
+// may have been re-allocated)
+static int nm_fused_spec_upload(nm_pipeline* p) {
+    if (!p->fused || p->fused_spec.empty()) return 0;
+    p->h_fused_spec.clear();
+    NmRows none{};
+    for (int k : p->fused_spec) {
+        const SpectralFam& f = *p->spectral[k];
+        NmOut o;
+        o.out = p->d_out.as<double>();
+        o.row0 = 0;
+        o.F = p->F;
+        o.colmap = f.d_colmap.as<int>();
+        o.per_ch = f.per_ch;
+        p->h_fused_spec.push_back(nm_spec_args(p, f, none, o, 0));
+    }
+    if (p->d_fused_spec.upload(p->h_fused_spec, p->stream)) return -1;
+    NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
 // per-window NaN-channel flags from the block map + NaN re-insertion by column list for windows [w0, w0 + n) of the current run
 static void nm_nan_fill(nm_pipeline* p, int w0, int n) {
     NmNanArgs na;
@@ -1581,21 +1635,7 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
     cudaSetDevice(p->device);
     if (p->d_starts.upload(starts, (size_t)n_windows, p->stream)) return -1;
     if (p->d_out.ensure((size_t)n_windows * p->F * sizeof(double))) return -1;
-    if (p->fused && !p->fused_spec.empty()) {  // argument blocks of the in-kernel DFT families (they hold the d_out pointer)
-        p->h_fused_spec.clear();
-        NmRows none{};
-        for (int k : p->fused_spec) {
-            const SpectralFam& f = *p->spectral[k];
-            NmOut o;
-            o.out = p->d_out.as<double>();
-            o.row0 = 0;
-            o.F = p->F;
-            o.colmap = f.d_colmap.as<int>();
-            o.per_ch = f.per_ch;
-            p->h_fused_spec.push_back(nm_spec_args(p, f, none, o, 0));
-        }
-        if (p->d_fused_spec.upload(p->h_fused_spec, p->stream)) return -1;
-    }
+    if (nm_fused_spec_upload(p)) return -1;
     p->out_rows = n_windows;
     NM_CUDA_CHECK(cudaMemsetAsync(p->d_out.p, 0, (size_t)n_windows * p->F * sizeof(double), p->stream));
     // without the (sequential) normaliser a chunk's rows are final when its kernels end: ship them chunk by chunk
@@ -1822,7 +1862,11 @@ extern "C" int nm_describe_plan(nm_pipeline* p, char* buf, int n) {
                  p->fused_sx ? " + segment DFT" : "", p->fused_bp ? " + band-pass bank" : "", (int)p->fused_spec.size());
         s += line;
     } else if (p->notch) {
-        if (nm_convx_pick<NmEpiStoreScan>(*p->notch)) nm_describe_fir<NmEpiStoreScan>(s, p->has_scan ? "notch+scan" : "notch", *p->notch, 0);
+        if (nm_convx_pick<NmEpiStoreScan>(*p->notch) && p->notch_tma && !p->f32_linear()) {
+            snprintf(line, sizeof(line), "%s: nm_notchx_kernel P=%d filters=1 taps=%d threads=%d smem=%zu (rows staged by cp.async.bulk + mbarrier)\n",
+                     p->has_scan ? "notch+scan" : "notch", p->notch->P, p->notch->L, p->notch->threads(), nm_notchx_smem(p->notch->P, p->Win));
+            s += line;
+        } else if (nm_convx_pick<NmEpiStoreScan>(*p->notch)) nm_describe_fir<NmEpiStoreScan>(s, p->has_scan ? "notch+scan" : "notch", *p->notch, 0);
         else nm_describe_fir<NmEpiStore>(s, "notch", *p->notch, 0);
     }
     if (p->has_scan && !p->fused && !(p->notch && nm_convx_pick<NmEpiStoreScan>(*p->notch))) s += "scan: nm_scan_kernel\n";

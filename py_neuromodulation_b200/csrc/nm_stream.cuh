@@ -73,6 +73,7 @@ extern "C" int nm_stream_open(nm_pipeline* p, int n_slots, int input_f32, int us
     if (p->d_starts.upload(&zero, 1, p->stream)) return -1;
     if (p->d_out.ensure((size_t)p->F * sizeof(double))) return -1;
     if (p->has_nan_cols && p->d_nanflags.ensure((size_t)p->C_all)) return -1;
+    if (nm_fused_spec_upload(p)) return -1;
     if (p->norm && p->norm->n_cols) {
         if (p->norm->d_ext.ensure((size_t)std::max(1, p->norm->n_keep) * p->norm->n_cols * sizeof(double))) return -1;
     }

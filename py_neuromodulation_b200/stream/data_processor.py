@@ -84,7 +84,7 @@ class _Plan:
             return
         pipe = Pipeline(dp.n_raw_rows, len(names), window_samples, columns, device=dp.device)
         pipe.set_precision(dp.precision)
-        pipe.set_fused(-1 if dp.fused is None else int(bool(dp.fused)))
+        pipe.set_fused(-1 if dp.fused is None else (2 if dp.fused == "front" else int(bool(dp.fused))))
         pipe.set_pick(dp.feature_idx)
         if dp.reref_factored is not None:  # channel-sharded run: coefficients come from the GLOBAL channel table
             pipe.set_reref_factored(*dp.reref_factored)
@@ -125,7 +125,7 @@ class DataProcessor:
         device: int = 0,
         reref_factored: tuple | None = None,
         precision: str | None = None,
-        fused: bool | None = None,
+        fused: "bool | str | None" = None,
     ) -> None:
         from .. import user_features
         from ..filter.notch_filter import NotchFilter
@@ -138,7 +138,8 @@ class DataProcessor:
         import os
 
         # kernel organisation: None = library default / NMB200_FUSED, True = one persistent kernel per (window, channel pair)
-        # (csrc/nm_fused.cuh), False = one kernel per stage
+        # (csrc/nm_fused.cuh), "front" = notch + scan + segment DFT in one kernel, band-pass bank separate (the default organisation),
+        # False = one kernel per stage
         self.fused = fused
         self.precision = precision or os.environ.get("NMB200_PRECISION", "f64")
         if self.precision not in ("f64", "f32"):

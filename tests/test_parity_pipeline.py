@@ -58,17 +58,20 @@ def test_window_processor_matches_reference_golden(backend, name, n_emu):
                 assert np.array_equal(mat[:, j], g["vals"][: len(starts), j]), k
 
 
+@pytest.mark.parametrize("mode", [True, "front"])
 @pytest.mark.parametrize("name,n_emu", [("dataprocessor_c3_nan", None), ("dataprocessor_fast", None), ("dataprocessor_default", 12),
                                         ("dataprocessor_realdata", 8)])
-def test_fused_window_kernel_matches_reference_golden(backend, name, n_emu):
-    """The same fixtures through the single persistent kernel (csrc/nm_fused.cuh: bulk-copy staged raw rows, re-reference folded
-    into the load, notch -> scan -> DFT band features -> band-pass bank on chip) -- and bit-identical to the staged kernels."""
+def test_fused_window_kernel_matches_reference_golden(backend, name, n_emu, mode):
+    """The same fixtures through the bulk-copy staged kernels of csrc/nm_fused.cuh (raw rows through cp.async.bulk + mbarrier,
+    re-reference folded into the load): the single persistent kernel (notch -> scan -> DFT band features -> band-pass bank on
+    chip) and the front kernel (the default: notch + scan + DFT, bank separate) -- both agree with the staged kernels."""
     g = load_golden(name)
     n = n_emu if backend == "emu" else None
-    dp, cols, mat, starts = run_dp(g, n, fused=True)
+    dp, cols, mat, starts = run_dp(g, n, fused=mode)
     # common average over < 5 channels is handed over as a sparse matrix (no group sum): not foldable into the load, so the
     # staged kernels serve that pipeline whatever was asked for
-    assert ("nm_fused_kernel" in dp.plan(1000).pipe.describe_plan()) == (g["x"].shape[0] >= 5)
+    kern = "nm_front_kernel" if mode == "front" else "nm_fused_kernel"
+    assert (kern in dp.plan(1000).pipe.describe_plan()) == (g["x"].shape[0] >= 5)
     normalized = bool(g["settings"]["postprocessing"]["feature_normalization"])
     check_matrix(cols, mat, g["keys"], g["vals"][: len(starts)], name + " (fused)", normalized=normalized)
     _, _, mat0, _ = run_dp(g, n, fused=False)
@@ -88,12 +91,12 @@ def test_fused_window_kernel_float64_recording_and_odd_channels(backend):
     s.features.welch = True
     s.postprocessing.feature_normalization = False
     s.sampling_rate_features_hz = 7  # stride 142.86 samples: starts 0, 142, 285, 428, ...
-    for dtype in (np.float64, np.float32):
+    for dtype, mode in ((np.float64, True), (np.float32, True), (np.float64, "front"), (np.float32, "front")):
         xs = x.astype(dtype)
-        dp = nm.DataProcessor(sfreq=1000, settings=s, channels=get_default_channels_from_data(x), line_noise=50, verbose=False, fused=True)
+        dp = nm.DataProcessor(sfreq=1000, settings=s, channels=get_default_channels_from_data(x), line_noise=50, verbose=False, fused=mode)
         starts, lengths, _ = window_grid(x.shape[1], 1000, 7, 1000)
         cols, mat = dp.process_windows(xs, starts, 1000)
-        assert "nm_fused_kernel" in dp.plan(1000).pipe.describe_plan()
+        assert ("nm_front_kernel" if mode == "front" else "nm_fused_kernel") in dp.plan(1000).pipe.describe_plan()
         ref_cols, ref = orc.run_offline(xs.astype(np.float64), 1000, s.model_dump())
         assert ref_cols[: len(cols)] == cols
         assert parity_err(cols, mat, ref[:, : len(cols)]).max() < 1e-9
@@ -475,5 +478,6 @@ def test_default_configurations_are_served_by_the_specialised_kernels(backend):
         plan = dp.plan(int(sfreq)).pipe.describe_plan()
         lines = plan.splitlines()[1:]
         assert len(lines) == 7, plan  # notch+scan, fft, welch, stft, bandpower, sharpwave, bursts
-        assert all(("nm_convx_kernel" in ln) or ("nm_specx_kernel" in ln) for ln in lines), plan
-        assert lines[0].startswith("notch+scan"), plan
+        assert all(("nm_convx_kernel" in ln) or ("nm_specx_kernel" in ln) or ("nm_notchx_kernel" in ln) for ln in lines), plan
+        # the notch gets its rows through the TMA engine (cp.async.bulk + mbarrier staged variant of nm_convx_kernel)
+        assert lines[0].startswith("notch+scan: nm_notchx_kernel"), plan
