@@ -625,14 +625,22 @@ class SharpwaveSpec:
                 raise NotImplementedError("sharp-wave 'no_filter' ranges are not supported")
             self.filters.append((f"range_{fr[0]:.0f}_{fr[1]:.0f}", design_fir(sfreq, fr[0], fr[1])))
         if len({len(t) for _, t in self.filters}) != 1:
-            raise NotImplementedError("sharp-wave filters of different lengths are not supported in one bank")
+            # The reference's branch for unequal lengths (features/sharpwaves.py:249-253) hands fftconvolve a (channels, taps) filter
+            # TILE next to the (channels, samples) data, i.e. it runs a 2-D convolution that sums neighbouring CHANNELS into every
+            # row (checked against the unmodified reference).  That is not a per-channel FIR and is not reproduced here.
+            raise NotImplementedError("sharp-wave filters of different lengths: the reference convolves across channels in that "
+                                      "branch (2-D fftconvolve); choose filter ranges with equal transition bands")
         self.used = sw.sharpwave_features.get_enabled()
         est_of = {ft: [e for e in SW_ESTIMATORS if ft in getattr(sw.estimator, e)]
                   for e in SW_ESTIMATORS for ft in getattr(sw.estimator, e)}
         self.combos = [(ft, e) for ft in self.used for e in est_of[ft]]
         self.pair = bool(sw.apply_estimator_between_peaks_and_troughs)
-        if not (sw.detect_peaks.estimate and sw.detect_troughs.estimate):
-            raise NotImplementedError("sharp-wave analysis needs both the peak and the trough pass (the reference indexes both)")
+        # one polarity only (detect_peaks.estimate / detect_troughs.estimate): fine for the un-paired "_analyze_Peak/_Trough" keys;
+        # the paired form indexes both values and raises in the reference too (features/sharpwaves.py:297-302)
+        self.polarities = [pol for pol, on in (("Peak", sw.detect_peaks.estimate), ("Trough", sw.detect_troughs.estimate)) if on]
+        if self.pair and len(self.polarities) != 2:
+            raise IndexError("list index out of range: apply_estimator_between_peaks_and_troughs needs both detect_peaks.estimate "
+                             "and detect_troughs.estimate (the reference raises the same IndexError)")
         self.num_peaks = bool(sw.sharpwave_features.num_peaks)
 
     def keys(self) -> list[str]:
@@ -649,7 +657,7 @@ class SharpwaveSpec:
                     # the reference flattens {key: {"Peak": v, "Trough": v}} in key-insertion order (features/sharpwaves.py:323-326):
                     # both polarities of a key are adjacent, num_peaks sits at its position among the enabled features
                     for ft, e in self.combos:
-                        for pol in ("Peak", "Trough"):
+                        for pol in self.polarities:
                             k = (f"{ch}_Sharpwave_num_peaks_{fname}" if ft == "num_peaks"
                                  else f"{ch}_Sharpwave_{e.title()}_{ft}_{fname}") + "_analyze_" + pol
                             if k not in out:
@@ -659,6 +667,10 @@ class SharpwaveSpec:
     def attach(self, pipe: Pipeline) -> None:
         n_combo = len(self.combos)
         slots: list[str | None] = []
+
+        def both(base: str) -> list[str | None]:  # (the kernel analyses both polarities; a disabled one has no column)
+            return [base + "_analyze_" + pol if pol in self.polarities else None for pol in ("Peak", "Trough")]
+
         for ch in self.ch_names:
             for fname, _ in self.filters:
                 for ft, e in self.combos:
@@ -668,7 +680,7 @@ class SharpwaveSpec:
                     elif self.pair:
                         slots += [base, None]
                     else:
-                        slots += [base + "_analyze_Peak", base + "_analyze_Trough"]
+                        slots += both(base)
                 base = f"{ch}_Sharpwave_num_peaks_{fname}"
                 listed = self.num_peaks and (self.pair or any(ft == "num_peaks" for ft, _ in self.combos))
                 if not listed:
@@ -676,7 +688,7 @@ class SharpwaveSpec:
                 elif self.pair:
                     slots += [base, None]
                 else:
-                    slots += [base + "_analyze_Peak", base + "_analyze_Trough"]
+                    slots += both(base)
         cm = pipe.colmap(slots)
         taps = _f64(np.vstack([t for _, t in self.filters]))
         feat = _i32([SW_FEATURES.index(ft) for ft, _ in self.combos] or [0])

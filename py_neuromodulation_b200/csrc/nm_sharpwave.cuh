@@ -30,12 +30,12 @@ struct NmSwCfg {
 
 struct NmSwLists {
     unsigned short *rawP, *rawT, *KP, *KT, *Lp, *Rp;
-    unsigned char* st;
+    unsigned char *st, *wn;  // per candidate: state (0 undecided, 1 kept, 2 suppressed) and "wins this round"
     double* tmp;
 };
 
 static NM_HD size_t nm_sw_list_bytes(int maxn) {
-    const size_t b = (size_t)6 * maxn * sizeof(unsigned short) + (size_t)maxn;
+    const size_t b = (size_t)6 * maxn * sizeof(unsigned short) + (size_t)2 * maxn;
     return (b + 7) & ~(size_t)7;
 }
 static NM_HD size_t nm_sw_row_bytes(int maxn, int tmp_in_tail) {
@@ -81,39 +81,41 @@ NM_DEV int nm_sw_local_maxima(const cx<double>* x, int comp, double sign, int W,
     return n;
 }
 
-// distance suppression; `kept` receives the surviving indices (ascending); returns their count
+// distance suppression; `kept` receives the surviving indices (ascending); returns their count.
+// Race-free by construction: in every phase a lane WRITES only the entries of its own candidates and READS other candidates'
+// entries only from an array that no lane writes in that phase (st in phase 1, wn in phase 2); __syncwarp separates the phases.
 NM_DEV int nm_sw_select(const cx<double>* x, int comp, double sign, const unsigned short* idx, int n, int D, unsigned char* st,
-                        unsigned short* kept, int lane) {
+                        unsigned char* wn, unsigned short* kept, int lane) {
     for (int k = lane; k < n; k += 32) st[k] = 0;
     __syncwarp();
     if (D > 1) {
         while (true) {
+            // phase 1: an undecided candidate wins the round iff it out-ranks every undecided neighbour closer than D
             for (int k = lane; k < n; k += 32) {
-                if (st[k] != 0) continue;
-                const int ik = idx[k];
-                const double hk = nm_sw_v(x, comp, sign, ik);
-                bool win = true;
-                // a neighbour flagged 3 by another lane during this very phase is still a competitor of this round
-                for (int q = k - 1; q >= 0 && ik - (int)idx[q] < D && win; --q)
-                    if ((st[q] == 0 || st[q] == 3) && nm_sw_v(x, comp, sign, idx[q]) > hk) win = false;
-                for (int q = k + 1; q < n && (int)idx[q] - ik < D && win; ++q)
-                    if ((st[q] == 0 || st[q] == 3) && nm_sw_v(x, comp, sign, idx[q]) >= hk) win = false;
-                if (win) st[k] = 3;
+                bool win = false;
+                if (st[k] == 0) {
+                    const int ik = idx[k];
+                    const double hk = nm_sw_v(x, comp, sign, ik);
+                    win = true;
+                    for (int q = k - 1; q >= 0 && ik - (int)idx[q] < D && win; --q)
+                        if (st[q] == 0 && nm_sw_v(x, comp, sign, idx[q]) > hk) win = false;
+                    for (int q = k + 1; q < n && (int)idx[q] - ik < D && win; ++q)
+                        if (st[q] == 0 && nm_sw_v(x, comp, sign, idx[q]) >= hk) win = false;
+                }
+                wn[k] = win ? 1 : 0;
             }
             __syncwarp();
-            for (int k = lane; k < n; k += 32) {
-                if (st[k] != 3) continue;
-                const int ik = idx[k];
-                for (int q = k - 1; q >= 0 && ik - (int)idx[q] < D; --q)
-                    if (st[q] == 0) st[q] = 2;
-                for (int q = k + 1; q < n && (int)idx[q] - ik < D; ++q)
-                    if (st[q] == 0) st[q] = 2;
-            }
-            __syncwarp();
+            // phase 2: winners are kept; an undecided candidate next to a winner is suppressed (each lane settles its OWN entries)
             bool pending = false;
             for (int k = lane; k < n; k += 32) {
-                if (st[k] == 3) st[k] = 1;
-                if (st[k] == 0) pending = true;
+                if (st[k] != 0) continue;
+                if (wn[k]) { st[k] = 1; continue; }
+                const int ik = idx[k];
+                bool lost = false;
+                for (int q = k - 1; q >= 0 && ik - (int)idx[q] < D && !lost; --q) lost = wn[q] != 0;
+                for (int q = k + 1; q < n && (int)idx[q] - ik < D && !lost; ++q) lost = wn[q] != 0;
+                if (lost) st[k] = 2;
+                else pending = true;
             }
             __syncwarp();
             if (!__ballot_sync(0xffffffffu, pending)) break;
@@ -186,8 +188,8 @@ NM_DEV bool nm_sw_feature(const cx<double>* x, int comp, double sign, int W, con
 // the two passes of a channel share their local-maxima scans)
 NM_DEV void nm_sw_analyze(const cx<double>* x, int comp, double sign, int W, const NmSwCfg& c, const NmSwLists& l, int nP0, int nT0,
                           double* results, int lane) {
-    const int nP = nm_sw_select(x, comp, sign, l.rawP, nP0, c.D_pk, l.st, l.KP, lane);
-    const int nT = nm_sw_select(x, comp, -sign, l.rawT, nT0, c.D_tr, l.st, l.KT, lane);
+    const int nP = nm_sw_select(x, comp, sign, l.rawP, nP0, c.D_pk, l.st, l.wn, l.KP, lane);
+    const int nT = nm_sw_select(x, comp, -sign, l.rawT, nT0, c.D_tr, l.st, l.wn, l.KT, lane);
 
     // pairing (features/sharpwaves.py:347-374)
     int first_valid = 0, n_valid = 0, last_valid = 0;
@@ -314,6 +316,7 @@ struct NmEpiSharpwave {
         l.Lp = l.KT + cfg.maxn;
         l.Rp = l.Lp + cfg.maxn;
         l.st = reinterpret_cast<unsigned char*>(l.Rp + cfg.maxn);
+        l.wn = l.st + cfg.maxn;
         l.tmp = cfg.tmp_in_tail ? const_cast<double*>(reinterpret_cast<const double*>(tail)) + (size_t)ar * cfg.maxn
                                 : reinterpret_cast<double*>(base + nm_sw_list_bytes(cfg.maxn));
     }

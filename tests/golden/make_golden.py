@@ -305,6 +305,20 @@ def resample_cases(nm):
     save("dataprocessor_resample_up_rawnorm", x=x.astype(np.float32), settings=dump_settings(st), keys=json.dumps(keys), vals=vals, sfreq=500.0)
 
 
+def sharpwave_option_cases(nm):
+    """Sharp-wave option the default fixtures do not reach (features/sharpwaves.py:269-272): a single polarity with the un-paired
+    key form.  (Filters of different lengths are not a fixture: that branch of the reference convolves across channels.)"""
+    x = neural_like(41, 3, 1000 + 100 * 7)
+    for pol in ("peaks", "troughs"):
+        st = nm.NMSettings.get_default().reset()
+        st.features.sharpwave_analysis = True
+        st.postprocessing.feature_normalization = False
+        st.sharpwave_analysis_settings.apply_estimator_between_peaks_and_troughs = False
+        (st.sharpwave_analysis_settings.detect_troughs if pol == "peaks" else st.sharpwave_analysis_settings.detect_peaks).estimate = False
+        keys, vals = _run_windows(nm, st, x)
+        save(f"dataprocessor_sharpwave_{pol}_only", x=x.astype(np.float32), settings=dump_settings(st), keys=json.dumps(keys), vals=vals, sfreq=1000.0)
+
+
 def burst_history_case(nm):
     """Bursts across 320 windows (history overflows after window 290): faithful reference values."""
     st = nm.NMSettings.get_default()
@@ -351,12 +365,16 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "next":  # only the SURVEY 8f "next row" fixtures
         next_row_cases(nm)
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "sharpwave":
+        sharpwave_option_cases(nm)
+        raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "resample":
         resample_cases(nm)
         raise SystemExit(0)
     plugin_cases(nm)
     preprocess_cases(nm)
     resample_cases(nm)
+    sharpwave_option_cases(nm)
     window_processor_cases(nm)
     burst_history_case(nm)
     real_data_case(nm)

@@ -111,7 +111,9 @@ def test_notch_shapes(name, line):
 NEXT_ROW_FIXTURES = ["dataprocessor_prefilter_default", "dataprocessor_prefilter_lphp", "dataprocessor_rawnorm_zscore",
                      "dataprocessor_rawnorm_mean", "dataprocessor_rawnorm_median", "dataprocessor_rawnorm_zscore_median",
                      # raw_resampling with a ratio != 1 (2 kHz defaults, ratio 0.8, up-sampling + raw normaliser)
-                     "dataprocessor_resample_2k_default", "dataprocessor_resample_1250", "dataprocessor_resample_up_rawnorm"]
+                     "dataprocessor_resample_2k_default", "dataprocessor_resample_1250", "dataprocessor_resample_up_rawnorm",
+                     # sharp-wave option: one polarity only (un-paired keys)
+                     "dataprocessor_sharpwave_peaks_only", "dataprocessor_sharpwave_troughs_only"]
 
 
 @pytest.mark.parametrize("name", ["dataprocessor_default", "dataprocessor_fast", "dataprocessor_c3_nan", "dataprocessor_realdata"]

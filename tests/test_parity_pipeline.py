@@ -45,7 +45,10 @@ def run_dp(g, n_windows=None, with_norm=True, fused=None):
                                         ("dataprocessor_rawnorm_zscore_median", None),
                                         # raw_resampling with a ratio != 1 (processing/resample.py:28-60; stale sampling rate downstream)
                                         ("dataprocessor_resample_2k_default", 8), ("dataprocessor_resample_1250", 10),
-                                        ("dataprocessor_resample_up_rawnorm", None)])
+                                        ("dataprocessor_resample_up_rawnorm", None),
+                                        # sharp waves with one polarity only (features/sharpwaves.py:269-272)
+                                        ("dataprocessor_sharpwave_peaks_only", None),
+                                        ("dataprocessor_sharpwave_troughs_only", None)])
 def test_window_processor_matches_reference_golden(backend, name, n_emu):
     g = load_golden(name)
     n = n_emu if backend == "emu" else None  # the thread emulator is slow: fewer windows on CPU, all on the GPU

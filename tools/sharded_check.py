@@ -21,8 +21,15 @@ from py_neuromodulation_b200.utils.channels import get_default_channels_from_dat
 
 def main():
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    native = "--native" in sys.argv  # collectives inside libnmb200 (nm_comm_*) instead of torch.distributed
+    comm = None
     torch.cuda.set_device(local)
-    dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    if native:
+        from py_neuromodulation_b200.parallel import NativeComm
+
+        comm = NativeComm.from_env(device=local)
+    else:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     c_total, T = 10 * world + 3, 90_000  # uneven shards, >= 65 536 samples: sliced upload with per-slice all-reduce
     rng = np.random.default_rng(7)
     x = (np.cumsum(rng.standard_normal((c_total, T)), axis=1) * 0.01 + rng.standard_normal((c_total, T))).astype(np.float32)
@@ -40,7 +47,7 @@ def main():
                               verbose=False, device=local, reref_factored=reref)
         starts, lengths, _ = window_grid(T, 1000, settings.sampling_rate_features_hz, settings.segment_length_features_ms)
         for shared in (True, False):
-            sh = ShardedRun(dp.plan(1000).pipe, on_gpu=True, shared_host=shared)
+            sh = ShardedRun(dp.plan(1000).pipe, on_gpu=True, shared_host=shared, comm=comm)
             for rep in range(2):
                 dp.plan(1000).pipe.reset_state()
                 sh.upload(x[lo:hi])
@@ -57,11 +64,14 @@ def main():
                 print(f"{name} shared_host={shared}: {len(starts)} windows x {len(cols)} columns, max rel err vs un-sharded run {err:.2e}, "
                       f"NaN pattern equal: {same_nan}", flush=True)
                 ok = ok and err < 1e-9 and same_nan
-            dist.barrier()
+            comm.barrier() if native else dist.barrier()
             sh.close()
     if rank == 0:
         print("SHARDED CHECK", "PASSED" if ok else "FAILED", flush=True)
-    dist.destroy_process_group()
+    if native:
+        comm.close()
+    else:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
