@@ -60,15 +60,21 @@ int nm_set_reref(nm_pipeline* p, int n_groups, const int* group_of, const double
 int nm_set_notch(nm_pipeline* p, const double* taps, int n_taps);
 /* Arithmetic of the linear FIR families (notch, band-pass power): 0 = float64 (default: agrees with the float64 reference to
  * ~1e-12), 1 = float32 inside the FFT convolution (faster; north-star tolerance 1e-5 relative; moments and outputs stay
- * float64).  Pipelines with threshold / peak decisions downstream of the notch (bursts, sharp waves, raw normaliser) keep the
- * notch in float64 regardless. */
+ * float64), 2 = the same arithmetic on PACKED float32 pairs (two channel pairs per item, Blackwell add/mul/fma.f32x2; measured
+ * slower than 1 on B200, kept for comparison).  Pipelines with threshold / peak decisions downstream of the notch (bursts, sharp
+ * waves, raw normaliser) keep the notch in float64 regardless. */
 int nm_set_precision(nm_pipeline* p, int float32_linear);
 /* Kernel organisation of the window chain.  0 (default): one kernel per stage -- re-reference (once per recording), notch (+ Hjorth /
  * line length / raw), segment DFTs, band-pass bank -- the notched rows travel through HBM / L2.  1: ONE persistent kernel per
  * (window, channel pair) (csrc/nm_fused.cuh): raw rows staged by cp.async.bulk + mbarrier, re-reference folded into the load, notch
  * -> scan -> DFT band features -> band-pass bank without the re-referenced recording or the notched rows ever existing in HBM.
  * Same results (tests run both); measured 15 % slower on B200 at float64 because the merged kernel runs every phase at the bank's
- * occupancy, hence opt-in.  -1: take the choice from the environment (NMB200_FUSED, default 0). */
+ * occupancy, hence opt-in.  2: the "front" kernel -- the same bulk-copy staged load with the folded
+ * re-reference, notch + Hjorth / line length / raw (+ the segment DFTs with NMB200_FRONT_DFT=1) in one kernel, band-pass bank
+ * separate; measured 2.5 % slower than 0 (the fold repeats per window what the re-reference kernel does once per sample).
+ * -1: take the choice from the environment (NMB200_FUSED, default 0).  Independently of this choice the staged notch kernel of
+ * mode 0 receives its float64 rows through the TMA engine (cp.async.bulk + mbarrier; NMB200_NOTCH_TMA=0 restores the register
+ * prefetch). */
 int nm_set_fused(nm_pipeline* p, int mode);
 
 /* RawNormalizer (processing/normalization.py:30-111, type "raw"): window 0 passes through and seeds the per-channel

@@ -130,10 +130,11 @@ class Pipeline:
         _lib.check(self.lib.nm_set_notch(self._h, _ptr(a, C.c_double), int(a.size)))
 
     def set_precision(self, precision: str) -> None:
-        """'f64' (default) or 'f32': float32 arithmetic inside the FFT convolution of the linear families (notch, band power)."""
-        if precision not in ("f64", "f32"):
-            raise ValueError("precision must be 'f64' or 'f32'")
-        _lib.check(self.lib.nm_set_precision(self._h, int(precision == "f32")))
+        """'f64' (default), 'f32' (float32 arithmetic inside the FFT convolution of the linear families: notch, band power) or
+        'f32x2' (the same on packed float32 pairs, two channel pairs per item)."""
+        if precision not in ("f64", "f32", "f32x2"):
+            raise ValueError("precision must be 'f64', 'f32' or 'f32x2'")
+        _lib.check(self.lib.nm_set_precision(self._h, ("f64", "f32", "f32x2").index(precision)))
 
     def set_fused(self, mode: int) -> None:
         """Organisation of the window chain: 2 = front kernel (bulk-copy staged raw rows, folded re-reference, notch + scan + segment

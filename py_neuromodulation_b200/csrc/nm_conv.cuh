@@ -49,6 +49,12 @@ NM_DEV cx<T> nm_mulw(cx<T> a, T wr, T wi) {  // a * (wr + i*wi), conjugated for 
     return INV ? cx<T>{a.re * wr + a.im * wi, a.im * wr - a.re * wi} : cx<T>{a.re * wr - a.im * wi, a.im * wr + a.re * wi};
 }
 
+template <bool INV>
+NM_DEV cx<f32x2> nm_mulw(cx<f32x2> a, f32x2 wr, f32x2 wi) {  // packed pairs: explicit FFMA2
+    return INV ? cx<f32x2>{nm_fma2(a.re, wr, a.im * wi), nm_fma2(a.im, wr, -(a.re * wi))}
+               : cx<f32x2>{nm_fma2(a.re, wr, -(a.im * wi)), nm_fma2(a.im, wr, a.re * wi)};
+}
+
 template <bool INV, typename T>
 NM_DEV void nm_r4(cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
     const cx<T> t0 = cx_add(a0, a2), t1 = cx_sub(a0, a2), t2 = cx_add(a1, a3);

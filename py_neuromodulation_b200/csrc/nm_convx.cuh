@@ -17,6 +17,8 @@
 // band-pass banks, 1651/3301-tap sharp-wave filters); other sizes keep using nm_conv_kernel / nm_fir_kernel.
 #pragma once
 
+#include <type_traits>
+
 #include "nm_conv.cuh"
 
 template <int P_>
@@ -119,6 +121,26 @@ NM_DEV void nm_cx_load_h(T* hv, const T* NM_RESTRICT hx, int tid) {
         }
     }
 }
+
+// packed float32 pairs: the float32 table, every value broadcast to both halves
+template <class PL>
+NM_DEV void nm_cx_load_h(f32x2* hv, const float* NM_RESTRICT hx, int tid) {
+    constexpr int R = PL::R2;
+#pragma unroll
+    for (int i = 0; i < 16 / R; ++i) {
+#pragma unroll
+        for (int t = 0; t < R / 2; ++t) {
+            const cx<float> d = nm_ldg(reinterpret_cast<const cx<float>*>(hx) + (i * (R / 2) + t) * PL::NT + tid);
+            hv[i * R + 2 * t] = f32x2(d.re);
+            hv[i * R + 2 * t + 1] = f32x2(d.im);
+        }
+    }
+}
+
+template <class PL, typename T>
+NM_DEV void nm_cx_load_hT(T* hv, const T* NM_RESTRICT hx, int tid) { nm_cx_load_h<PL, T>(hv, hx, tid); }
+template <class PL, typename T>
+NM_DEV void nm_cx_load_hT(f32x2* hv, const float* NM_RESTRICT hx, int tid) { nm_cx_load_h<PL>(hv, hx, tid); }
 
 // host side: slot-ordered spectrum block (P values) -> thread-interleaved block
 template <int P, typename T>
@@ -344,22 +366,72 @@ NM_DEV void nm_cx_load_item(cx<T>* v, const NmConvArgs& a, int item, int npair, 
     }
 }
 
-// float64 / float32 views of the twiddle and filter-spectrum tables of a launch
-template <typename T> NM_DEV const cx<T>* nm_cx_tw(const NmConvArgs& a);
-template <> NM_DEV const cx<double>* nm_cx_tw<double>(const NmConvArgs& a) { return a.fft.tw; }
-template <> NM_DEV const cx<float>* nm_cx_tw<float>(const NmConvArgs& a) { return a.tw32; }
-template <typename T> NM_DEV const T* nm_cx_hx(const NmConvArgs& a);
-template <> NM_DEV const double* nm_cx_hx<double>(const NmConvArgs& a) { return a.hx; }
-template <> NM_DEV const float* nm_cx_hx<float>(const NmConvArgs& a) { return a.hx32; }
+// float32 mode: one item = (window, channel QUAD); sub-item A = rows (c0, c0 + 1) in the .x halves, B = rows (c0 + 2, c0 + 3) in
+// the .y halves.  Same reflection / zero-padding arithmetic in float64 as above, rounded once to float32.
+template <int P, bool REFLECT>
+NM_DEV void nm_cx_load_item4(cx<f32x2>* v, const NmConvArgs& a, int item, int nquad, int tid, int& w, int& c0) {
+    constexpr int NT = NmCxPlan<P>::NT;
+    const int W = a.in.W, E = a.E;
+    w = item / nquad;
+    c0 = (item - w * nquad) * 4;
+    const int nv = min(4, a.in.n_ch - c0);  // valid rows of the quad
+    const double* NM_RESTRICT r0 = a.in.base + (size_t)c0 * a.in.ch_stride + nm_ldg(a.in.off + w);
+    const double* NM_RESTRICT r1 = r0 + (nv > 1 ? a.in.ch_stride : 0);
+    const double* NM_RESTRICT r2 = r0 + (nv > 2 ? 2 * a.in.ch_stride : 0);
+    const double* NM_RESTRICT r3 = r0 + (nv > 3 ? 3 * a.in.ch_stride : 0);
+    const bool h1 = nv > 1, h2 = nv > 2, h3 = nv > 3;
+    if (REFLECT) {
+        const double e0[4] = {2.0 * r0[0], 2.0 * r1[0], 2.0 * r2[0], 2.0 * r3[0]};
+        const double e1[4] = {2.0 * r0[W - 1], 2.0 * r1[W - 1], 2.0 * r2[W - 1], 2.0 * r3[W - 1]};
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int n = tid + NT * t;
+            const bool left = n < E, mid = !left && n < E + W, right = !left && !mid && n < W + 2 * E;
+            int idx = left ? E - n : (mid ? n - E : 2 * W + E - 2 - n);
+            idx = (left || mid || right) ? idx : 0;
+            const double sgn = mid ? 1.0 : ((left || right) ? -1.0 : 0.0);
+            const double x0 = fma(sgn, r0[idx], left ? e0[0] : (right ? e1[0] : 0.0));
+            const double x1 = fma(sgn, r1[idx], left ? e0[1] : (right ? e1[1] : 0.0));
+            const double x2 = fma(sgn, r2[idx], left ? e0[2] : (right ? e1[2] : 0.0));
+            const double x3 = fma(sgn, r3[idx], left ? e0[3] : (right ? e1[3] : 0.0));
+            v[t] = {f32x2((float)x0, (float)(h2 ? x2 : 0.0)), f32x2((float)(h1 ? x1 : 0.0), (float)(h3 ? x3 : 0.0))};
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int n = tid + NT * t;
+            const int idx = n < W ? n : 0;
+            const bool in = n < W;
+            v[t] = {f32x2((float)(in ? r0[idx] : 0.0), (float)((in && h2) ? r2[idx] : 0.0)),
+                    f32x2((float)((in && h1) ? r1[idx] : 0.0), (float)((in && h3) ? r3[idx] : 0.0))};
+        }
+    }
+}
 
-#ifndef NM_CX_F32_MINB1
-#define NM_CX_F32_MINB1 5  // resident CTAs per SM (128-thread plans) the float32 instantiations are register-limited to
-#define NM_CX_F32_MINBK 6
+template <typename T> struct NmIsPacked { static constexpr bool value = false; };
+template <> struct NmIsPacked<f32x2> { static constexpr bool value = true; };
+
+// float64 / float32 views of the twiddle and filter-spectrum tables of a launch
+// twiddle generator k of the table, in the arithmetic type of the kernel
+NM_DEV cx<double> nm_cx_twid(const NmConvArgs& a, int k, double) { return nm_ldg(a.fft.tw + k); }
+NM_DEV cx<f32x2> nm_cx_twid(const NmConvArgs& a, int k, f32x2) {
+    const cx<float> w = nm_ldg(a.tw32 + k);
+    return {f32x2(w.re), f32x2(w.im)};
+}
+NM_DEV cx<float> nm_cx_twid(const NmConvArgs& a, int k, float) { return nm_ldg(a.tw32 + k); }
+NM_DEV const double* nm_cx_hx(const NmConvArgs& a, double) { return a.hx; }
+NM_DEV const float* nm_cx_hx(const NmConvArgs& a, f32x2) { return a.hx32; }
+NM_DEV const float* nm_cx_hx(const NmConvArgs& a, float) { return a.hx32; }
+
+#ifndef NM_CXP_MINB1_128
+#define NM_CXP_MINB1_128 4  // packed single-filter kernel, 128-thread plan: resident CTAs per SM the registers are capped for
 #endif
 template <typename T, int P, bool BANK>
-struct NmCxOcc {
-    static constexpr int f32 = (BANK ? NM_CX_F32_MINBK : NM_CX_F32_MINB1) * 128 / NmCxPlan<P>::NT;
-    static constexpr int value = sizeof(T) == 4 ? (f32 < 1 ? 1 : f32) : (BANK ? NmCxPlan<P>::MINBK : NmCxPlan<P>::MINB1);
+struct NmCxOcc {  // (packed float32 pairs use the float64 kernel's shared-memory footprint; scalar float32 has half of it)
+    static constexpr int f32 = (BANK ? 6 : 5) * 128 / NmCxPlan<P>::NT;
+    static constexpr int value = sizeof(T) == 4 ? (f32 < 1 ? 1 : f32)
+                                 : (BANK ? NmCxPlan<P>::MINBK
+                                         : ((NmIsPacked<T>::value && NmCxPlan<P>::NT == 128) ? NM_CXP_MINB1_128 : NmCxPlan<P>::MINB1));
 };
 template <typename T, int P, bool REFLECT, bool BANK, class Epi>
 NM_GLOBAL void NM_LAUNCH_BOUNDS(NmCxPlan<P>::NT, (NmCxOcc<T, P, BANK>::value))
@@ -374,24 +446,26 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
                                                : reinterpret_cast<unsigned char*>(red) + NM_CX_RED_BYTES;
     const int tid = threadIdx.x;
     const int W = a.in.W;
-    const int npair = (a.in.n_ch + 1) >> 1;
+    constexpr bool PACKED = NmIsPacked<T>::value;
+    // items per window: channel pairs (float64) or channel quads (packed float32 pairs)
+    const int npair = PACKED ? (a.in.n_ch + 3) >> 2 : (a.in.n_ch + 1) >> 1;
     const int o0 = REFLECT ? a.E : 0;
     const int nF = BANK ? a.nF : 1;
-    const cx<T>* NM_RESTRICT tw = nm_cx_tw<T>(a);
-    const T* NM_RESTRICT hx = nm_cx_hx<T>(a);
+    const auto* NM_RESTRICT hx = nm_cx_hx(a, T());
     cx<T>* const p0w = work + tid + (tid >> PL::PAD);
     cx<T>* const p0s = spec + tid + (tid >> PL::PAD);
     // twiddle generators; tid == 0 / j == 0 multiply by exactly 1, so no thread needs a special case
-    const cx<T> wA = nm_ldg(tw + tid);                          // exp(-2*pi*i*tid/P): pass 0
-    const cx<T> wB = nm_ldg(tw + (tid & (PL::M1 - 1)) * 16);    // exp(-2*pi*i*j/NT): pass 1 (table stride P/NT)
+    const cx<T> wA = nm_cx_twid(a, tid, T());                          // exp(-2*pi*i*tid/P): pass 0
+    const cx<T> wB = nm_cx_twid(a, (tid & (PL::M1 - 1)) * 16, T());    // exp(-2*pi*i*j/NT): pass 1 (table stride P/NT)
 
     cx<T> v[16];
     T hv[16];
     int item = blockIdx.x, w = 0, c0 = 0;
     bool has2 = false;
     if (item >= a.n_items) return;
-    nm_cx_load_item<P, REFLECT, T>(v, a, item, npair, tid, w, c0, has2);
-    if (BANK) nm_cx_load_h<PL, T>(hv, hx, tid);
+    if constexpr (PACKED) nm_cx_load_item4<P, REFLECT>(v, a, item, npair, tid, w, c0);
+    else nm_cx_load_item<P, REFLECT, T>(v, a, item, npair, tid, w, c0, has2);
+    if (BANK) nm_cx_load_hT<PL, T>(hv, hx, tid);
 
     while (item < a.n_items) {
         const int next = item + gridDim.x;
@@ -403,7 +477,7 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
 #pragma unroll
         for (int t = 0; t < 16; ++t) p0s[t * PL::S0] = v[t];
         __syncthreads();
-        if (!BANK) nm_cx_load_h<PL, T>(hv, hx, tid);  // (L1 resident) lands while pass 1 computes
+        if (!BANK) nm_cx_load_hT<PL, T>(hv, hx, tid);  // (L1 resident) lands while pass 1 computes
         nm_cx_pass1<PL, false>(spec, wB, tid);
         __syncthreads();
         if (BANK) {
@@ -417,7 +491,7 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
                 nm_cx_pass2<PL, 2>(work, spec, hv, tid);
 #ifdef NM_CX_HV_EARLY
                 // prefetch the next filter's spectrum (wrapping to filter 0 for the next item) one phase ahead
-                nm_cx_load_h<PL, T>(hv, hx + (size_t)(last ? 0 : fi + 1) * P, tid);
+                nm_cx_load_hT<PL, T>(hv, hx + (size_t)(last ? 0 : fi + 1) * P, tid);
 #endif
             } else {
                 nm_cx_pass2<PL, 1>(work, work, hv, tid);
@@ -434,14 +508,42 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
             // next filter's spectrum (wrapping to filter 0 for the next item): issued where the register pressure is lowest -- a
             // load that the compiler has to spill right away stalls on its own L2 latency (ncu: STL of the loaded pair right
             // behind the LDG, round 2) -- and it lands during the epilogue's reduction and barrier
-            if (BANK) nm_cx_load_h<PL, T>(hv, hx + (size_t)(last ? 0 : fi + 1) * P, tid);
+            if (BANK) nm_cx_load_hT<PL, T>(hv, hx + (size_t)(last ? 0 : fi + 1) * P, tid);
 #endif
             // `work` may still be read by slower threads: an epilogue (or the next filter's pass) must not write it
             // before a barrier.  Register epilogues either synchronise inside (kSyncsInside) or get a trailing barrier.
             bool in_regs = Epi::kRegsOnly;
             if constexpr (Epi::kRegs && !Epi::kRegsOnly) in_regs = epi.regs_ok();
             if (in_regs) {
-                if constexpr (Epi::kRegs) {
+                if constexpr (Epi::kRegs && PACKED) {
+                    // the two sub-items leave the packed registers as float32 pairs and run the float32 form of the epilogue one
+                    // after the other (B in its own half of `work` / of the reduction scratch where the epilogue overlaps its tail
+                    // with the next phase)
+                    cx<float>* const wf = reinterpret_cast<cx<float>*>(work);
+                    const int nv = min(4, a.in.n_ch - c0);
+                    {
+                        cx<float> u[16];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) u[k] = {v[k].re.x, v[k].im.x};
+                        typename Epi::State st;
+                        epi.template consume<PL, float>(u, wf, red, st, o0, W, a.in.n_ch, w, c0, nv > 1, fi, tid);
+                        epi.template finish<PL, float>(wf, red, st, o0, W, a.in.n_ch, w, c0, nv > 1, fi, tid);
+                    }
+                    if (nv > 2) {
+                        cx<float> u[16];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) u[k] = {v[k].re.y, v[k].im.y};
+                        double* const redb = Epi::kSyncsInside ? red + NM_CX_RED_BYTES / 16 : red;
+                        typename Epi::State st;
+                        cx<float>* const wb = wf + PL::NBUF;  // second half of the (16-byte element) transform buffer
+                        epi.template consume<PL, float>(u, wb, redb, st, o0, W, a.in.n_ch, w, c0 + 2, nv > 3, fi, tid);
+                        epi.template finish<PL, float>(wb, redb, st, o0, W, a.in.n_ch, w, c0 + 2, nv > 3, fi, tid);
+                    }
+                    if (last && next < a.n_items) nm_cx_load_item4<P, REFLECT>(v, a, next, npair, tid, nw, nc0);
+                    if constexpr (!Epi::kSyncsInside) {
+                        if (epi.needs_trailing_barrier()) __syncthreads();
+                    }
+                } else if constexpr (Epi::kRegs) {
                     typename Epi::State st;
                     epi.template consume<PL, T>(v, work, red, st, o0, W, a.in.n_ch, w, c0, has2, fi, tid);
                     if (last && next < a.n_items) nm_cx_load_item<P, REFLECT, T>(v, a, next, npair, tid, nw, nc0, nhas2);
@@ -451,7 +553,7 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
                     }
                 }
             } else {
-                if constexpr (!Epi::kRegsOnly && sizeof(T) == 8) {  // (the shared-memory epilogues take float64 rows)
+                if constexpr (!Epi::kRegsOnly && std::is_same<T, double>::value) {  // (the shared-memory epilogues take float64 rows)
                     __syncthreads();
 #pragma unroll
                     for (int t = 0; t < 16; ++t) work[tid + NT * t] = v[t];

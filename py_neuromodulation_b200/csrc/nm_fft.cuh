@@ -35,6 +35,49 @@ NM_DEV cx<float> nm_ldg(const cx<float>* p) {
 }
 #endif
 
+// ---- packed float32 pair: the arithmetic type of the float32 mode of the FIR kernels (nm_convx.cuh).
+// Two INDEPENDENT transforms (channel pairs A and B of one item) travel side by side in the two halves of a 64-bit register pair,
+// so every butterfly instruction is a Blackwell packed-f32 instruction (add / sub / mul / fma .f32x2 -> FADD2 / FMUL2 / FFMA2 in
+// SASS): half the issue slots of scalar FADD / FFMA for the same flops, and 16-byte (re, im) x 2 shared-memory elements -- the
+// float64 kernel's conflict-free layout -- instead of 8-byte ones.
+struct alignas(8) f32x2 {
+    float x, y;
+    f32x2() = default;
+    NM_HD f32x2(float a, float b) : x(a), y(b) {}
+    NM_HD explicit f32x2(double v) : x((float)v), y((float)v) {}  // broadcast (butterfly constants)
+    NM_HD explicit f32x2(float v) : x(v), y(v) {}
+};
+#ifndef NM_EMULATE
+NM_DEV unsigned long long nm_f2_bits(f32x2 a) { return *reinterpret_cast<unsigned long long*>(&a); }
+NM_DEV f32x2 nm_f2_from(unsigned long long u) { return *reinterpret_cast<f32x2*>(&u); }
+NM_DEV f32x2 operator+(f32x2 a, f32x2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(nm_f2_bits(a)), "l"(nm_f2_bits(b)));
+    return nm_f2_from(d);
+}
+NM_DEV f32x2 operator-(f32x2 a, f32x2 b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(nm_f2_bits(a)), "l"(nm_f2_bits(b)));
+    return nm_f2_from(d);
+}
+NM_DEV f32x2 operator*(f32x2 a, f32x2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(nm_f2_bits(a)), "l"(nm_f2_bits(b)));
+    return nm_f2_from(d);
+}
+NM_DEV f32x2 nm_fma2(f32x2 a, f32x2 b, f32x2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(nm_f2_bits(a)), "l"(nm_f2_bits(b)), "l"(nm_f2_bits(c)));
+    return nm_f2_from(d);
+}
+#else
+NM_DEV f32x2 operator+(f32x2 a, f32x2 b) { return {a.x + b.x, a.y + b.y}; }
+NM_DEV f32x2 operator-(f32x2 a, f32x2 b) { return {a.x - b.x, a.y - b.y}; }
+NM_DEV f32x2 operator*(f32x2 a, f32x2 b) { return {a.x * b.x, a.y * b.y}; }
+NM_DEV f32x2 nm_fma2(f32x2 a, f32x2 b, f32x2 c) { return {fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+#endif
+NM_DEV f32x2 operator-(f32x2 a) { return {-a.x, -a.y}; }
+
 template <typename T>
 struct NmFft {
     int n;
@@ -53,6 +96,10 @@ template <typename T>
 NM_DEV cx<T> cx_add(cx<T> a, cx<T> b) { return {a.re + b.re, a.im + b.im}; }
 template <typename T>
 NM_DEV cx<T> cx_sub(cx<T> a, cx<T> b) { return {a.re - b.re, a.im - b.im}; }
+
+// packed pairs: explicit fused multiply-adds (inline PTX is opaque to the compiler's own contraction)
+NM_DEV cx<f32x2> cx_mul(cx<f32x2> a, cx<f32x2> b) { return {nm_fma2(a.re, b.re, -(a.im * b.im)), nm_fma2(a.re, b.im, a.im * b.re)}; }
+NM_DEV cx<f32x2> cx_mulc(cx<f32x2> a, cx<f32x2> b) { return {nm_fma2(a.re, b.re, a.im * b.im), nm_fma2(a.im, b.re, -(a.re * b.im))}; }
 
 // multiply by -i (forward) or +i (inverse)
 template <typename T, bool INV>

@@ -128,7 +128,9 @@ struct FirBank {
     bool epi_fits_tail(size_t epi) const { return pow2 && epi > 0 && epi <= (nm_conv_buf_elems(P, pad) - (size_t)P) * sizeof(cx<double>); }
     int threads() const { return pow2 ? P / 16 : NM_FFT_THREADS; }
     // nm_convx_kernel: reflect mode is single-filter (one buffer), 'same' mode always runs the bank code (two buffers)
-    size_t smem_x(size_t epi, bool f32 = false) const {
+    // f32: 0 float64, 1 scalar float32 (8-byte elements), 2 packed float32 pairs (16-byte elements like cx<double>)
+    size_t smem_x(size_t epi, int f32 = 0) const {
+        if (f32 == 2) f32 = 0;
         return nm_conv_buf_elems(P, pad) * (f32 ? sizeof(cx<float>) : sizeof(cx<double>)) * (mode == NM_FIR_REFLECT ? 1 : 2) + NM_CX_RED_BYTES +
                (epi_fits_tail(epi) ? 0 : epi);
     }

@@ -177,8 +177,8 @@ struct nm_pipeline {
     int chunk = 1, Wp = 0;
     // arithmetic of the LINEAR families (notch, band power): 0 float64 (default), 1 float32 inside the FFT convolution.  Rows that
     // feed threshold / peak decisions (bursts, sharp waves, raw normaliser clip) always stay float64, and so does the notch then.
-    int precision = 0;
-    bool f32_linear() const { return precision == 1 && !bursts && !sharpwave && !rawnorm; }
+    int precision = 0;  // 0 float64, 1 scalar float32, 2 packed float32 pairs
+    int f32_linear() const { return (precision != 0 && !bursts && !sharpwave && !rawnorm) ? precision : 0; }
     std::vector<long long> h_starts_one;
     DevBuf d_win_in;  // staging of a single streamed window
     std::unique_ptr<NmStream> strm;  // streaming entry (nm_stream.cuh): page-locked slot ring, parameter blocks, CUDA graphs
@@ -277,12 +277,14 @@ static NmConvKernel<Epi> nm_convx_pick_t(const FirBank& b) {
     return nullptr;
 }
 
-// f32: float32 arithmetic inside the transform (optional fast mode; only epilogues that work from registers offer it)
+// f32: float32 arithmetic inside the transform (optional fast mode; only epilogues that work from registers offer it):
+// 1 = scalar float32, 2 = packed float32 pairs (two channel pairs per item, FFMA2 / FADD2 / FMUL2)
 template <class Epi>
-static NmConvKernel<Epi> nm_convx_pick(const FirBank& b, bool f32 = false) {
+static NmConvKernel<Epi> nm_convx_pick(const FirBank& b, int f32 = 0) {
     if (!b.pow2 || !nm_convx_supported(b.P)) return nullptr;
     if constexpr (Epi::kF32Ok) {
-        if (f32) return nm_convx_pick_t<float, Epi>(b);
+        if (f32 == 2) return nm_convx_pick_t<f32x2, Epi>(b);
+        if (f32 == 1) return nm_convx_pick_t<float, Epi>(b);
     }
     return nm_convx_pick_t<double, Epi>(b);
 }
@@ -303,8 +305,8 @@ static size_t nm_fir_smem(const FirBank& bank, size_t epi_bytes) {
 }
 
 template <class Epi>
-static int nm_allow_fir_smem(const FirBank& bank, size_t epi_bytes, const nm_pipeline* p, bool f32 = false) {
-    if (auto k = nm_convx_pick<Epi>(bank, f32)) return nm_allow_smem(k, bank.smem_x(epi_bytes, f32 && Epi::kF32Ok), p);
+static int nm_allow_fir_smem(const FirBank& bank, size_t epi_bytes, const nm_pipeline* p, int f32 = 0) {
+    if (auto k = nm_convx_pick<Epi>(bank, f32)) return nm_allow_smem(k, bank.smem_x(epi_bytes, Epi::kF32Ok ? f32 : 0), p);
     if constexpr (!Epi::kConvxOnly) {
         const size_t sm = bank.smem(epi_bytes, nm_fir_split<Epi>(bank, epi_bytes, p) ? 1 : -1);
         if (bank.pow2) return nm_allow_smem(nm_conv_kernel<Epi>, sm, p);
@@ -323,12 +325,13 @@ static int nm_resident_grid(const nm_pipeline* p, K kernel, int threads, size_t 
 
 template <class Epi>
 static void nm_launch_fir(nm_pipeline* p, const FirBank& bank, const NmRows& rows, const Epi& epi, cudaStream_t stream, size_t epi_bytes,
-                          bool f32 = false) {
+                          int f32 = 0) {
     const int threads = bank.threads();
     if (auto k = nm_convx_pick<Epi>(bank, f32)) {
         NmConvArgs a = bank.conv_args(rows);
         a.scratch_in_tail = bank.epi_fits_tail(epi_bytes) ? 1 : 0;
-        const size_t sm = bank.smem_x(epi_bytes, f32 && Epi::kF32Ok);
+        if (f32 == 2 && Epi::kF32Ok) a.n_items = rows.n_windows * ((rows.n_ch + 3) / 4);  // channel quads
+        const size_t sm = bank.smem_x(epi_bytes, Epi::kF32Ok ? f32 : 0);
         const int grid = nm_resident_grid(p, k, threads, sm, a.n_items);
         NM_LAUNCH(k, dim3(grid), dim3(threads), sm, stream, a, epi);
         return;
@@ -681,7 +684,7 @@ static int nm_fused_plan(nm_pipeline* p) {
         want = env ? atoi(env) : 0;  // staged kernels are the fastest organisation measured on B200
     }
     if (want == 0) return 0;
-    if (!p->notch || !p->reref_foldable || !p->prefilters.empty() || p->rawnorm || p->has_resampler || p->f32_linear() || p->precision == 1) return 0;
+    if (!p->notch || !p->reref_foldable || !p->prefilters.empty() || p->rawnorm || p->has_resampler || p->f32_linear() || p->precision != 0) return 0;
     const FirBank& nb = *p->notch;
     if (!nb.pow2 || !nm_convx_supported(nb.P) || nb.nF != 1 || nb.mode != NM_FIR_REFLECT) return 0;
     const size_t buf_bytes = nm_fused_nbuf(nb.P) * sizeof(cx<double>);
@@ -1098,7 +1101,8 @@ extern "C" int nm_add_feature_normalizer(nm_pipeline* p, int method, double clip
 extern "C" int nm_set_precision(nm_pipeline* p, int float32_linear) {
     NM_P_CHECK(p);
     NM_CHECK(!p->finalized, "pipeline already finalized");
-    p->precision = float32_linear ? 1 : 0;
+    NM_CHECK(float32_linear >= 0 && float32_linear <= 2, "precision must be 0 (float64), 1 (float32) or 2 (packed float32 pairs)");
+    p->precision = float32_linear;
     return 0;
 }
 
@@ -1181,10 +1185,11 @@ extern "C" int nm_finalize(nm_pipeline* p) {
     }
     // opt in to large dynamic shared memory once
     if (p->notch && (nm_allow_fir_smem<NmEpiStore>(*p->notch, 0, p) || nm_allow_fir_smem<NmEpiStoreScan>(*p->notch, 0, p) ||
-                     nm_allow_fir_smem<NmEpiStoreScan>(*p->notch, 0, p, true)))
+                     nm_allow_fir_smem<NmEpiStoreScan>(*p->notch, 0, p, 1) || nm_allow_fir_smem<NmEpiStoreScan>(*p->notch, 0, p, 2)))
         return -1;
     if (p->bandpower && (nm_allow_fir_smem<NmEpiBandpower>(p->bandpower->bank, p->bandpower->epi_smem(), p) ||
-                         nm_allow_fir_smem<NmEpiBandpower>(p->bandpower->bank, p->bandpower->epi_smem(), p, true)))
+                         nm_allow_fir_smem<NmEpiBandpower>(p->bandpower->bank, p->bandpower->epi_smem(), p, 1) ||
+                         nm_allow_fir_smem<NmEpiBandpower>(p->bandpower->bank, p->bandpower->epi_smem(), p, 2)))
         return -1;
     size_t spec_max = 0;
     for (auto& f : p->spectral)
@@ -1563,7 +1568,7 @@ static int nm_run_chunk(nm_pipeline* p, int w0, int n) {
         epi.want_act = f.act; epi.want_mob = f.mob; epi.want_comp = f.comp; epi.log_act = f.logt;
         epi.out = out_for(f.d_colmap, f.bank.nF * 3);
         p->prof_begin();
-        nm_launch_fir(p, f.bank, rows, epi, p->stream, f.epi_smem(), p->precision == 1 && !(f.mob || f.comp));
+        nm_launch_fir(p, f.bank, rows, epi, p->stream, f.epi_smem(), (f.mob || f.comp) ? 0 : p->precision);
         p->prof_end(NM_PROF_BANDPOWER);
         p->launches++;
     }

@@ -142,8 +142,8 @@ class DataProcessor:
         # False = one kernel per stage
         self.fused = fused
         self.precision = precision or os.environ.get("NMB200_PRECISION", "f64")
-        if self.precision not in ("f64", "f32"):
-            raise ValueError("precision must be 'f64' or 'f32'")
+        if self.precision not in ("f64", "f32", "f32x2"):
+            raise ValueError("precision must be 'f64', 'f32' or 'f32x2'")
         self.settings = NMSettings.load(settings)
         self.channels = io.load_channels(channels)
         self.sfreq_features: float = self.settings.sampling_rate_features_hz

@@ -189,3 +189,26 @@ def test_window_stream_slot_ring_equals_batched_run(backend, graph):
         assert stats["graph_launches"] == len(starts) - 2 and stats["graph_kernel_nodes"] > 5 and stats["patched_arguments"] > 0
     else:
         assert stats["graph_launches"] == 0 or backend == "gpu"
+
+
+@pytest.mark.parametrize("precision", ["f32x2", "f32"])
+@pytest.mark.parametrize("n_ch", [5, 6, 7, 8])
+def test_packed_float32_kernels_all_quad_remainders(backend, n_ch, precision):
+    """float32 mode of the FIR families: two channel PAIRS share one item (packed float32 pairs, csrc/nm_convx.cuh); every remainder
+    of the channel count modulo 4 leaves a differently filled last quad.  Gate: the task's 1e-5 (relative for |ref| >= 1)."""
+    x = neural_like(50 + n_ch, n_ch, 1000 + 100 * 5)
+    s = nm.NMSettings.get_default().reset()
+    for f in ("fft", "bandpass_filter", "raw_hjorth", "linelength", "return_raw"):
+        s.features[f] = True
+    s.postprocessing.feature_normalization = False
+    ch = get_default_channels_from_data(x)
+    starts = np.arange(0, 600, 100)
+    dp32 = nm.DataProcessor(sfreq=1000, settings=s, channels=ch, line_noise=50, verbose=False, precision=precision)
+    cols, got = dp32.process_windows(x, starts, 1000)
+    ref_cols, ref = orc.run_offline(x, 1000, s.model_dump())
+    assert ref_cols[: len(cols)] == cols
+    ref = ref[:, : len(cols)]
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
+    assert np.isfinite(got).all() and err.max() < 1e-5, (float(err.max()), cols[int(np.argmax(err.max(axis=0)))])
+    _, got64 = nm.DataProcessor(sfreq=1000, settings=s, channels=ch, line_noise=50, verbose=False).process_windows(x, starts, 1000)
+    assert np.abs(got - got64).max() > 0.0  # the float32 kernels really ran
