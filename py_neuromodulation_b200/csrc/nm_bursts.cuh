@@ -19,7 +19,7 @@
 
 struct NmEpiBursts {
     static constexpr bool kRegs = false;
-    static constexpr bool kRegsOnly = false, kReflectOk = false, kSameOk = true, kConvxOnly = false, kF32Ok = false;  // nm_convx_kernel instantiation traits
+    static constexpr bool kRegsOnly = false, kReflectOk = false, kSameOk = true, kConvxOnly = false, kF32Ok = false, kSplitOk = true;  // nm_convx_kernel instantiation traits
     NmFft<double> hfft;     // W-point transform
     int need_scratch;
     double* env;            // chunk envelopes (n_windows, n_ch, nB, Wp)

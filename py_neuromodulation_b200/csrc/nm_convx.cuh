@@ -213,7 +213,7 @@ struct NmEpiStoreScan {
     int want_hjorth, want_raw, want_ll, want_scan;
     NmOut out;  // per_ch = 5: activity, mobility, complexity, raw, linelength
     static constexpr bool kRegs = true;
-    static constexpr bool kRegsOnly = true, kReflectOk = true, kSameOk = false, kConvxOnly = true, kF32Ok = true;
+    static constexpr bool kRegsOnly = true, kReflectOk = true, kSameOk = false, kConvxOnly = true, kF32Ok = true, kSplitOk = false;
     static constexpr bool kSyncsInside = false;  // (not on every path) -> the kernel adds the trailing barrier
     static NM_HD size_t smem_bytes(int /*nt*/) { return 0; }  // reductions use the padding tail of `work`
     NM_DEV bool regs_ok() const { return true; }
@@ -545,9 +545,9 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
                     }
                 } else if constexpr (Epi::kRegs) {
                     typename Epi::State st;
-                    epi.template consume<PL, T>(v, work, red, st, o0, W, a.in.n_ch, w, c0, has2, fi, tid);
+                    epi.template consume<PL, T>(v, work, red, st, o0, W, a.in.n_ch, w, c0, has2, fi + a.f0, tid);
                     if (last && next < a.n_items) nm_cx_load_item<P, REFLECT, T>(v, a, next, npair, tid, nw, nc0, nhas2);
-                    epi.template finish<PL, T>(work, red, st, o0, W, a.in.n_ch, w, c0, has2, fi, tid);
+                    epi.template finish<PL, T>(work, red, st, o0, W, a.in.n_ch, w, c0, has2, fi + a.f0, tid);
                     if constexpr (!Epi::kSyncsInside) {
                         if (epi.needs_trailing_barrier()) __syncthreads();
                     }
@@ -558,7 +558,7 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
 #pragma unroll
                     for (int t = 0; t < 16; ++t) work[tid + NT * t] = v[t];
                     __syncthreads();
-                    epi.run(work, o0, W, a.in.n_ch, w, c0, has2, fi, scratch, tid, NT);
+                    epi.run(work, o0, W, a.in.n_ch, w, c0, has2, fi + a.f0, scratch, tid, NT);
                     __syncthreads();
                     // (no early prefetch here: these epilogues are register hungry and long enough to hide nothing)
                     if (last && next < a.n_items) nm_cx_load_item<P, REFLECT, T>(v, a, next, npair, tid, nw, nc0, nhas2);

@@ -38,7 +38,7 @@ struct NmEpiStore {
     long long Wp;
     int nF;
     static constexpr bool kRegs = true;   // nm_conv_kernel hands over the 16 outputs of each thread in registers
-    static constexpr bool kRegsOnly = true, kReflectOk = false, kSameOk = true, kConvxOnly = false, kF32Ok = false;  // nm_convx_kernel instantiation traits
+    static constexpr bool kRegsOnly = true, kReflectOk = false, kSameOk = true, kConvxOnly = false, kF32Ok = false, kSplitOk = false;  // nm_convx_kernel instantiation traits
     static NM_HD size_t smem_bytes(int /*nt*/) { return 0; }
     NM_DEV bool regs_ok() const { return true; }
     static constexpr bool kSyncsInside = false;
@@ -92,7 +92,7 @@ struct NmEpiBandpower {
     int want_act, want_mob, want_comp, log_act;
     NmOut out;             // per_ch = nF * 3  (activity, mobility, complexity)
     static constexpr bool kRegs = true;
-    static constexpr bool kRegsOnly = false, kReflectOk = false, kSameOk = true, kConvxOnly = false, kF32Ok = true;
+    static constexpr bool kRegsOnly = false, kReflectOk = false, kSameOk = true, kConvxOnly = false, kF32Ok = true, kSplitOk = false;
     static NM_HD size_t smem_bytes(int /*nt*/) { return 12 * 32 * sizeof(double); }
     // nm_convx_kernel register epilogue: tail moments from the registers, one barrier, then ONE warp (rotating with the
     // filter index) finishes the two channels on two lanes while the other warps already run the next filter.

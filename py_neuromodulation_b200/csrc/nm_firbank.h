@@ -114,8 +114,8 @@ struct FirBank {
         a.fft.pad = pad;
         a.fft.tw = fft.d_tw.as<cx<double>>();
         a.hperm = d_hperm.as<double>() + (size_t)f0 * P;
-        a.hx = d_hx.as<double>();
-        a.hx32 = d_hx32.as<float>();
+        a.hx = d_hx.as<double>() + (size_t)f0 * P;
+        a.hx32 = d_hx32.as<float>() + (size_t)f0 * P;
         a.tw32 = d_tw32.as<cx<float>>();
         a.nF = n < 0 ? nF : n;
         a.f0 = f0;
@@ -129,10 +129,11 @@ struct FirBank {
     int threads() const { return pow2 ? P / 16 : NM_FFT_THREADS; }
     // nm_convx_kernel: reflect mode is single-filter (one buffer), 'same' mode always runs the bank code (two buffers)
     // f32: 0 float64, 1 scalar float32 (8-byte elements), 2 packed float32 pairs (16-byte elements like cx<double>)
-    size_t smem_x(size_t epi, int f32 = 0) const {
+    // single: one filter per launch (BANK = false instantiation: the spectrum is multiplied in place, one transform buffer)
+    size_t smem_x(size_t epi, int f32 = 0, bool single = false) const {
         if (f32 == 2) f32 = 0;
-        return nm_conv_buf_elems(P, pad) * (f32 ? sizeof(cx<float>) : sizeof(cx<double>)) * (mode == NM_FIR_REFLECT ? 1 : 2) + NM_CX_RED_BYTES +
-               (epi_fits_tail(epi) ? 0 : epi);
+        return nm_conv_buf_elems(P, pad) * (f32 ? sizeof(cx<float>) : sizeof(cx<double>)) * ((mode == NM_FIR_REFLECT || single) ? 1 : 2) +
+               NM_CX_RED_BYTES + (epi_fits_tail(epi) ? 0 : epi);
     }
     size_t smem(size_t epi, int n_filters = -1) const {
         const size_t buf = pow2 ? nm_conv_buf_elems(P, pad) : (size_t)P;

@@ -289,6 +289,26 @@ static NmConvKernel<Epi> nm_convx_pick(const FirBank& b, int f32 = 0) {
     return nm_convx_pick_t<double, Epi>(b);
 }
 
+// 'same'-mode bank run filter by filter on the single-buffer instantiation (BANK = false): one more forward transform per extra
+// filter, but half the shared memory per CTA -> more resident CTAs for the latency-bound shared-memory epilogues (sharp waves,
+// burst envelopes).  Chosen per family at nm_finalize (split_filters); NMB200_SPLIT_BANKS=0 disables it.
+template <class Epi>
+static NmConvKernel<Epi> nm_convx_pick_single(const FirBank& b) {
+    if (!b.pow2 || !nm_convx_supported(b.P) || b.mode != NM_FIR_SAME) return nullptr;
+    if constexpr (Epi::kSameOk && Epi::kSplitOk) {
+        switch (b.P) {
+            case 1024: return nm_convx_kernel<double, 1024, false, false, Epi>;
+            case 2048: return nm_convx_kernel<double, 2048, false, false, Epi>;
+            default: return nm_convx_kernel<double, 4096, false, false, Epi>;
+        }
+    }
+    return nullptr;
+}
+static bool nm_split_banks_enabled() {
+    const char* env = getenv("NMB200_SPLIT_BANKS");
+    return env ? atoi(env) != 0 : true;
+}
+
 // a bank whose spectrum + work buffers do not fit the shared memory of one CTA (long filters at high sampling rates: P = 8192
 // and more than one filter) runs filter by filter: the forward transform is repeated, the buffers are not
 template <class Epi>
@@ -306,6 +326,11 @@ static size_t nm_fir_smem(const FirBank& bank, size_t epi_bytes) {
 
 template <class Epi>
 static int nm_allow_fir_smem(const FirBank& bank, size_t epi_bytes, const nm_pipeline* p, int f32 = 0) {
+    if constexpr (Epi::kSplitOk) {
+        if (auto k1 = nm_convx_pick_single<Epi>(bank)) {
+            if (nm_allow_smem(k1, bank.smem_x(epi_bytes, 0, true), p)) return -1;
+        }
+    }
     if (auto k = nm_convx_pick<Epi>(bank, f32)) return nm_allow_smem(k, bank.smem_x(epi_bytes, Epi::kF32Ok ? f32 : 0), p);
     if constexpr (!Epi::kConvxOnly) {
         const size_t sm = bank.smem(epi_bytes, nm_fir_split<Epi>(bank, epi_bytes, p) ? 1 : -1);
@@ -327,6 +352,18 @@ template <class Epi>
 static void nm_launch_fir(nm_pipeline* p, const FirBank& bank, const NmRows& rows, const Epi& epi, cudaStream_t stream, size_t epi_bytes,
                           int f32 = 0) {
     const int threads = bank.threads();
+    if constexpr (Epi::kSplitOk) {
+        if (auto k1 = (bank.nF > 1 && nm_split_banks_enabled()) ? nm_convx_pick_single<Epi>(bank) : nullptr) {
+            const size_t sm = bank.smem_x(epi_bytes, 0, true);
+            for (int f = 0; f < bank.nF; ++f) {
+                NmConvArgs a = bank.conv_args(rows, f, 1);
+                a.scratch_in_tail = bank.epi_fits_tail(epi_bytes) ? 1 : 0;
+                const int grid = nm_resident_grid(p, k1, threads, sm, a.n_items);
+                NM_LAUNCH(k1, dim3(grid), dim3(threads), sm, stream, a, epi);
+            }
+            return;
+        }
+    }
     if (auto k = nm_convx_pick<Epi>(bank, f32)) {
         NmConvArgs a = bank.conv_args(rows);
         a.scratch_in_tail = bank.epi_fits_tail(epi_bytes) ? 1 : 0;
@@ -1839,6 +1876,14 @@ extern "C" int nm_set_burst_threshold_mode(nm_pipeline* p, int incremental) {
 template <class Epi>
 static void nm_describe_fir(std::string& s, const char* family, const FirBank& b, size_t epi_bytes) {
     char line[256];
+    if constexpr (Epi::kSplitOk) {
+        if (b.nF > 1 && nm_split_banks_enabled() && nm_convx_pick_single<Epi>(b)) {
+            snprintf(line, sizeof(line), "%s: nm_convx_kernel P=%d filters=%d (one launch per filter, single transform buffer) taps=%d threads=%d smem=%zu\n",
+                     family, b.P, b.nF, b.L, b.threads(), b.smem_x(epi_bytes, 0, true));
+            s += line;
+            return;
+        }
+    }
     const bool x = nm_convx_pick<Epi>(b) != nullptr;
     snprintf(line, sizeof(line), "%s: %s P=%d filters=%d taps=%d threads=%d smem=%zu\n", family,
              x ? "nm_convx_kernel" : (b.pow2 ? "nm_conv_kernel" : "nm_fir_kernel"), b.P, b.nF, b.L, b.threads(), nm_fir_smem<Epi>(b, epi_bytes));

@@ -33,7 +33,7 @@ struct NmEpiStoreDecim {
     long long Wp;
     int D;            // keep window samples t = 0, D, 2D, ...
     static constexpr bool kRegs = true;
-    static constexpr bool kRegsOnly = true, kReflectOk = true, kSameOk = false, kConvxOnly = true, kF32Ok = false;
+    static constexpr bool kRegsOnly = true, kReflectOk = true, kSameOk = false, kConvxOnly = true, kF32Ok = false, kSplitOk = false;
     static constexpr bool kSyncsInside = false;
     static NM_HD size_t smem_bytes(int /*nt*/) { return 0; }
     NM_DEV bool regs_ok() const { return true; }

@@ -301,7 +301,7 @@ NM_DEV double nm_sw_join(int est, double a, double b) {
 
 struct NmEpiSharpwave {
     static constexpr bool kRegs = false;
-    static constexpr bool kRegsOnly = false, kReflectOk = false, kSameOk = true, kConvxOnly = false, kF32Ok = false;  // nm_convx_kernel instantiation traits
+    static constexpr bool kRegsOnly = false, kReflectOk = false, kSameOk = true, kConvxOnly = false, kF32Ok = false, kSplitOk = true;  // nm_convx_kernel instantiation traits
     NmSwCfg cfg;
     NmOut out;  // per_ch = nF * (n_combo + 1) * 2 ; slot (f*(n_combo+1) + combo)*2 + polarity
     static NM_HD size_t smem_bytes_for(int maxn, int n_combo, int tmp_in_tail) {
