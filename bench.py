@@ -134,9 +134,9 @@ def pinned_array(lib, shape, dtype) -> np.ndarray:
 
 
 def ncu_traffic(kernel: str, windows_per_launch: float) -> tuple[float | None, dict]:
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r1_ncu_traffic.json), rescaled to this
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r2_ncu_traffic.json), rescaled to this
     run's windows per launch; None if the capture does not cover the kernel."""
-    f = ROOT / "profiles" / "r1_ncu_traffic.json"
+    f = ROOT / "profiles" / "r2_ncu_traffic.json"
     try:
         d = json.loads(f.read_text())
         k = d["kernels"][kernel]
