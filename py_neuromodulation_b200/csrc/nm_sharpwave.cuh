@@ -26,6 +26,8 @@ struct NmSwCfg {
     int want_num_peaks;
     int maxn;            // capacity of the per-row peak lists (W/2 + 2)
     int tmp_in_tail;     // the median scratch (4 x maxn doubles) lives behind the filtered rows in the transform buffer
+    int need_tmp;        // some estimator is a median (only then the scratch is needed at all)
+    int rows_in_tail;    // the peak lists of the first k analysis rows live in that tail too (fewer bytes per CTA -> more CTAs per SM)
 };
 
 struct NmSwLists {
@@ -304,11 +306,15 @@ struct NmEpiSharpwave {
     static constexpr bool kRegsOnly = false, kReflectOk = false, kSameOk = true, kConvxOnly = false, kF32Ok = false, kSplitOk = true;  // nm_convx_kernel instantiation traits
     NmSwCfg cfg;
     NmOut out;  // per_ch = nF * (n_combo + 1) * 2 ; slot (f*(n_combo+1) + combo)*2 + polarity
-    static NM_HD size_t smem_bytes_for(int maxn, int n_combo, int tmp_in_tail) {
-        return 4 * nm_sw_row_bytes(maxn, tmp_in_tail) + (size_t)4 * (n_combo + 1) * sizeof(double) + 4 * sizeof(int) + 16;
+    static NM_HD size_t smem_bytes_for(int maxn, int n_combo, int tmp_in_tail, int rows_in_tail = 0) {
+        return (4 - rows_in_tail) * nm_sw_row_bytes(maxn, tmp_in_tail) + (size_t)4 * (n_combo + 1) * sizeof(double) + 4 * sizeof(int) + 16;
     }
+    // tail layout: [median scratch: 4 x maxn doubles, if needed and resident there][lists of rows 0 .. rows_in_tail - 1]
     NM_DEV void lists_for(NmSwLists& l, unsigned char* scratch, const cx<double>* tail, int ar) const {
-        unsigned char* base = scratch + (size_t)ar * nm_sw_row_bytes(cfg.maxn, cfg.tmp_in_tail);
+        unsigned char* tail_lists = const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(tail)) +
+                                    ((cfg.tmp_in_tail && cfg.need_tmp) ? (size_t)4 * cfg.maxn * sizeof(double) : 0);
+        unsigned char* base = ar < cfg.rows_in_tail ? tail_lists + (size_t)ar * nm_sw_list_bytes(cfg.maxn)
+                                                    : scratch + (size_t)(ar - cfg.rows_in_tail) * nm_sw_row_bytes(cfg.maxn, cfg.tmp_in_tail);
         l.rawP = reinterpret_cast<unsigned short*>(base);
         l.rawT = l.rawP + cfg.maxn;
         l.KP = l.rawT + cfg.maxn;
@@ -324,7 +330,7 @@ struct NmEpiSharpwave {
                     int tid, int nt) const {
         const int lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
         const size_t rb = nm_sw_row_bytes(cfg.maxn, cfg.tmp_in_tail);
-        double* results = reinterpret_cast<double*>(scratch + 4 * rb);
+        double* results = reinterpret_cast<double*>(scratch + (4 - cfg.rows_in_tail) * rb);
         int* nraw = reinterpret_cast<int*>(results + (size_t)4 * (cfg.n_combo + 1));  // local-maxima counts of the 4 rows
         const cx<double>* x = buf + o0;
         const cx<double>* tail = x + W;  // free part of the transform buffer (host checked the capacity: tmp_in_tail)
@@ -392,11 +398,18 @@ struct SharpwaveFam {
         cfg.want_num_peaks = want_num_peaks;
         cfg.maxn = W / 2 + 2;
         // the transform buffer holds P >= W + (L-1)/2 elements; whatever follows the W filtered samples is free
-        cfg.tmp_in_tail = ((size_t)(bank.P - W) * sizeof(cx<double>) >= (size_t)4 * cfg.maxn * sizeof(double)) ? 1 : 0;
+        const size_t tail_bytes = (size_t)(bank.P - W) * sizeof(cx<double>), tmp_bytes = (size_t)4 * cfg.maxn * sizeof(double);
+        cfg.need_tmp = 0;
+        for (int i = 0; i < n_combo; ++i) cfg.need_tmp |= (est_ids[i] == 1) ? 1 : 0;
+        cfg.tmp_in_tail = (tail_bytes >= tmp_bytes) ? 1 : 0;
+        // whatever the median scratch leaves of the tail takes the peak lists of the first rows (no median configured -- the
+        // default -- frees all of it): 2 rows at P = 2048 / W = 1000 (4 instead of 3 CTAs per SM), all 4 at P = 4096
+        const size_t used = (cfg.tmp_in_tail && cfg.need_tmp) ? tmp_bytes : 0;
+        cfg.rows_in_tail = cfg.tmp_in_tail ? (int)std::min<size_t>(4, (tail_bytes - used) / nm_sw_list_bytes(cfg.maxn)) : 0;
         per_ch = nF * (n_combo + 1) * 2;
         return d_colmap.upload(colmap, (size_t)C * per_ch, s);
     }
-    size_t epi_smem() const { return NmEpiSharpwave::smem_bytes_for(cfg.maxn, cfg.n_combo, cfg.tmp_in_tail); }
+    size_t epi_smem() const { return NmEpiSharpwave::smem_bytes_for(cfg.maxn, cfg.n_combo, cfg.tmp_in_tail, cfg.rows_in_tail); }
     int allow_smem(const nm_pipeline* p);
     int run(nm_pipeline* p, const NmRows& rows, int w0);
 };
