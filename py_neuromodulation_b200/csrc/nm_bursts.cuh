@@ -149,7 +149,25 @@ struct NmBurstThrArgs {
     unsigned long long* qkey;  // [n_ch * nB][NM_BQ_CAP]
     unsigned* qidx;            // [n_ch * nB][NM_BQ_CAP] low 32 bits of the logical sample index
     int incremental;         // 0: re-select from the ring for every window (reference implementation of this kernel)
+    // Few rows (channel-sharded runs: 32 channels x 2 bands = 64 rows on 148 SMs): the windows of a launch are split into n_split
+    // consecutive ranges per row, one CTA each.  Range 0 continues from the persisted state, the others start with a bracket
+    // rebuild from the ring (all envelope samples of the launch are already there), the last one persists its state.  Every
+    // threshold is the exact order statistic either way.
+    int n_split;
+    // where the last range leaves the state for the next launch: the buffers above when n_split == 1 (in place), the other half
+    // of a double buffer (zeroed by the host before the launch) otherwise -- range 0 of a row may still be reading the old state
+    // while the last range of the same row finishes
+    NmBurstQRow* qrow_out;
+    unsigned long long* qkey_out;
+    unsigned* qidx_out;
 };
+
+static inline int nm_burst_thr_split(int n_rows, int n_windows, int n_sm) {
+    int s = (2 * n_sm) / (n_rows > 0 ? n_rows : 1);
+    if (s > 8) s = 8;
+    while (s > 1 && n_windows / s < 8) --s;  // a rebuild costs about three incremental steps: keep the ranges long enough
+    return s < 1 ? 1 : s;
+}
 
 #define NM_SEL_BINS 4096
 #define NM_SEL_CAND 1024
@@ -532,15 +550,18 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
     sm.wcnt = reinterpret_cast<int*>(sm.res + 4);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
     const int n_rows = a.n_ch * a.nB;
+    const int n_split = a.n_split > 1 ? a.n_split : 1;
 
-    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    for (int vb = blockIdx.x; vb < n_rows * n_split; vb += gridDim.x) {
+        const int row = vb / n_split, part = vb - row * n_split;
+        const int w_begin = (int)((long long)a.n_windows * part / n_split), w_end = (int)((long long)a.n_windows * (part + 1) / n_split);
         const double* rrow = a.ring + (size_t)row * a.cap;
         NmBurstQRow st = a.qrow[row];
         unsigned long long lo_key = st.lo_key, hi_key = st.hi_key;
         long long e_prev = st.e_prev, first_prev = st.first_prev;
         int cnt_below = st.cnt_below, count = st.count, head = 0;
-        int n_rebuild = st.rebuilds, n_direct = st.directs, n_recentre = st.pad;
-        bool valid = a.incremental && st.valid != 0;
+        int n_rebuild = 0, n_direct = 0, n_recentre = 0;  // (deltas of this launch: added to the row's counters at the end)
+        bool valid = a.incremental && st.valid != 0 && part == 0;
         if (valid) {
             for (int j = tid; j < count; j += nt) {
                 sm.qk[j] = a.qkey[(size_t)row * NM_BQ_CAP + j];
@@ -549,7 +570,7 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
         }
         __syncthreads();
 
-        for (int w = 0; w < a.n_windows; ++w) {
+        for (int w = w_begin; w < w_end; ++w) {
             const long long e = a.e_end[w];
             const int n = a.n_hist[w];
             const long long first = e - n;
@@ -661,19 +682,26 @@ NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
         }
         // ---- persist the state of this row
         if (a.incremental) {
-            if (valid) {
+            const bool keeper = part == n_split - 1;  // the range that ends the launch hands its state to the next one
+            if (valid && keeper) {
                 for (int j = tid; j < count; j += nt) {
-                    a.qkey[(size_t)row * NM_BQ_CAP + j] = sm.qk[(head + j) & NM_BQ_MASK];
-                    a.qidx[(size_t)row * NM_BQ_CAP + j] = sm.qi[(head + j) & NM_BQ_MASK];
+                    a.qkey_out[(size_t)row * NM_BQ_CAP + j] = sm.qk[(head + j) & NM_BQ_MASK];
+                    a.qidx_out[(size_t)row * NM_BQ_CAP + j] = sm.qi[(head + j) & NM_BQ_MASK];
                 }
             }
             if (tid == 0) {
-                NmBurstQRow o;
-                o.lo_key = lo_key; o.hi_key = hi_key;
-                o.e_prev = e_prev; o.first_prev = first_prev;
-                o.cnt_below = cnt_below; o.count = count; o.valid = valid ? 1 : 0;
-                o.rebuilds = n_rebuild; o.directs = n_direct; o.pad = n_recentre;
-                a.qrow[row] = o;
+                NmBurstQRow* o = a.qrow_out + row;
+                if (part == 0 && a.qrow_out != a.qrow) {  // (double-buffered: carry the counters over)
+                    n_rebuild += st.rebuilds; n_direct += st.directs; n_recentre += st.pad;
+                }
+                if (keeper) {  // (field by field: the counters below are updated atomically by every range of the row)
+                    o->lo_key = lo_key; o->hi_key = hi_key;
+                    o->e_prev = e_prev; o->first_prev = first_prev;
+                    o->cnt_below = cnt_below; o->count = count; o->valid = valid ? 1 : 0;
+                }
+                if (n_rebuild) atomicAdd(&o->rebuilds, n_rebuild);
+                if (n_direct) atomicAdd(&o->directs, n_direct);
+                if (n_recentre) atomicAdd(&o->pad, n_recentre);
             }
         }
         __syncthreads();
@@ -786,10 +814,47 @@ NM_GLOBAL void nm_burst_feat_kernel(NmBurstFeatArgs a) {
 }
 
 // ------------------------------------------------------------------ host side
+// Persistent per-row state of nm_burst_thr_kernel.  Double-buffered: a launch that splits the windows of a row over several CTAs
+// reads the state from one half and leaves the new state in the other (no CTA ever writes what another one may still read).
+struct NmBqState {
+    DevBuf qrow[2], qkey[2], qidx[2];
+    int cur = 0;
+    size_t rows = 0;
+    int alloc(size_t rows_) {
+        rows = rows_;
+        for (int h = 0; h < 2; ++h) {
+            if (qrow[h].ensure(rows * sizeof(NmBurstQRow)) || qkey[h].ensure(rows * NM_BQ_CAP * 8) || qidx[h].ensure(rows * NM_BQ_CAP * 4)) return -1;
+            NM_CUDA_CHECK(cudaMemset(qrow[h].p, 0, rows * sizeof(NmBurstQRow)));
+        }
+        NM_CUDA_CHECK(cudaDeviceSynchronize());  // (legacy-stream memset: finish before any non-blocking stream uses the rows)
+        return 0;
+    }
+    bool allocated() const { return qrow[0].p != nullptr; }
+    // stream-ordered: kernels of a run that has not been synchronised yet may still use the queue state (the pipeline's streams
+    // are non-blocking, so a cudaMemset on the legacy stream would NOT wait for them)
+    void reset(cudaStream_t s) {
+        if (allocated()) cudaMemsetAsync(qrow[cur].p, 0, rows * sizeof(NmBurstQRow), s);  // valid = 0 for every row
+    }
+    const NmBurstQRow* current() const { return qrow[cur].as<NmBurstQRow>(); }
+    // fills the state pointers of a launch (ta.n_split already chosen) and makes the written half the current one
+    void bind(NmBurstThrArgs& ta, cudaStream_t s) {
+        const int o = ta.n_split > 1 ? cur ^ 1 : cur;
+        ta.qrow = qrow[cur].as<NmBurstQRow>();
+        ta.qkey = qkey[cur].as<unsigned long long>();
+        ta.qidx = qidx[cur].as<unsigned>();
+        ta.qrow_out = qrow[o].as<NmBurstQRow>();
+        ta.qkey_out = qkey[o].as<unsigned long long>();
+        ta.qidx_out = qidx[o].as<unsigned>();
+        if (o != cur) cudaMemsetAsync(qrow[o].p, 0, rows * sizeof(NmBurstQRow), s);
+        cur = o;
+    }
+};
+
 struct BurstsFam {
     FirBank bank;
     FftPlanHost hfft;
-    DevBuf d_env, d_ring, d_thr, d_colmap, d_e_end, d_n, d_lo, d_hi, d_gamma, d_qrow, d_qkey, d_qidx;
+    DevBuf d_env, d_ring, d_thr, d_colmap, d_e_end, d_n, d_lo, d_hi, d_gamma;
+    NmBqState qstate;
     int incremental = 1;  // nm_set_burst_threshold_mode(0) selects the per-window re-selection (reference of the kernel)
     int nB = 0, C = 0, W = 0, S = 0, ring_n = 0, chunk = 0;
     long long cap = 0, Wp = 0, batch = 0;
@@ -809,17 +874,11 @@ struct BurstsFam {
         if (d_env.ensure((size_t)chunk * C * nB * Wp * sizeof(double))) return -1;
         if (d_ring.ensure((size_t)C * nB * cap * sizeof(double))) return -1;
         if (d_thr.ensure((size_t)chunk * C * nB * sizeof(double))) return -1;
-        const size_t rows = (size_t)C * nB;
-        if (d_qrow.ensure(rows * sizeof(NmBurstQRow)) || d_qkey.ensure(rows * NM_BQ_CAP * 8) || d_qidx.ensure(rows * NM_BQ_CAP * 4)) return -1;
-        NM_CUDA_CHECK(cudaMemset(d_qrow.p, 0, rows * sizeof(NmBurstQRow)));
-        NM_CUDA_CHECK(cudaDeviceSynchronize());  // (legacy-stream memset: finish before any non-blocking stream uses the rows)
-        return 0;
+        return qstate.alloc((size_t)C * nB);
     }
-    // stream-ordered: kernels of a run that has not been synchronised yet may still use the queue state (the pipeline's streams
-    // are non-blocking, so a cudaMemset on the legacy stream would NOT wait for them)
     void reset(cudaStream_t s) {
         batch = 0;
-        if (d_qrow.p) cudaMemsetAsync(d_qrow.p, 0, (size_t)C * nB * sizeof(NmBurstQRow), s);  // valid = 0 for every row
+        qstate.reset(s);
     }
     int fast_n() const { return (nm_specx_supported(W) && bank.threads() >= (W == 500 ? NmSx500::NA : NmSx1000::NA)) ? W : 0; }
     size_t epi_smem() const { return NmEpiBursts::smem_bytes_for(W, hfft.generic, fast_n()); }

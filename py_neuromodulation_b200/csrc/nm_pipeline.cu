@@ -505,13 +505,12 @@ int BurstsFam::run(nm_pipeline* p, const NmRows& rows, int w0) {
     ta.k_lo = a_lo + k0; ta.k_hi = a_hi + k0;
     ta.gamma = a_gamma + k0;
     ta.thr = d_thr.as<double>();
-    ta.qrow = d_qrow.as<NmBurstQRow>();
-    ta.qkey = d_qkey.as<unsigned long long>();
-    ta.qidx = d_qidx.as<unsigned>();
     ta.incremental = incremental;
+    ta.n_split = incremental ? nm_burst_thr_split(C * nB, n, p->n_sm) : 1;
+    qstate.bind(ta, p->stream);
     const int n_thr = n * C * nB;
     p->prof_begin();
-    NM_LAUNCH(nm_burst_thr_kernel, dim3(C * nB), dim3(NM_BQ_THREADS), thr_smem(), p->stream, ta);
+    NM_LAUNCH(nm_burst_thr_kernel, dim3(C * nB * ta.n_split), dim3(NM_BQ_THREADS), thr_smem(), p->stream, ta);
     p->prof_end(NM_PROF_BURST_THR);
 
     NmBurstFeatArgs ba;
@@ -609,11 +608,10 @@ int RawNormFam::run(nm_pipeline* p, NmRows& rows) {
         ta.k_lo = m_lo; ta.k_hi = m_hi;
         ta.gamma = m_gamma;
         ta.thr = d_med.as<double>();
-        ta.qrow = d_qrow.as<NmBurstQRow>();
-        ta.qkey = d_qkey.as<unsigned long long>();
-        ta.qidx = d_qidx.as<unsigned>();
         ta.incremental = 1;
-        NM_LAUNCH(nm_burst_thr_kernel, dim3(C), dim3(NM_BQ_THREADS), BurstsFam::thr_smem(), p->stream, ta);
+        ta.n_split = nm_burst_thr_split(C, n, p->n_sm);
+        qstate.bind(ta, p->stream);
+        NM_LAUNCH(nm_burst_thr_kernel, dim3(C * ta.n_split), dim3(NM_BQ_THREADS), BurstsFam::thr_smem(), p->stream, ta);
         p->launches++;
     }
     NM_LAUNCH(nm_rawnorm_apply_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
@@ -1850,11 +1848,11 @@ extern "C" int nm_chunk_windows(nm_pipeline* p) { return p ? p->chunk : 0; }
 extern "C" int nm_burst_threshold_stats(nm_pipeline* p, long long* rebuilds, long long* direct_windows) {
     NM_P_CHECK(p);
     long long r = 0, d = 0;
-    if (p->bursts && p->bursts->d_qrow.p) {
+    if (p->bursts && p->bursts->qstate.allocated()) {
         cudaSetDevice(p->device);
         NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
         std::vector<NmBurstQRow> rows((size_t)p->bursts->C * p->bursts->nB);
-        NM_CUDA_CHECK(cudaMemcpy(rows.data(), p->bursts->d_qrow.p, rows.size() * sizeof(NmBurstQRow), cudaMemcpyDeviceToHost));
+        NM_CUDA_CHECK(cudaMemcpy(rows.data(), p->bursts->qstate.current(), rows.size() * sizeof(NmBurstQRow), cudaMemcpyDeviceToHost));
         for (const auto& q : rows) { r += q.rebuilds; d += q.directs; }
     }
     if (rebuilds) *rebuilds = r;

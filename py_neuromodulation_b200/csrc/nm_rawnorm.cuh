@@ -153,7 +153,8 @@ struct RawNormFam {
     long long cap = 0, Wp = 0, batch = 0, len_prev = 0;  // len_prev: history length after the last processed window
     DevBuf d_ring, d_blk, d_out, d_lo;
     // sliding median (methods 1, 3): per-window bookkeeping + persistent state of nm_burst_thr_kernel, one row per channel
-    DevBuf d_e_end, d_n, d_klo, d_khi, d_gamma, d_med, d_qrow, d_qkey, d_qidx;
+    DevBuf d_e_end, d_n, d_klo, d_khi, d_gamma, d_med;
+    NmBqState qstate;
     bool need_median() const { return method == 1 || method == 3; }
     int build(int method_, double clip_, int n_keep_, int add_, int C_, int W_) {
         method = method_; clip = clip_; n_keep = n_keep_; C = C_; W = W_;
@@ -171,16 +172,14 @@ struct RawNormFam {
         if (d_out.ensure((size_t)chunk * C * Wp * sizeof(double))) return -1;
         if (need_median()) {
             if (d_med.ensure((size_t)chunk * C * sizeof(double))) return -1;
-            if (d_qrow.ensure((size_t)C * sizeof(NmBurstQRow)) || d_qkey.ensure((size_t)C * NM_BQ_CAP * 8) || d_qidx.ensure((size_t)C * NM_BQ_CAP * 4)) return -1;
-            NM_CUDA_CHECK(cudaMemset(d_qrow.p, 0, (size_t)C * sizeof(NmBurstQRow)));
-            NM_CUDA_CHECK(cudaDeviceSynchronize());  // (legacy-stream memset: finish before any non-blocking stream uses the rows)
+            if (qstate.alloc((size_t)C)) return -1;
         }
         return 0;
     }
     void reset(cudaStream_t s) {  // (stream-ordered, see BurstsFam::reset)
         batch = 0;
         len_prev = 0;
-        if (d_qrow.p) cudaMemsetAsync(d_qrow.p, 0, (size_t)C * sizeof(NmBurstQRow), s);
+        qstate.reset(s);
     }
     int run(nm_pipeline* p, NmRows& rows);
 };

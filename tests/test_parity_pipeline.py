@@ -288,11 +288,13 @@ def _burst_stress_signal(seed, c, t):
     return x.astype(np.float32).astype(np.float64)
 
 
-@pytest.mark.parametrize("duration_s,n_windows", [(3.0, 420), (30.0, 150)])
-def test_burst_thresholds_incremental_equals_direct(backend, duration_s, n_windows):
+@pytest.mark.parametrize("duration_s,n_windows,n_ch", [(3.0, 420, 3), (30.0, 150, 3), (3.0, 420, 1), (30.0, 200, 1)])
+def test_burst_thresholds_incremental_equals_direct(backend, duration_s, n_windows, n_ch):
     """The sliding order-statistic state (bracket + FIFO queue) must reproduce the per-window re-selection bit for
-    bit: short history (constant expiry), chunk boundaries, streamed single windows, rebuilds, ties."""
-    x = _burst_stress_signal(3, 3, 46000)
+    bit: short history (constant expiry), chunk boundaries, streamed single windows, rebuilds, ties.  With few rows
+    (one channel: 2 rows on the 4 emulated / 148 real SMs) the windows of a launch are split into ranges that run on
+    CTAs of their own, each later range starting with a bracket rebuild (`nm_burst_thr_split`)."""
+    x = _burst_stress_signal(3, n_ch, 46000)
     s = nm.NMSettings.get_default().reset()
     s.features.bursts = True
     s.bursts_settings.time_duration_s = duration_s
@@ -309,8 +311,8 @@ def test_burst_thresholds_incremental_equals_direct(backend, duration_s, n_windo
         outs.append(mat)
         if incremental:  # the sliding path must carry most windows: 6 rows x n_windows row-windows in total
             rebuilds, direct = plan.pipe.burst_threshold_stats()
-            print(f"burst thresholds: {rebuilds} rebuilds, {direct} direct windows of {6 * n_windows}")
-            assert rebuilds + direct < 0.35 * 6 * n_windows
+            print(f"burst thresholds: {rebuilds} rebuilds, {direct} direct windows of {2 * n_ch * n_windows}")
+            assert rebuilds + direct < 0.35 * 2 * n_ch * n_windows
     assert np.array_equal(outs[0], outs[1]), np.argwhere(outs[0] != outs[1])[:5]
     # and against the oracle (true-ring variant) on the same windows
     ref_cols, ref = orc.run_offline(x, 1000, s.model_dump(), max_windows=n_windows)  # faithful_bursts=False: true ring
