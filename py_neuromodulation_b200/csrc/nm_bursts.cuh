@@ -163,7 +163,8 @@ struct NmBurstThrArgs {
 };
 
 static inline int nm_burst_thr_split(int n_rows, int n_windows, int n_sm) {
-    int s = (2 * n_sm) / (n_rows > 0 ? n_rows : 1);
+    static const int per_sm = [] { const char* e = getenv("NMB200_BURST_SPLIT_OCC"); const int v = e ? atoi(e) : 4; return v < 0 ? 0 : (v > 4 ? 4 : v); }();
+    int s = (per_sm * n_sm) / (n_rows > 0 ? n_rows : 1);
     if (s > 8) s = 8;
     while (s > 1 && n_windows / s < 8) --s;  // a rebuild costs about three incremental steps: keep the ranges long enough
     return s < 1 ? 1 : s;
@@ -539,7 +540,8 @@ NM_DEV void nm_bq_select_queue(const NmBqSmem& sm, int head, int count, unsigned
     }
 }
 
-NM_GLOBAL void nm_burst_thr_kernel(NmBurstThrArgs a) {
+// (64 registers: 4 resident CTAs per SM, so that the 512 rows of 256 channels x 2 bands are ONE wave on 148 SMs)
+NM_GLOBAL void NM_LAUNCH_BOUNDS(NM_BQ_THREADS, 4) nm_burst_thr_kernel(NmBurstThrArgs a) {
     NM_SHARED_BYTES(smem);
     NmBqSmem sm;
     sm.hist = reinterpret_cast<int*>(smem);

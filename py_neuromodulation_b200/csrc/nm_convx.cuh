@@ -21,31 +21,46 @@
 
 #include "nm_conv.cuh"
 
+//
+// Round 2: P = 3 * 2^k.  A 'same'-mode FIR of L taps over W samples needs a circular length P >= W + (L-1)/2 only (1499 for the
+// 999-tap band-pass banks at 1 kHz, 2999 at 2 kHz), so 1536 = 12*8*16 and 3072 = 12*16*16 replace 2048 / 4096 there: a quarter
+// fewer points through every pass.  Pass 0 becomes a radix-12 prime-factor butterfly (3 x 4, no internal twiddles) on V0 = 12
+// values per thread with NT = P/12 threads (the CTA size); passes 1 and 2 keep 16 values per thread and therefore run on the
+// first NT1 = P/16 threads (three of every four warps), the others only meet the barriers.
+#ifndef NM_CX_MINBK_1536
+#define NM_CX_MINBK_1536 3  // resident CTAs per SM the registers of the 1536-point bank kernels are capped for (4 fit the shared memory)
+#endif
 template <int P_>
 struct NmCxPlan {
     static constexpr int P = P_;
-    static constexpr int NT = P / 16;
-    static constexpr int R1 = (P == 1024) ? 8 : 16;
-    static constexpr int R2 = P / 16 / R1;
+    static constexpr bool MIXED = (P % 3) == 0;
+    static constexpr int V0 = MIXED ? 12 : 16;                // radix of pass 0 == values a thread owns in pass 0 and in the epilogue
+    static constexpr int NT = P / V0;                         // CTA threads
+    static constexpr int NT1 = P / 16;                        // threads of passes 1 and 2
+    static constexpr int R1 = (P == 1024 || P == 1536) ? 8 : 16;
+    static constexpr int R2 = P / V0 / R1;
     static constexpr int PAD = (R2 == 16) ? 4 : 3;
-    static constexpr int M1 = NT / R1;                        // butterfly stride of pass 1
+    static constexpr int M1 = NT / R1;                        // butterfly stride of pass 1 (block length NT)
     static constexpr int S0 = NT + (NT >> PAD);               // physical strides (see header comment)
     static constexpr int S1 = M1 + (M1 >> PAD);
-    static constexpr int B1 = NT * R1 + ((NT * R1) >> PAD);
-    static constexpr int B2 = NT * R2 + ((NT * R2) >> PAD);
+    static constexpr int B1 = NT1 * R1 + ((NT1 * R1) >> PAD);
+    static constexpr int B2 = NT1 * R2 + ((NT1 * R2) >> PAD);
     static constexpr int NBUF = P + (P >> PAD) + 2;
     // resident CTAs per SM the register allocation is tuned for: single-filter kernels run at 128 registers,
     // bank kernels (shared-memory limited anyway) at ~168 so that the prefetched filter spectrum stays in registers
     static constexpr int MINB1 = (NT >= 256) ? 2 : (NT == 128 ? 4 : 8);
-    static constexpr int MINBK = (NT >= 256) ? 1 : (NT == 128 ? 3 : 6);
+    static constexpr int MINBK = (NT >= 256) ? 1 : (NT == 128 ? (P == 1536 ? NM_CX_MINBK_1536 : 3) : 6);
     static_assert(R2 == (1 << PAD), "padding unit must equal the last radix");
     static_assert(M1 % R2 == 0 && NT % R2 == 0, "strides must be multiples of the padding unit");
-    static_assert(R1 * R2 * 16 == P, "three-pass plan");
+    static_assert(NT1 % M1 == 0 && (NT1 * R1) % R2 == 0, "the butterflies of a thread share one twiddle set");
+    static_assert(R1 * R2 * V0 == P && NT1 % 32 == 0, "three-pass plan");
 };
 
 #define NM_CX_RED_BYTES 512  // 8 values x 8 warps of doubles, owned by the register epilogues
 
-static inline bool nm_convx_supported(int P) { return P == 1024 || P == 2048 || P == 4096; }
+static inline bool nm_convx_supported(int P) { return P == 1024 || P == 2048 || P == 4096 || P == 1536 || P == 3072; }
+// CTA size of the compile-time plan
+static inline int nm_convx_threads(int P) { return (P % 3 == 0) ? P / 12 : P / 16; }
 
 // multiply the R-1 upper values of a butterfly by the powers of w1 (conjugated for the inverse)
 template <int R, bool INV, typename T>
@@ -66,18 +81,47 @@ NM_DEV void nm_twiddle_w1(cx<T>* v, cx<T> w1) {
         v[9] = cx_mul(v[9], cx_mul(w8, w1));
         v[10] = cx_mul(v[10], cx_mul(w8, w2));
         v[11] = cx_mul(v[11], cx_mul(w8, w3));
-        const cx<T> w12 = cx_mul(w8, w4);
-        v[12] = cx_mul(v[12], w12);
-        v[13] = cx_mul(v[13], cx_mul(w12, w1));
-        v[14] = cx_mul(v[14], cx_mul(w12, w2));
-        v[15] = cx_mul(v[15], cx_mul(w12, w3));
+        if (R > 12) {
+            const cx<T> w12 = cx_mul(w8, w4);
+            v[12] = cx_mul(v[12], w12);
+            v[13] = cx_mul(v[13], cx_mul(w12, w1));
+            v[14] = cx_mul(v[14], cx_mul(w12, w2));
+            v[15] = cx_mul(v[15], cx_mul(w12, w3));
+        }
     }
+}
+
+// 12-point DFT in registers, natural order in and out: prime-factor (Good-Thomas) 3 x 4, n = (4*n1 + 3*n2) mod 12,
+// k = (4*k1 + 9*k2) mod 12, so that w12^(n*k) = w3^(n1*k1) * w4^(n2*k2) -- no twiddles between the two stages
+template <bool INV, typename T>
+NM_DEV void nm_bfly12(cx<T>* v) {
+    cx<T> u[4][3];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        cx<T> a[3] = {v[(3 * n2) % 12], v[(4 + 3 * n2) % 12], v[(8 + 3 * n2) % 12]};
+        nm_bfly3<T, INV>(a);
+        u[n2][0] = a[0]; u[n2][1] = a[1]; u[n2][2] = a[2];
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 3; ++k1) {
+        nm_r4<INV>(u[0][k1], u[1][k1], u[2][k1], u[3][k1]);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) v[(4 * k1 + 9 * k2) % 12] = u[k2][k1];
+    }
+}
+
+// pass-0 butterfly of a plan: radix 16 or 12
+template <int R, bool INV, typename T>
+NM_DEV void nm_bfly0(cx<T>* v) {
+    if (R == 16) nm_bfly16<INV>(v);
+    else nm_bfly12<INV>(v);
 }
 
 // interior pass (pass 1): 16/R1 butterflies per thread, all sharing the same twiddle set
 template <class PL, bool INV, typename T>
 NM_DEV void nm_cx_pass1(cx<T>* sm, const cx<T> w1, int tid) {
     constexpr int R = PL::R1;
+    if (PL::NT1 < PL::NT && tid >= PL::NT1) return;  // (warp-uniform: NT1 is a multiple of 32)
     const int j = tid & (PL::M1 - 1);
     const int base = (tid - j) * R + j;
     cx<T>* p = sm + base + (base >> PL::PAD);
@@ -104,18 +148,19 @@ NM_DEV void nm_cx_pass1(cx<T>* sm, const cx<T> w1, int tid) {
 // phase ahead of their use.
 template <class PL>
 static NM_HD int nm_cx_hx_index(int tid, int i, int t) {  // position of slot (tid + NT*i)*R2 + t inside one filter's hx block
-    return ((i * (PL::R2 / 2) + (t >> 1)) * PL::NT + tid) * 2 + (t & 1);
+    return ((i * (PL::R2 / 2) + (t >> 1)) * PL::NT1 + tid) * 2 + (t & 1);
 }
 
 template <class PL, typename T>
 NM_DEV void nm_cx_load_h(T* hv, const T* NM_RESTRICT hx, int tid) {
     constexpr int R = PL::R2;
+    if (PL::NT1 < PL::NT && tid >= PL::NT1) return;
 #pragma unroll
     for (int i = 0; i < 16 / R; ++i) {
 #pragma unroll
         for (int t = 0; t < R / 2; ++t) {
             // one (2 x T)-wide load per pair: consecutive lanes read consecutive pairs
-            const cx<T> d = nm_ldg(reinterpret_cast<const cx<T>*>(hx) + (i * (R / 2) + t) * PL::NT + tid);
+            const cx<T> d = nm_ldg(reinterpret_cast<const cx<T>*>(hx) + (i * (R / 2) + t) * PL::NT1 + tid);
             hv[i * R + 2 * t] = d.re;
             hv[i * R + 2 * t + 1] = d.im;
         }
@@ -126,11 +171,12 @@ NM_DEV void nm_cx_load_h(T* hv, const T* NM_RESTRICT hx, int tid) {
 template <class PL>
 NM_DEV void nm_cx_load_h(f32x2* hv, const float* NM_RESTRICT hx, int tid) {
     constexpr int R = PL::R2;
+    if (PL::NT1 < PL::NT && tid >= PL::NT1) return;
 #pragma unroll
     for (int i = 0; i < 16 / R; ++i) {
 #pragma unroll
         for (int t = 0; t < R / 2; ++t) {
-            const cx<float> d = nm_ldg(reinterpret_cast<const cx<float>*>(hx) + (i * (R / 2) + t) * PL::NT + tid);
+            const cx<float> d = nm_ldg(reinterpret_cast<const cx<float>*>(hx) + (i * (R / 2) + t) * PL::NT1 + tid);
             hv[i * R + 2 * t] = f32x2(d.re);
             hv[i * R + 2 * t + 1] = f32x2(d.im);
         }
@@ -146,14 +192,16 @@ NM_DEV void nm_cx_load_hT(f32x2* hv, const float* NM_RESTRICT hx, int tid) { nm_
 template <int P, typename T>
 static inline void nm_cx_interleave_h(const double* h, T* hx) {
     using PL = NmCxPlan<P>;
-    for (int tid = 0; tid < PL::NT; ++tid)
+    for (int tid = 0; tid < PL::NT1; ++tid)
         for (int i = 0; i < 16 / PL::R2; ++i)
-            for (int t = 0; t < PL::R2; ++t) hx[nm_cx_hx_index<PL>(tid, i, t)] = (T)h[(tid + PL::NT * i) * PL::R2 + t];
+            for (int t = 0; t < PL::R2; ++t) hx[nm_cx_hx_index<PL>(tid, i, t)] = (T)h[(tid + PL::NT1 * i) * PL::R2 + t];
 }
 template <typename T>
 static inline void nm_cx_interleave_h(int P, const double* h, T* hx) {
     if (P == 1024) nm_cx_interleave_h<1024>(h, hx);
     else if (P == 2048) nm_cx_interleave_h<2048>(h, hx);
+    else if (P == 1536) nm_cx_interleave_h<1536>(h, hx);
+    else if (P == 3072) nm_cx_interleave_h<3072>(h, hx);
     else nm_cx_interleave_h<4096>(h, hx);
 }
 
@@ -163,6 +211,7 @@ static inline void nm_cx_interleave_h(int P, const double* h, T* hx) {
 template <class PL, int MODE, typename T>
 NM_DEV void nm_cx_pass2(cx<T>* dst, const cx<T>* src, const T* hv, int tid) {
     constexpr int R = PL::R2;
+    if (PL::NT1 < PL::NT && tid >= PL::NT1) return;
     const int off = tid * (R + 1);  // tid*R + ((tid*R) >> PAD)
 #pragma unroll
     for (int i = 0; i < 16 / R; ++i) {
@@ -231,7 +280,7 @@ struct NmEpiStoreScan {
         if (y) {
             double* r0 = y + ((size_t)w * n_ch + c0) * Wp;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
+            for (int k = 0; k < PL::V0; ++k) {
                 const int t = tid + NT * k - o0;
                 if (t >= 0 && t < W) {
                     r0[t] = v[k].re;
@@ -242,7 +291,7 @@ struct NmEpiStoreScan {
         if (!want_scan) return;
         __syncthreads();  // every thread has read its pass-0 inputs from `work`
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < PL::V0; ++k) {
             const int u = tid + NT * k - o0;
             if (u >= 0 && u < W) work[phys(u)] = v[k];
         }
@@ -333,7 +382,7 @@ struct NmEpiStoreScan {
 // freed registers, so their latency overlaps the reductions / barriers instead of stalling the next pass 0.
 template <int P, bool REFLECT, typename T>
 NM_DEV void nm_cx_load_item(cx<T>* v, const NmConvArgs& a, int item, int npair, int tid, int& w, int& c0, bool& has2) {
-    constexpr int NT = NmCxPlan<P>::NT;
+    constexpr int NT = NmCxPlan<P>::NT, V0 = NmCxPlan<P>::V0;
     const int W = a.in.W, E = a.E;
     w = item / npair;
     c0 = (item - w * npair) * 2;
@@ -345,7 +394,7 @@ NM_DEV void nm_cx_load_item(cx<T>* v, const NmConvArgs& a, int item, int npair, 
         // region, so all 32 loads of a thread are issued back to back (c - x == fma(-1, x, c): same rounding)
         const double a0 = 2.0 * r0[0], b0 = 2.0 * r1[0], a1 = 2.0 * r0[W - 1], b1 = 2.0 * r1[W - 1];
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
+        for (int t = 0; t < V0; ++t) {
             const int n = tid + NT * t;
             const bool left = n < E, mid = !left && n < E + W, right = !left && !mid && n < W + 2 * E;
             int idx = left ? E - n : (mid ? n - E : 2 * W + E - 2 - n);  // right: W-1-k with k = n-(E+W)+1
@@ -357,7 +406,7 @@ NM_DEV void nm_cx_load_item(cx<T>* v, const NmConvArgs& a, int item, int npair, 
         }
     } else {
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
+        for (int t = 0; t < V0; ++t) {
             const int n = tid + NT * t;
             const int idx = n < W ? n : 0;
             const double va = r0[idx], vb = r1[idx];
@@ -370,7 +419,7 @@ NM_DEV void nm_cx_load_item(cx<T>* v, const NmConvArgs& a, int item, int npair, 
 // the .y halves.  Same reflection / zero-padding arithmetic in float64 as above, rounded once to float32.
 template <int P, bool REFLECT>
 NM_DEV void nm_cx_load_item4(cx<f32x2>* v, const NmConvArgs& a, int item, int nquad, int tid, int& w, int& c0) {
-    constexpr int NT = NmCxPlan<P>::NT;
+    constexpr int NT = NmCxPlan<P>::NT, V0 = NmCxPlan<P>::V0;
     const int W = a.in.W, E = a.E;
     w = item / nquad;
     c0 = (item - w * nquad) * 4;
@@ -384,7 +433,7 @@ NM_DEV void nm_cx_load_item4(cx<f32x2>* v, const NmConvArgs& a, int item, int nq
         const double e0[4] = {2.0 * r0[0], 2.0 * r1[0], 2.0 * r2[0], 2.0 * r3[0]};
         const double e1[4] = {2.0 * r0[W - 1], 2.0 * r1[W - 1], 2.0 * r2[W - 1], 2.0 * r3[W - 1]};
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
+        for (int t = 0; t < V0; ++t) {
             const int n = tid + NT * t;
             const bool left = n < E, mid = !left && n < E + W, right = !left && !mid && n < W + 2 * E;
             int idx = left ? E - n : (mid ? n - E : 2 * W + E - 2 - n);
@@ -398,7 +447,7 @@ NM_DEV void nm_cx_load_item4(cx<f32x2>* v, const NmConvArgs& a, int item, int nq
         }
     } else {
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
+        for (int t = 0; t < V0; ++t) {
             const int n = tid + NT * t;
             const int idx = n < W ? n : 0;
             const bool in = n < W;
@@ -456,9 +505,9 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
     cx<T>* const p0s = spec + tid + (tid >> PL::PAD);
     // twiddle generators; tid == 0 / j == 0 multiply by exactly 1, so no thread needs a special case
     const cx<T> wA = nm_cx_twid(a, tid, T());                          // exp(-2*pi*i*tid/P): pass 0
-    const cx<T> wB = nm_cx_twid(a, (tid & (PL::M1 - 1)) * 16, T());    // exp(-2*pi*i*j/NT): pass 1 (table stride P/NT)
+    const cx<T> wB = nm_cx_twid(a, (tid & (PL::M1 - 1)) * PL::V0, T());  // exp(-2*pi*i*j/NT): pass 1 (table stride P/NT)
 
-    cx<T> v[16];
+    cx<T> v[PL::V0];
     T hv[16];
     int item = blockIdx.x, w = 0, c0 = 0;
     bool has2 = false;
@@ -472,10 +521,10 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
         int nw = 0, nc0 = 0;
         bool nhas2 = false;
         // ---- pass 0 on the window that is already in registers
-        nm_bfly16<false>(v);
-        nm_twiddle_w1<16, false>(v, wA);
+        nm_bfly0<PL::V0, false>(v);
+        nm_twiddle_w1<PL::V0, false>(v, wA);
 #pragma unroll
-        for (int t = 0; t < 16; ++t) p0s[t * PL::S0] = v[t];
+        for (int t = 0; t < PL::V0; ++t) p0s[t * PL::S0] = v[t];
         __syncthreads();
         if (!BANK) nm_cx_load_hT<PL, T>(hv, hx, tid);  // (L1 resident) lands while pass 1 computes
         nm_cx_pass1<PL, false>(spec, wB, tid);
@@ -501,9 +550,9 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
             __syncthreads();
             // ---- final inverse pass: padded slots -> registers, natural order n = tid + NT * t
 #pragma unroll
-            for (int t = 0; t < 16; ++t) v[t] = p0w[t * PL::S0];
-            nm_twiddle_w1<16, true>(v, wA);
-            nm_bfly16<true>(v);
+            for (int t = 0; t < PL::V0; ++t) v[t] = p0w[t * PL::S0];
+            nm_twiddle_w1<PL::V0, true>(v, wA);
+            nm_bfly0<PL::V0, true>(v);
 #ifndef NM_CX_HV_EARLY
             // next filter's spectrum (wrapping to filter 0 for the next item): issued where the register pressure is lowest -- a
             // load that the compiler has to spill right away stalls on its own L2 latency (ncu: STL of the loaded pair right
@@ -522,17 +571,17 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
                     cx<float>* const wf = reinterpret_cast<cx<float>*>(work);
                     const int nv = min(4, a.in.n_ch - c0);
                     {
-                        cx<float> u[16];
+                        cx<float> u[PL::V0];
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) u[k] = {v[k].re.x, v[k].im.x};
+                        for (int k = 0; k < PL::V0; ++k) u[k] = {v[k].re.x, v[k].im.x};
                         typename Epi::State st;
                         epi.template consume<PL, float>(u, wf, red, st, o0, W, a.in.n_ch, w, c0, nv > 1, fi, tid);
                         epi.template finish<PL, float>(wf, red, st, o0, W, a.in.n_ch, w, c0, nv > 1, fi, tid);
                     }
                     if (nv > 2) {
-                        cx<float> u[16];
+                        cx<float> u[PL::V0];
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) u[k] = {v[k].re.y, v[k].im.y};
+                        for (int k = 0; k < PL::V0; ++k) u[k] = {v[k].re.y, v[k].im.y};
                         double* const redb = Epi::kSyncsInside ? red + NM_CX_RED_BYTES / 16 : red;
                         typename Epi::State st;
                         cx<float>* const wb = wf + PL::NBUF;  // second half of the (16-byte element) transform buffer
@@ -556,7 +605,7 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
                 if constexpr (!Epi::kRegsOnly && std::is_same<T, double>::value) {  // (the shared-memory epilogues take float64 rows)
                     __syncthreads();
 #pragma unroll
-                    for (int t = 0; t < 16; ++t) work[tid + NT * t] = v[t];
+                    for (int t = 0; t < PL::V0; ++t) work[tid + NT * t] = v[t];
                     __syncthreads();
                     epi.run(work, o0, W, a.in.n_ch, w, c0, has2, fi + a.f0, scratch, tid, NT);
                     __syncthreads();

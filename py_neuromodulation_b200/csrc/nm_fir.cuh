@@ -48,7 +48,7 @@ struct NmEpiStore {
                         bool has2, int f, int tid) const {
         double* r0 = y + (((size_t)w * n_ch + c0) * nF + f) * Wp;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < PL::V0; ++k) {
             const int t = tid + PL::NT * k - o0;
             if (t >= 0 && t < W) {
                 r0[t] = (double)v[k].re;
@@ -109,7 +109,7 @@ struct NmEpiBandpower {
         // band-pass outputs have (near) zero mean, so the one-pass moments lose nothing in float64
         st.s[0] = st.s[1] = st.s[2] = st.s[3] = 0.0;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < PL::V0; ++k) {
             const int n = tid + NT * k;
             if (n >= lo && n < hi) {
                 const double re = (double)v[k].re, im = (double)v[k].im;  // moments are accumulated in float64 in either mode

@@ -13,8 +13,14 @@ struct FirBank {
     int nF = 0, L = 0, Lh = 0, P = 0, mode = NM_FIR_SAME, E = 0;
     FftPlanHost fft;
     DevBuf d_hperm, d_hx, d_hx32, d_tw32;  // *32: float32 copies for the optional float32 mode of nm_convx_kernel
-    bool pow2 = false;  // register-blocked power-of-two kernel (nm_conv.cuh) vs generic mixed-radix kernel (nm_fir.cuh)
+    bool pow2 = false;  // register-blocked kernel (nm_convx.cuh / nm_conv.cuh) vs generic mixed-radix kernel (nm_fir.cuh)
+    bool mixed = false; // P = 3 * 2^k on nm_convx_kernel's 12 x R1 x 16 plans ('same' mode only; there is no nm_conv_kernel fallback)
     int pad = 3;
+    // 'same'-mode banks need P >= W + (L-1)/2 only: 1536 / 3072 instead of 2048 / 4096 (NMB200_MIXED_RADIX=0: powers of two only)
+    static bool mixed_enabled() {
+        const char* env = getenv("NMB200_MIXED_RADIX");
+        return env ? atoi(env) != 0 : true;
+    }
     int build(const double* taps, int nF_, int L_, int W, int mode_, cudaStream_t s) {
         nF = nF_; L = L_; Lh = (L - 1) / 2; mode = mode_;
         int need;
@@ -31,7 +37,12 @@ struct FirBank {
         int p2 = 1;
         while (p2 < need) p2 <<= 1;
         pow2 = p2 >= 512 && p2 <= 8192;  // P/16 threads per CTA: 32 .. 512 (larger transforms use the generic kernel)
-        if (pow2) {
+        mixed = pow2 && mode == NM_FIR_SAME && (p2 == 2048 || p2 == 4096) && need <= p2 / 4 * 3 && mixed_enabled();
+        if (mixed) {
+            P = p2 / 4 * 3;
+            pad = 4;
+            if (fft.build_with(P, std::vector<int>{12, P == 1536 ? 8 : 16, 16}, s)) return -1;
+        } else if (pow2) {
             P = p2;
             std::vector<int> radices{16};
             int rem = P / 16;
@@ -71,7 +82,7 @@ struct FirBank {
     // samples per side to exactly P_ points and multiplied with H[k] = 1 for |k| <= P_/(2D), else 0 (circular: no taps).
     int build_lowpass(int W, int P_, int pad_each, int D, cudaStream_t s) {
         nF = 1; L = 1; Lh = 0; mode = NM_FIR_REFLECT; E = pad_each; P = P_; pow2 = true;
-        NM_CHECK(nm_convx_supported(P) && W + 2 * pad_each == P && P % (2 * D) == 0, "internal: bad down-sampling plan");
+        NM_CHECK(nm_convx_supported(P) && (P & (P - 1)) == 0 && W + 2 * pad_each == P && P % (2 * D) == 0, "internal: bad down-sampling plan");
         std::vector<int> radices{16};
         int rem = P / 16;
         if (rem == 64) { radices.push_back(8); radices.push_back(8); rem = 1; }
@@ -126,7 +137,7 @@ struct FirBank {
         return a;
     }
     bool epi_fits_tail(size_t epi) const { return pow2 && epi > 0 && epi <= (nm_conv_buf_elems(P, pad) - (size_t)P) * sizeof(cx<double>); }
-    int threads() const { return pow2 ? P / 16 : NM_FFT_THREADS; }
+    int threads() const { return pow2 ? (mixed ? nm_convx_threads(P) : P / 16) : NM_FFT_THREADS; }
     // nm_convx_kernel: reflect mode is single-filter (one buffer), 'same' mode always runs the bank code (two buffers)
     // f32: 0 float64, 1 scalar float32 (8-byte elements), 2 packed float32 pairs (16-byte elements like cx<double>)
     // single: one filter per launch (BANK = false instantiation: the spectrum is multiplied in place, one transform buffer)

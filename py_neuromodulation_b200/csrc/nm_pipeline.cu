@@ -258,7 +258,7 @@ template <typename T, class Epi>
 static NmConvKernel<Epi> nm_convx_pick_t(const FirBank& b) {
     if (b.mode == NM_FIR_REFLECT) {
         if constexpr (Epi::kReflectOk) {
-            if (b.nF != 1) return nullptr;
+            if (b.nF != 1 || b.mixed) return nullptr;
             switch (b.P) {
                 case 1024: return nm_convx_kernel<T, 1024, true, false, Epi>;
                 case 2048: return nm_convx_kernel<T, 2048, true, false, Epi>;
@@ -269,7 +269,9 @@ static NmConvKernel<Epi> nm_convx_pick_t(const FirBank& b) {
         if constexpr (Epi::kSameOk) {
             switch (b.P) {
                 case 1024: return nm_convx_kernel<T, 1024, false, true, Epi>;
+                case 1536: return nm_convx_kernel<T, 1536, false, true, Epi>;
                 case 2048: return nm_convx_kernel<T, 2048, false, true, Epi>;
+                case 3072: return nm_convx_kernel<T, 3072, false, true, Epi>;
                 default: return nm_convx_kernel<T, 4096, false, true, Epi>;
             }
         }
@@ -298,7 +300,9 @@ static NmConvKernel<Epi> nm_convx_pick_single(const FirBank& b) {
     if constexpr (Epi::kSameOk && Epi::kSplitOk) {
         switch (b.P) {
             case 1024: return nm_convx_kernel<double, 1024, false, false, Epi>;
+            case 1536: return nm_convx_kernel<double, 1536, false, false, Epi>;
             case 2048: return nm_convx_kernel<double, 2048, false, false, Epi>;
+            case 3072: return nm_convx_kernel<double, 3072, false, false, Epi>;
             default: return nm_convx_kernel<double, 4096, false, false, Epi>;
         }
     }

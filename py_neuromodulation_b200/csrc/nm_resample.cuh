@@ -43,7 +43,7 @@ struct NmEpiStoreDecim {
                         bool has2, int /*f*/, int tid) const {
         double* r0 = y + ((size_t)w * n_ch + c0) * Wp;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < PL::V0; ++k) {
             const int t = tid + PL::NT * k - o0;
             if (t >= 0 && t < W && t % D == 0) {
                 r0[t / D] = (double)v[k].re;

@@ -212,3 +212,37 @@ def test_packed_float32_kernels_all_quad_remainders(backend, n_ch, precision):
     assert np.isfinite(got).all() and err.max() < 1e-5, (float(err.max()), cols[int(np.argmax(err.max(axis=0)))])
     _, got64 = nm.DataProcessor(sfreq=1000, settings=s, channels=ch, line_noise=50, verbose=False).process_windows(x, starts, 1000)
     assert np.abs(got - got64).max() > 0.0  # the float32 kernels really ran
+
+
+@pytest.mark.parametrize("sfreq,precision", [(1000, "f64"), (2000, "f64"), (1000, "f32"), (1000, "f32x2")])
+def test_same_mode_banks_on_three_times_power_of_two_plans(backend, monkeypatch, sfreq, precision):
+    """'same'-mode FIR banks (band-pass power, burst envelopes) need a circular length of W + (L-1)/2 only and run on the
+    12 x R1 x 16 plans of csrc/nm_convx.cuh (1536 points at 1 kHz, 3072 at 2 kHz) instead of 2048 / 4096: same results as the
+    power-of-two plans (NMB200_MIXED_RADIX=0) to rounding, and as the oracle; odd channel count (half-filled last pair)."""
+    W = int(sfreq)
+    x = neural_like(77, 5, W + 100 * 7 * (W // 1000))
+    s = nm.NMSettings.get_default().reset()
+    for f in ("bandpass_filter", "bursts", "raw_hjorth"):
+        s.features[f] = True
+    if precision != "f64":
+        s.features.bursts = False  # (threshold decisions keep every float32 pipeline's notch in float64: test the banks alone)
+    s.postprocessing.feature_normalization = False
+    s.raw_resampling_settings.resample_freq_hz = sfreq
+    ch = get_default_channels_from_data(x)
+    starts = np.arange(0, 7) * (W // 10)
+    outs = {}
+    for mixed in ("1", "0"):
+        monkeypatch.setenv("NMB200_MIXED_RADIX", mixed)
+        dp = nm.DataProcessor(sfreq=sfreq, settings=s, channels=ch, line_noise=50, verbose=False, precision=precision)
+        cols, outs[mixed] = dp.process_windows(x, starts, W)
+        plan = dp.plan(W).pipe.describe_plan()
+        want = (f"P={3 * 512 * (W // 1000)}" if mixed == "1" else f"P={2048 * (W // 1000)}")
+        assert all(want in line for line in plan.splitlines() if line.startswith(("bandpower", "bursts"))), plan
+    tol = 1e-11 if precision == "f64" else 2e-5
+    d = np.abs(outs["1"] - outs["0"]) / np.maximum(np.abs(outs["0"]), 1e-3 if precision == "f64" else 1.0)
+    assert d.max() < tol, (float(d.max()), cols[int(np.argmax(d.max(axis=0)))])
+    assert np.abs(outs["1"] - outs["0"]).max() > 0.0  # two different transforms really ran
+    ref_cols, ref = orc.run_offline(x, sfreq, s.model_dump(), max_windows=len(starts))
+    assert ref_cols[: len(cols)] == cols
+    err = np.abs(outs["1"] - ref[:, : len(cols)]) / np.maximum(np.abs(ref[:, : len(cols)]), 1.0)
+    assert err.max() < (1e-9 if precision == "f64" else 1e-5), float(err.max())
