@@ -44,6 +44,7 @@ def main():
     pipe.run(starts, download=False)
     ms = pipe.timer_stop()
     wall = (time.perf_counter() - t0) * 1e3
+    stats = pipe.burst_threshold_stats() if s.features.bursts else None
     pipe.reset_state()
     pipe.set_profiling(True)
     pipe.run(starts, download=False)
@@ -51,6 +52,8 @@ def main():
     prof = pipe.profile()
     print(f"{cfg}: {n_ch} ch x {dur} s @ {sfreq:g} Hz, {starts.size} windows, F = {pipe.F}, chunk = {pipe.chunk_windows} windows")
     print(f"  device time {ms:.2f} ms (wall {wall:.2f} ms) -> {starts.size / ms * 1e3:.0f} windows/s")
+    if stats:
+        print(f"  burst thresholds: {stats[0]} bracket rebuilds, {stats[1]} windows by direct selection of {starts.size * n_ch * len(s.bursts_settings.frequency_bands)} row-windows")
     for k, (t, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
         print(f"  {k:16s} {t:9.3f} ms  {n:5d} launches")
 
