@@ -27,6 +27,9 @@
 // fewer points through every pass.  Pass 0 becomes a radix-12 prime-factor butterfly (3 x 4, no internal twiddles) on V0 = 12
 // values per thread with NT = P/12 threads (the CTA size); passes 1 and 2 keep 16 values per thread and therefore run on the
 // first NT1 = P/16 threads (three of every four warps), the others only meet the barriers.
+#ifndef NM_CX_MINB1_NT128
+#define NM_CX_MINB1_NT128 4  // single-filter kernels of the 128-thread plans: resident CTAs per SM the registers are capped for
+#endif
 #ifndef NM_CX_MINBK_1536
 #define NM_CX_MINBK_1536 3  // resident CTAs per SM the registers of the 1536-point bank kernels are capped for (4 fit the shared memory)
 #endif
@@ -48,7 +51,7 @@ struct NmCxPlan {
     static constexpr int NBUF = P + (P >> PAD) + 2;
     // resident CTAs per SM the register allocation is tuned for: single-filter kernels run at 128 registers,
     // bank kernels (shared-memory limited anyway) at ~168 so that the prefetched filter spectrum stays in registers
-    static constexpr int MINB1 = (NT >= 256) ? 2 : (NT == 128 ? 4 : 8);
+    static constexpr int MINB1 = (NT >= 256) ? 2 : (NT == 128 ? NM_CX_MINB1_NT128 : 8);
     static constexpr int MINBK = (NT >= 256) ? 1 : (NT == 128 ? (P == 1536 ? NM_CX_MINBK_1536 : 3) : 6);
     static_assert(R2 == (1 << PAD), "padding unit must equal the last radix");
     static_assert(M1 % R2 == 0 && NT % R2 == 0, "strides must be multiples of the padding unit");
