@@ -418,23 +418,6 @@ NM_DEV void nm_cx_load_item(cx<T>* v, const NmConvArgs& a, int item, int npair, 
     }
 }
 
-// The shared-memory epilogues (sharp waves, burst envelopes) are register hungry, so the next item's rows are not loaded ahead of
-// them; this only asks L2 for the lines (ncu: the item load was the top stall site of those kernels -- the chunk of notched rows is
-// larger than L2, so every item started with a DRAM round trip).  'same' mode: samples [0, W) of the two rows.
-template <int P>
-NM_DEV void nm_cx_prefetch_item(const NmConvArgs& a, int item, int npair, int tid) {
-    constexpr int NT = NmCxPlan<P>::NT;
-    const int W = a.in.W;
-    const int w = item / npair;
-    const int c0 = (item - w * npair) * 2;
-    const double* NM_RESTRICT r0 = a.in.base + (size_t)c0 * a.in.ch_stride + nm_ldg(a.in.off + w);
-    const double* NM_RESTRICT r1 = r0 + ((c0 + 1 < a.in.n_ch) ? a.in.ch_stride : 0);
-    for (int n = tid * 16; n < W; n += NT * 16) {  // one request per 128-byte line
-        nm_prefetch_l2(r0 + n);
-        nm_prefetch_l2(r1 + n);
-    }
-}
-
 // float32 mode: one item = (window, channel QUAD); sub-item A = rows (c0, c0 + 1) in the .x halves, B = rows (c0 + 2, c0 + 3) in
 // the .y halves.  Same reflection / zero-padding arithmetic in float64 as above, rounded once to float32.
 template <int P, bool REFLECT>
@@ -627,10 +610,10 @@ nm_convx_kernel(NmConvArgs a, Epi epi) {
 #pragma unroll
                     for (int t = 0; t < PL::V0; ++t) work[tid + NT * t] = v[t];
                     __syncthreads();
-                    if (!REFLECT && last && next < a.n_items) nm_cx_prefetch_item<P>(a, next, npair, tid);
                     epi.run(work, o0, W, a.in.n_ch, w, c0, has2, fi + a.f0, scratch, tid, NT);
                     __syncthreads();
-                    // (no early prefetch here: these epilogues are register hungry and long enough to hide nothing)
+                    // (no early prefetch here: these epilogues are register hungry and long enough to hide nothing; a prefetch.global.L2 of the
+                    // next item's lines in front of the epilogue measured +-0: sharp waves 8.03 -> 8.12 ms, envelopes 6.34 -> 6.35 ms per 591 windows)
                     if (last && next < a.n_items) nm_cx_load_item<P, REFLECT, T>(v, a, next, npair, tid, nw, nc0, nhas2);
                 }
             }

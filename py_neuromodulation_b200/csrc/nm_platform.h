@@ -133,8 +133,6 @@ static inline void nm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 
 template <typename T>
 NM_DEV T nm_ldg(const T* p) { return __ldg(p); }
-// bring the line of `p` into L2 without holding a register for it
-NM_DEV void nm_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #endif
 
 // ---- error handling shared by both builds -------------------------------------------------

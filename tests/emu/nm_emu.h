@@ -311,7 +311,6 @@ inline int __ffs(int v) { return __builtin_ffs(v); }
 
 template <typename T>
 inline T nm_ldg(const T* p) { return *p; }
-inline void nm_prefetch_l2(const void*) {}
 
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
