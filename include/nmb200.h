@@ -154,7 +154,9 @@ int nm_add_sharpwave(nm_pipeline* p, int n_filters, const double* taps, int n_ta
 
 /* FeatureNormalizer (processing/normalization.py:81-111): rolling normalisation of the columns listed in
  * `cols` over the previous n_keep windows (current included); method 0 mean, 1 median, 2 zscore,
- * 3 zscore-median; clip <= 0 disables clipping. */
+ * 3 zscore-median, and the scikit-learn transformers the reference wraps (processing/normalization.py:58-70,173-190),
+ * restated: 4 minmax (MinMaxScaler), 5 robust (RobustScaler), 6 quantile (QuantileTransformer(n_quantiles=300), n_keep <= 300);
+ * clip <= 0 disables clipping. */
 int nm_add_feature_normalizer(nm_pipeline* p, int method, double clip, int n_keep, int n_cols, const int* cols);
 
 /* ---- data path ------------------------------------------------------------------------------ */

@@ -606,8 +606,47 @@ class SharpwaveOracle:
 
 
 # ----------------------------------------------------------------------------- 8f-1: feature normaliser
+def sklearn_restated(method: str, hist: np.ndarray, v: np.ndarray) -> np.ndarray:
+    """processing/normalization.py:173-190 (`norm_sklearn`): `transformer.fit(nan_to_num(previous)).transform(current)` for the
+    transformers of lines 58-70, restated from scikit-learn 1.9 `sklearn/preprocessing/_data.py` (scikit-learn is a third-party
+    dependency of the reference; pinned here by fixtures the unmodified reference generated WITH the real scikit-learn):
+    MinMaxScaler (`X * scale_ + min_`), RobustScaler (median, 25-75 percentile range), QuantileTransformer(n_quantiles=300,
+    uniform output: mean of the ascending and the descending `np.interp`, bounds applied afterwards).  Scales below 10 * eps
+    become 1 (`_handle_zeros_in_scale`)."""
+    tiny = 10 * np.finfo(np.float64).eps
+    v = np.asarray(v, dtype=np.float64)
+    if method == "minmax":
+        mn, mx = hist.min(axis=0), hist.max(axis=0)
+        rng = mx - mn
+        rng[rng < tiny] = 1.0
+        scale = 1.0 / rng
+        return v * scale + (0.0 - mn * scale)
+    if method == "robust":
+        centre = np.nanmedian(hist, axis=0)
+        q = np.nanpercentile(hist, (25.0, 75.0), axis=0)
+        scale = q[1] - q[0]
+        scale[scale < tiny] = 1.0
+        return (v - centre) / scale
+    n = hist.shape[0]
+    nq = max(1, min(300, n))
+    refs = np.linspace(0, 1, nq, endpoint=True)
+    quant = np.maximum.accumulate(np.nanpercentile(hist, refs * 100, axis=0))
+    out = np.array(v, dtype=np.float64)
+    for j in range(out.size):
+        qj = quant[:, j]
+        x = out[j]
+        lower, upper = x == qj[0], x == qj[-1]
+        if not np.isnan(x):
+            out[j] = 0.5 * (np.interp(x, qj, refs) - np.interp(-x, -qj[::-1], -refs[::-1]))
+        if upper:
+            out[j] = 1.0
+        if lower:
+            out[j] = 0.0
+    return out
+
+
 class FeatureNormalizerOracle:
-    """processing/normalization.py:81-111,151-170 ('feature' type; numpy methods only)."""
+    """processing/normalization.py:81-111,151-190 ('feature' type; numpy methods and the restated scikit-learn transformers)."""
 
     def __init__(self, settings: dict):
         cfg = settings["feature_normalization_settings"]
@@ -634,6 +673,8 @@ class FeatureNormalizerOracle:
                 std[std == 0] = 1
                 centre = mean if self.method == "zscore" else (np.nanmedian if has_nan else np.median)(self.prev, axis=0)
                 out = (v - centre) / std
+            elif self.method in ("minmax", "robust", "quantile"):
+                out = sklearn_restated(self.method, np.nan_to_num(self.prev), v)
             else:
                 raise NotImplementedError(f"sklearn normaliser '{self.method}' is out of scope")
         if self.clip:

@@ -23,7 +23,10 @@ OSC_ESTIMATORS = ("mean", "median", "std", "max")
 SW_FEATURES = ("peak_left", "peak_right", "num_peaks", "trough", "width", "prominence", "interval", "decay_time",
                "rise_time", "sharpness", "rise_steepness", "decay_steepness", "slope_ratio")
 SW_ESTIMATORS = ("mean", "median", "max", "min", "var")
-NORM_METHODS = ("mean", "median", "zscore", "zscore-median")
+NORM_METHODS = ("mean", "median", "zscore", "zscore-median")  # raw normaliser (csrc/nm_rawnorm.cuh)
+# feature normaliser (csrc/nm_norm.cuh): the numpy methods + the scikit-learn transformers the reference wraps, restated on the GPU
+# ("power" -- Yeo-Johnson with a per-window maximum-likelihood search -- stays out of scope)
+FEATURE_NORM_METHODS = NORM_METHODS + ("minmax", "robust", "quantile")
 
 
 def _i32(a) -> np.ndarray:
@@ -273,7 +276,7 @@ class Pipeline:
 
     def add_feature_normalizer(self, method: str, clip: float, n_keep: int, columns: Sequence[str]) -> None:
         cols = _i32([self.col_of[k] for k in columns] or [0])
-        _lib.check(self.lib.nm_add_feature_normalizer(self._h, NORM_METHODS.index(method), float(clip or 0.0), int(n_keep),
+        _lib.check(self.lib.nm_add_feature_normalizer(self._h, FEATURE_NORM_METHODS.index(method), float(clip or 0.0), int(n_keep),
                                                       len(columns), _ptr(cols, C.c_int)))
 
     # -- measurement
@@ -736,7 +739,7 @@ class IdentityNormPipeline:
         cols = [f"{c}_raw" for c in names]
         self.pipe = Pipeline(n, n, 3, cols, device=device)
         ScanSpec(names, raw=True).attach(self.pipe)
-        self.pipe.add_feature_normalizer(NORM_METHODS[method_index], clip, n_keep, cols)
+        self.pipe.add_feature_normalizer(FEATURE_NORM_METHODS[method_index], clip, n_keep, cols)
         self.pipe.finalize()
 
     def step(self, v: np.ndarray) -> np.ndarray:

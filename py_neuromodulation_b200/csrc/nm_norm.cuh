@@ -17,7 +17,7 @@ struct NmNormArgs {
     const int* cols;      // column in `out` of compact column j
     long long g0;         // global index of the batch's first window
     int n_keep;
-    int method;           // 0 mean, 1 median, 2 zscore, 3 zscore-median
+    int method;           // 0 mean, 1 median, 2 zscore, 3 zscore-median, 4 minmax, 5 robust, 6 quantile (the last three: restated scikit-learn transformers)
     double clip;
     double* out;
     int F;
@@ -51,6 +51,131 @@ NM_DEV double nm_norm_median(const double* col, int stride, int n) {
     return (r_lo == r_hi) ? vlo : 0.5 * (vlo + vhi);
 }
 
+// ---- scikit-learn transformers the reference wraps (processing/normalization.py:58-70,173-190), restated ------------------------
+// fit on nan_to_num(history), transform the RAW current value; sklearn.preprocessing._data (1.9): _handle_zeros_in_scale sets scales
+// below 10 * eps to 1.
+#define NM_NORM_TINY_SCALE (10.0 * 2.220446049250313e-16)
+
+// numpy 'linear' percentile of the nan_to_num'ed history: virtual index (n - 1) * q, numpy's _lerp
+NM_DEV double nm_norm_lerp(double a, double b, double t) {
+    const double diff = b - a;
+    double r = a + diff * t;
+    if (t >= 0.5) r = b - diff * (1.0 - t);
+    return (diff == 0.0) ? a : r;
+}
+
+// RobustScaler: (v - median) / (q75 - q25); one O(n^2) rank-counting pass collects the six order statistics
+NM_DEV double nm_norm_robust(const double* col, int stride, int n, double v) {
+    const double vi25 = (double)(n - 1) * 0.25, vi75 = (double)(n - 1) * 0.75;
+    const int k25 = (int)floor(vi25), k75 = (int)floor(vi75);
+    const int want[6] = {(n - 1) / 2, n / 2, k25, k25 + 1 < n ? k25 + 1 : n - 1, k75, k75 + 1 < n ? k75 + 1 : n - 1};
+    double os[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        const double x = nm_nan_to_num(col[(size_t)i * stride]);
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const double y = nm_nan_to_num(col[(size_t)j * stride]);
+            rank += (y < x || (y == x && j < i)) ? 1 : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+            if (rank == want[q]) os[q] = x;
+    }
+    const double med = (want[0] == want[1]) ? os[0] : 0.5 * (os[0] + os[1]);
+    const double q25 = nm_norm_lerp(os[2], os[3], vi25 - k25), q75 = nm_norm_lerp(os[4], os[5], vi75 - k75);
+    double scale = q75 - q25;
+    if (scale < NM_NORM_TINY_SCALE) scale = 1.0;
+    return (v - med) / scale;
+}
+
+// MinMaxScaler(feature_range = (0, 1)): X * scale_ + min_
+NM_DEV double nm_norm_minmax(const double* col, int stride, int n, double v) {
+    double mn = nm_nan_to_num(col[0]), mx = mn;
+    for (int i = 1; i < n; ++i) {
+        const double x = nm_nan_to_num(col[(size_t)i * stride]);
+        mn = x < mn ? x : mn;
+        mx = x > mx ? x : mx;
+    }
+    double range = mx - mn;
+    if (range < NM_NORM_TINY_SCALE) range = 1.0;
+    const double scale = 1.0 / range;
+    const double min_ = 0.0 - mn * scale;
+    return v * scale + min_;
+}
+
+// QuantileTransformer(n_quantiles = 300, uniform output) for histories of n <= 300 rows: n_quantiles_ = n, references
+// linspace(0, 1, n), quantiles = np.nanpercentile(history, references * 100) -- the sorted history up to the last bit: the virtual
+// index (n - 1) * ((j * step * 100) / 100) is not always exactly j, and then the quantile is a lerp that lands one ulp-ish next to
+// the order statistic.  For distinct values that moves the result by ~1e-16; among TIES it decides which of the equal quantiles is
+// "the last one <= v" (ascending np.interp) and "the first one >= v" (descending np.interp), i.e. a whole reference step.  So the
+// roundings of numpy / scikit-learn are replayed exactly for the first and the last tie (no fused multiply-adds: nm_*_rn).
+// The transform of a member v of the history (the current row always is one) is 0.5 * (R[j1] + R[m1]); values equal to the largest /
+// smallest quantile map to 1 / 0 (the lower bound is applied last).
+NM_DEV double nm_norm_vindex(int j, int n) {
+    const double step = 1.0 / (double)(n - 1);                                   // numpy.linspace: arange(n) * step, last element := 1
+    const double ref = (j == n - 1) ? 1.0 : nm_mul_rn((double)j, step);
+    const double q = nm_mul_rn(ref, 100.0) / 100.0;                              // references_ * 100, then percentile's q / 100
+    return nm_mul_rn((double)(n - 1), q);                                        // 'linear': (n - 1) * quantiles
+}
+NM_DEV double nm_norm_qlerp(double a, double b, double t) {                      // numpy _lerp
+    const double diff = b - a;
+    if (t >= 0.5) return nm_sub_rn(b, nm_mul_rn(diff, 1.0 - t));
+    return nm_add_rn(a, nm_mul_rn(diff, t));
+}
+
+NM_DEV double nm_norm_quantile(const double* col, int stride, int n, double v) {
+    if (v != v) return v;
+    int lt = 0, le = 0;
+    double mn = nm_nan_to_num(col[0]), mx = mn, pred = -NM_DBL_MAX, succ = NM_DBL_MAX;
+    for (int i = 0; i < n; ++i) {
+        const double x = nm_nan_to_num(col[(size_t)i * stride]);
+        lt += (x < v) ? 1 : 0;
+        le += (x <= v) ? 1 : 0;
+        mn = x < mn ? x : mn;
+        mx = x > mx ? x : mx;
+        if (x < v && x > pred) pred = x;
+        if (x > v && x < succ) succ = x;
+    }
+    const double step = 1.0 / (double)(n - 1);
+    double up, dn;  // R[j1] and R[m1]
+    if (le == lt) {
+        // v is not a member of the history (only +-inf can get here: the history holds nan_to_num'ed values): np.interp's end values,
+        // or a plain interpolation between the neighbouring order statistics
+        if (le == 0) up = dn = 0.0;
+        else if (lt == n) up = dn = 1.0;
+        else {
+            const double r0 = (double)(lt - 1) * step, r1 = (lt == n - 1) ? 1.0 : (double)lt * step;
+            up = dn = r0 + (r1 - r0) / (succ - pred) * (v - pred);
+        }
+    } else {
+        // order statistics around the ties of v: sorted[k] = pred (k = lt - 1), v (lt <= k < le), succ (k = le)
+        const int ties = le - lt;
+        int j1 = le - 1, m1 = lt;
+        {
+            const double vi = nm_norm_vindex(le - 1, n);
+            int f = (int)floor(vi);
+            if (f > n - 1) f = n - 1;
+            const int nx = f + 1 < n ? f + 1 : n - 1;
+            const double a = f < lt ? pred : (f < le ? v : succ), b = nx < lt ? pred : (nx < le ? v : succ);
+            if (nm_norm_qlerp(a, b, vi - (double)f) > v && ties >= 2) j1 = le - 2;  // the last tie's quantile was nudged above v
+        }
+        {
+            const double vi = nm_norm_vindex(lt, n);
+            int f = (int)floor(vi);
+            if (f > n - 1) f = n - 1;
+            const int nx = f + 1 < n ? f + 1 : n - 1;
+            const double a = f < lt ? pred : (f < le ? v : succ), b = nx < lt ? pred : (nx < le ? v : succ);
+            if (nm_norm_qlerp(a, b, vi - (double)f) < v && ties >= 2) m1 = lt + 1;  // the first tie's quantile was nudged below v
+        }
+        up = (j1 == n - 1) ? 1.0 : nm_mul_rn((double)j1, step);
+        dn = (m1 == n - 1) ? 1.0 : nm_mul_rn((double)m1, step);
+    }
+    double r = 0.5 * (up + dn);
+    if (v == mx) r = 1.0;
+    if (v == mn) r = 0.0;
+    return r;
+}
+
 NM_GLOBAL void nm_norm_kernel(NmNormArgs a) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)a.n_windows * a.n_cols) return;
@@ -70,7 +195,13 @@ NM_GLOBAL void nm_norm_kernel(NmNormArgs a) {
     }
     const double mean = sum / cnt;
     double r;
-    if (a.method == 0) {
+    if (a.method == 4) {
+        r = nm_norm_minmax(col, a.n_cols, (int)nh, v);
+    } else if (a.method == 5) {
+        r = nm_norm_robust(col, a.n_cols, (int)nh, v);
+    } else if (a.method == 6) {
+        r = nm_norm_quantile(col, a.n_cols, (int)nh, v);
+    } else if (a.method == 0) {
         r = (v - mean) / mean;
     } else if (a.method == 1) {
         const double med = nm_norm_median(col, a.n_cols, (int)nh);

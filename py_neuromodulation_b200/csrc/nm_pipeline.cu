@@ -1126,8 +1126,9 @@ extern "C" int nm_add_sharpwave(nm_pipeline* p, int n_filters, const double* tap
 extern "C" int nm_add_feature_normalizer(nm_pipeline* p, int method, double clip, int n_keep, int n_cols, const int* cols) {
     NM_P_CHECK(p);
     NM_CHECK(!p->finalized, "pipeline already finalized");
-    NM_CHECK(method >= 0 && method <= 3, "normalisation method must be 0..3 (mean, median, zscore, zscore-median)");
+    NM_CHECK(method >= 0 && method <= 6, "normalisation method must be 0..6 (mean, median, zscore, zscore-median, minmax, robust, quantile)");
     NM_CHECK(n_keep >= 1 && n_cols >= 0, "bad normaliser configuration");
+    NM_CHECK(method != 6 || n_keep <= 300, "the quantile normaliser covers histories of at most 300 windows (n_quantiles = 300)");
     for (int i = 0; i < n_cols; ++i) NM_CHECK(cols[i] >= 0 && cols[i] < p->F, "normaliser column out of range");
     cudaSetDevice(p->device);
     auto f = std::make_unique<NormFam>();

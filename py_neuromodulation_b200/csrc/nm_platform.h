@@ -133,6 +133,10 @@ static inline void nm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 
 template <typename T>
 NM_DEV T nm_ldg(const T* p) { return __ldg(p); }
+// single IEEE operations the compiler must not contract into fused multiply-adds (replays of numpy arithmetic)
+NM_DEV double nm_mul_rn(double a, double b) { return __dmul_rn(a, b); }
+NM_DEV double nm_add_rn(double a, double b) { return __dadd_rn(a, b); }
+NM_DEV double nm_sub_rn(double a, double b) { return __dsub_rn(a, b); }
 #endif
 
 // ---- error handling shared by both builds -------------------------------------------------

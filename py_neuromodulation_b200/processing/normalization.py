@@ -12,7 +12,18 @@ from ..utils.types import NORM_METHOD, NMBaseModel
 if TYPE_CHECKING:
     from ..stream.settings import NMSettings
 
-GPU_NORM_METHODS = ("mean", "median", "zscore", "zscore-median")
+GPU_NORM_METHODS = ("mean", "median", "zscore", "zscore-median")  # raw normaliser
+# feature normaliser: + the scikit-learn transformers of the reference (processing/normalization.py:58-70), restated in
+# csrc/nm_norm.cuh: MinMaxScaler, RobustScaler, QuantileTransformer(n_quantiles=300); PowerTransformer stays out of scope
+GPU_FEATURE_NORM_METHODS = GPU_NORM_METHODS + ("minmax", "robust", "quantile")
+
+
+def check_feature_norm_method(method: str, n_keep: int) -> None:
+    if method not in GPU_FEATURE_NORM_METHODS:
+        raise NotImplementedError(f"normalisation method '{method}' (scikit-learn PowerTransformer) is out of scope")
+    if method == "quantile" and n_keep > 300:
+        raise NotImplementedError("the quantile normaliser covers histories of at most 300 windows (n_quantiles = 300): "
+                                  "normalization_time_s * sampling_rate_features_hz <= 300")
 
 
 class NormalizationSettings(NMBaseModel):
@@ -39,9 +50,8 @@ class FeatureNormalizer:
     def __init__(self, settings: "NMSettings") -> None:
         self.settings = settings.feature_normalization_settings.validate()
         self.method = self.settings.normalization_method
-        if self.method not in GPU_NORM_METHODS:
-            raise NotImplementedError(f"normalisation method '{self.method}' (scikit-learn transformer) is out of scope")
         self.num_samples_normalize = int(self.settings.normalization_time_s * settings.sampling_rate_features_hz)
+        check_feature_norm_method(self.method, self.num_samples_normalize)
         self._pipe = None
 
     def process(self, data: np.ndarray) -> np.ndarray:
@@ -49,7 +59,7 @@ class FeatureNormalizer:
 
         v = np.asarray(data, dtype=np.float64).ravel()
         if self._pipe is None:
-            self._pipe = IdentityNormPipeline(v.size, GPU_NORM_METHODS.index(self.method), float(self.settings.clip or 0.0),
+            self._pipe = IdentityNormPipeline(v.size, GPU_FEATURE_NORM_METHODS.index(self.method), float(self.settings.clip or 0.0),
                                               self.num_samples_normalize)
         return self._pipe.step(v)
 

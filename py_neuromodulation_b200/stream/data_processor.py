@@ -130,7 +130,7 @@ class DataProcessor:
         from .. import user_features
         from ..filter.notch_filter import NotchFilter
         from ..processing.data_preprocessor import preprocessing_plan
-        from ..processing.normalization import GPU_NORM_METHODS
+        from ..processing.normalization import check_feature_norm_method
         from ..processing.rereference import build_reference_matrix
 
         # arithmetic of the linear FIR families: "f64" (default; ~1e-12 from the float64 reference) or "f32" (float32 inside the
@@ -207,9 +207,8 @@ class DataProcessor:
         self.normalize = bool(self.settings.postprocessing.feature_normalization)
         if self.normalize:
             ns = self.settings.feature_normalization_settings.validate()
-            if ns.normalization_method not in GPU_NORM_METHODS:
-                raise NotImplementedError(f"normalisation method '{ns.normalization_method}' (scikit-learn) is out of scope")
             self.norm_keep = int(ns.normalization_time_s * self.settings.sampling_rate_features_hz)
+            check_feature_norm_method(ns.normalization_method, self.norm_keep)
 
         self.user_feature_names = list(user_features.keys())
         self._user_plugins = {name: cls(self.settings, self.ch_names_used_features, self.sfreq_raw) for name, cls in user_features.items()}
@@ -285,7 +284,7 @@ class DataProcessor:
     def _user_features(self, plan: _Plan, data: np.ndarray) -> dict:
         """User-defined Python plugins see the same preprocessed window the GPU families see."""
         from .._pipeline import IdentityNormPipeline
-        from ..processing.normalization import GPU_NORM_METHODS
+        from ..processing.normalization import GPU_FEATURE_NORM_METHODS
 
         # a pipeline of its own: the feature pipeline has already advanced its (stateful) raw normaliser for this window, and
         # preprocessing the window a second time on it would advance it twice
@@ -299,7 +298,7 @@ class DataProcessor:
             keys = [k for k in out if ns.normalize_psd or "psd" not in k]
             if keys:
                 if self._user_norm is None:
-                    self._user_norm = IdentityNormPipeline(len(keys), GPU_NORM_METHODS.index(ns.normalization_method),
+                    self._user_norm = IdentityNormPipeline(len(keys), GPU_FEATURE_NORM_METHODS.index(ns.normalization_method),
                                                            float(ns.clip or 0.0), self.norm_keep, device=self.device)
                 normed = self._user_norm.step(np.array([float(out[k]) for k in keys]))
                 out.update(zip(keys, normed))

@@ -311,6 +311,9 @@ inline int __ffs(int v) { return __builtin_ffs(v); }
 
 template <typename T>
 inline T nm_ldg(const T* p) { return *p; }
+inline double nm_mul_rn(double a, double b) { volatile double r = a * b; return r; }  // (volatile: no contraction whatever the flags)
+inline double nm_add_rn(double a, double b) { volatile double r = a + b; return r; }
+inline double nm_sub_rn(double a, double b) { volatile double r = a - b; return r; }
 
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

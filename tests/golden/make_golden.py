@@ -248,6 +248,25 @@ def next_row_cases(nm):
              vals=vals, sfreq=1000.0)
 
 
+def sklearn_norm_cases(nm):
+    """Feature normalisation through the scikit-learn transformers the reference wraps (processing/normalization.py:58-70,173-190):
+    MinMaxScaler, RobustScaler, QuantileTransformer(n_quantiles=300); history of 30 windows, trimmed inside the run; one channel
+    with a flat stretch (constant features -> zero scales)."""
+    x = neural_like(31, 4, 1000 + 100 * 44)
+    x[2, :2600] = x[2, 0]  # constant samples for the first windows of channel 2
+    for method in ("minmax", "robust", "quantile"):
+        st = nm.NMSettings.get_default().reset()
+        for f in ("fft", "raw_hjorth", "linelength", "return_raw"):
+            st.features[f] = True
+        st.postprocessing.feature_normalization = True
+        st.feature_normalization_settings.normalization_method = method
+        st.feature_normalization_settings.normalization_time_s = 3.0
+        st.feature_normalization_settings.clip = 0.8 if method == "robust" else 3.0
+        keys, vals = _run_windows(nm, st, x)
+        save(f"dataprocessor_featnorm_{method}", x=x.astype(np.float32), settings=dump_settings(st), keys=json.dumps(keys), vals=vals,
+             sfreq=1000.0)
+
+
 def stream_cases():
     nm = load_reference_stream()
     import tempfile
@@ -365,6 +384,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "next":  # only the SURVEY 8f "next row" fixtures
         next_row_cases(nm)
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "sklearn_norm":
+        sklearn_norm_cases(nm)
+        raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sharpwave":
         sharpwave_option_cases(nm)
         raise SystemExit(0)
@@ -376,6 +398,7 @@ if __name__ == "__main__":
     resample_cases(nm)
     sharpwave_option_cases(nm)
     window_processor_cases(nm)
+    sklearn_norm_cases(nm)
     burst_history_case(nm)
     real_data_case(nm)
     stream_cases()

@@ -113,7 +113,9 @@ NEXT_ROW_FIXTURES = ["dataprocessor_prefilter_default", "dataprocessor_prefilter
                      # raw_resampling with a ratio != 1 (2 kHz defaults, ratio 0.8, up-sampling + raw normaliser)
                      "dataprocessor_resample_2k_default", "dataprocessor_resample_1250", "dataprocessor_resample_up_rawnorm",
                      # sharp-wave option: one polarity only (un-paired keys)
-                     "dataprocessor_sharpwave_peaks_only", "dataprocessor_sharpwave_troughs_only"]
+                     "dataprocessor_sharpwave_peaks_only", "dataprocessor_sharpwave_troughs_only",
+                     # feature normalisation through the scikit-learn transformers the reference wraps (generated with scikit-learn 1.9)
+                     "dataprocessor_featnorm_minmax", "dataprocessor_featnorm_robust", "dataprocessor_featnorm_quantile"]
 
 
 @pytest.mark.parametrize("name", ["dataprocessor_default", "dataprocessor_fast", "dataprocessor_c3_nan", "dataprocessor_realdata"]

@@ -48,7 +48,11 @@ def run_dp(g, n_windows=None, with_norm=True, fused=None):
                                         ("dataprocessor_resample_up_rawnorm", None),
                                         # sharp waves with one polarity only (features/sharpwaves.py:269-272)
                                         ("dataprocessor_sharpwave_peaks_only", None),
-                                        ("dataprocessor_sharpwave_troughs_only", None)])
+                                        ("dataprocessor_sharpwave_troughs_only", None),
+                                        # MinMaxScaler / RobustScaler / QuantileTransformer feature normalisation
+                                        # (processing/normalization.py:58-70,173-190), restated in csrc/nm_norm.cuh
+                                        ("dataprocessor_featnorm_minmax", None), ("dataprocessor_featnorm_robust", None),
+                                        ("dataprocessor_featnorm_quantile", None)])
 def test_window_processor_matches_reference_golden(backend, name, n_emu):
     g = load_golden(name)
     n = n_emu if backend == "emu" else None  # the thread emulator is slow: fewer windows on CPU, all on the GPU

@@ -246,3 +246,39 @@ def test_same_mode_banks_on_three_times_power_of_two_plans(backend, monkeypatch,
     assert ref_cols[: len(cols)] == cols
     err = np.abs(outs["1"] - ref[:, : len(cols)]) / np.maximum(np.abs(ref[:, : len(cols)]), 1.0)
     assert err.max() < (1e-9 if precision == "f64" else 1e-5), float(err.max())
+
+
+@pytest.mark.parametrize("method", ["minmax", "robust", "quantile"])
+def test_sklearn_feature_normalizers_restated_on_the_gpu(backend, method):
+    """processing/normalization.py:58-70,173-190: the reference hands the history to a scikit-learn transformer.  The stand-alone
+    `FeatureNormalizer` (same kernel as inside the pipeline) against the oracle's restatement on vectors with ties (quantised
+    values), a constant column and a history that is trimmed many times; `power` and long quantile histories raise."""
+    rng = np.random.default_rng(5)
+    s = nm.NMSettings.get_default()
+    s.feature_normalization_settings.normalization_method = method
+    s.feature_normalization_settings.normalization_time_s = 1.2  # 12 windows
+    s.feature_normalization_settings.clip = 0.9 if method == "robust" else 3
+    fn = nm.FeatureNormalizer(s) if hasattr(nm, "FeatureNormalizer") else None
+    if fn is None:
+        from py_neuromodulation_b200.processing.normalization import FeatureNormalizer
+        fn = FeatureNormalizer(s)
+    ora = orc.FeatureNormalizerOracle(s.model_dump())
+    worst = 0.0
+    for k in range(40):
+        v = rng.standard_normal(9)
+        v[1] = np.round(v[1] * 2) / 2          # ties
+        v[2] = 0.25                            # constant column: zero scale -> 1
+        v[3] = np.round(v[3])                  # heavy ties
+        got = fn.process(v.copy())
+        ref = ora.process(v.copy())
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), k
+        worst = max(worst, float(np.nanmax(np.abs(got - ref))))
+    assert worst < 1e-12, worst
+    from py_neuromodulation_b200.processing.normalization import FeatureNormalizer
+    s.feature_normalization_settings.normalization_method = "power"
+    with pytest.raises(NotImplementedError):
+        FeatureNormalizer(s)
+    s.feature_normalization_settings.normalization_method = "quantile"
+    s.feature_normalization_settings.normalization_time_s = 31  # 310 windows > n_quantiles
+    with pytest.raises(NotImplementedError):
+        FeatureNormalizer(s)
