@@ -224,6 +224,107 @@ NM_GLOBAL void nm_norm_kernel(NmNormArgs a) {
     a.out[(size_t)k * a.F + a.cols[j]] = nm_nan_to_num(r);
 }
 
+// ---- order-statistic methods over many windows: one thread per COLUMN walks the windows in order ------------------------------
+// median / zscore-median / robust need order statistics of a history that slides by one row per window.  Rank counting per
+// (window, column) is O(n_keep^2) -- 135 ms (median) and 412 ms (robust) per 591 windows x 7 936 columns, five to fifteen times the
+// rest of the default pipeline.  Here a thread keeps the valid history values of its column SORTED in shared memory (column-
+// interleaved: bank-conflict free) and updates it by one insertion and one removal per window (binary search + shift), so the order
+// statistics are plain indexing: O(n_keep) per window.  Used for batched runs; a single streamed window keeps the kernel above.
+struct NmNormOrderArgs {
+    const double* ext;
+    int n_prev, n_windows, n_cols;
+    const int* cols;
+    long long g0;
+    int n_keep;
+    int method;  // 1 median, 3 zscore-median, 5 robust
+    double clip;
+    double* out;
+    int F;
+};
+
+NM_GLOBAL void nm_norm_order_kernel(NmNormOrderArgs a) {
+    NM_SHARED_BYTES(smem);
+    double* S = reinterpret_cast<double*>(smem);
+    const int t = threadIdx.x, T = blockDim.x;
+    const int j = blockIdx.x * T + t;
+    if (j >= a.n_cols) return;  // (no barriers below)
+    const bool to_num = a.method == 5;  // RobustScaler is fitted on nan_to_num(history); the numpy medians skip NaNs
+    int m = 0;                          // sorted values S[0 .. m)
+#define NM_NS(i) S[(size_t)(i) * T + t]
+    auto insert = [&](double x) {
+        if (to_num) x = nm_nan_to_num(x);
+        if (x != x) return;
+        int lo = 0, hi = m;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (NM_NS(mid) <= x) lo = mid + 1; else hi = mid;
+        }
+        for (int i = m; i > lo; --i) NM_NS(i) = NM_NS(i - 1);
+        NM_NS(lo) = x;
+        ++m;
+    };
+    auto remove = [&](double x) {
+        if (to_num) x = nm_nan_to_num(x);
+        if (x != x) return;
+        int lo = 0, hi = m;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (NM_NS(mid) < x) lo = mid + 1; else hi = mid;
+        }
+        for (int i = lo; i + 1 < m; ++i) NM_NS(i) = NM_NS(i + 1);
+        --m;
+    };
+    int first_row = -1;  // the structure holds rows [first_row, row of the previous window]
+    for (int k = 0; k < a.n_windows; ++k) {
+        const long long g = a.g0 + k;
+        const int row = a.n_prev + k;
+        long long nh = g + 1 < a.n_keep ? g + 1 : a.n_keep;
+        if (nh > row + 1) nh = row + 1;
+        const int want_first = row - (int)(nh - 1);
+        if (first_row < 0) {
+            for (int r = want_first; r <= row; ++r) insert(a.ext[(size_t)r * a.n_cols + j]);
+            first_row = want_first;
+        } else {
+            for (; first_row < want_first; ++first_row) remove(a.ext[(size_t)first_row * a.n_cols + j]);  // (first: m <= n_keep always)
+            insert(a.ext[(size_t)row * a.n_cols + j]);
+        }
+        if (g == 0) continue;  // first window passes through untouched
+        const double v = a.ext[(size_t)row * a.n_cols + j];
+        double r;
+        if (m == 0) {
+            r = __longlong_as_double(0x7ff8000000000000LL);
+        } else {
+            const int r_lo = (m - 1) / 2, r_hi = m / 2;
+            const double med = (r_lo == r_hi) ? NM_NS(r_lo) : 0.5 * (NM_NS(r_lo) + NM_NS(r_hi));
+            if (a.method == 1) {
+                r = (v - med) / med;
+            } else if (a.method == 3) {
+                double sum = 0.0, q = 0.0;
+                for (int i = 0; i < m; ++i) sum += NM_NS(i);
+                const double mean = sum / m;
+                for (int i = 0; i < m; ++i) { const double d = NM_NS(i) - mean; q += d * d; }
+                double sd = sqrt(q / m);
+                if (sd == 0.0) sd = 1.0;
+                r = (v - med) / sd;
+            } else {
+                const double vi25 = (double)(m - 1) * 0.25, vi75 = (double)(m - 1) * 0.75;
+                const int k25 = (int)floor(vi25), k75 = (int)floor(vi75);
+                const double q25 = nm_norm_lerp(NM_NS(k25), NM_NS(k25 + 1 < m ? k25 + 1 : m - 1), vi25 - k25);
+                const double q75 = nm_norm_lerp(NM_NS(k75), NM_NS(k75 + 1 < m ? k75 + 1 : m - 1), vi75 - k75);
+                double scale = q75 - q25;
+                if (scale < NM_NORM_TINY_SCALE) scale = 1.0;
+                r = (v - med) / scale;
+            }
+        }
+        if (a.clip > 0.0) {
+            if (r < -a.clip) r = -a.clip;
+            if (r > a.clip) r = a.clip;
+        }
+        a.out[(size_t)k * a.F + a.cols[j]] = nm_nan_to_num(r);
+    }
+#undef NM_NS
+}
+
 struct NormFam {
     int method = 2, n_keep = 300, n_cols = 0;
     double clip = 3.0;

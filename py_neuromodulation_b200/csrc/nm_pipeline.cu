@@ -660,7 +660,23 @@ int NormFam::run(nm_pipeline* p, int n_windows) {
     a.out = p->d_out.as<double>();
     a.F = p->F;
     p->prof_begin();
-    NM_LAUNCH(nm_norm_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
+    // order-statistic methods over a batch of windows: the sliding sorted history (one thread per column); else one thread per
+    // (window, column)
+    int order_threads = 0;
+    if ((method == 1 || method == 3 || method == 5) && n_windows > 1) {
+        for (int tpb : {64, 32})
+            if (!order_threads && (size_t)n_keep * tpb * sizeof(double) <= (size_t)p->smem_max) order_threads = tpb;
+    }
+    if (order_threads) {
+        NmNormOrderArgs o;
+        o.ext = ext; o.n_prev = prev; o.n_windows = n_windows; o.n_cols = n_cols; o.cols = d_cols.as<int>();
+        o.g0 = batch; o.n_keep = n_keep; o.method = method; o.clip = clip; o.out = p->d_out.as<double>(); o.F = p->F;
+        const size_t sm = (size_t)n_keep * order_threads * sizeof(double);
+        if (nm_allow_smem(nm_norm_order_kernel, sm, p)) return -1;
+        NM_LAUNCH(nm_norm_order_kernel, dim3((n_cols + order_threads - 1) / order_threads), dim3(order_threads), sm, p->stream, o);
+    } else {
+        NM_LAUNCH(nm_norm_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
+    }
     p->prof_end(NM_PROF_NORM);
     p->launches += 2;
     // keep the last cap raw rows for the next call (right-aligned)
