@@ -517,7 +517,8 @@ def run_gpu_arm(args) -> None:
 
         if not args.quick:
             reps = 3
-            stream = nm.Stream(sfreq=sfreq, data=x, settings=settings, line_noise=LINE_NOISE, verbose=False)
+            x_user = np.array(x)  # what a reference user holds: an ordinary (pageable) numpy array, not the page-locked bench buffer
+            stream = nm.Stream(sfreq=sfreq, data=x_user, settings=settings, line_noise=LINE_NOISE, verbose=False)
             with tempfile.TemporaryDirectory() as td:
                 stream.run(out_dir=td, experiment_name="bench", save_csv=False)  # first call: builds the GPU plans (warm-up)
                 ts = []
@@ -528,8 +529,10 @@ def run_gpu_arm(args) -> None:
             t_med = float(np.median(ts))
             stream_info = {"value": n_win / t_med, "unit": UNIT, "ms_per_step": 1e3 * t_med, "frame_shape": list(df.shape),
                            "note": "nm.Stream.run(data, save_csv=False) wall clock, median of 3 after one warm-up call: window grid, H2D from the "
-                                   "caller's (pageable) array, kernels, D2H straight into the final table, pandas DataFrame, side files; the "
-                                   "processor of an unchanged configuration is kept across calls; CSV writing excluded"}
+                                   "caller's PAGEABLE array (staged slice by slice through page-locked buffers by a host thread of the library, "
+                                   "overlapping the kernels), kernels, rows of finished chunks through a page-locked buffer into the final "
+                                   "(pageable) table, pandas DataFrame, side files; the processor of an unchanged configuration is kept across "
+                                   "calls; CSV writing excluded"}
 
     if rank == 0:
         tile = f"{n_loc}x{W}"

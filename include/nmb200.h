@@ -164,7 +164,10 @@ int nm_add_feature_normalizer(nm_pipeline* p, int method, double clip, int n_kee
  * window-independent preprocessing (nan_to_num, pick, re-reference).  Recordings of >= 65 536 samples are copied
  * ASYNCHRONOUSLY in time slices on a second stream (each slice is re-referenced right before the first chunk of
  * windows that needs it, so the transfer overlaps the window kernels): `data` must stay valid and unchanged until
- * the next nm_run_windows / nm_synchronize on this pipeline has returned. */
+ * the next nm_run_windows / nm_synchronize on this pipeline has returned.  Page-locked buffers are read by the copy engine
+ * directly; PAGEABLE buffers are packed slice by slice into two page-locked staging buffers by a host thread of the library,
+ * so the call returns at once and the staging overlaps the window kernels too (NMB200_DEFERRED_UPLOAD=0: the driver's
+ * synchronous staged copy instead). */
 int nm_upload_f32(nm_pipeline* p, const float* data, long long n_samples, long long pitch);
 int nm_upload_f64(nm_pipeline* p, const double* data, long long n_samples, long long pitch);
 /* RawDataGenerator windows (stream/generator.py:41-53): window k = samples [starts[k], starts[k]+W).

@@ -9,8 +9,11 @@
 //       Y / xr rows --scan / spectral / band-power / bursts / sharp-wave kernels--> out columns
 //   out --normaliser--> out, NaN re-insertion                                      [whole run]
 //   out (n_windows x F, f64) --D2H--> host
+#include <condition_variable>
 #include <cstdarg>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -100,6 +103,22 @@ struct nm_pipeline {
     // copy engine overlap: H2D of the recording in time slices and D2H of finished chunks run on `copy_stream` while the
     // window kernels run on `stream`; slices are re-referenced lazily, right before the first chunk that needs them
     cudaStream_t copy_stream = nullptr;
+    // deferred upload of a PAGEABLE recording: a host thread packs time slices into two page-locked staging
+    // buffers and enqueues their H2D copies while the caller already launches window kernels; `up_enqueued` slices have their
+    // events recorded (a cudaStreamWaitEvent on an event that has not been recorded yet would not wait)
+    std::thread up_thread;
+    std::mutex up_mu;
+    std::condition_variable up_cv;
+    int up_enqueued = 0;
+    bool up_active = false, up_failed = false;
+    // pageable result matrix: finished chunks are copied into this page-locked buffer asynchronously and moved on to the caller's
+    // rows by the host while later chunks still compute (a D2H straight into pageable memory blocks the launching thread per chunk)
+    void* out_stage = nullptr;
+    size_t out_stage_bytes = 0;
+    std::vector<cudaEvent_t> d2h_ev;
+    void* up_stage[2] = {nullptr, nullptr};
+    size_t up_stage_bytes = 0;
+    cudaEvent_t up_free[2] = {nullptr, nullptr};
     cudaEvent_t ev_sync = nullptr;
     // independent feature families of a chunk (spectral + band power | sharp waves | bursts) run on side streams between a
     // fork after the notch and a join before the next chunk: their kernels are latency / occupancy limited in different ways
@@ -849,9 +868,17 @@ extern "C" int nm_pipeline_create(int device, int n_raw_rows, int n_ch, int wind
 
 static void nm_stream_release(nm_pipeline* p);
 
+static void nm_upload_join(nm_pipeline* p);
 extern "C" void nm_pipeline_destroy(nm_pipeline* p) {
     if (!p) return;
     cudaSetDevice(p->device);
+    nm_upload_join(p);
+    if (p->out_stage) cudaFreeHost(p->out_stage);
+    for (auto e : p->d2h_ev) cudaEventDestroy(e);
+    for (int b = 0; b < 2; ++b) {
+        if (p->up_stage[b]) cudaFreeHost(p->up_stage[b]);
+        if (p->up_free[b]) cudaEventDestroy(p->up_free[b]);
+    }
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
@@ -1305,6 +1332,18 @@ static NmPrepArgs nm_prep_args(nm_pipeline* p) {
 #define NM_UPLOAD_MIN_PIPELINED (1 << 16)  // samples; shorter recordings are copied and re-referenced in one go
 
 // re-reference every uploaded time slice that holds samples below `upto` and has not been processed yet
+static void nm_upload_join(nm_pipeline* p) {
+    if (p->up_thread.joinable()) p->up_thread.join();
+    p->up_active = false;
+}
+// block until the upload thread has enqueued slice k (its event is recorded); false if the thread failed
+static bool nm_upload_wait_enqueued(nm_pipeline* p, int k) {
+    if (!p->up_active) return true;
+    std::unique_lock<std::mutex> lk(p->up_mu);
+    p->up_cv.wait(lk, [&] { return p->up_enqueued > k || p->up_failed; });
+    return !p->up_failed;
+}
+
 static int nm_ensure_prepped(nm_pipeline* p, long long upto) {
     while (p->slices_prepped < p->n_slices && (long long)p->slices_prepped * p->slice_len < upto) {
         const int k = p->slices_prepped;
@@ -1316,6 +1355,7 @@ static int nm_ensure_prepped(nm_pipeline* p, long long upto) {
             a.gsum_pitch = p->gsum_pitch;
             a.gsum_out = nullptr;
         } else {
+            NM_CHECK(nm_upload_wait_enqueued(p, k), "the deferred upload failed");
             NM_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->slice_ev[k], 0));
         }
         a.t0 = (long long)k * p->slice_len;
@@ -1363,7 +1403,7 @@ static int nm_stage_raw(nm_pipeline* p, const void* data, bool f64, long long n_
 }
 
 // geometry + asynchronous H2D of the recording in `n_slices` time slices on the copy stream (slice_ev[k] = slice k has landed)
-static int nm_stage_slices(nm_pipeline* p, const void* data, bool f64, long long n_samples, long long pitch, int n_slices) {
+static int nm_stage_slices(nm_pipeline* p, const void* data, bool f64, long long n_samples, long long pitch, int n_slices, bool deferred = false) {
     const size_t esz = f64 ? 8 : 4;
     p->raw_f64 = f64;
     p->T = n_samples;
@@ -1385,6 +1425,62 @@ static int nm_stage_slices(nm_pipeline* p, const void* data, bool f64, long long
     // kernels of the previous run may still read the buffers that are about to be overwritten
     NM_CUDA_CHECK(cudaEventRecord(p->ev_sync, p->stream));
     NM_CUDA_CHECK(cudaStreamWaitEvent(p->copy_stream, p->ev_sync, 0));
+    if (deferred) {
+        // two page-locked staging buffers of one slice each; the thread below owns them and the copy stream's H2D work until it ends
+        const size_t need = (size_t)p->C_all * p->slice_len * esz;
+        if (need > p->up_stage_bytes) {
+            for (int b = 0; b < 2; ++b) {
+                if (p->up_stage[b]) cudaFreeHost(p->up_stage[b]);
+                p->up_stage[b] = nullptr;
+                NM_CUDA_CHECK(cudaMallocHost(&p->up_stage[b], need));
+                if (!p->up_free[b]) NM_CUDA_CHECK(cudaEventCreateWithFlags(&p->up_free[b], cudaEventDisableTiming));
+            }
+            p->up_stage_bytes = need;
+        }
+        p->up_enqueued = 0;
+        p->up_failed = false;
+        p->up_active = true;
+        auto body = [p, data, esz, n_samples, pitch]() {
+            cudaSetDevice(p->device);
+            bool ok = true;
+            for (int k = 0; k < p->n_slices && ok; ++k) {
+                const int b = k & 1;
+                const long long t0 = (long long)k * p->slice_len, len = std::min<long long>(p->slice_len, n_samples - t0);
+                if (k >= 2) ok = ok && cudaEventSynchronize(p->up_free[b]) == cudaSuccess;  // slice k - 2 has left this buffer
+                char* st = (char*)p->up_stage[b];
+                // (one thread moves ~6 GB/s out of pageable memory: the rows of a slice are dealt to a few helpers)
+                auto pack = [&](int r0, int r1) {
+                    for (int r = r0; r < r1; ++r)
+                        memcpy(st + (size_t)r * len * esz, (const char*)data + ((size_t)r * pitch + t0) * esz, (size_t)len * esz);
+                };
+                const int nh = (size_t)p->C_all * len * esz >= ((size_t)4 << 20) ? std::min(4, std::max(1, (int)std::thread::hardware_concurrency() / 2)) : 1;
+                if (nh > 1) {
+                    std::vector<std::thread> helpers;
+                    for (int h = 1; h < nh; ++h) helpers.emplace_back(pack, (int)((long long)p->C_all * h / nh), (int)((long long)p->C_all * (h + 1) / nh));
+                    pack(0, p->C_all / nh);
+                    for (auto& t : helpers) t.join();
+                } else {
+                    pack(0, p->C_all);
+                }
+                ok = ok && cudaMemcpy2DAsync((char*)p->d_raw.p + (size_t)t0 * esz, (size_t)p->raw_pitch * esz, st, (size_t)len * esz,
+                                             (size_t)len * esz, (size_t)p->C_all, cudaMemcpyHostToDevice, p->copy_stream) == cudaSuccess;
+                ok = ok && cudaEventRecord(p->up_free[b], p->copy_stream) == cudaSuccess;
+                ok = ok && cudaEventRecord(p->slice_ev[k], p->copy_stream) == cudaSuccess;
+                {
+                    std::lock_guard<std::mutex> lk(p->up_mu);
+                    if (ok) p->up_enqueued = k + 1;
+                    else p->up_failed = true;
+                }
+                p->up_cv.notify_all();
+            }
+        };
+#ifdef NM_EMULATE
+        body();  // (the test build copies synchronously)
+#else
+        p->up_thread = std::thread(body);
+#endif
+        return 0;
+    }
     for (int k = 0; k < p->n_slices; ++k) {
         const long long t0 = (long long)k * p->slice_len, len = std::min<long long>(p->slice_len, n_samples - t0);
         NM_CUDA_CHECK(cudaMemcpy2DAsync((char*)p->d_raw.p + (size_t)t0 * esz, (size_t)p->raw_pitch * esz, (const char*)data + (size_t)t0 * esz,
@@ -1394,19 +1490,28 @@ static int nm_stage_slices(nm_pipeline* p, const void* data, bool f64, long long
     return 0;
 }
 
-static int nm_upload_impl(nm_pipeline* p, const void* data, bool f64, long long n_samples, long long pitch) {
+static int nm_upload_impl(nm_pipeline* p, const void* data, bool f64, long long n_samples, long long pitch, bool deferred = false) {
     NM_P_CHECK(p);
     NM_CHECK(p->finalized, "call nm_finalize first");
     NM_CHECK(data && n_samples >= p->Win && pitch >= n_samples, "bad recording geometry (n_samples %lld, pitch %lld, W %d)", n_samples,
              pitch, p->Win);
     cudaSetDevice(p->device);
+    nm_upload_join(p);     // (a deferred upload that was never consumed)
     nm_stream_release(p);  // a streaming session (captured graphs, one-window geometry) does not survive a batched upload
     p->n_slices = 0;
     p->slices_prepped = 0;
     if (n_samples >= NM_UPLOAD_MIN_PIPELINED) {
         // pipelined upload: time slices on the copy stream, each followed by an event; nm_ensure_prepped() makes the compute
-        // stream wait for (and re-reference) a slice only when a chunk of windows first needs it
-        if (nm_stage_slices(p, data, f64, n_samples, pitch, NM_UPLOAD_SLICES)) return -1;
+        // stream wait for (and re-reference) a slice only when a chunk of windows first needs it.  Deferred: only for pageable
+        // memory (page-locked buffers are copied asynchronously by the copy engine as they are)
+#ifndef NM_EMULATE
+        if (deferred) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, data) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) deferred = false;
+            cudaGetLastError();
+        }
+#endif
+        if (nm_stage_slices(p, data, f64, n_samples, pitch, NM_UPLOAD_SLICES, deferred)) return -1;
     } else {
         if (nm_stage_raw(p, data, f64, n_samples, pitch)) return -1;
         nm_launch_prep(p, nm_prep_args(p));
@@ -1435,12 +1540,18 @@ extern "C" int nm_prepare_resident(nm_pipeline* p) {
     return 0;
 }
 
+// pageable recordings are staged by a host thread (deferred upload) unless NMB200_DEFERRED_UPLOAD=0
+static bool nm_deferred_upload_enabled() {
+    const char* env = getenv("NMB200_DEFERRED_UPLOAD");
+    return env ? atoi(env) != 0 : true;
+}
 extern "C" int nm_upload_f32(nm_pipeline* p, const float* data, long long n_samples, long long pitch) {
-    return nm_upload_impl(p, data, false, n_samples, pitch);
+    return nm_upload_impl(p, data, false, n_samples, pitch, nm_deferred_upload_enabled());
 }
 extern "C" int nm_upload_f64(nm_pipeline* p, const double* data, long long n_samples, long long pitch) {
-    return nm_upload_impl(p, data, true, n_samples, pitch);
+    return nm_upload_impl(p, data, true, n_samples, pitch, nm_deferred_upload_enabled());
 }
+
 
 // PreprocessingFilter stages of one batch of windows; on return `rows` describes the last stage's output buffer
 static void nm_run_prefilters(nm_pipeline* p, NmRows& rows) {
@@ -1701,6 +1812,23 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
     NM_CUDA_CHECK(cudaMemsetAsync(p->d_out.p, 0, (size_t)n_windows * p->F * sizeof(double), p->stream));
     // without the (sequential) normaliser a chunk's rows are final when its kernels end: ship them chunk by chunk
     const bool per_chunk = !p->norm && out_host != nullptr;
+    bool stage_out = false;
+#ifndef NM_EMULATE
+    if (per_chunk && nm_deferred_upload_enabled()) {
+        cudaPointerAttributes at;
+        stage_out = cudaPointerGetAttributes(&at, out_host) == cudaSuccess && at.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        const size_t need = (size_t)n_windows * p->F * sizeof(double);
+        if (stage_out && need > p->out_stage_bytes) {
+            if (p->out_stage) cudaFreeHost(p->out_stage);
+            p->out_stage = nullptr;
+            p->out_stage_bytes = 0;
+            if (cudaMallocHost(&p->out_stage, need) == cudaSuccess) p->out_stage_bytes = need;
+            else { stage_out = false; cudaGetLastError(); }
+        }
+    }
+#endif
+    std::vector<std::pair<int, int>> staged;  // (first window, windows) of the chunks copied into out_stage
     if (p->has_nan_cols && p->d_nanflags.ensure((size_t)n_windows * p->C_all)) return -1;
     auto nan_fill = [&](int w0, int n) { nm_nan_fill(p, w0, n); };
     if (p->bursts && p->bursts->prepare(p, n_windows)) return -1;
@@ -1722,14 +1850,27 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
                 NM_CUDA_CHECK(cudaEventRecord(p->chunk_ev[n_ev], p->stream));
                 NM_CUDA_CHECK(cudaStreamWaitEvent(p->copy_stream, p->chunk_ev[n_ev], 0));
                 const size_t hp = (size_t)(p->out_pitch ? p->out_pitch : p->F);
-                NM_CUDA_CHECK(cudaMemcpy2DAsync(out_host + (size_t)w0 * hp, hp * sizeof(double), p->d_out.as<double>() + (size_t)w0 * p->F,
-                                                (size_t)p->F * sizeof(double), (size_t)p->F * sizeof(double), (size_t)n, cudaMemcpyDeviceToHost,
-                                                p->copy_stream));
+                if (stage_out) {
+                    NM_CUDA_CHECK(cudaMemcpyAsync((double*)p->out_stage + (size_t)w0 * p->F, p->d_out.as<double>() + (size_t)w0 * p->F,
+                                                  (size_t)n * p->F * sizeof(double), cudaMemcpyDeviceToHost, p->copy_stream));
+                    if ((int)p->d2h_ev.size() <= n_ev) {
+                        cudaEvent_t e;
+                        NM_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                        p->d2h_ev.push_back(e);
+                    }
+                    NM_CUDA_CHECK(cudaEventRecord(p->d2h_ev[n_ev], p->copy_stream));
+                    staged.emplace_back(w0, n);
+                } else {
+                    NM_CUDA_CHECK(cudaMemcpy2DAsync(out_host + (size_t)w0 * hp, hp * sizeof(double), p->d_out.as<double>() + (size_t)w0 * p->F,
+                                                    (size_t)p->F * sizeof(double), (size_t)p->F * sizeof(double), (size_t)n,
+                                                    cudaMemcpyDeviceToHost, p->copy_stream));
+                }
                 ++n_ev;
             }
         }
     }
     if (nm_ensure_prepped(p, p->T)) return -1;  // leave no slice event un-consumed (nm_prepare_resident, NaN maps)
+    nm_upload_join(p);                           // (every slice of a deferred upload has been enqueued by now)
     if (!per_chunk) {
         if (p->norm && p->norm->run(p, n_windows)) return -1;
         if (p->has_nan_cols) nan_fill(0, n_windows);
@@ -1737,6 +1878,16 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
     NM_CUDA_CHECK(cudaGetLastError());
     if (out_host) {
         if (!per_chunk) return nm_download(p, out_host, n_windows);
+        // rows of the staged chunks -> the caller's (pageable, possibly pitched) matrix, chunk by chunk as their copies land
+        const size_t hp = (size_t)(p->out_pitch ? p->out_pitch : p->F);
+        for (size_t i = 0; i < staged.size(); ++i) {
+            NM_CUDA_CHECK(cudaEventSynchronize(p->d2h_ev[i]));
+            const int w0 = staged[i].first, n = staged[i].second;
+            const double* src = (const double*)p->out_stage + (size_t)w0 * p->F;
+            if (hp == (size_t)p->F) memcpy(out_host + (size_t)w0 * hp, src, (size_t)n * p->F * sizeof(double));
+            else
+                for (int r = 0; r < n; ++r) memcpy(out_host + (size_t)(w0 + r) * hp, src + (size_t)r * p->F, (size_t)p->F * sizeof(double));
+        }
         NM_CUDA_CHECK(cudaStreamSynchronize(p->copy_stream));
         NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
     }
@@ -1959,6 +2110,7 @@ extern "C" int nm_describe_plan(nm_pipeline* p, char* buf, int n) {
 extern "C" int nm_synchronize(nm_pipeline* p) {
     NM_P_CHECK(p);
     cudaSetDevice(p->device);
+    nm_upload_join(p);
     NM_CUDA_CHECK(cudaStreamSynchronize(p->copy_stream));
     NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
     return 0;
