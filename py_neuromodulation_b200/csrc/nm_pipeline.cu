@@ -1453,7 +1453,7 @@ static int nm_stage_slices(nm_pipeline* p, const void* data, bool f64, long long
                     for (int r = r0; r < r1; ++r)
                         memcpy(st + (size_t)r * len * esz, (const char*)data + ((size_t)r * pitch + t0) * esz, (size_t)len * esz);
                 };
-                const int nh = (size_t)p->C_all * len * esz >= ((size_t)4 << 20) ? std::min(4, std::max(1, (int)std::thread::hardware_concurrency() / 2)) : 1;
+                const int nh = (size_t)p->C_all * len * esz >= ((size_t)4 << 20) ? ((int)std::thread::hardware_concurrency() >= 4 ? 4 : 2) : 1;
                 if (nh > 1) {
                     std::vector<std::thread> helpers;
                     for (int h = 1; h < nh; ++h) helpers.emplace_back(pack, (int)((long long)p->C_all * h / nh), (int)((long long)p->C_all * (h + 1) / nh));
