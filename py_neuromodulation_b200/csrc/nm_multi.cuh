@@ -20,6 +20,7 @@ extern "C" int nm_upload_begin_f32(nm_pipeline* p, const float* data, long long 
     NM_CHECK(data && n_samples >= p->Win && pitch >= n_samples, "bad recording geometry");
     NM_CHECK(p->G > 0, "nm_upload_begin_f32 needs a re-reference with at least one channel group");
     cudaSetDevice(p->device);
+    nm_upload_join(p);  // (a deferred single-GPU upload may still be staging)
     nm_stream_release(p);
     const int n_slices = n_samples >= NM_UPLOAD_MIN_PIPELINED ? NM_UPLOAD_SLICES : 1;
     if (nm_stage_slices(p, data, false, n_samples, pitch, n_slices)) return -1;

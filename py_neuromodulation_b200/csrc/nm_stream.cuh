@@ -37,6 +37,7 @@ extern "C" int nm_stream_open(nm_pipeline* p, int n_slots, int input_f32, int us
     NM_CHECK(p->finalized, "call nm_finalize first");
     NM_CHECK(n_slots >= 1 && n_slots <= 64, "n_slots must be in [1, 64]");
     cudaSetDevice(p->device);
+    nm_upload_join(p);  // (a deferred batched upload may still be staging)
     nm_stream_release(p);
     NM_CUDA_CHECK(cudaStreamSynchronize(p->copy_stream));
     NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
