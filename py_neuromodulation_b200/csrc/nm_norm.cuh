@@ -337,5 +337,9 @@ struct NormFam {
         return d_hist.ensure((size_t)std::max(1, n_keep) * std::max(1, n_cols) * sizeof(double));
     }
     void reset() { batch = 0; n_prev = 0; }
-    int run(nm_pipeline* p, int n_windows);
+    // normalise result rows [w0, w0 + n_windows) of the current run (successive calls continue the history)
+    int run(nm_pipeline* p, int n_windows, int w0 = 0, int total = -1);
+    // O(n_keep) methods can follow every chunk of a batched run (its rows are then final and can be shipped while later chunks
+    // compute); the order-statistic methods keep one sliding pass over all windows at the end
+    bool per_chunk_ok() const { return method == 0 || method == 2 || method == 4 || method == 6; }
 };

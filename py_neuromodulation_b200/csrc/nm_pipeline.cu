@@ -648,35 +648,43 @@ int RawNormFam::run(nm_pipeline* p, NmRows& rows) {
 }
 
 
-int NormFam::run(nm_pipeline* p, int n_windows) {
+int NormFam::run(nm_pipeline* p, int n_windows, int w0, int total) {
     if (n_cols == 0) return 0;
     // History of RAW rows: a fixed-capacity block of cap = n_keep - 1 rows, the valid ones RIGHT-aligned.  The streaming entry
     // (one window per call) then always copies cap rows in and out -- constant sizes, so its CUDA graph never changes shape --
     // and passes n_prev = cap: the kernel reads rows [row - (nh - 1), row] with nh <= g + 1, i.e. never an unwritten one.
+    // Chunked (total > 0): rows [w0, w0 + n_windows) of a run of `total` windows; the history is copied in with the first chunk and
+    // out with the last one, the raw rows of the run accumulate in `ext` in between.
     const int cap = std::max(0, n_keep - 1);
     const bool streaming = p->strm && p->strm->cur >= 0 && n_windows == 1;
+    const bool chunked = total > 0;
+    const int run_windows = chunked ? total : n_windows;
     const int prev = streaming ? cap : n_prev;
-    const size_t rows = (size_t)prev + n_windows;
-    if (d_ext.ensure(std::max(rows, (size_t)cap + 1) * n_cols * sizeof(double))) return -1;
+    const size_t rows = (size_t)prev + run_windows;
+    if (!chunked || w0 == 0) {
+        if (d_ext.ensure(std::max(rows, (size_t)cap + 1) * n_cols * sizeof(double))) return -1;
+    }
     double* ext = d_ext.as<double>();
     const double* hist_valid = d_hist.as<double>() + (size_t)(cap - prev) * n_cols;
-    if (prev)
+    if (prev && (!chunked || w0 == 0))
         NM_STREAM_OP(cudaMemcpyAsync(ext, hist_valid, (size_t)prev * n_cols * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    const int r0 = chunked ? w0 : 0;  // first row of this call behind the history block
     const long long tot = (long long)n_windows * n_cols;
     const unsigned grid = (unsigned)((tot + NM_ROW_THREADS - 1) / NM_ROW_THREADS);
-    NM_LAUNCH(nm_norm_gather_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, (const double*)p->d_out.as<double>(), p->F,
-              (const int*)d_cols.as<int>(), n_cols, n_windows, ext + (size_t)prev * n_cols);
+    double* const out_rows = p->d_out.as<double>() + (size_t)w0 * p->F;
+    NM_LAUNCH(nm_norm_gather_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, (const double*)out_rows, p->F,
+              (const int*)d_cols.as<int>(), n_cols, n_windows, ext + ((size_t)prev + r0) * n_cols);
     NmNormArgs a;
     a.ext = ext;
-    a.n_prev = prev;
+    a.n_prev = prev + r0;
     a.n_windows = n_windows;
     a.n_cols = n_cols;
     a.cols = d_cols.as<int>();
-    a.g0 = batch;
+    a.g0 = batch + r0;
     a.n_keep = n_keep;
     a.method = method;
     a.clip = clip;
-    a.out = p->d_out.as<double>();
+    a.out = out_rows;
     a.F = p->F;
     p->prof_begin();
     // order-statistic methods over a batch of windows: the sliding sorted history (one thread per column); else one thread per
@@ -688,8 +696,8 @@ int NormFam::run(nm_pipeline* p, int n_windows) {
     }
     if (order_threads) {
         NmNormOrderArgs o;
-        o.ext = ext; o.n_prev = prev; o.n_windows = n_windows; o.n_cols = n_cols; o.cols = d_cols.as<int>();
-        o.g0 = batch; o.n_keep = n_keep; o.method = method; o.clip = clip; o.out = p->d_out.as<double>(); o.F = p->F;
+        o.ext = ext; o.n_prev = a.n_prev; o.n_windows = n_windows; o.n_cols = n_cols; o.cols = d_cols.as<int>();
+        o.g0 = a.g0; o.n_keep = n_keep; o.method = method; o.clip = clip; o.out = out_rows; o.F = p->F;
         const size_t sm = (size_t)n_keep * order_threads * sizeof(double);
         if (nm_allow_smem(nm_norm_order_kernel, sm, p)) return -1;
         NM_LAUNCH(nm_norm_order_kernel, dim3((n_cols + order_threads - 1) / order_threads), dim3(order_threads), sm, p->stream, o);
@@ -698,13 +706,14 @@ int NormFam::run(nm_pipeline* p, int n_windows) {
     }
     p->prof_end(NM_PROF_NORM);
     p->launches += 2;
+    if (chunked && w0 + n_windows < total) return 0;
     // keep the last cap raw rows for the next call (right-aligned)
     const int keep = streaming ? cap : (int)std::min<size_t>(rows, (size_t)cap);
     if (keep)
         NM_STREAM_OP(cudaMemcpyAsync(d_hist.as<double>() + (size_t)(cap - keep) * n_cols, ext + (rows - keep) * n_cols,
                                      (size_t)keep * n_cols * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
-    n_prev = (int)std::min<size_t>((size_t)n_prev + n_windows, (size_t)cap);
-    batch += n_windows;
+    n_prev = (int)std::min<size_t>((size_t)n_prev + run_windows, (size_t)cap);
+    batch += run_windows;
     return 0;
 }
 
@@ -1811,7 +1820,8 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
     p->out_rows = n_windows;
     NM_CUDA_CHECK(cudaMemsetAsync(p->d_out.p, 0, (size_t)n_windows * p->F * sizeof(double), p->stream));
     // without the (sequential) normaliser a chunk's rows are final when its kernels end: ship them chunk by chunk
-    const bool per_chunk = !p->norm && out_host != nullptr;
+    const bool norm_per_chunk = p->norm && p->norm->per_chunk_ok();
+    const bool per_chunk = (!p->norm || norm_per_chunk) && out_host != nullptr;
     bool stage_out = false;
 #ifndef NM_EMULATE
     if (per_chunk && nm_deferred_upload_enabled()) {
@@ -1839,6 +1849,7 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
         for (int k = 0; k < n; ++k) upto = std::max(upto, starts[w0 + k] + p->Win);
         if (nm_ensure_prepped(p, upto)) return -1;
         if (nm_run_chunk(p, w0, n)) return -1;
+        if (norm_per_chunk && p->norm->run(p, n, w0, n_windows)) return -1;
         if (per_chunk) {
             if (p->has_nan_cols) nan_fill(w0, n);
             if (out_host) {  // ship the finished rows while the next chunk computes
@@ -1872,7 +1883,7 @@ extern "C" int nm_run_windows(nm_pipeline* p, const long long* starts, int n_win
     if (nm_ensure_prepped(p, p->T)) return -1;  // leave no slice event un-consumed (nm_prepare_resident, NaN maps)
     nm_upload_join(p);                           // (every slice of a deferred upload has been enqueued by now)
     if (!per_chunk) {
-        if (p->norm && p->norm->run(p, n_windows)) return -1;
+        if (p->norm && !norm_per_chunk && p->norm->run(p, n_windows)) return -1;
         if (p->has_nan_cols) nan_fill(0, n_windows);
     }
     NM_CUDA_CHECK(cudaGetLastError());

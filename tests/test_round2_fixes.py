@@ -282,3 +282,29 @@ def test_sklearn_feature_normalizers_restated_on_the_gpu(backend, method):
     s.feature_normalization_settings.normalization_time_s = 31  # 310 windows > n_quantiles
     with pytest.raises(NotImplementedError):
         FeatureNormalizer(s)
+
+
+@pytest.mark.parametrize("method", ["zscore", "minmax", "quantile", "median", "robust"])
+def test_feature_normalizer_across_chunks_of_a_batched_run(backend, method):
+    """150 windows = three chunks of a batched run: the O(n_keep) methods normalise every chunk right behind its kernels (its rows
+    are then shipped while later chunks compute), the order-statistic methods in one sliding pass at the end; history of 50
+    windows, a NaN span (features NaN after the normaliser, history built from the nan_to_num'ed samples)."""
+    from py_neuromodulation_b200.stream.generator import window_grid
+    x = neural_like(3, 3, 1000 + 100 * 149)
+    x[1, 7000:7300] = np.nan
+    s = nm.NMSettings.get_default().reset()
+    for f in ("raw_hjorth", "return_raw", "linelength"):
+        s.features[f] = True
+    s.preprocessing = ["re_referencing"]
+    s.postprocessing.feature_normalization = True
+    s.feature_normalization_settings.normalization_method = method
+    s.feature_normalization_settings.normalization_time_s = 5.0
+    dp = nm.DataProcessor(sfreq=1000, settings=s, channels=get_default_channels_from_data(x), line_noise=50, verbose=False)
+    starts, _, _ = window_grid(x.shape[1], 1000, 10, 1000)
+    cols, got = dp.process_windows(x, starts, 1000)
+    assert dp.plan(1000).pipe.chunk_windows < len(starts)
+    ref_cols, ref = orc.run_offline(x, 1000, s.model_dump())
+    assert ref_cols[: len(cols)] == cols
+    ref = ref[:, : len(cols)]
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert float(np.nanmax(np.abs(got - ref))) < 1e-10
