@@ -1438,14 +1438,26 @@ static int nm_stage_slices(nm_pipeline* p, const void* data, bool f64, long long
         // two page-locked staging buffers of one slice each; the thread below owns them and the copy stream's H2D work until it ends
         const size_t need = (size_t)p->C_all * p->slice_len * esz;
         if (need > p->up_stage_bytes) {
+            p->up_stage_bytes = 0;
+            bool got = true;
             for (int b = 0; b < 2; ++b) {
                 if (p->up_stage[b]) cudaFreeHost(p->up_stage[b]);
                 p->up_stage[b] = nullptr;
-                NM_CUDA_CHECK(cudaMallocHost(&p->up_stage[b], need));
+                got = got && cudaMallocHost(&p->up_stage[b], need) == cudaSuccess;
                 if (!p->up_free[b]) NM_CUDA_CHECK(cudaEventCreateWithFlags(&p->up_free[b], cudaEventDisableTiming));
             }
-            p->up_stage_bytes = need;
+            if (got) p->up_stage_bytes = need;
+            else {  // no page-locked memory for the staging buffers: the driver's own staged copies below
+                cudaGetLastError();
+                for (int b = 0; b < 2; ++b) {
+                    if (p->up_stage[b]) cudaFreeHost(p->up_stage[b]);
+                    p->up_stage[b] = nullptr;
+                }
+                deferred = false;
+            }
         }
+    }
+    if (deferred) {
         p->up_enqueued = 0;
         p->up_failed = false;
         p->up_active = true;
