@@ -79,7 +79,9 @@ int nm_set_fused(nm_pipeline* p, int mode);
 
 /* RawNormalizer (processing/normalization.py:30-111, type "raw"): window 0 passes through and seeds the per-channel
  * history; window g >= 1 appends its last add_samples = int(sfreq / rate) preprocessed samples, is normalised against the
- * whole history (method 0 mean, 2 zscore), clipped (clip == 0: off) and the history is trimmed to n_keep - 1 samples
+ * whole history (method 0 mean, 1 median, 2 zscore, 3 zscore-median, 4 minmax = scikit-learn MinMaxScaler, 5 robust = RobustScaler;
+ * the order statistics come from the sliding quantile kernel of the burst thresholds), clipped (clip == 0: off) and the history is
+ * trimmed to n_keep - 1 samples
  * (n_keep = int(normalization_time_s * sfreq)).  Runs after the notch / re-reference, before every feature. */
 int nm_set_raw_normalizer(nm_pipeline* p, int method, double clip, int n_keep, int add_samples);
 

@@ -743,6 +743,8 @@ class RawNormalizerOracle:
                 std[std == 0] = 1
                 centre = mean if self.method == "zscore" else (np.nanmedian if has_nan else np.median)(self.prev, axis=0)
                 out = (d - centre) / std
+            elif self.method in ("minmax", "robust"):
+                out = sklearn_restated(self.method, np.nan_to_num(self.prev), d)  # (samples x channels: column-wise like sklearn)
             else:
                 raise NotImplementedError(f"sklearn normaliser '{self.method}' is out of scope")
         if self.clip:

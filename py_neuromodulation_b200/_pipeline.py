@@ -27,6 +27,9 @@ NORM_METHODS = ("mean", "median", "zscore", "zscore-median")  # raw normaliser (
 # feature normaliser (csrc/nm_norm.cuh): the numpy methods + the scikit-learn transformers the reference wraps, restated on the GPU
 # ("power" -- Yeo-Johnson with a per-window maximum-likelihood search -- stays out of scope)
 FEATURE_NORM_METHODS = NORM_METHODS + ("minmax", "robust", "quantile")
+# raw normaliser: MinMaxScaler / RobustScaler on the sliding order-statistic kernel; the reference's QuantileTransformer draws a RANDOM
+# subsample of 10 000 of the 30 000 history samples per window (no reproducible answer), PowerTransformer as above
+RAW_NORM_METHODS = NORM_METHODS + ("minmax", "robust")
 
 
 def _i32(a) -> np.ndarray:
@@ -147,9 +150,9 @@ class Pipeline:
 
     def set_raw_normalizer(self, method: str, clip: float, n_keep: int, add_samples: int) -> None:
         """RawNormalizer in front of the features (mean / median / zscore / zscore-median; scikit-learn methods are out of scope)."""
-        if method not in NORM_METHODS:
-            raise NotImplementedError(f"raw normalisation method '{method}' (scikit-learn transformer) is out of scope")
-        _lib.check(self.lib.nm_set_raw_normalizer(self._h, NORM_METHODS.index(method), float(clip or 0.0), int(n_keep), int(add_samples)))
+        if method not in RAW_NORM_METHODS:
+            raise NotImplementedError(f"raw normalisation method '{method}' (scikit-learn quantile / power transformer) is out of scope")
+        _lib.check(self.lib.nm_set_raw_normalizer(self._h, RAW_NORM_METHODS.index(method), float(clip or 0.0), int(n_keep), int(add_samples)))
 
     def set_prefilters(self, stages: Sequence[np.ndarray] | None) -> None:
         """PreprocessingFilter stages (one tap vector each, possibly of different lengths), applied in order before the notch."""

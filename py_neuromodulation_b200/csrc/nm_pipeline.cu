@@ -569,8 +569,10 @@ int RawNormFam::run(nm_pipeline* p, NmRows& rows) {
     const int n = rows.n_windows;
     // history bookkeeping per window (processing/normalization.py:92-107): statistics range [lo, end of block g)
     std::vector<long long> lo(n, 0), e_end(n, 0);
-    std::vector<int> nh(n, 0), klo(n, 0), khi(n, 0);
-    std::vector<double> gam(n, 0.0);
+    const int nt = n_tracks();
+    std::vector<int> nh(n, 0), klo[3], khi[3];
+    std::vector<double> gam[3];
+    for (int t = 0; t < nt; ++t) { klo[t].assign(n, 0); khi[t].assign(n, 0); gam[t].assign(n, 0.0); }
     for (int k = 0; k < n; ++k) {
         const long long g = batch + k;
         long long hist = W;
@@ -582,11 +584,24 @@ int RawNormFam::run(nm_pipeline* p, NmRows& rows) {
             lo[k] = e_end[k] - hist;
             len_prev = (n_keep > 1) ? std::min<long long>(hist, n_keep - 1) : hist;  // previous[-n_keep + 1:] keeps everything for n_keep == 1
         }
-        // numpy.median == 'linear' quantile at 0.5: order statistics (hist - 1) / 2 rounded down / up, averaged
+        // numpy 'linear' quantile: virtual index (hist - 1) * q, the order statistics below / above it and the lerp weight
+        // (q = 0.5: numpy.median, the two middle values averaged)
         nh[k] = (int)hist;
-        klo[k] = (int)((hist - 1) / 2);
-        khi[k] = (int)(hist / 2);
-        gam[k] = (hist % 2 == 0) ? 0.5 : 0.0;
+        for (int t = 0; t < nt; ++t) {
+            const double q = track_q(t);
+            if (q == 0.5) {
+                klo[t][k] = (int)((hist - 1) / 2);
+                khi[t][k] = (int)(hist / 2);
+                gam[t][k] = (hist % 2 == 0) ? 0.5 : 0.0;
+            } else {
+                const double vi = (double)(hist - 1) * q;
+                const long long f = (long long)std::floor(vi);
+                klo[t][k] = (int)f;
+                khi[t][k] = (int)std::min<long long>(f + 1, hist - 1);
+                gam[t][k] = vi - (double)f;
+                if (gam[t][k] == 0.0) khi[t][k] = klo[t][k];
+            }
+        }
     }
     NM_CHECK(n_keep > 1 || (long long)W + (batch + n) * add < cap, "raw normalisation history exceeds the ring (normalization_time_s * sfreq == 1)");
     const long long* a_lo = nullptr;
@@ -606,36 +621,42 @@ int RawNormFam::run(nm_pipeline* p, NmRows& rows) {
     a.lo = a_lo;
     a.method = method;
     a.clip = clip;
-    a.med = need_median() ? d_med.as<double>() : nullptr;
+    a.med = nt > 0 ? d_med[0].as<double>() : nullptr;
+    a.q1 = nt > 1 ? d_med[1].as<double>() : nullptr;
+    a.q2 = nt > 2 ? d_med[2].as<double>() : nullptr;
     const int wpc = NM_ROW_THREADS / 32;
     const long long n_rows = (long long)n * C;
     const int grid = (int)std::max<long long>(1, std::min<long long>((n_rows + wpc - 1) / wpc, (long long)p->n_sm * 16));
     p->prof_begin();
     NM_LAUNCH(nm_rawnorm_append_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
-    if (need_median()) {
+    if (nt > 0) {
         const long long* m_e_end = nullptr;
-        const int *m_n = nullptr, *m_lo = nullptr, *m_hi = nullptr;
-        const double* m_gamma = nullptr;
+        const int* m_n = nullptr;
         bool msync = false;
-        if (nm_param_upload(p, d_e_end, e_end, &m_e_end, &msync) || nm_param_upload(p, d_n, nh, &m_n, &msync) ||
-            nm_param_upload(p, d_klo, klo, &m_lo, &msync) || nm_param_upload(p, d_khi, khi, &m_hi, &msync) ||
-            nm_param_upload(p, d_gamma, gam, &m_gamma, &msync))
-            return -1;
+        if (nm_param_upload(p, d_e_end, e_end, &m_e_end, &msync) || nm_param_upload(p, d_n, nh, &m_n, &msync)) return -1;
+        const int *m_lo[3] = {nullptr, nullptr, nullptr}, *m_hi[3] = {nullptr, nullptr, nullptr};
+        const double* m_gamma[3] = {nullptr, nullptr, nullptr};
+        for (int t = 0; t < nt; ++t)
+            if (nm_param_upload(p, d_klo[t], klo[t], &m_lo[t], &msync) || nm_param_upload(p, d_khi[t], khi[t], &m_hi[t], &msync) ||
+                nm_param_upload(p, d_gamma[t], gam[t], &m_gamma[t], &msync))
+                return -1;
         if (msync) NM_CUDA_CHECK(cudaStreamSynchronize(p->stream));
-        NmBurstThrArgs ta;
-        ta.ring = d_ring.as<double>();
-        ta.cap = cap;
-        ta.n_ch = C; ta.nB = 1; ta.n_windows = n;
-        ta.e_end = m_e_end;
-        ta.n_hist = m_n;
-        ta.k_lo = m_lo; ta.k_hi = m_hi;
-        ta.gamma = m_gamma;
-        ta.thr = d_med.as<double>();
-        ta.incremental = 1;
-        ta.n_split = nm_burst_thr_split(C, n, p->n_sm);
-        qstate.bind(ta, p->stream);
-        NM_LAUNCH(nm_burst_thr_kernel, dim3(C * ta.n_split), dim3(NM_BQ_THREADS), BurstsFam::thr_smem(), p->stream, ta);
-        p->launches++;
+        for (int t = 0; t < nt; ++t) {
+            NmBurstThrArgs ta;
+            ta.ring = d_ring.as<double>();
+            ta.cap = cap;
+            ta.n_ch = C; ta.nB = 1; ta.n_windows = n;
+            ta.e_end = m_e_end;
+            ta.n_hist = m_n;
+            ta.k_lo = m_lo[t]; ta.k_hi = m_hi[t];
+            ta.gamma = m_gamma[t];
+            ta.thr = d_med[t].as<double>();
+            ta.incremental = 1;
+            ta.n_split = nm_burst_thr_split(C, n, p->n_sm);
+            qstate[t].bind(ta, p->stream);
+            NM_LAUNCH(nm_burst_thr_kernel, dim3(C * ta.n_split), dim3(NM_BQ_THREADS), BurstsFam::thr_smem(), p->stream, ta);
+            p->launches++;
+        }
     }
     NM_LAUNCH(nm_rawnorm_apply_kernel, dim3(grid), dim3(NM_ROW_THREADS), 0, p->stream, a);
     p->prof_end(NM_PROF_NOTCH);
@@ -1209,7 +1230,7 @@ extern "C" int nm_set_fused(nm_pipeline* p, int mode) {
 extern "C" int nm_set_raw_normalizer(nm_pipeline* p, int method, double clip, int n_keep, int add_samples) {
     NM_P_CHECK(p);
     NM_CHECK(!p->finalized, "pipeline already finalized");
-    NM_CHECK(method >= 0 && method <= 3, "raw normalisation method must be 0..3 (mean, median, zscore, zscore-median); got %d", method);
+    NM_CHECK(method >= 0 && method <= 5, "raw normalisation method must be 0..5 (mean, median, zscore, zscore-median, minmax, robust); got %d", method);
     NM_CHECK(n_keep >= 1 && add_samples >= 1 && clip >= 0.0, "bad raw normaliser configuration");
     auto f = std::make_unique<RawNormFam>();
     if (f->build(method, clip, n_keep, add_samples, p->C, p->W)) return -1;

@@ -13,6 +13,9 @@
 // once their blocks are appended: kernel 1 appends (warp per (window, channel)), kernel 2 combines and normalises.
 // Methods: 0 mean, 2 zscore; 1 median and 3 zscore-median take the median of the same history from the sliding
 // order-statistic kernel of the burst thresholds (nm_burst_thr_kernel on signed keys, q = 0.5) between the two kernels.
+// Round 2: 4 minmax and 5 robust -- the scikit-learn MinMaxScaler / RobustScaler the reference wraps
+// (processing/normalization.py:58-70,173-190) -- run the same kernel once per order statistic they need (q = 0, 1 and
+// q = 0.5, 0.25, 0.75), each track with a bracket state of its own.
 #pragma once
 
 #include "nm_bursts.cuh"
@@ -30,7 +33,10 @@ struct NmRawNormArgs {
     const long long* lo;    // [n_windows] first stream position of the statistics range of window k (unused for g == 0)
     int method;
     double clip;
-    const double* med;      // (n_windows, n_ch) medians of the histories (methods 1 and 3), else nullptr
+    const double* med;      // (n_windows, n_ch) order statistics of the histories from the sliding quantile kernel: the median
+                            // (methods 1, 3, 5) or the minimum (method 4), else nullptr
+    const double* q1;       // second track: maximum (method 4) / 25th percentile (method 5)
+    const double* q2;       // third track: 75th percentile (method 5)
 };
 
 struct NmStat { double n, mean, m2; };
@@ -130,12 +136,24 @@ NM_GLOBAL void nm_rawnorm_apply_kernel(NmRawNormArgs a) {
         double centre = s.mean;
         if (a.method == 1 || a.method == 3) centre = nm_ldg(a.med + (size_t)k * a.in.n_ch + c);
         double scale = centre;
-        if (a.method >= 2) {
+        if (a.method == 2 || a.method == 3) {
             scale = sqrt(s.m2 / s.n);
             if (scale == 0.0) scale = 1.0;  // same behaviour as the reference (and sklearn)
         }
+        double mm_scale = 0.0, mm_min = 0.0;
+        if (a.method == 4) {  // MinMaxScaler: X * scale_ + min_ (sklearn _handle_zeros_in_scale: ranges below 10 eps -> 1)
+            const double mn = nm_ldg(a.med + (size_t)k * a.in.n_ch + c), mx = nm_ldg(a.q1 + (size_t)k * a.in.n_ch + c);
+            double range = mx - mn;
+            if (range < 10.0 * 2.220446049250313e-16) range = 1.0;
+            mm_scale = 1.0 / range;
+            mm_min = 0.0 - mn * mm_scale;
+        } else if (a.method == 5) {  // RobustScaler: (X - median) / (q75 - q25)
+            centre = nm_ldg(a.med + (size_t)k * a.in.n_ch + c);
+            scale = nm_ldg(a.q2 + (size_t)k * a.in.n_ch + c) - nm_ldg(a.q1 + (size_t)k * a.in.n_ch + c);
+            if (scale < 10.0 * 2.220446049250313e-16) scale = 1.0;
+        }
         for (int t = lane; t < W; t += 32) {
-            double v = (x[t] - centre) / scale;
+            double v = (a.method == 4) ? x[t] * mm_scale + mm_min : (x[t] - centre) / scale;
             if (a.clip != 0.0) {  // (NaN compares false both ways and survives the clip like numpy.clip)
                 if (v > a.clip) v = a.clip;
                 if (v < -a.clip) v = -a.clip;
@@ -153,9 +171,16 @@ struct RawNormFam {
     long long cap = 0, Wp = 0, batch = 0, len_prev = 0;  // len_prev: history length after the last processed window
     DevBuf d_ring, d_blk, d_out, d_lo;
     // sliding median (methods 1, 3): per-window bookkeeping + persistent state of nm_burst_thr_kernel, one row per channel
-    DevBuf d_e_end, d_n, d_klo, d_khi, d_gamma, d_med;
-    NmBqState qstate;
-    bool need_median() const { return method == 1 || method == 3; }
+    // (methods 4, 5: up to three order statistics per window -- "tracks" -- each with parameters, results and a bracket state of its own)
+    DevBuf d_e_end, d_n, d_klo[3], d_khi[3], d_gamma[3], d_med[3];
+    NmBqState qstate[3];
+    int n_tracks() const { return (method == 1 || method == 3) ? 1 : (method == 4 ? 2 : (method == 5 ? 3 : 0)); }
+    double track_q(int t) const {  // quantile of track t
+        if (method == 4) return t == 0 ? 0.0 : 1.0;
+        if (method == 5) return t == 0 ? 0.5 : (t == 1 ? 0.25 : 0.75);
+        return 0.5;
+    }
+    bool need_median() const { return n_tracks() > 0; }
     int build(int method_, double clip_, int n_keep_, int add_, int C_, int W_) {
         method = method_; clip = clip_; n_keep = n_keep_; C = C_; W = W_;
         add = std::max(1, std::min(add_, W));
@@ -170,16 +195,16 @@ struct RawNormFam {
         if (d_ring.ensure((size_t)C * cap * sizeof(double))) return -1;
         if (d_blk.ensure((size_t)C * blk_cap * 3 * sizeof(double))) return -1;
         if (d_out.ensure((size_t)chunk * C * Wp * sizeof(double))) return -1;
-        if (need_median()) {
-            if (d_med.ensure((size_t)chunk * C * sizeof(double))) return -1;
-            if (qstate.alloc((size_t)C)) return -1;
+        for (int t = 0; t < n_tracks(); ++t) {
+            if (d_med[t].ensure((size_t)chunk * C * sizeof(double))) return -1;
+            if (qstate[t].alloc((size_t)C)) return -1;
         }
         return 0;
     }
     void reset(cudaStream_t s) {  // (stream-ordered, see BurstsFam::reset)
         batch = 0;
         len_prev = 0;
-        qstate.reset(s);
+        for (int t = 0; t < 3; ++t) qstate[t].reset(s);
     }
     int run(nm_pipeline* p, NmRows& rows);
 };

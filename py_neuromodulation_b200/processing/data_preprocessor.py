@@ -42,7 +42,8 @@ def preprocessing_plan(settings: "NMSettings", sfreq: float) -> list[str]:
                 continue
         if name == "raw_normalization":
             method = settings.raw_normalization_settings.normalization_method
-            if method not in ("mean", "median", "zscore", "zscore-median"):
+            if method not in ("mean", "median", "zscore", "zscore-median", "minmax", "robust"):
+                # (quantile: the reference's QuantileTransformer subsamples the history at random; power: per-window likelihood search)
                 raise NotImplementedError(f"raw_normalization with the scikit-learn method '{method}' is out of scope")
         plan.append(name)
     return plan

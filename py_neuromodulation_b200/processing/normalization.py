@@ -16,6 +16,9 @@ GPU_NORM_METHODS = ("mean", "median", "zscore", "zscore-median")  # raw normalis
 # feature normaliser: + the scikit-learn transformers of the reference (processing/normalization.py:58-70), restated in
 # csrc/nm_norm.cuh: MinMaxScaler, RobustScaler, QuantileTransformer(n_quantiles=300); PowerTransformer stays out of scope
 GPU_FEATURE_NORM_METHODS = GPU_NORM_METHODS + ("minmax", "robust", "quantile")
+# raw normaliser: MinMaxScaler / RobustScaler too (csrc/nm_rawnorm.cuh); `quantile` is not reproducible in the reference itself there
+# (QuantileTransformer subsamples 10 000 of the 30 000 history samples at random)
+GPU_RAW_NORM_METHODS = GPU_NORM_METHODS + ("minmax", "robust")
 
 
 def check_feature_norm_method(method: str, n_keep: int) -> None:
@@ -70,10 +73,10 @@ class RawNormalizer:
     Stateful like the reference: window 0 passes through and seeds the history, later windows append their last
     ``int(sfreq / sampling_rate_features_hz)`` samples and are normalised against the whole history
     (``csrc/nm_rawnorm.cuh``; the medians come from the sliding order-statistic kernel of the burst thresholds).
-    The scikit-learn transformers raise ``NotImplementedError``.
+    Of the scikit-learn transformers ``minmax`` and ``robust`` are restated on the GPU; ``quantile`` / ``power`` raise ``NotImplementedError``.
     """
 
-    GPU_METHODS = GPU_NORM_METHODS
+    GPU_METHODS = GPU_RAW_NORM_METHODS
 
     def __init__(self, sfreq: float, settings: "NMSettings", **kwargs) -> None:
         self.settings = settings.raw_normalization_settings.validate()

@@ -267,6 +267,24 @@ def sklearn_norm_cases(nm):
              sfreq=1000.0)
 
 
+def sklearn_rawnorm_cases(nm):
+    """RawNormalizer through the scikit-learn MinMaxScaler / RobustScaler (processing/normalization.py:58-70,173-190): history of
+    2.5 s of samples, trimmed inside the run."""
+    x = neural_like(32, 4, 1000 + 100 * 44)
+    for method in ("minmax", "robust"):
+        st = nm.NMSettings.get_default().reset()
+        for f in ("fft", "raw_hjorth", "linelength", "return_raw"):
+            st.features[f] = True
+        st.postprocessing.feature_normalization = False
+        st.preprocessing = ["notch_filter", "re_referencing", "raw_normalization"]
+        st.raw_normalization_settings.normalization_time_s = 2.5
+        st.raw_normalization_settings.normalization_method = method
+        st.raw_normalization_settings.clip = 1.5 if method == "robust" else 3.0
+        keys, vals = _run_windows(nm, st, x)
+        save(f"dataprocessor_rawnorm_{method}", x=x.astype(np.float32), settings=dump_settings(st), keys=json.dumps(keys), vals=vals,
+             sfreq=1000.0)
+
+
 def stream_cases():
     nm = load_reference_stream()
     import tempfile
@@ -386,6 +404,7 @@ if __name__ == "__main__":
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sklearn_norm":
         sklearn_norm_cases(nm)
+        sklearn_rawnorm_cases(nm)
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sharpwave":
         sharpwave_option_cases(nm)
@@ -399,6 +418,7 @@ if __name__ == "__main__":
     sharpwave_option_cases(nm)
     window_processor_cases(nm)
     sklearn_norm_cases(nm)
+    sklearn_rawnorm_cases(nm)
     burst_history_case(nm)
     real_data_case(nm)
     stream_cases()

@@ -115,7 +115,9 @@ NEXT_ROW_FIXTURES = ["dataprocessor_prefilter_default", "dataprocessor_prefilter
                      # sharp-wave option: one polarity only (un-paired keys)
                      "dataprocessor_sharpwave_peaks_only", "dataprocessor_sharpwave_troughs_only",
                      # feature normalisation through the scikit-learn transformers the reference wraps (generated with scikit-learn 1.9)
-                     "dataprocessor_featnorm_minmax", "dataprocessor_featnorm_robust", "dataprocessor_featnorm_quantile"]
+                     "dataprocessor_featnorm_minmax", "dataprocessor_featnorm_robust", "dataprocessor_featnorm_quantile",
+                     # ... and the raw normaliser through MinMaxScaler / RobustScaler
+                     "dataprocessor_rawnorm_minmax", "dataprocessor_rawnorm_robust"]
 
 
 @pytest.mark.parametrize("name", ["dataprocessor_default", "dataprocessor_fast", "dataprocessor_c3_nan", "dataprocessor_realdata"]

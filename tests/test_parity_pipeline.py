@@ -52,7 +52,10 @@ def run_dp(g, n_windows=None, with_norm=True, fused=None):
                                         # MinMaxScaler / RobustScaler / QuantileTransformer feature normalisation
                                         # (processing/normalization.py:58-70,173-190), restated in csrc/nm_norm.cuh
                                         ("dataprocessor_featnorm_minmax", None), ("dataprocessor_featnorm_robust", None),
-                                        ("dataprocessor_featnorm_quantile", None)])
+                                        ("dataprocessor_featnorm_quantile", None),
+                                        # RawNormalizer through MinMaxScaler / RobustScaler: sliding min / max and 25 / 50 / 75th
+                                        # percentiles from the order-statistic kernel of the burst thresholds
+                                        ("dataprocessor_rawnorm_minmax", None), ("dataprocessor_rawnorm_robust", None)])
 def test_window_processor_matches_reference_golden(backend, name, n_emu):
     g = load_golden(name)
     n = n_emu if backend == "emu" else None  # the thread emulator is slow: fewer windows on CPU, all on the GPU
