@@ -415,7 +415,7 @@ def test_raw_normalizer_streaming_and_standalone(backend):
         got, ref = rn.process(w), ora.process(w)
         assert np.max(np.abs(got - ref)) < 1e-10, k
     s2 = nm.NMSettings(**g["settings"])
-    s2.raw_normalization_settings.normalization_method = "robust"  # scikit-learn transformer
+    s2.raw_normalization_settings.normalization_method = "power"  # scikit-learn PowerTransformer: not offered (minmax / robust are)
     with pytest.raises(NotImplementedError):
         nm.DataProcessor(sfreq=1000, settings=s2, channels=ch, line_noise=50, verbose=False)
 
