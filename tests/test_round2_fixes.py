@@ -308,3 +308,23 @@ def test_feature_normalizer_across_chunks_of_a_batched_run(backend, method):
     ref = ref[:, : len(cols)]
     assert np.array_equal(np.isnan(got), np.isnan(ref))
     assert float(np.nanmax(np.abs(got - ref))) < 1e-10
+
+
+@pytest.mark.parametrize("method", ["minmax", "robust"])
+def test_standalone_raw_normalizer_with_sklearn_methods(backend, method):
+    """`RawNormalizer.process(window)` (reference class name and interface) with the restated MinMaxScaler / RobustScaler: sliding
+    minimum / maximum / percentiles of a 1.7 s sample history against the oracle, window by window."""
+    from py_neuromodulation_b200.processing.normalization import RawNormalizer
+    x = neural_like(8, 3, 1000 + 100 * 39)
+    s = nm.NMSettings.get_default()
+    s.raw_normalization_settings.normalization_method = method
+    s.raw_normalization_settings.normalization_time_s = 1.7
+    rn = RawNormalizer(1000, s)
+    ora = orc.RawNormalizerOracle(s.model_dump(), 1000)
+    changed = 0.0
+    for k in range(40):
+        w = x[:, 100 * k : 100 * k + 1000]
+        got, ref = rn.process(w), ora.process(w)
+        assert np.max(np.abs(got - ref)) < 1e-10, k
+        changed = max(changed, float(np.max(np.abs(got - w))))
+    assert changed > 0.1  # the windows really were normalised
